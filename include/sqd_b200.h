@@ -1,0 +1,236 @@
+/* sqd_b200 -- C-ABI of the B200-native SQD hot path (libsqd_b200.so).
+ *
+ * Drop-in boundary for the three hot-path entry points of Qiskit/qiskit-addon-sqd (reference paths
+ * are relative to /root/reference):
+ *   - fermion.solve_fermion / solve_sci / solve_sci_batch      qiskit_addon_sqd/fermion.py:643-845
+ *       (the work the reference delegates to pyscf: fci.selected_ci.kernel_fixed_space,
+ *        make_rdm1s, make_rdm1/make_rdm2 energy, spin_square -- fermion.py:713-729, 803-830)
+ *   - qubit.project_operator_to_subspace / matrix_elements_from_pauli / solve_qubit
+ *                                                               qiskit_addon_sqd/qubit.py:29-300
+ *   - configuration_recovery.recover_configurations             qiskit_addon_sqd/configuration_recovery.py:59-306
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer on the current CUDA device; h_* is a host pointer;
+ *   - the library never allocates or frees memory that outlives a call: the caller (Python: torch
+ *     tensors) owns all buffers and sizes them with the *_count / *_bytes queries;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - return value 0 = ok, < 0 = error; sqd_last_error() returns a thread-local message;
+ *   - no function synchronises the stream unless its comment says so.
+ */
+#ifndef SQD_B200_H
+#define SQD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQD_B200_VERSION 100
+#define SQD_MAX_SPACE 32 /* largest Davidson subspace the device-side Rayleigh-Ritz supports */
+
+int sqd_version(void);
+const char* sqd_last_error(void);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Determinant strings and excitation tables
+ * replaces: pyscf selected_ci._all_linkstr_index (cre_des_linkstr / des_des_linkstr) reached from
+ *           fermion.py:721,810; string checks fermion.py:1075-1097; packing counts.py:186-201
+ * ------------------------------------------------------------------------------------------ */
+
+/* Pack a bool bitstring matrix (n rows, nbits columns, 1 byte per bit, column 0 = most significant)
+ * into two uint64 halves per row: left = columns [0, nbits/2) (beta), right = columns [nbits/2, nbits)
+ * (alpha).  nbits/2 <= 64.  (counts.py:186-201, fermion.py:1026-1030) */
+int sqd_pack_bitstrings(const uint8_t* d_bits, int64_t n, int nbits, uint64_t* d_left,
+                        uint64_t* d_right, void* stream);
+
+/* popcount of every string; h_bad_index receives the first index whose popcount differs from string
+ * 0, or -1.  Synchronises the stream.  (fermion.py:1075-1097) */
+int sqd_check_hamming(const uint64_t* d_strs, int64_t n, int* d_scratch2, int* h_bad_index,
+                      int* h_weight0, int* h_weight_bad, void* stream);
+
+/* Pass 1: for each string i count the in-set single (xor-popcount 2) and single+double (2 or 4)
+ * excitation partners.  d_n_single, d_n_total: int[n]. */
+int sqd_excitation_count(const uint64_t* d_strs, int n, int* d_n_single, int* d_n_total,
+                         void* stream);
+
+/* Exclusive prefix sum of int[n] into int[n+1] (out[n] = total); h_total (pinned or pageable host
+ * int) receives out[n] -- synchronises the stream when h_total != NULL. */
+int sqd_exclusive_scan(const int* d_in, int* d_out, int n, int* h_total, void* stream);
+
+/* Pass 2: fill the per-string excitation table, CSR over strings; inside each row the single
+ * excitations come first (ascending partner index) followed by the doubles (ascending).
+ *   d_col [nnz]  partner string index (source string s of <t|H|s>, row = target t)
+ *   d_val [nnz]  same-spin Hamiltonian element <t| h + 1/2 (pq|rs) |s> (Slater-Condon rules)
+ *   d_meta[nnz]  singles: (p*norb+q) | sign_bit<<31 for t = sign * a+_p a_q s ; doubles: 0
+ *   d_diag[n]    <s|H_same-spin|s>
+ * d_h: double[norb*norb]; d_g: double[norb^4] chemist order (pq|rs), C-contiguous. */
+int sqd_excitation_fill(const uint64_t* d_strs, int n, int norb, const double* d_h,
+                        const double* d_g, const int* d_row_ptr, const int* d_n_single,
+                        uint32_t* d_col, double* d_val, uint32_t* d_meta, double* d_diag,
+                        void* stream);
+
+/* Opposite-spin tensor with pyscf fix_spin_'s linear penalty folded in:
+ *   g_ab[pq*ldg + rs] = (pq|rs) - shift * delta_ps delta_qr       
+ * mode 0: as above; mode 1: ignore d_g and write the S^2 tensor  -delta_ps delta_qr.
+ * ldg = norb*norb rounded up to a multiple of 2 (16-byte rows for bulk copies). */
+int sqd_make_gab(const double* d_g, int norb, double shift, int mode, double* d_gab, int ldg,
+                 void* stream);
+
+/* One-electron-like contractions of g_ab with the occupation of the other spin:
+ *   Wa[a*ldg + rs] = sum_{p in a} g_ab[pp, rs]      (na x ldg)
+ *   Wb[pq*ldc + b] = sum_{r in b} g_ab[pq, rr]      (norb^2 x ldc)
+ * and the diagonal of the operator (ldc = nb rounded up to a multiple of 2; pad entries get
+ * `pad_value`):
+ *   diag[a*ldc + b] = da[a] + db[b] + sum_{p in a} Wb[pp, b] + diag_const
+ * d_da / d_db may be NULL (treated as 0: S^2 operator). */
+int sqd_opposite_spin_tables(const uint64_t* d_strs_a, int na, const uint64_t* d_strs_b, int nb,
+                             int norb, const double* d_gab, int ldg, const double* d_da,
+                             const double* d_db, double diag_const, double pad_value, double* d_Wa,
+                             double* d_Wb, double* d_diag, int ldc, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * sigma-vector build and Davidson
+ * replaces: pyscf selected_ci.contract_2e (SCIcontract_2e_aaaa / _bbaa), make_hdiag,
+ *           lib.davidson1 inside kernel_fixed_space  (fermion.py:721-723, 810-818)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int n;                   /* number of strings */
+    const uint64_t* strs;    /* [n] sorted ascending */
+    const int* row_ptr;      /* [n+1] */
+    const int* n_single;     /* [n] */
+    const uint32_t* col;     /* [nnz] */
+    const double* val;       /* [nnz] */
+    const uint32_t* meta;    /* [nnz] */
+} sqd_spin_table;
+
+typedef struct {
+    sqd_spin_table a, b;     /* alpha strings index rows, beta strings index columns */
+    int norb;
+    int ldc;                 /* leading dimension of CI matrices (>= nb, multiple of 2) */
+    int ldg;                 /* row stride of gab / Wa (>= norb^2, multiple of 2) */
+    const double* diag;      /* [na*ldc] operator diagonal */
+    const double* gab;       /* [norb^2 * ldg] */
+    const double* Wa;        /* [na*ldg] or NULL */
+    const double* Wb;        /* [norb^2*ldc] or NULL */
+    int use_same_spin;       /* 1: include table values (Hamiltonian); 0: opposite-spin only (S^2) */
+} sqd_operator;
+
+/* Dynamic shared memory the sigma kernel needs for this operator, or <0 if the shape is unsupported. */
+int64_t sqd_sigma_smem_bytes(const sqd_operator* op);
+
+/* d_sigma[a*ldc+b] = sum_{a'b'} <ab|O|a'b'> d_c[a'*ldc+b'];  pads of d_sigma are written as 0. */
+int sqd_sigma(const sqd_operator* op, const double* d_c, double* d_sigma, void* stream);
+
+typedef struct {
+    int max_space;       /* <= SQD_MAX_SPACE; pyscf default 12 */
+    int max_cycle;       /* pyscf default 100 */
+    double tol;          /* converged when |d theta| < tol and |r| < tol_residual */
+    double tol_residual; /* pyscf: sqrt(tol) */
+    double lindep;       /* pyscf default 1e-14 */
+    double level_shift;  /* preconditioner: r / (hdiag - theta + level_shift), pyscf 1e-4 */
+    int check_every;     /* host polls the device-side convergence flag every this many cycles */
+    /* quadratic spin penalty  shift*(S^2-ss)^2  (pyscf fix_spin_ when ss >= sz(sz+1)+0.1) */
+    const sqd_operator* ss_op; /* NULL unless the quadratic form is requested */
+    double ss_shift, ss_value;
+} sqd_davidson_params;
+
+typedef struct {
+    int converged;   /* 1 converged, 0 hit max_cycle, 2 stopped on linear dependency */
+    int cycles;      /* Davidson cycles (= sigma builds inside the loop) */
+    int sigma_builds;
+    double theta;    /* last Ritz value of the (possibly spin-penalised) operator */
+    double residual; /* last residual norm */
+} sqd_davidson_info;
+
+/* bytes of device workspace for sqd_davidson on an operator of na x ldc */
+int64_t sqd_davidson_workspace_bytes(int na, int ldc, int max_space);
+
+/* Ground state of `op`.  d_hdiag: preconditioner diagonal [na*ldc] (bare Hamiltonian diagonal, as in
+ * pyscf where fix_spin_ leaves hdiag untouched).  d_x0: start vector [na*ldc] (unit vector at
+ * argmin(hdiag) + pyscf's 1e-5 noise is produced by sqd_init_guess).  d_x receives the normalised
+ * Ritz vector.  Synchronises the stream before returning. */
+int sqd_davidson(const sqd_operator* op, const double* d_hdiag, const double* d_x0, double* d_x,
+                 void* d_workspace, int64_t workspace_bytes, const sqd_davidson_params* params,
+                 sqd_davidson_info* h_info, void* stream);
+
+/* pyscf direct_spin1._get_init_guess: e_argmin(hdiag), +1e-5 on element 0 and -1e-5 on the last. */
+int sqd_init_guess(const double* d_hdiag, int na, int nb, int ldc, double* d_x0, void* d_scratch,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Expectation values   (fermion.py:821-830: make_rdm1s diagonals, energy, spin_square)
+ * ------------------------------------------------------------------------------------------ */
+/* d_out[0] = sum_i x_i y_i over na*ldc (deterministic two-stage reduction; scratch >= 1024 doubles) */
+int sqd_dot(const double* d_x, const double* d_y, int64_t n, double* d_out, double* d_scratch,
+            void* stream);
+
+/* occ_a[p] = sum_{a: p in a} sum_b c[a,b]^2, occ_b[p] likewise.  d_occ: double[2*norb] (alpha first).
+ * d_scratch: double[na + nb]. */
+int sqd_occupancies(const double* d_c, const uint64_t* d_strs_a, int na, const uint64_t* d_strs_b,
+                    int nb, int ldc, int norb, double* d_occ, double* d_scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Qubit path   (qubit.py:78-300)
+ * ------------------------------------------------------------------------------------------ */
+/* big-endian bool rows -> int64 keys (qubit.py:280-300); nbits <= 63 */
+int sqd_bits_to_keys(const uint8_t* d_bits, int64_t n, int nbits, int64_t* d_keys, void* stream);
+
+/* One Pauli term (qubit.py:167-240): for every row i whose image key_i ^ xmask is in the sorted key
+ * list, amplitude (-1)^popc(key_i & zmask) * i^ny, row i, col index of the image.
+ * d_hit[d]: 0/1 flag; d_col[d]; amplitude is derived on the host from the parity bit d_par[d]. */
+int sqd_pauli_connect(const int64_t* d_keys, int64_t d, uint64_t xmask, uint64_t zmask, int32_t* d_col,
+                      uint8_t* d_par, void* stream);
+
+/* Projection of a whole operator (qubit.py:78-144).  Terms are pre-grouped by X mask on the host:
+ * group k owns terms [grp_ptr[k], grp_ptr[k+1]) (original order kept inside a group), each with a
+ * zmask, a number of Y's and a complex coefficient.  Pass 1 counts, pass 2 fills a CSR matrix whose
+ * row i holds A[i, col] for every group that connects row i (transpose convention of the reference:
+ * A[source, image]), columns ascending, exact zeros dropped (scipy canonical format). */
+int sqd_pauli_project_count(const int64_t* d_keys, int64_t d, const uint64_t* d_grp_xmask,
+                            const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
+                            const int32_t* d_ny, const double* d_coeff /* re,im pairs */,
+                            int32_t* d_row_nnz, void* stream);
+int sqd_pauli_project_fill(const int64_t* d_keys, int64_t d, const uint64_t* d_grp_xmask,
+                           const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
+                           const int32_t* d_ny, const double* d_coeff, const int32_t* d_row_ptr,
+                           int32_t* d_col_tmp, double* d_val_tmp /* scratch, nnz entries each */,
+                           int32_t* d_col, double* d_val /* re,im pairs */, void* stream);
+
+/* y = A x for a complex128 CSR matrix (warp per row). */
+int sqd_csr_matvec_c128(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col,
+                        const double* d_val, const double* d_x, double* d_y, void* stream);
+
+/* Lowest `k` eigenpairs of the Hermitian matrix M = A^T (the reference hands A, the transpose of the
+ * operator, to eigsh -- qubit.py:73) by a locked single-vector Davidson, replacing ARPACK.
+ * d_evecs: complex128 [k][d] (row = eigenvector); h_evals: double[k]. Synchronises. */
+int64_t sqd_csr_davidson_workspace_bytes(int64_t d, int k, int max_space);
+int sqd_csr_davidson(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, const double* d_val,
+                     int k, int max_space, int max_cycle, double tol, double* d_evecs,
+                     double* h_evals, int* h_cycles, void* d_workspace, int64_t workspace_bytes,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Configuration recovery   (configuration_recovery.py:59-306)
+ * ------------------------------------------------------------------------------------------ */
+/* Per-bitstring correction.  Rows are packed halves (left = beta, right = alpha) as produced by
+ * sqd_pack_bitstrings.  d_occ_left / d_occ_right: occupancy of every bit in COLUMN order of the half
+ * (configuration_recovery.py:113).
+ * mode 0 = exact stream: d_rng_state holds numpy's PCG64 (state_hi, state_lo, inc_hi, inc_lo); rows are
+ *   processed in order and consume uniform doubles exactly as Generator.choice does
+ *   (left half first, `size - n_uniq` doubles per retry round); the advanced state is written back, so
+ *   the caller's Generator continues as if numpy had run.
+ * mode 1 = one PCG64 substream per row derived from (seed, row): same distribution, fully parallel.
+ * d_status[0] != 0: numpy would have raised "Fewer non-zero entries in p than size" at row
+ * d_status[1]. */
+int64_t sqd_recover_workspace_bytes(int64_t n, int norb);
+int sqd_recover(const uint64_t* d_left, const uint64_t* d_right, int64_t n, int norb,
+                const double* d_occ_left, const double* d_occ_right, int hamming_left,
+                int hamming_right, int mode, uint64_t* d_rng_state, uint64_t seed,
+                uint64_t* d_left_out, uint64_t* d_right_out, int32_t* d_status, void* d_workspace,
+                int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SQD_B200_H */

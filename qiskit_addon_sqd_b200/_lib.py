@@ -1,0 +1,170 @@
+"""ctypes binding of ``libsqd_b200.so`` (C-ABI declared in ``include/sqd_b200.h``).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``build.sh``.  There is NO CPU
+fallback: if the library is missing, or no CUDA device is visible, every product entry point raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsqd_b200.so")
+
+MAX_SPACE = 32
+
+
+class SpinTable(C.Structure):
+    _fields_ = [
+        ("n", C.c_int),
+        ("strs", C.c_void_p),
+        ("row_ptr", C.c_void_p),
+        ("n_single", C.c_void_p),
+        ("col", C.c_void_p),
+        ("val", C.c_void_p),
+        ("meta", C.c_void_p),
+    ]
+
+
+class Operator(C.Structure):
+    _fields_ = [
+        ("a", SpinTable),
+        ("b", SpinTable),
+        ("norb", C.c_int),
+        ("ldc", C.c_int),
+        ("ldg", C.c_int),
+        ("diag", C.c_void_p),
+        ("gab", C.c_void_p),
+        ("Wa", C.c_void_p),
+        ("Wb", C.c_void_p),
+        ("use_same_spin", C.c_int),
+    ]
+
+
+class DavidsonParams(C.Structure):
+    _fields_ = [
+        ("max_space", C.c_int),
+        ("max_cycle", C.c_int),
+        ("tol", C.c_double),
+        ("tol_residual", C.c_double),
+        ("lindep", C.c_double),
+        ("level_shift", C.c_double),
+        ("check_every", C.c_int),
+        ("ss_op", C.POINTER(Operator)),
+        ("ss_shift", C.c_double),
+        ("ss_value", C.c_double),
+    ]
+
+
+class DavidsonInfo(C.Structure):
+    _fields_ = [
+        ("converged", C.c_int),
+        ("cycles", C.c_int),
+        ("sigma_builds", C.c_int),
+        ("theta", C.c_double),
+        ("residual", C.c_double),
+    ]
+
+
+_vp, _i, _i64, _u64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
+_pi = C.POINTER(C.c_int)
+
+# name -> (restype, argtypes).  Must list every function declared in include/sqd_b200.h.
+SIGNATURES: dict[str, tuple] = {
+    "sqd_version": (_i, []),
+    "sqd_last_error": (C.c_char_p, []),
+    "sqd_pack_bitstrings": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
+    "sqd_check_hamming": (_i, [_vp, _i64, _vp, _pi, _pi, _pi, _vp]),
+    "sqd_excitation_count": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "sqd_exclusive_scan": (_i, [_vp, _vp, _i, _pi, _vp]),
+    "sqd_excitation_fill": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sqd_make_gab": (_i, [_vp, _i, _d, _i, _vp, _i, _vp]),
+    "sqd_opposite_spin_tables": (
+        _i,
+        [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _d, _d, _vp, _vp, _vp, _i, _vp],
+    ),
+    "sqd_sigma_smem_bytes": (_i64, [C.POINTER(Operator)]),
+    "sqd_sigma": (_i, [C.POINTER(Operator), _vp, _vp, _vp]),
+    "sqd_davidson_workspace_bytes": (_i64, [_i, _i, _i]),
+    "sqd_davidson": (
+        _i,
+        [C.POINTER(Operator), _vp, _vp, _vp, _vp, _i64, C.POINTER(DavidsonParams),
+         C.POINTER(DavidsonInfo), _vp],
+    ),
+    "sqd_init_guess": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
+    "sqd_dot": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
+    "sqd_occupancies": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "sqd_bits_to_keys": (_i, [_vp, _i64, _i, _vp, _vp]),
+    "sqd_pauli_connect": (_i, [_vp, _i64, _u64, _u64, _vp, _vp, _vp]),
+    "sqd_pauli_project_count": (_i, [_vp, _i64, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "sqd_pauli_project_fill": (
+        _i, [_vp, _i64, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    ),
+    "sqd_csr_matvec_c128": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sqd_csr_davidson_workspace_bytes": (_i64, [_i64, _i, _i]),
+    "sqd_csr_davidson": (
+        _i, [_i64, _vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _pi, _vp, _i64, _vp]
+    ),
+    "sqd_recover_workspace_bytes": (_i64, [_i64, _i]),
+    "sqd_recover": (
+        _i,
+        [_vp, _vp, _i64, _i, _vp, _vp, _i, _i, _i, _vp, _u64, _vp, _vp, _vp, _vp, _i64, _vp],
+    ),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class SqdCudaError(RuntimeError):
+    """An ``sqd_*`` C-ABI call returned a non-zero status."""
+
+
+def load():
+    """Load the CUDA library (no compute call is made).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+                "g.build()'` (nvcc, sm_100a).  qiskit_addon_sqd_b200 has no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the header and the library diverge
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def require_cuda():
+    """Import torch and insist on a CUDA device: the product path never runs on the CPU."""
+    import torch
+
+    if not torch.cuda.is_available():
+        raise RuntimeError(
+            "qiskit_addon_sqd_b200 needs a CUDA device (B200, sm_100a); no CPU fallback exists."
+        )
+    return torch
+
+
+def check(status: int, what: str = "") -> None:
+    if status != 0:
+        msg = load().sqd_last_error()
+        raise SqdCudaError(f"{what or 'sqd call'} failed ({status}): {msg.decode() if msg else ''}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr(torch) -> int:
+    return torch.cuda.current_stream().cuda_stream

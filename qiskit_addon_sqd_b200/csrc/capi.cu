@@ -1,0 +1,35 @@
+// Error plumbing and version of the C-ABI (include/sqd_b200.h).
+#include <stdarg.h>
+
+#include "common.cuh"
+#include "../../include/sqd_b200.h"
+
+namespace sqd {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
+        return -2;
+    }
+    return 0;
+}
+
+}  // namespace sqd
+
+extern "C" {
+
+int sqd_version(void) { return SQD_B200_VERSION; }
+
+const char* sqd_last_error(void) { return sqd::g_err; }
+
+}  // extern "C"

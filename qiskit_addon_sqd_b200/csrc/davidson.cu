@@ -1,0 +1,778 @@
+// Single-root Davidson eigensolver with every step on the device.
+//
+// Replaces pyscf.lib.davidson1 as driven by selected_ci.kernel_fixed_space (recalled semantics:
+// unit start vector at argmin(hdiag), preconditioner r/(hdiag - theta + 1e-4), max_space 12 with a
+// collapse onto the Ritz vector, converged when |d theta| < tol and |r| < sqrt(tol); a stalled run
+// returns the current vector and is not an error) -- reference call sites
+// qiskit_addon_sqd/fermion.py:721-723 and :810-818.
+//
+// B200 design: the host only enqueues kernels; the Rayleigh-Ritz problem (parallel-order Jacobi in one
+// CTA), the convergence test and the Gram-Schmidt coefficients live in a device-side state block, and
+// every kernel returns immediately once the state says "done".  The host polls that flag every
+// `check_every` cycles, so a cycle costs no host round trip.  The O(n_det) work is three fused
+// streaming passes per cycle:
+//   gram      : new column of V^T W                                  reads (m+1) vectors
+//   residual  : x = V y, Hx = W y, r = Hx - theta x, t = r/(hdiag - theta + shift),
+//               <v_i,t>, |r|^2, |t|^2 (+ collapse of V,W on restart)    reads (2m+1), writes 2..4
+//   ortho1/2  : two classical Gram-Schmidt passes (the second fused with normalisation)
+// All reductions are two-stage with a fixed order -> results are bit-reproducible run to run.
+#include <math.h>
+
+#include <functional>
+#include <type_traits>
+
+#include "common.cuh"
+#include "../../include/sqd_b200.h"
+
+namespace sqd {
+
+int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sigma,
+                        const int* d_done, cudaStream_t st);
+int csr_matvec_flag(const int* d_done, int64_t d, const int32_t* row_ptr, const int32_t* col,
+                    const double* val, const double* x, double* y, cudaStream_t st);
+int csr_diag_embed(int64_t d, const int32_t* row_ptr, const int32_t* col, const double* val,
+                   double* out, cudaStream_t st);
+
+constexpr int kMaxS = SQD_MAX_SPACE;
+constexpr int kRedBlocks = 2 * kNumSMs;  // CTAs of every streaming reduction pass
+constexpr int kRedThreads = 256;
+constexpr int kPartialRows = kMaxS + 4;
+
+struct DavState {
+    int status;  // 0 running, 1 converged, 2 linear dependency, 3 (host) max_cycle
+    int cycles;
+    double theta, theta_prev, rnorm, tnorm2, inv_norm;
+    double G[kMaxS * kMaxS];
+    double y[kMaxS];
+    double c1[kMaxS];
+    double c2[kMaxS];
+};
+
+// ---------------------------------------------------------------------------------------------
+// streaming passes
+// ---------------------------------------------------------------------------------------------
+template <int MV>
+__global__ void __launch_bounds__(kRedThreads)
+gram_kernel(const DavState* __restrict__ st, const double* __restrict__ V,
+            const double* __restrict__ w, int64_t n, int m, double* __restrict__ partials) {
+    if (st->status != 0) return;
+    __shared__ double red[MV * (kRedThreads / 32)];
+    double acc[MV];
+#pragma unroll
+    for (int i = 0; i < MV; ++i) acc[i] = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        const double wj = w[j];
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            if (i < m) acc[i] = fma(V[(int64_t)i * n + j], wj, acc[i]);
+    }
+    block_sum<MV>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            if (i < m) partials[i * gridDim.x + blockIdx.x] = acc[i];
+    }
+}
+
+template <int MV>
+__global__ void __launch_bounds__(kRedThreads)
+residual_kernel(const DavState* __restrict__ st, double* __restrict__ V, double* __restrict__ W,
+                const double* __restrict__ hdiag, int64_t n, int m, int restart, double level_shift,
+                double* __restrict__ X, double* __restrict__ T, double* __restrict__ partials) {
+    if (st->status != 0) return;
+    __shared__ double red[(MV + 2) * (kRedThreads / 32)];
+    __shared__ double ys[MV];
+    if (threadIdx.x < MV) ys[threadIdx.x] = threadIdx.x < m ? st->y[threadIdx.x] : 0.0;
+    __syncthreads();
+    const double theta = st->theta;
+    double acc[MV + 2];
+#pragma unroll
+    for (int i = 0; i < MV + 2; ++i) acc[i] = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        double v[MV];
+        double x = 0.0, hx = 0.0;
+#pragma unroll
+        for (int i = 0; i < MV; ++i) {
+            v[i] = 0.0;
+            if (i < m) {
+                v[i] = V[(int64_t)i * n + j];
+                x = fma(ys[i], v[i], x);
+                hx = fma(ys[i], W[(int64_t)i * n + j], hx);
+            }
+        }
+        const double r = hx - theta * x;
+        double den = hdiag[j] - theta + level_shift;
+        if (fabs(den) < 1e-8) den = den < 0.0 ? -1e-8 : 1e-8;
+        const double t = r / den;
+        X[j] = x;
+        T[j] = t;
+        if (restart) {
+            V[j] = x;   // slot 0 <- Ritz vector (element-wise, the only reader of V[0][j] is this thread)
+            W[j] = hx;  // slot 0 <- H x
+        }
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            if (i < m) acc[i] = fma(v[i], t, acc[i]);
+        acc[MV] = fma(r, r, acc[MV]);
+        acc[MV + 1] = fma(t, t, acc[MV + 1]);
+    }
+    block_sum<MV + 2>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            if (i < m) partials[i * gridDim.x + blockIdx.x] = acc[i];
+        partials[kMaxS * gridDim.x + blockIdx.x] = acc[MV];
+        partials[(kMaxS + 1) * gridDim.x + blockIdx.x] = acc[MV + 1];
+    }
+}
+
+// T <- T - sum c1_i V_i ; partial <V_i, T>, |T|^2
+template <int MV>
+__global__ void __launch_bounds__(kRedThreads)
+ortho1_kernel(const DavState* __restrict__ st, const double* __restrict__ V, int64_t n, int m,
+              double* __restrict__ T, double* __restrict__ partials) {
+    if (st->status != 0) return;
+    __shared__ double red[(MV + 1) * (kRedThreads / 32)];
+    __shared__ double cs[MV];
+    if (threadIdx.x < MV) cs[threadIdx.x] = threadIdx.x < m ? st->c1[threadIdx.x] : 0.0;
+    __syncthreads();
+    double acc[MV + 1];
+#pragma unroll
+    for (int i = 0; i < MV + 1; ++i) acc[i] = 0.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        double v[MV];
+        double t = T[j];
+#pragma unroll
+        for (int i = 0; i < MV; ++i) {
+            v[i] = 0.0;
+            if (i < m) {
+                v[i] = V[(int64_t)i * n + j];
+                t = fma(-cs[i], v[i], t);
+            }
+        }
+        T[j] = t;
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            if (i < m) acc[i] = fma(v[i], t, acc[i]);
+        acc[MV] = fma(t, t, acc[MV]);
+    }
+    block_sum<MV + 1>(acc, red);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            if (i < m) partials[i * gridDim.x + blockIdx.x] = acc[i];
+        partials[kMaxS * gridDim.x + blockIdx.x] = acc[MV];
+    }
+}
+
+// V_new <- (T - sum c2_i V_i) * inv_norm
+template <int MV>
+__global__ void __launch_bounds__(kRedThreads)
+ortho2_kernel(const DavState* __restrict__ st, const double* __restrict__ V, int64_t n, int m,
+              const double* __restrict__ T, double* __restrict__ vnew) {
+    if (st->status != 0) return;
+    __shared__ double cs[MV];
+    if (threadIdx.x < MV) cs[threadIdx.x] = threadIdx.x < m ? st->c2[threadIdx.x] : 0.0;
+    __syncthreads();
+    const double inv = st->inv_norm;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        double t = T[j];
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            if (i < m) t = fma(-cs[i], V[(int64_t)i * n + j], t);
+        vnew[j] = t * inv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small (single CTA) steps
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double reduce_partials(const double* partials, int row, int nblk) {
+    double s = 0.0;
+    for (int b = 0; b < nblk; ++b) s += partials[row * nblk + b];
+    return s;
+}
+
+// Rayleigh-Ritz: fold the new Gram column into G, diagonalise G (m x m) by parallel-order Jacobi.
+__global__ void __launch_bounds__(256)
+rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ partials, int nblk, int m,
+                     int slot) {
+    if (st->status != 0) return;
+    __shared__ double A[kMaxS][kMaxS + 1];
+    __shared__ double Q[kMaxS][kMaxS + 1];
+    __shared__ double cs_c[kMaxS / 2], cs_s[kMaxS / 2];
+    __shared__ int pr_p[kMaxS / 2], pr_q[kMaxS / 2];
+    __shared__ double off_s;
+    const int tid = threadIdx.x;
+
+    if (tid < m) {
+        const double g = reduce_partials(partials, tid, nblk);
+        st->G[tid * kMaxS + slot] = g;
+        st->G[slot * kMaxS + tid] = g;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < m * m; idx += blockDim.x) {
+        const int i = idx / m, j = idx % m;
+        A[i][j] = st->G[i * kMaxS + j];
+        Q[i][j] = i == j ? 1.0 : 0.0;
+    }
+    __syncthreads();
+
+    const int np = (m + 1) / 2;      // pairs per step
+    const int nplayers = 2 * np;     // even
+    for (int sweep = 0; sweep < 30 && m > 1; ++sweep) {
+        // convergence test on the off-diagonal norm
+        if (tid == 0) {
+            double off = 0.0, dia = 0.0;
+            for (int i = 0; i < m; ++i)
+                for (int j = 0; j < m; ++j) (i == j ? dia : off) += A[i][j] * A[i][j];
+            off_s = (off <= 1e-30 * dia || off == 0.0) ? 0.0 : 1.0;
+        }
+        __syncthreads();
+        if (off_s == 0.0) break;
+        for (int step = 0; step < nplayers - 1; ++step) {
+            if (tid < np) {
+                int p, q;
+                if (tid == 0) {
+                    p = nplayers - 1;
+                    q = step;
+                } else {
+                    p = (step + tid) % (nplayers - 1);
+                    q = (step - tid + (nplayers - 1)) % (nplayers - 1);
+                }
+                if (p > q) {
+                    const int t = p;
+                    p = q;
+                    q = t;
+                }
+                double c = 1.0, s = 0.0;
+                if (q < m) {
+                    const double apq = A[p][q];
+                    if (fabs(apq) > 1e-300) {
+                        const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        s = t * c;
+                    }
+                } else {
+                    q = p;  // dummy pair: identity
+                }
+                pr_p[tid] = p;
+                pr_q[tid] = q;
+                cs_c[tid] = c;
+                cs_s[tid] = s;
+            }
+            __syncthreads();
+            // column update: A <- A J, Q <- Q J
+            for (int idx = tid; idx < 2 * m * np; idx += blockDim.x) {
+                const int which = idx / (m * np);
+                const int rem = idx % (m * np);
+                const int i = rem / np, k = rem % np;
+                const int p = pr_p[k], q = pr_q[k];
+                if (p != q) {
+                    const double c = cs_c[k], s = cs_s[k];
+                    double(*M)[kMaxS + 1] = which ? Q : A;
+                    const double xp = M[i][p], xq = M[i][q];
+                    M[i][p] = c * xp - s * xq;
+                    M[i][q] = s * xp + c * xq;
+                }
+            }
+            __syncthreads();
+            // row update: A <- J^T A
+            for (int idx = tid; idx < m * np; idx += blockDim.x) {
+                const int j = idx / np, k = idx % np;
+                const int p = pr_p[k], q = pr_q[k];
+                if (p != q) {
+                    const double c = cs_c[k], s = cs_s[k];
+                    const double xp = A[p][j], xq = A[q][j];
+                    A[p][j] = c * xp - s * xq;
+                    A[q][j] = s * xp + c * xq;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        int best = 0;
+        for (int i = 1; i < m; ++i)
+            if (A[i][i] < A[best][best]) best = i;
+        // sign: largest component positive
+        int big = 0;
+        for (int i = 1; i < m; ++i)
+            if (fabs(Q[i][best]) > fabs(Q[big][best])) big = i;
+        const double sg = Q[big][best] < 0.0 ? -1.0 : 1.0;
+        double nrm = 0.0;
+        for (int i = 0; i < m; ++i) nrm += Q[i][best] * Q[i][best];
+        nrm = sg / sqrt(nrm);
+        for (int i = 0; i < m; ++i) st->y[i] = Q[i][best] * nrm;
+        st->theta_prev = st->theta;
+        st->theta = A[best][best];
+    }
+}
+
+__global__ void convergence_kernel(DavState* __restrict__ st, const double* __restrict__ partials,
+                                   int nblk, int m, int restart, double tol, double tol_residual) {
+    if (st->status != 0) return;
+    __shared__ double p[kMaxS + 2];
+    const int tid = threadIdx.x;
+    if (tid < m) p[tid] = reduce_partials(partials, tid, nblk);
+    if (tid == kMaxS) p[kMaxS] = reduce_partials(partials, kMaxS, nblk);
+    if (tid == kMaxS + 1) p[kMaxS + 1] = reduce_partials(partials, kMaxS + 1, nblk);
+    __syncthreads();
+    if (tid == 0) {
+        const double rnorm = sqrt(p[kMaxS]);
+        st->rnorm = rnorm;
+        st->tnorm2 = p[kMaxS + 1];
+        st->cycles += 1;
+        if (fabs(st->theta - st->theta_prev) < tol && rnorm < tol_residual) {
+            st->status = 1;
+        } else if (restart) {
+            double c = 0.0;
+            for (int i = 0; i < m; ++i) c += st->y[i] * p[i];
+            st->c1[0] = c;
+            st->G[0] = st->theta;
+            st->y[0] = 1.0;
+        } else {
+            for (int i = 0; i < m; ++i) st->c1[i] = p[i];
+        }
+    }
+}
+
+__global__ void norm_kernel(DavState* __restrict__ st, const double* __restrict__ partials, int nblk,
+                            int m, double lindep) {
+    if (st->status != 0) return;
+    __shared__ double p[kMaxS + 1];
+    const int tid = threadIdx.x;
+    if (tid < m) p[tid] = reduce_partials(partials, tid, nblk);
+    if (tid == kMaxS) p[kMaxS] = reduce_partials(partials, kMaxS, nblk);
+    __syncthreads();
+    if (tid == 0) {
+        double n2 = p[kMaxS];
+        for (int i = 0; i < m; ++i) {
+            st->c2[i] = p[i];
+            n2 -= p[i] * p[i];
+        }
+        if (!(n2 > lindep)) {
+            st->status = 2;  // cannot expand the space any further: current Ritz vector is final
+            st->inv_norm = 0.0;
+        } else {
+            st->inv_norm = 1.0 / sqrt(n2);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// helpers: init, dot, axpby, scale
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRedThreads)
+dot_partial_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t n,
+                   double* __restrict__ partials) {
+    __shared__ double red[kRedThreads / 32];
+    double acc[1] = {0.0};
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x)
+        acc[0] = fma(x[j], y[j], acc[0]);
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc[0];
+}
+
+__global__ void dot_final_kernel(const double* __restrict__ partials, int nblk, double* out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int b = 0; b < nblk; ++b) s += partials[b];
+        out[0] = s;
+    }
+}
+
+// y <- alpha * x * (1/sqrt(*norm2) if norm2 else 1)
+__global__ void scale_copy_kernel(const double* __restrict__ x, double* __restrict__ y, int64_t n,
+                                  const double* __restrict__ norm2) {
+    const double f = norm2 ? 1.0 / sqrt(norm2[0]) : 1.0;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x)
+        y[j] = x[j] * f;
+}
+
+// z <- a*x + b*y   (x, y, z may alias)
+__global__ void axpby_kernel(const int* __restrict__ done, double a, const double* x, double b,
+                             const double* y, double* z, int64_t n) {
+    if (done && *done) return;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x)
+        z[j] = a * x[j] + b * y[j];
+}
+
+__global__ void init_state_kernel(DavState* st) {
+    if (threadIdx.x == 0) {
+        st->status = 0;
+        st->cycles = 0;
+        st->theta = 0.0;
+        st->theta_prev = INFINITY;
+        st->rnorm = INFINITY;
+        st->tnorm2 = 0.0;
+        st->inv_norm = 0.0;
+    }
+    for (int i = threadIdx.x; i < kMaxS * kMaxS; i += blockDim.x) st->G[i] = 0.0;
+    for (int i = threadIdx.x; i < kMaxS; i += blockDim.x) st->y[i] = st->c1[i] = st->c2[i] = 0.0;
+}
+
+// argmin over the (na, nb) block of hdiag (pads excluded): stage 1 per-CTA, stage 2 single thread.
+__global__ void __launch_bounds__(kRedThreads)
+argmin_partial_kernel(const double* __restrict__ hdiag, int na, int nb, int ldc,
+                      double* __restrict__ pval, int64_t* __restrict__ pidx) {
+    __shared__ double sv[kRedThreads];
+    __shared__ int64_t si[kRedThreads];
+    double best = INFINITY;
+    int64_t bi = -1;
+    const int64_t total = (int64_t)na * nb;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t a = k / nb, b = k % nb;
+        const double v = hdiag[a * ldc + b];
+        if (v < best || (v == best && k < bi)) {
+            best = v;
+            bi = k;
+        }
+    }
+    sv[threadIdx.x] = best;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double v2 = sv[threadIdx.x + o];
+            const int64_t i2 = si[threadIdx.x + o];
+            if (i2 >= 0 && (v2 < sv[threadIdx.x] || si[threadIdx.x] < 0 ||
+                            (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x]))) {
+                sv[threadIdx.x] = v2;
+                si[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        pval[blockIdx.x] = sv[0];
+        pidx[blockIdx.x] = si[0];
+    }
+}
+
+__global__ void init_guess_kernel(const double* __restrict__ pval, const int64_t* __restrict__ pidx,
+                                  int nblk, int na, int nb, int ldc, double* __restrict__ x0) {
+    // x0 was zero-filled before this launch
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double best = INFINITY;
+        int64_t bi = -1;
+        for (int b = 0; b < nblk; ++b) {
+            if (pidx[b] >= 0 && (pval[b] < best || bi < 0 || (pval[b] == best && pidx[b] < bi))) {
+                best = pval[b];
+                bi = pidx[b];
+            }
+        }
+        const int64_t a = bi / nb, b = bi % nb;
+        x0[a * ldc + b] = 1.0;
+        // pyscf direct_spin1._get_init_guess: ci0[0][0] += 1e-5; ci0[0][-1] -= 1e-5
+        x0[0] += 1e-5;
+        x0[(int64_t)(na - 1) * ldc + (nb - 1)] -= 1e-5;
+    }
+}
+
+// row / column weights of c^2 and orbital occupancies
+__global__ void row_weight_kernel(const double* __restrict__ c, int na, int nb, int ldc,
+                                  double* __restrict__ wa) {
+    const int lane = threadIdx.x & 31;
+    const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (a >= na) return;
+    double s = 0.0;
+    for (int b = lane; b < nb; b += 32) {
+        const double v = c[(int64_t)a * ldc + b];
+        s = fma(v, v, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) wa[a] = s;
+}
+
+__global__ void col_weight_kernel(const double* __restrict__ c, int na, int nb, int ldc,
+                                  double* __restrict__ wb) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    double s = 0.0;
+    for (int a = 0; a < na; ++a) {
+        const double v = c[(int64_t)a * ldc + b];
+        s = fma(v, v, s);
+    }
+    wb[b] = s;
+}
+
+// one CTA per (spin, orbital)
+__global__ void __launch_bounds__(kRedThreads)
+occupancy_kernel(const double* __restrict__ wa, const uint64_t* __restrict__ sa, int na,
+                 const double* __restrict__ wb, const uint64_t* __restrict__ sb, int nb, int norb,
+                 double* __restrict__ occ) {
+    __shared__ double red[kRedThreads / 32];
+    const int spin = blockIdx.x / norb, p = blockIdx.x % norb;
+    const double* w = spin ? wb : wa;
+    const uint64_t* s = spin ? sb : sa;
+    const int n = spin ? nb : na;
+    double acc[1] = {0.0};
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if ((s[i] >> p) & 1ull) acc[0] += w[i];
+    block_sum<1>(acc, red);
+    if (threadIdx.x == 0) occ[blockIdx.x] = acc[0];
+}
+
+static inline int red_blocks(int64_t n) {
+    int64_t b = (n + kRedThreads - 1) / kRedThreads;
+    if (b > kRedBlocks) b = kRedBlocks;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+template <typename F>
+static int dispatch_mv(int m, F&& f) {
+    if (m <= 4) return f(std::integral_constant<int, 4>());
+    if (m <= 8) return f(std::integral_constant<int, 8>());
+    if (m <= 12) return f(std::integral_constant<int, 12>());
+    if (m <= 16) return f(std::integral_constant<int, 16>());
+    if (m <= 24) return f(std::integral_constant<int, 24>());
+    return f(std::integral_constant<int, 32>());
+}
+
+struct Workspace {
+    double *V, *W, *T, *X, *tmp1, *tmp2, *partials;
+    DavState* state;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static int64_t workspace_bytes(int64_t n, int max_space) {
+    size_t b = 0;
+    b += align_up((size_t)max_space * n * sizeof(double)) * 2;  // V, W
+    b += align_up((size_t)n * sizeof(double)) * 4;              // T, X, tmp1, tmp2
+    b += align_up((size_t)kPartialRows * kRedBlocks * sizeof(double));
+    b += align_up(sizeof(DavState));
+    return (int64_t)b;
+}
+
+static void carve(void* base, int64_t n, int max_space, Workspace* ws) {
+    char* p = (char*)base;
+    ws->V = (double*)p;
+    p += align_up((size_t)max_space * n * sizeof(double));
+    ws->W = (double*)p;
+    p += align_up((size_t)max_space * n * sizeof(double));
+    ws->T = (double*)p;
+    p += align_up((size_t)n * sizeof(double));
+    ws->X = (double*)p;
+    p += align_up((size_t)n * sizeof(double));
+    ws->tmp1 = (double*)p;
+    p += align_up((size_t)n * sizeof(double));
+    ws->tmp2 = (double*)p;
+    p += align_up((size_t)n * sizeof(double));
+    ws->partials = (double*)p;
+    p += align_up((size_t)kPartialRows * kRedBlocks * sizeof(double));
+    ws->state = (DavState*)p;
+}
+
+// w <- O v (+ quadratic spin penalty)
+static int apply_operator(const sqd_operator* op, const sqd_davidson_params* prm, const double* v,
+                          double* w, Workspace& ws, int64_t n, cudaStream_t st) {
+    const int* done = &ws.state->status;
+    if (sigma_dispatch_flag(op, v, w, done, st)) return -2;
+    if (prm->ss_op) {
+        // w += shift * (S^2 - ss)^2 v   (pyscf fix_spin_, quadratic branch)
+        const int blocks = red_blocks(n);
+        if (sigma_dispatch_flag(prm->ss_op, v, ws.tmp1, done, st)) return -2;
+        axpby_kernel<<<blocks, kRedThreads, 0, st>>>(done, 1.0, ws.tmp1, -prm->ss_value, v, ws.tmp1, n);
+        if (sigma_dispatch_flag(prm->ss_op, ws.tmp1, ws.tmp2, done, st)) return -2;
+        axpby_kernel<<<blocks, kRedThreads, 0, st>>>(done, 1.0, ws.tmp2, -prm->ss_value, ws.tmp1,
+                                                     ws.tmp2, n);
+        axpby_kernel<<<blocks, kRedThreads, 0, st>>>(done, 1.0, w, prm->ss_shift, ws.tmp2, w, n);
+        if (check_launch("axpby_kernel")) return -2;
+    }
+    return 0;
+}
+
+using ApplyFn = std::function<int(const double*, double*, Workspace&)>;
+
+static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag, const double* d_x0,
+                         double* d_x, void* d_workspace, int64_t ws_bytes,
+                         const sqd_davidson_params* prm, sqd_davidson_info* h_info, cudaStream_t st) {
+    const int M = prm->max_space;
+    SQD_REQUIRE(M >= 2 && M <= kMaxS, "sqd_davidson: max_space must be in [2, %d] (got %d)", kMaxS, M);
+    SQD_REQUIRE(ws_bytes >= workspace_bytes(n, M), "sqd_davidson: workspace too small");
+    SQD_REQUIRE(prm->max_cycle >= 1, "sqd_davidson: max_cycle must be >= 1");
+    Workspace ws;
+    carve(d_workspace, n, M, &ws);
+    const int blocks = red_blocks(n);
+    const int check_every = prm->check_every > 0 ? prm->check_every : 4;
+
+    init_state_kernel<<<1, 256, 0, st>>>(ws.state);
+    // V_0 = x0 / |x0|
+    dot_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_x0, d_x0, n, ws.partials);
+    dot_final_kernel<<<1, 32, 0, st>>>(ws.partials, blocks, ws.partials + kRedBlocks);
+    scale_copy_kernel<<<blocks, kRedThreads, 0, st>>>(d_x0, ws.V, n, ws.partials + kRedBlocks);
+    if (check_launch("davidson init")) return -2;
+
+    int m = 1, slot = 0, status = 0, cycle = 0, sigma_builds = 0;
+    for (; cycle < prm->max_cycle; ++cycle) {
+        if (apply(ws.V + (int64_t)slot * n, ws.W + (int64_t)slot * n, ws)) return -2;
+        ++sigma_builds;
+        const int restart = (m == M) ? 1 : 0;
+        int rc = dispatch_mv(m, [&](auto mv) {
+            constexpr int MV = decltype(mv)::value;
+            gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n,
+                                                            m, ws.partials);
+            rayleigh_ritz_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m, slot);
+            residual_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, d_hdiag, n, m,
+                                                                restart, prm->level_shift, ws.X, ws.T,
+                                                                ws.partials);
+            convergence_kernel<<<1, 64, 0, st>>>(ws.state, ws.partials, blocks, m, restart, prm->tol,
+                                                 prm->tol_residual);
+            return check_launch("davidson cycle (1)");
+        });
+        if (rc) return -2;
+        const int me = restart ? 1 : m;
+        rc = dispatch_mv(me, [&](auto mv) {
+            constexpr int MV = decltype(mv)::value;
+            ortho1_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T, ws.partials);
+            norm_kernel<<<1, 64, 0, st>>>(ws.state, ws.partials, blocks, me, prm->lindep);
+            ortho2_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T,
+                                                              ws.V + (int64_t)me * n);
+            return check_launch("davidson cycle (2)");
+        });
+        if (rc) return -2;
+        m = me + 1;
+        slot = me;
+        if ((cycle + 1) % check_every == 0 || cycle + 1 == prm->max_cycle) {
+            SQD_CUDA_OK(cudaMemcpyAsync(&status, &ws.state->status, sizeof(int),
+                                        cudaMemcpyDeviceToHost, st));
+            SQD_CUDA_OK(cudaStreamSynchronize(st));
+            if (status != 0) {
+                ++cycle;
+                break;
+            }
+        }
+    }
+    DavState hs;
+    SQD_CUDA_OK(cudaMemcpyAsync(&hs, ws.state, sizeof(DavState), cudaMemcpyDeviceToHost, st));
+    SQD_CUDA_OK(cudaMemcpyAsync(d_x, ws.X, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    SQD_CUDA_OK(cudaStreamSynchronize(st));
+    if (h_info) {
+        h_info->converged = hs.status == 1 ? 1 : (hs.status == 2 ? 2 : 0);
+        h_info->cycles = hs.cycles;
+        h_info->sigma_builds = sigma_builds;
+        h_info->theta = hs.theta;
+        h_info->residual = hs.rnorm;
+    }
+    return 0;
+}
+
+
+}  // namespace sqd
+
+using namespace sqd;
+
+extern "C" {
+
+int64_t sqd_davidson_workspace_bytes(int na, int ldc, int max_space) {
+    if (na <= 0 || ldc <= 0 || max_space < 2 || max_space > kMaxS) return -1;
+    return workspace_bytes((int64_t)na * ldc, max_space);
+}
+
+int sqd_dot(const double* d_x, const double* d_y, int64_t n, double* d_out, double* d_scratch,
+            void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = red_blocks(n);
+    dot_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_x, d_y, n, d_scratch);
+    dot_final_kernel<<<1, 32, 0, st>>>(d_scratch, blocks, d_out);
+    return check_launch("dot kernels");
+}
+
+int sqd_init_guess(const double* d_hdiag, int na, int nb, int ldc, double* d_x0, void* d_scratch,
+                   void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SQD_REQUIRE(na > 0 && nb > 0 && ldc >= nb, "sqd_init_guess: bad shape");
+    const int64_t n = (int64_t)na * ldc;
+    const int blocks = red_blocks((int64_t)na * nb);
+    double* pval = (double*)d_scratch;
+    int64_t* pidx = (int64_t*)(pval + kRedBlocks);
+    SQD_CUDA_OK(cudaMemsetAsync(d_x0, 0, n * sizeof(double), st));
+    argmin_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_hdiag, na, nb, ldc, pval, pidx);
+    init_guess_kernel<<<1, 32, 0, st>>>(pval, pidx, blocks, na, nb, ldc, d_x0);
+    return check_launch("init_guess kernels");
+}
+
+int sqd_occupancies(const double* d_c, const uint64_t* d_strs_a, int na, const uint64_t* d_strs_b,
+                    int nb, int ldc, int norb, double* d_occ, double* d_scratch, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    double* wa = d_scratch;
+    double* wb = d_scratch + na;
+    row_weight_kernel<<<(na + 7) / 8, 256, 0, st>>>(d_c, na, nb, ldc, wa);
+    col_weight_kernel<<<(nb + 127) / 128, 128, 0, st>>>(d_c, na, nb, ldc, wb);
+    occupancy_kernel<<<2 * norb, kRedThreads, 0, st>>>(wa, d_strs_a, na, wb, d_strs_b, nb, norb, d_occ);
+    return check_launch("occupancy kernels");
+}
+
+int sqd_davidson(const sqd_operator* op, const double* d_hdiag, const double* d_x0, double* d_x,
+                 void* d_workspace, int64_t ws_bytes, const sqd_davidson_params* prm,
+                 sqd_davidson_info* h_info, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)op->a.n * op->ldc;
+    auto apply = [&](const double* v, double* w, Workspace& ws) {
+        return apply_operator(op, prm, v, w, ws, n, st);
+    };
+    return davidson_core(n, apply, d_hdiag, d_x0, d_x, d_workspace, ws_bytes, prm, h_info, st);
+}
+
+int64_t sqd_csr_davidson_workspace_bytes(int64_t d, int k, int max_space) {
+    if (d <= 0 || k != 1 || max_space < 2 || max_space > kMaxS) return -1;
+    // Davidson workspace on the (re, im) embedding + embedded diagonal + start vector
+    return workspace_bytes(2 * d, max_space) + 2 * (int64_t)align_up((size_t)2 * d * sizeof(double));
+}
+
+int sqd_csr_davidson(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, const double* d_val,
+                     int k, int max_space, int max_cycle, double tol, double* d_evecs,
+                     double* h_evals, int* h_cycles, void* d_workspace, int64_t ws_bytes,
+                     void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SQD_REQUIRE(k == 1, "sqd_csr_davidson: only the lowest eigenpair (k=1) runs natively (got k=%d)", k);
+    SQD_REQUIRE(d > 0, "sqd_csr_davidson: empty matrix");
+    SQD_REQUIRE(ws_bytes >= sqd_csr_davidson_workspace_bytes(d, k, max_space),
+                "sqd_csr_davidson: workspace too small");
+    // A complex Hermitian matrix acting on interleaved (re, im) storage is a real symmetric operator
+    // on 2d doubles with the real inner product; every eigenvalue appears twice (z and i z), which
+    // is harmless for the lowest pair.
+    const int64_t n = 2 * d;
+    char* p = (char*)d_workspace;
+    double* hdiag = (double*)p;
+    p += align_up((size_t)n * sizeof(double));
+    double* x0 = (double*)p;
+    p += align_up((size_t)n * sizeof(double));
+    if (csr_diag_embed(d, d_row_ptr, d_col, d_val, hdiag, st)) return -2;
+    // scratch for the argmin lives in the (not yet used) Davidson workspace
+    if (sqd_init_guess(hdiag, 1, (int)n, (int)n, x0, p, stream)) return -2;
+    sqd_davidson_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.max_space = max_space;
+    prm.max_cycle = max_cycle;
+    prm.tol = tol;
+    prm.tol_residual = sqrt(tol);
+    prm.lindep = 1e-14;
+    prm.level_shift = 1e-4;
+    prm.check_every = 4;
+    sqd_davidson_info info;
+    auto apply = [&](const double* v, double* w, Workspace& ws) {
+        return csr_matvec_flag(&ws.state->status, d, d_row_ptr, d_col, d_val, v, w, st);
+    };
+    const int rc = davidson_core(n, apply, hdiag, x0, d_evecs, p,
+                                 ws_bytes - 2 * (int64_t)align_up((size_t)n * sizeof(double)), &prm,
+                                 &info, st);
+    if (rc) return rc;
+    h_evals[0] = info.theta;
+    if (h_cycles) *h_cycles = info.cycles;
+    return 0;
+}
+
+}  // extern "C"

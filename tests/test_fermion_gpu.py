@@ -1,0 +1,252 @@
+"""Parity of the CUDA fermion path (through the C-ABI) against the CPU oracle."""
+
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import fermion_oracle as fo
+from qiskit_addon_sqd_b200._synthetic import (
+    hf_centred_strings,
+    random_integrals,
+    strings_to_bitstring_matrix,
+    uniform_strings,
+)
+
+pytestmark = pytest.mark.gpu
+
+ETOL = 1e-8  # Ha, north_star tolerance for ground-state energies
+
+
+def _all_strings(norb, nel):
+    return np.array(sorted(sum(1 << i for i in c) for c in itertools.combinations(range(norb), nel)),
+                    dtype=np.int64)
+
+
+def _table_to_dense(tab):
+    n = tab.n
+    ptr = tab.row_ptr.cpu().numpy()
+    col = tab.col.cpu().numpy()
+    val = tab.val.cpu().numpy()
+    H = np.diag(tab.diag.cpu().numpy())
+    for i in range(n):
+        for e in range(ptr[i], ptr[i + 1]):
+            H[i, col[e]] = val[e]
+    return H
+
+
+CASES = [
+    # norb, (n_alpha, n_beta), (na, nb), generator
+    (4, (2, 2), (6, 6), "full"),
+    (5, (2, 3), (7, 5), "hf"),
+    (6, (3, 3), (20, 20), "full"),
+    (8, (4, 3), (30, 21), "hf"),
+    (12, (6, 6), (40, 33), "uniform"),
+    (7, (1, 4), (7, 11), "hf"),
+]
+
+
+def _strings(norb, nel, n, kind, seed):
+    if kind == "full":
+        return _all_strings(norb, nel)
+    if kind == "hf":
+        return hf_centred_strings(norb, nel, n, seed)
+    return uniform_strings(norb, nel, n, seed)
+
+
+@pytest.mark.parametrize("norb,nelec,dims,kind", CASES)
+def test_excitation_tables_match_slater_condon(cuda_lib, norb, nelec, dims, kind):
+    from qiskit_addon_sqd_b200.fermion import _Subspace
+
+    h, g = random_integrals(norb, 11 + norb)
+    sa = _strings(norb, nelec[0], dims[0], kind, 1)
+    sb = _strings(norb, nelec[1], dims[1], kind, 2)
+    sub = _Subspace(sa, sb, norb, h, g)
+    for tab, strs in ((sub.ta, sa), (sub.tb, sb)):
+        ref = fo.same_spin_matrix(strs, h, g, norb)
+        got = _table_to_dense(tab)
+        assert np.abs(got - ref).max() < 1e-12
+        # bit-exact structure: singles first (ascending), then doubles (ascending), signs and pq
+        ptr = tab.row_ptr.cpu().numpy()
+        ns = tab.n_single.cpu().numpy()
+        col = tab.col.cpu().numpy()
+        meta = tab.meta.cpu().numpy().view(np.uint32)
+        links = {(t, s): (p, q, sg) for (t, s, p, q, sg) in
+                 fo.single_excitation_links(strs, norb, include_diagonal=False)}
+        assert int(ns.sum()) == len(links)
+        for i in range(tab.n):
+            singles = col[ptr[i]:ptr[i] + ns[i]]
+            doubles = col[ptr[i] + ns[i]:ptr[i + 1]]
+            assert list(singles) == sorted(singles) and list(doubles) == sorted(doubles)
+            for e in range(ptr[i], ptr[i] + ns[i]):
+                p, q, sg = links[(i, int(col[e]))]
+                assert int(meta[e] & 0x7FFFFFFF) == p * norb + q
+                assert (-1 if meta[e] >> 31 else 1) == sg
+            for j in doubles:
+                assert bin(int(strs[i]) ^ int(strs[j])).count("1") == 4
+
+
+@pytest.mark.parametrize("norb,nelec,dims,kind", CASES)
+def test_sigma_matches_dense_operator(cuda_lib, norb, nelec, dims, kind):
+    import torch
+
+    from qiskit_addon_sqd_b200.fermion import _Subspace
+
+    h, g = random_integrals(norb, 21 + norb)
+    sa = _strings(norb, nelec[0], dims[0], kind, 3)
+    sb = _strings(norb, nelec[1], dims[1], kind, 4)
+    na, nb = len(sa), len(sb)
+    sub = _Subspace(sa, sb, norb, h, g)
+    H = fo.projected_hamiltonian(sa, sb, h, g, norb)
+    S2 = fo.spin_square_matrix(sa, sb, norb)
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((na, nb))
+    ham = sub.hamiltonian()
+    hd = ham.diag.reshape(na, sub.ldc)[:, :nb].cpu().numpy()
+    assert np.abs(hd.reshape(-1) - np.diag(H)).max() < 1e-12
+    c = sub.upload_amplitudes(x)
+    y = sub.download_amplitudes(sub.apply(ham, c))
+    assert np.abs(y.reshape(-1) - H @ x.reshape(-1)).max() < 1e-11
+    y2 = sub.download_amplitudes(sub.apply(sub.spin_operator(), c))
+    assert np.abs(y2.reshape(-1) - S2 @ x.reshape(-1)).max() < 1e-12
+    # linear spin penalty folded into the opposite-spin integrals
+    pen = sub.hamiltonian(penalty_shift=0.37, penalty_ss=0.75)
+    y3 = sub.download_amplitudes(sub.apply(pen, c))
+    ref3 = (H + 0.37 * (S2 - 0.75 * np.eye(na * nb))) @ x.reshape(-1)
+    assert np.abs(y3.reshape(-1) - ref3).max() < 1e-11
+    # reproducibility: bit-identical on a second launch
+    y_again = sub.download_amplitudes(sub.apply(ham, c))
+    assert np.array_equal(y, y_again)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("norb,nelec,dims,kind", CASES)
+@pytest.mark.parametrize("spin_sq", [None, 0.0])
+def test_solve_fermion_matches_dense_eigh(cuda_lib, norb, nelec, dims, kind, spin_sq):
+    from qiskit_addon_sqd_b200 import fermion
+
+    h, g = random_integrals(norb, 31 + norb)
+    sa = _strings(norb, nelec[0], dims[0], kind, 6)
+    sb = _strings(norb, nelec[1], dims[1], kind, 7)
+    if spin_sq is not None and nelec[0] != nelec[1]:
+        spin_sq = 0.25 * (nelec[0] - nelec[1]) ** 2 + 0.5 * abs(nelec[0] - nelec[1])  # sz(sz+1)
+    e, state, occ, s2 = fermion.solve_fermion((sa, sb), h, g, spin_sq=spin_sq, shift=0.1)
+    e_ref, c_ref, occ_ref, s2_ref, _ = fo.solve_dense(sa, sb, h, g, norb, spin_sq=spin_sq, shift=0.1)
+    assert abs(e - e_ref) < ETOL
+    assert state.amplitudes.shape == (len(sa), len(sb))
+    assert abs(np.linalg.norm(state.amplitudes) - 1.0) < 1e-10
+    # eigenvector up to sign (non-degenerate synthetic spectra)
+    ov = abs(np.vdot(state.amplitudes, c_ref))
+    assert ov > 1 - 1e-8
+    assert np.allclose(occ[0], occ_ref[0], atol=1e-6) and np.allclose(occ[1], occ_ref[1], atol=1e-6)
+    assert abs(sum(occ[0]) - nelec[0]) < 1e-9 and abs(sum(occ[1]) - nelec[1]) < 1e-9
+    assert abs(s2 - s2_ref) < 1e-6
+    assert state.nelec == nelec and state.norb == norb
+
+
+def test_quadratic_spin_penalty(cuda_lib):
+    from qiskit_addon_sqd_b200 import fermion
+
+    norb, nel = 6, 3
+    h, g = random_integrals(norb, 77)
+    sa = _all_strings(norb, nel)
+    # target the triplet (ss = 2) in the Sz = 0 sector -> pyscf's quadratic branch
+    e, state, occ, s2 = fermion.solve_fermion((sa, sa), h, g, spin_sq=2.0, shift=0.5)
+    e_ref, c_ref, _, s2_ref, _ = fo.solve_dense(sa, sa, h, g, norb, spin_sq=2.0, shift=0.5)
+    assert abs(e - e_ref) < ETOL
+    assert abs(s2 - s2_ref) < 1e-6
+
+
+def test_bitstring_matrix_entry_and_closed_shell_union(cuda_lib):
+    from qiskit_addon_sqd_b200 import fermion
+
+    norb, nel = 6, 3
+    h, g = random_integrals(norb, 5)
+    sa = hf_centred_strings(norb, nel, 9, 1)
+    sb = hf_centred_strings(norb, nel, 9, 2)
+    bs = strings_to_bitstring_matrix(sa, sb, norb)
+    a, b = fermion.bitstring_matrix_to_ci_strs(bs, open_shell=True)
+    assert np.array_equal(a, np.unique(sa)) and np.array_equal(b, np.unique(sb))
+    a2, b2 = fermion.bitstring_matrix_to_ci_strs(bs, open_shell=False)
+    assert np.array_equal(a2, np.union1d(sa, sb)) and a2 is b2
+    e, state, occ, s2 = fermion.solve_fermion(bs, h, g, open_shell=False)
+    u = np.union1d(sa, sb)
+    e_ref = fo.solve_dense(u, u, h, g, norb)[0]
+    assert abs(e - e_ref) < ETOL
+    # notebook golden (docs/guides/select_open_closed_shell.ipynb:180,438)
+    rows = ["00010010", "01001000", "00010001"]
+    m = np.array([[c == "1" for c in r] for r in rows])
+    ca, cb = fermion.bitstring_matrix_to_ci_strs(m, open_shell=False)
+    assert list(ca) == [1, 2, 4, 8] and list(cb) == [1, 2, 4, 8]
+    oa, ob = fermion.bitstring_matrix_to_ci_strs(m, open_shell=True)
+    assert list(oa) == [1, 2, 8] or (list(oa), list(ob)) == ([2, 8], [1, 4])
+
+
+def test_check_ci_strs_error_messages(cuda_lib):
+    from qiskit_addon_sqd_b200 import fermion
+
+    h, g = random_integrals(4, 1)
+    with pytest.raises(ValueError, match=r"Spin-up CI string in index 0 has hamming weight 2, but CI "
+                                         r"string in index 1 has hamming weight 1\."):
+        fermion.solve_fermion((np.array([3, 4]), np.array([3, 5])), h, g)
+    with pytest.raises(ValueError, match=r"Spin-down CI string in index 0 has hamming weight 2, but CI "
+                                         r"string in index 2 has hamming weight 3\."):
+        fermion.solve_fermion((np.array([3, 5]), np.array([3, 5, 7])), h, g)
+
+
+def test_solve_sci_batch_plugin_contract(cuda_lib):
+    from qiskit_addon_sqd_b200 import fermion
+
+    norb, nel = 8, 4
+    h, g = random_integrals(norb, 9)
+    batches = []
+    for k in range(5):
+        s = hf_centred_strings(norb, nel, 20 + k, 40 + k)
+        batches.append((s, s))  # symmetrize_spin: same array object for both spins (fermion.py:544)
+    res = fermion.solve_sci_batch(batches, h, g, norb, (nel, nel), spin_sq=0.0)
+    assert len(res) == 5
+    for (s, _), r in zip(batches, res):
+        e_ref, c_ref, occ_ref, _, _ = fo.solve_dense(s, s, h, g, norb, spin_sq=0.0, shift=0.2)
+        assert abs(r.energy - e_ref) < ETOL
+        assert r.sci_state.amplitudes.shape == (len(s), len(s))
+        assert r.sci_state.amplitudes.flags["C_CONTIGUOUS"]
+        assert np.allclose(r.orbital_occupancies[0], occ_ref[0], atol=1e-6)
+    # same inputs twice -> identical results (reference test_fermion.py:285-342)
+    res2 = fermion.solve_sci_batch(batches, h, g, norb, (nel, nel), spin_sq=0.0)
+    for r, r2 in zip(res, res2):
+        assert r.energy == r2.energy
+        assert np.array_equal(r.sci_state.amplitudes, r2.sci_state.amplitudes)
+
+
+def test_medium_subspace_against_sparse_oracle(cuda_lib):
+    """(16e,30o)-like connectivity at a size the scipy oracle finishes in seconds."""
+    from qiskit_addon_sqd_b200 import fermion
+
+    norb, nel = 14, 5
+    h, g = random_integrals(norb, 100)
+    sa = hf_centred_strings(norb, nel, 120, 100)
+    sb = hf_centred_strings(norb, nel, 97, 101)
+    e, state, occ, s2 = fermion.solve_fermion((sa, sb), h, g)
+    op = fo.SparseProjectedHamiltonian(sa, sb, h, g, norb)
+    e_ref, c_ref = op.ground_state()
+    assert abs(e - e_ref) < ETOL
+    assert abs(abs(np.vdot(state.amplitudes, c_ref)) - 1) < 1e-7
+
+
+def test_state_methods_and_npz_roundtrip(cuda_lib, tmp_path):
+    from qiskit_addon_sqd_b200 import fermion
+
+    norb, nel = 6, 3
+    h, g = random_integrals(norb, 3)
+    sa = hf_centred_strings(norb, nel, 10, 1)
+    sb = hf_centred_strings(norb, 2, 8, 2)
+    e, state, occ, s2 = fermion.solve_fermion((sa, sb), h, g)
+    assert abs(state.spin_square() - s2) < 1e-10
+    oa, ob = state.orbital_occupancies()
+    assert np.allclose(oa, occ[0], atol=1e-12) and np.allclose(ob, occ[1], atol=1e-12)
+    f = tmp_path / "state.npz"
+    state.save(f)
+    st2 = fermion.SCIState.load(f)
+    assert np.array_equal(st2.amplitudes, state.amplitudes) and st2.nelec == state.nelec
+    with pytest.raises(ValueError, match=r"'amplitudes' shape must be \(2, 2\) but got \(3, 2\)"):
+        fermion.SCIState(np.zeros((3, 2)), np.array([1, 2]), np.array([1, 2]), 2, (1, 1))
