@@ -31,6 +31,8 @@ extern "C" {
 
 int sqd_version(void);
 const char* sqd_last_error(void);
+/* number of CUDA kernels this library has launched in this process (reset != 0: return and clear) */
+long long sqd_launch_count(int reset);
 
 /* ------------------------------------------------------------------------------------------ *
  * Determinant strings and excitation tables
@@ -133,6 +135,7 @@ typedef struct {
     /* quadratic spin penalty  shift*(S^2-ss)^2  (pyscf fix_spin_ when ss >= sz(sz+1)+0.1) */
     const sqd_operator* ss_op; /* NULL unless the quadratic form is requested */
     double ss_shift, ss_value;
+    int profile;         /* != 0: bracket every operator application with CUDA events (measurement) */
 } sqd_davidson_params;
 
 typedef struct {
@@ -141,6 +144,8 @@ typedef struct {
     int sigma_builds;
     double theta;    /* last Ritz value of the (possibly spin-penalised) operator */
     double residual; /* last residual norm */
+    double sigma_ms; /* profile != 0: summed device time of the operator applications, else 0 */
+    double total_ms; /* profile != 0: device time of the whole Davidson loop */
 } sqd_davidson_info;
 
 /* bytes of device workspace for sqd_davidson on an operator of na x ldc */

@@ -55,6 +55,7 @@ class DavidsonParams(C.Structure):
         ("ss_op", C.POINTER(Operator)),
         ("ss_shift", C.c_double),
         ("ss_value", C.c_double),
+        ("profile", C.c_int),
     ]
 
 
@@ -65,6 +66,8 @@ class DavidsonInfo(C.Structure):
         ("sigma_builds", C.c_int),
         ("theta", C.c_double),
         ("residual", C.c_double),
+        ("sigma_ms", C.c_double),
+        ("total_ms", C.c_double),
     ]
 
 
@@ -75,6 +78,7 @@ _pi = C.POINTER(C.c_int)
 SIGNATURES: dict[str, tuple] = {
     "sqd_version": (_i, []),
     "sqd_last_error": (C.c_char_p, []),
+    "sqd_launch_count": (C.c_longlong, [_i]),
     "sqd_pack_bitstrings": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "sqd_check_hamming": (_i, [_vp, _i64, _vp, _pi, _pi, _pi, _vp]),
     "sqd_excitation_count": (_i, [_vp, _i, _vp, _vp, _vp]),

@@ -1,0 +1,146 @@
+"""Configuration recovery on B200.
+
+Host-side mirror of ``qiskit_addon_sqd/configuration_recovery.py:59-128`` (same signature, return
+layout, deprecation warning and error messages).  The per-bitstring correction
+(``_bipartite_bitstring_correcting`` :181-306, ``_p_flip_*`` :131-178 and the four
+``numpy.random.Generator.choice`` call sites) runs in the ``sqd_recover`` CUDA kernels.
+
+Randomness: with the default ``rng_mode="exact"`` the kernels consume the caller's PCG64 stream
+exactly as the reference would, so seeded results (rows, probabilities AND the generator's state after
+the call -- the SQD loop shares one generator between recovery and subsampling, ``fermion.py:374,
+508, 517``) are bit-identical to the reference.  ``rng_mode="parallel"`` draws one substream per row
+instead: same distribution, every row independent.
+"""
+
+from __future__ import annotations
+
+import warnings
+from collections.abc import Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+def _pcg64_words(rng: np.random.Generator) -> np.ndarray | None:
+    st = rng.bit_generator.state
+    if st.get("bit_generator") != "PCG64":
+        return None
+    s, inc = int(st["state"]["state"]), int(st["state"]["inc"])
+    m = (1 << 64) - 1
+    return np.array([s >> 64, s & m, inc >> 64, inc & m], dtype=np.uint64)
+
+
+def _set_pcg64_words(rng: np.random.Generator, words: np.ndarray) -> None:
+    st = rng.bit_generator.state
+    st["state"]["state"] = (int(words[0]) << 64) | int(words[1])
+    rng.bit_generator.state = st
+
+
+def _unpack_halves(left: np.ndarray, right: np.ndarray, norb: int) -> np.ndarray:
+    shifts = np.arange(norb - 1, -1, -1, dtype=np.uint64)
+    lb = ((left[:, None] >> shifts[None, :]) & np.uint64(1)).astype(bool)
+    rb = ((right[:, None] >> shifts[None, :]) & np.uint64(1)).astype(bool)
+    return np.concatenate([lb, rb], axis=1)
+
+
+def recover_configurations(
+    bitstring_matrix: np.ndarray,
+    probabilities: Sequence[float] | np.ndarray,
+    avg_occupancies: tuple[np.ndarray, np.ndarray],
+    num_elec_a: int,
+    num_elec_b: int,
+    rand_seed: np.random.Generator | int | None = None,
+    *,
+    rng_mode: str = "exact",
+) -> tuple[np.ndarray, np.ndarray]:
+    """Refine bitstrings based on average orbital occupancy and a target hamming weight.
+
+    Same contract as the reference (``configuration_recovery.py:59-128``): bit ``i`` of a row is the
+    spin-down orbital matching the spin-up orbital in bit ``i + N``; returns the refined bitstring
+    matrix (duplicates merged, first-seen order) and the renormalised probabilities.
+    """
+    rng = np.random.default_rng(rand_seed)
+
+    occ_dims = len(np.array(avg_occupancies).shape)
+    bitstring_matrix = np.asarray(bitstring_matrix)
+    if occ_dims == 1:
+        warnings.warn(
+            "Passing avg_occupancies as a 1D array is deprecated. Pass a length-2 tuple containing the spin-up and spin-down occupancies respectively.",
+            DeprecationWarning,
+            stacklevel=2,
+        )
+        norb = bitstring_matrix.shape[1] // 2
+        avg_occupancies = (np.flip(avg_occupancies[norb:]), np.flip(avg_occupancies[:norb]))
+
+    if num_elec_a < 0 or num_elec_b < 0:
+        raise ValueError("The numbers of electrons must be specified as non-negative integers.")
+    if rng_mode not in ("exact", "parallel"):
+        raise ValueError("rng_mode must be 'exact' or 'parallel'")
+
+    n = bitstring_matrix.shape[0]
+    if n == 0:
+        empty = np.array([])
+        return np.array([]), np.abs(empty) / np.sum(np.abs(empty)) if empty.size else empty
+
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    nbits = bitstring_matrix.shape[1]
+    norb = nbits // 2
+    if norb > 64 or nbits % 2:
+        raise ValueError("qiskit_addon_sqd_b200 needs an even number of bits with at most 64 per spin.")
+    occs = np.ascontiguousarray(np.flip(avg_occupancies).flatten(), dtype=np.float64)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    st = _lib.stream_ptr(torch)
+
+    bits = torch.from_numpy(np.ascontiguousarray(bitstring_matrix, dtype=np.uint8)).to(dev)
+    left = torch.empty(n, dtype=torch.int64, device=dev)
+    right = torch.empty(n, dtype=torch.int64, device=dev)
+    _lib.check(lib.sqd_pack_bitstrings(_lib.ptr(bits), n, nbits, _lib.ptr(left), _lib.ptr(right), st),
+               "sqd_pack_bitstrings")
+    occ_dev = torch.from_numpy(occs).to(dev)
+    left_out = torch.empty_like(left)
+    right_out = torch.empty_like(right)
+    status = torch.zeros(2, dtype=torch.int32, device=dev)
+    ws_bytes = lib.sqd_recover_workspace_bytes(n, norb)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+
+    words = _pcg64_words(rng) if rng_mode == "exact" else None
+    if words is not None:
+        state_dev = torch.from_numpy(words.view(np.int64)).to(dev)
+        mode, seed = 0, 0
+    else:
+        # non-PCG64 generators cannot be continued on the device: seed per-row substreams from it
+        state_dev = None
+        mode, seed = 1, int(rng.integers(0, 2**63 - 1))
+    _lib.check(
+        lib.sqd_recover(_lib.ptr(left), _lib.ptr(right), n, norb, _lib.ptr(occ_dev),
+                        occ_dev.data_ptr() + 8 * norb, int(num_elec_b), int(num_elec_a), mode,
+                        _lib.ptr(state_dev), seed, _lib.ptr(left_out), _lib.ptr(right_out),
+                        _lib.ptr(status), _lib.ptr(ws), ws_bytes, st),
+        "sqd_recover")
+    status_h = status.cpu().numpy()
+    if status_h[0] != 0:
+        raise ValueError("Fewer non-zero entries in p than size")
+    if words is not None:
+        _set_pcg64_words(rng, state_dev.cpu().numpy().view(np.uint64))
+    lo = left_out.cpu().numpy().view(np.uint64)
+    ro = right_out.cpu().numpy().view(np.uint64)
+
+    # merge duplicates: first-seen order, probabilities summed in input order (:112-126)
+    if norb <= 32:
+        keys = (lo << np.uint64(norb)) | ro
+        _, first, inverse = np.unique(keys, return_index=True, return_inverse=True)
+    else:
+        keys2 = np.stack([lo, ro], axis=1)
+        _, first, inverse = np.unique(keys2, axis=0, return_index=True, return_inverse=True)
+        inverse = inverse.reshape(-1)
+    order = np.argsort(first, kind="stable")          # unique groups in first-seen order
+    rank = np.empty_like(order)
+    rank[order] = np.arange(len(order))
+    sums = np.zeros(len(first), dtype=np.float64)
+    np.add.at(sums, rank[inverse], np.asarray(probabilities, dtype=np.float64))
+    sel = first[order]
+    bs_mat_out = _unpack_halves(lo[sel], ro[sel], norb)
+    freqs_out = np.abs(sums) / np.sum(np.abs(sums))
+    return bs_mat_out, freqs_out

@@ -1,6 +1,8 @@
 // Error plumbing and version of the C-ABI (include/sqd_b200.h).
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "../../include/sqd_b200.h"
 
@@ -15,7 +17,10 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-int check_launch(const char* what) {
+static std::atomic<long long> g_launches{0};
+
+int check_launch(const char* what, int n_launched) {
+    g_launches.fetch_add(n_launched, std::memory_order_relaxed);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("launch of %s failed: %s", what, cudaGetErrorString(e));
@@ -31,5 +36,9 @@ extern "C" {
 int sqd_version(void) { return SQD_B200_VERSION; }
 
 const char* sqd_last_error(void) { return sqd::g_err; }
+
+long long sqd_launch_count(int reset) {
+    return reset ? sqd::g_launches.exchange(0) : sqd::g_launches.load();
+}
 
 }  // extern "C"

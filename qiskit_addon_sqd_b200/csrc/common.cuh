@@ -9,7 +9,7 @@ namespace sqd {
 
 // ---- error plumbing (C-ABI: 0 = ok, <0 = error, message via sqd_last_error) ------------------
 void set_error(const char* fmt, ...);
-int check_launch(const char* what);
+int check_launch(const char* what, int n_launched = 1);  // also counts kernel launches
 
 #define SQD_CUDA_OK(expr)                                                              \
     do {                                                                               \

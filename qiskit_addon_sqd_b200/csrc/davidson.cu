@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include <functional>
+#include <vector>
 #include <type_traits>
 
 #include "common.cuh"
@@ -479,6 +480,20 @@ __global__ void init_guess_kernel(const double* __restrict__ pval, const int64_t
     }
 }
 
+// x0[j] += scale * u_j, u_j in [-1, 1) from a counter hash: seeds every invariant block of a
+// block-diagonal operator (a unit start vector can never leave its own connected component)
+__global__ void add_noise_kernel(double* __restrict__ x0, int64_t n, double scale) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+         j += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = (uint64_t)j * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const double u = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        x0[j] += scale * u;
+    }
+}
+
 // row / column weights of c^2 and orbital occupancies
 __global__ void row_weight_kernel(const double* __restrict__ c, int na, int nb, int ldc,
                                   double* __restrict__ wa) {
@@ -589,7 +604,7 @@ static int apply_operator(const sqd_operator* op, const sqd_davidson_params* prm
         axpby_kernel<<<blocks, kRedThreads, 0, st>>>(done, 1.0, ws.tmp2, -prm->ss_value, ws.tmp1,
                                                      ws.tmp2, n);
         axpby_kernel<<<blocks, kRedThreads, 0, st>>>(done, 1.0, w, prm->ss_shift, ws.tmp2, w, n);
-        if (check_launch("axpby_kernel")) return -2;
+        if (check_launch("axpby_kernel", 3)) return -2;
     }
     return 0;
 }
@@ -613,11 +628,27 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
     dot_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_x0, d_x0, n, ws.partials);
     dot_final_kernel<<<1, 32, 0, st>>>(ws.partials, blocks, ws.partials + kRedBlocks);
     scale_copy_kernel<<<blocks, kRedThreads, 0, st>>>(d_x0, ws.V, n, ws.partials + kRedBlocks);
-    if (check_launch("davidson init")) return -2;
+    if (check_launch("davidson init", 4)) return -2;
 
+    std::vector<cudaEvent_t> ev;  // profile mode only: (before, after) per operator application
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    if (prm->profile) {
+        SQD_CUDA_OK(cudaEventCreate(&ev_begin));
+        SQD_CUDA_OK(cudaEventCreate(&ev_end));
+        SQD_CUDA_OK(cudaEventRecord(ev_begin, st));
+    }
     int m = 1, slot = 0, status = 0, cycle = 0, sigma_builds = 0;
     for (; cycle < prm->max_cycle; ++cycle) {
+        if (prm->profile) {
+            cudaEvent_t e0, e1;
+            SQD_CUDA_OK(cudaEventCreate(&e0));
+            SQD_CUDA_OK(cudaEventCreate(&e1));
+            ev.push_back(e0);
+            ev.push_back(e1);
+            SQD_CUDA_OK(cudaEventRecord(e0, st));
+        }
         if (apply(ws.V + (int64_t)slot * n, ws.W + (int64_t)slot * n, ws)) return -2;
+        if (prm->profile) SQD_CUDA_OK(cudaEventRecord(ev.back(), st));
         ++sigma_builds;
         const int restart = (m == M) ? 1 : 0;
         int rc = dispatch_mv(m, [&](auto mv) {
@@ -630,7 +661,7 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
                                                                 ws.partials);
             convergence_kernel<<<1, 64, 0, st>>>(ws.state, ws.partials, blocks, m, restart, prm->tol,
                                                  prm->tol_residual);
-            return check_launch("davidson cycle (1)");
+            return check_launch("davidson cycle (1)", 4);
         });
         if (rc) return -2;
         const int me = restart ? 1 : m;
@@ -640,7 +671,7 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
             norm_kernel<<<1, 64, 0, st>>>(ws.state, ws.partials, blocks, me, prm->lindep);
             ortho2_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T,
                                                               ws.V + (int64_t)me * n);
-            return check_launch("davidson cycle (2)");
+            return check_launch("davidson cycle (2)", 3);
         });
         if (rc) return -2;
         m = me + 1;
@@ -658,8 +689,28 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
     DavState hs;
     SQD_CUDA_OK(cudaMemcpyAsync(&hs, ws.state, sizeof(DavState), cudaMemcpyDeviceToHost, st));
     SQD_CUDA_OK(cudaMemcpyAsync(d_x, ws.X, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (prm->profile) SQD_CUDA_OK(cudaEventRecord(ev_end, st));
     SQD_CUDA_OK(cudaStreamSynchronize(st));
+    double sigma_ms = 0.0, total_ms = 0.0;
+    if (prm->profile) {
+        // only cycles that ran before the device-side stop flag was raised did real work
+        const int real = hs.cycles < (int)(ev.size() / 2) ? hs.cycles : (int)(ev.size() / 2);
+        for (int i = 0; i < (int)(ev.size() / 2); ++i) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+            if (i < real) sigma_ms += ms;
+            cudaEventDestroy(ev[2 * i]);
+            cudaEventDestroy(ev[2 * i + 1]);
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev_begin, ev_end);
+        total_ms = ms;
+        cudaEventDestroy(ev_begin);
+        cudaEventDestroy(ev_end);
+    }
     if (h_info) {
+        h_info->sigma_ms = sigma_ms;
+        h_info->total_ms = total_ms;
         h_info->converged = hs.status == 1 ? 1 : (hs.status == 2 ? 2 : 0);
         h_info->cycles = hs.cycles;
         h_info->sigma_builds = sigma_builds;
@@ -687,7 +738,7 @@ int sqd_dot(const double* d_x, const double* d_y, int64_t n, double* d_out, doub
     const int blocks = red_blocks(n);
     dot_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_x, d_y, n, d_scratch);
     dot_final_kernel<<<1, 32, 0, st>>>(d_scratch, blocks, d_out);
-    return check_launch("dot kernels");
+    return check_launch("dot kernels", 2);
 }
 
 int sqd_init_guess(const double* d_hdiag, int na, int nb, int ldc, double* d_x0, void* d_scratch,
@@ -701,7 +752,7 @@ int sqd_init_guess(const double* d_hdiag, int na, int nb, int ldc, double* d_x0,
     SQD_CUDA_OK(cudaMemsetAsync(d_x0, 0, n * sizeof(double), st));
     argmin_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_hdiag, na, nb, ldc, pval, pidx);
     init_guess_kernel<<<1, 32, 0, st>>>(pval, pidx, blocks, na, nb, ldc, d_x0);
-    return check_launch("init_guess kernels");
+    return check_launch("init_guess kernels", 2);
 }
 
 int sqd_occupancies(const double* d_c, const uint64_t* d_strs_a, int na, const uint64_t* d_strs_b,
@@ -712,7 +763,7 @@ int sqd_occupancies(const double* d_c, const uint64_t* d_strs_a, int na, const u
     row_weight_kernel<<<(na + 7) / 8, 256, 0, st>>>(d_c, na, nb, ldc, wa);
     col_weight_kernel<<<(nb + 127) / 128, 128, 0, st>>>(d_c, na, nb, ldc, wb);
     occupancy_kernel<<<2 * norb, kRedThreads, 0, st>>>(wa, d_strs_a, na, wb, d_strs_b, nb, norb, d_occ);
-    return check_launch("occupancy kernels");
+    return check_launch("occupancy kernels", 3);
 }
 
 int sqd_davidson(const sqd_operator* op, const double* d_hdiag, const double* d_x0, double* d_x,
@@ -753,6 +804,10 @@ int sqd_csr_davidson(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, 
     if (csr_diag_embed(d, d_row_ptr, d_col, d_val, hdiag, st)) return -2;
     // scratch for the argmin lives in the (not yet used) Davidson workspace
     if (sqd_init_guess(hdiag, 1, (int)n, (int)n, x0, p, stream)) return -2;
+    // the projected Pauli operator is often block diagonal (disconnected sets of configurations):
+    // give every block a small component, as ARPACK's random start vector does in the reference
+    add_noise_kernel<<<red_blocks(n), kRedThreads, 0, st>>>(x0, n, 0.1 / sqrt((double)n));
+    if (check_launch("add_noise_kernel")) return -2;
     sqd_davidson_params prm;
     memset(&prm, 0, sizeof(prm));
     prm.max_space = max_space;

@@ -204,11 +204,12 @@ class _SpinTableDev:
     """Excitation table of one string list (CSR; singles first then doubles)."""
 
     def __init__(self, torch, lib, strs_u64: np.ndarray, ints: _DeviceIntegrals | None, norb: int,
-                 device):
+                 device, strs_dev=None):
         n = len(strs_u64)
         self.n = n
         st = _lib.stream_ptr(torch)
-        self.strs = torch.from_numpy(strs_u64.view(np.int64).copy()).to(device)
+        self.strs = strs_dev if strs_dev is not None else \
+            torch.from_numpy(strs_u64.view(np.int64).copy()).to(device)
         self.n_single = torch.empty(n, dtype=torch.int32, device=device)
         n_total = torch.empty(n, dtype=torch.int32, device=device)
         self.row_ptr = torch.empty(n + 1, dtype=torch.int32, device=device)
@@ -277,7 +278,8 @@ class _OperatorDev:
 class _Subspace:
     """Device state of one product subspace A x B on the current CUDA device / stream."""
 
-    def __init__(self, strs_a, strs_b, norb: int, hcore, eri, ints: _DeviceIntegrals | None = None):
+    def __init__(self, strs_a, strs_b, norb: int, hcore, eri, ints: _DeviceIntegrals | None = None,
+                 strs_dev=(None, None)):
         self.torch = torch = _lib.require_cuda()
         self.lib = lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -298,9 +300,9 @@ class _Subspace:
         self.ldg = (norb * norb + 1) // 2 * 2
         self.n_alpha = int(np.bitwise_count(ua[0]))
         self.n_beta = int(np.bitwise_count(ub[0]))
-        self.ta = _SpinTableDev(torch, lib, ua, ints, norb, self.device)
+        self.ta = _SpinTableDev(torch, lib, ua, ints, norb, self.device, strs_dev[0])
         self.tb = self.ta if (same or (ua.shape == ub.shape and np.array_equal(ua, ub))) else \
-            _SpinTableDev(torch, lib, ub, ints, norb, self.device)
+            _SpinTableDev(torch, lib, ub, ints, norb, self.device, strs_dev[1])
         self._ss_op = None
         self._scratch = torch.empty(4096, dtype=torch.float64, device=self.device)
         self._scalar = torch.empty(8, dtype=torch.float64, device=self.device)
@@ -369,7 +371,7 @@ class _Subspace:
 
     # -- eigensolver -------------------------------------------------------------------------
     def ground_state(self, op: _OperatorDev, *, tol, tol_residual, max_cycle, max_space, lindep,
-                     level_shift, ci0=None, quad_penalty=None, check_every=4):
+                     level_shift, ci0=None, quad_penalty=None, check_every=4, profile=False):
         torch, lib = self.torch, self.lib
         st = _lib.stream_ptr(torch)
         n = self.na * self.ldc
@@ -385,7 +387,8 @@ class _Subspace:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
         x = self.new_vector()
         prm = _lib.DavidsonParams(max_space, int(max_cycle), float(tol), float(tol_residual),
-                                  float(lindep), float(level_shift), int(check_every), None, 0.0, 0.0)
+                                  float(lindep), float(level_shift), int(check_every), None, 0.0, 0.0,
+                                  1 if profile else 0)
         if quad_penalty is not None:
             ss_op, shift, ss = quad_penalty
             prm.ss_op = C.pointer(ss_op.struct)
@@ -442,6 +445,11 @@ class SolveStats:
     nnz_b: int = 0
     singles_a: int = 0
     singles_b: int = 0
+    sigma_ms: float = 0.0   # profile mode only
+    davidson_ms: float = 0.0
+    na: int = 0
+    nb: int = 0
+    norb: int = 0
 
 
 _tls = threading.local()
@@ -452,9 +460,11 @@ def last_solve_stats() -> list[SolveStats]:
 
 
 def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq, shift, opts,
-                     want_spin: bool, want_rdm: bool):
-    """Ground state of H projected on A x B.  Returns dict of results (host arrays)."""
-    sub = _Subspace(strs_a, strs_b, norb, None, None, ints=ints)
+                     want_spin: bool, want_rdm: bool, *, strs_dev=(None, None), download: bool = True,
+                     profile: bool = False):
+    """Ground state of H projected on A x B.  Returns dict of results (host arrays; with
+    ``download=False`` the amplitudes stay on the device as a padded ``(na, ldc)`` tensor)."""
+    sub = _Subspace(strs_a, strs_b, norb, None, None, ints=ints, strs_dev=strs_dev)
     sz = 0.5 * abs(sub.n_alpha - sub.n_beta)
     quad = None
     if spin_sq is None:
@@ -471,7 +481,7 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
     x, info = sub.ground_state(ham, tol=opts["tol"], tol_residual=opts["tol_residual"],
                                max_cycle=opts["max_cycle"], max_space=opts["max_space"],
                                lindep=opts["lindep"], level_shift=opts["level_shift"],
-                               ci0=opts.get("ci0"), quad_penalty=quad)
+                               ci0=opts.get("ci0"), quad_penalty=quad, profile=profile)
     # energy = <x|H_bare|x>  (reference computes it from the RDMs and ignores the solver's eigenvalue,
     # fermion.py:806-809, 824-827)
     hx = sub.apply(ham, x)
@@ -482,12 +492,15 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
         s2 = sub.spin_square(x)
     energy = e_pen - lin_shift * (s2 - float(spin_sq)) if lin_shift != 0.0 else e_pen
     occ = sub.occupancies(x)
-    amps = sub.download_amplitudes(x)
-    # eigenvector sign: pyscf's is whatever LAPACK returns for the small problem; fix the convention
-    # "largest-magnitude amplitude positive" so that results are reproducible.
-    k = np.unravel_index(np.argmax(np.abs(amps)), amps.shape)
-    if amps[k] < 0:
-        amps = -amps
+    if download:
+        amps = sub.download_amplitudes(x)
+        # eigenvector sign: pyscf's is whatever LAPACK returns for the small problem; fix the
+        # convention "largest-magnitude amplitude positive" so that results are reproducible.
+        k = np.unravel_index(np.argmax(np.abs(amps)), amps.shape)
+        if amps[k] < 0:
+            amps = -amps
+    else:
+        amps = x.reshape(sub.na, sub.ldc)
     rdm1 = rdm2 = None
     if want_rdm:
         from ._rdm import subspace_rdms
@@ -495,7 +508,8 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
         rdm1, rdm2 = subspace_rdms(sub, x)
     stats = SolveStats(info.cycles, info.sigma_builds, info.converged, info.residual, info.theta,
                        sub.na * sub.nb, sub.ta.nnz, sub.tb.nnz,
-                       int(sub.ta.n_single.sum().item()), int(sub.tb.n_single.sum().item()))
+                       int(sub.ta.n_single.sum().item()), int(sub.tb.n_single.sum().item()),
+                       info.sigma_ms, info.total_ms, sub.na, sub.nb, norb)
     if not hasattr(_tls, "stats"):
         _tls.stats = []
     _tls.stats.append(stats)

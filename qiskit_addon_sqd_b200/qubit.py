@@ -1,0 +1,254 @@
+"""Qubit-operator subspace projection + diagonalisation on B200.
+
+Host-side mirror of ``qiskit_addon_sqd/qubit.py`` (``solve_qubit`` :29-75,
+``project_operator_to_subspace`` :78-144, ``sort_and_remove_duplicates`` :147-164,
+``matrix_elements_from_pauli`` :167-240): same names, arguments, return layout and error message.
+``hamiltonian`` is duck-typed exactly as the reference uses it: ``.paulis`` (objects with little-endian
+bool arrays ``.x`` and ``.z``), ``.coeffs`` and ``.size`` -- a ``qiskit.quantum_info.SparsePauliOp``
+works unchanged, qiskit itself is not required.
+
+The reference loops over Pauli terms in Python (jax vmap + numpy isin/searchsorted + a scipy sparse add
+per term).  Here all terms are projected by one pair of CUDA launches (``sqd_pauli_project_count`` /
+``_fill``) and the ground state comes from the device-resident Davidson (``sqd_csr_davidson``) instead
+of ARPACK; anything other than "the lowest eigenpair" still goes through ``scipy.sparse.linalg.eigsh``
+-- the reference's own solver -- but with the matrix-vector product on the GPU.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+from scipy.sparse import csr_matrix, spmatrix
+from scipy.sparse.linalg import LinearOperator, eigsh
+
+from . import _lib
+
+_LEN_ERR = "Bitstrings (rows) in bitstring_matrix must have length < 64."
+
+
+def _keys_device(torch, lib, bitstring_matrix: np.ndarray):
+    n, nq = bitstring_matrix.shape
+    dev = torch.device("cuda", torch.cuda.current_device())
+    bits = torch.from_numpy(np.ascontiguousarray(bitstring_matrix, dtype=np.uint8)).to(dev)
+    keys = torch.empty(n, dtype=torch.int64, device=dev)
+    _lib.check(lib.sqd_bits_to_keys(_lib.ptr(bits), n, nq, _lib.ptr(keys), _lib.stream_ptr(torch)),
+               "sqd_bits_to_keys")
+    return keys
+
+
+def _masks(x: np.ndarray, z: np.ndarray) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Per-term (xmask, zmask, #Y); bit k of a mask <-> qubit k <-> column nq-1-k (``qubit.py:214-216``)."""
+    x = np.atleast_2d(np.asarray(x, dtype=bool))
+    z = np.atleast_2d(np.asarray(z, dtype=bool))
+    w = np.uint64(1) << np.arange(x.shape[1], dtype=np.uint64)
+    xm = (x.astype(np.uint64) * w[None, :]).sum(axis=1, dtype=np.uint64)
+    zm = (z.astype(np.uint64) * w[None, :]).sum(axis=1, dtype=np.uint64)
+    ny = np.count_nonzero(x & z, axis=1).astype(np.int32)
+    return xm, zm, ny
+
+
+def sort_and_remove_duplicates(bitstring_matrix: np.ndarray) -> np.ndarray:
+    """Sort a bitstring matrix by integer value and drop repeated rows (reference ``qubit.py:147-164``)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    bitstring_matrix = np.asarray(bitstring_matrix)
+    if bitstring_matrix.shape[0] == 0:
+        return bitstring_matrix
+    keys = _keys_device(torch, lib, bitstring_matrix).cpu().numpy()
+    _, indices = np.unique(keys, return_index=True)
+    return bitstring_matrix[indices, :]
+
+
+def matrix_elements_from_pauli(bitstring_matrix: np.ndarray, pauli):
+    """Sparse matrix elements of one Pauli in the subspace (reference ``qubit.py:167-240``).
+
+    Returns ``(amplitudes, rows, cols)`` with ``A[rows[k], cols[k]] = amplitudes[k]``; rows are the
+    source configurations, cols the index of the connected configuration.
+    """
+    bitstring_matrix = np.asarray(bitstring_matrix)
+    if bitstring_matrix.shape[1] > 63:
+        raise ValueError(_LEN_ERR)
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    d = bitstring_matrix.shape[0]
+    if d == 0:
+        return np.zeros(0, dtype=np.complex128), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
+    keys = _keys_device(torch, lib, bitstring_matrix)
+    xm, zm, ny = _masks(pauli.x, pauli.z)
+    col = torch.empty(d, dtype=torch.int32, device=keys.device)
+    par = torch.empty(d, dtype=torch.uint8, device=keys.device)
+    _lib.check(lib.sqd_pauli_connect(_lib.ptr(keys), d, int(xm[0]), int(zm[0]), _lib.ptr(col),
+                                     _lib.ptr(par), _lib.stream_ptr(torch)), "sqd_pauli_connect")
+    col_h = col.cpu().numpy().astype(np.int64)
+    par_h = par.cpu().numpy()
+    mask = col_h >= 0
+    amp = (1.0 - 2.0 * par_h.astype(np.float64)) * (1j ** int(ny[0] % 4))
+    return amp[mask].astype(np.complex128), np.arange(d)[mask], col_h[mask]
+
+
+class _DeviceCSR:
+    def __init__(self, d, row_ptr, col, val):
+        self.d, self.row_ptr, self.col, self.val = d, row_ptr, col, val
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+    def to_scipy(self) -> csr_matrix:
+        data = self.val.cpu().numpy().view(np.complex128).reshape(-1)
+        return csr_matrix((data, self.col.cpu().numpy(), self.row_ptr.cpu().numpy()),
+                          shape=(self.d, self.d))
+
+
+def _project_device(torch, lib, keys, hamiltonian) -> _DeviceCSR:
+    d = int(keys.numel())
+    dev = keys.device
+    st = _lib.stream_ptr(torch)
+    paulis = list(hamiltonian.paulis)
+    T = len(paulis)
+    coeffs = np.asarray(hamiltonian.coeffs, dtype=np.complex128).reshape(-1)
+    if T == 0 or d == 0:
+        z = torch.zeros(d + 1, dtype=torch.int32, device=dev)
+        return _DeviceCSR(d, z, torch.zeros(0, dtype=torch.int32, device=dev),
+                          torch.zeros(0, dtype=torch.float64, device=dev))
+    xm, zm, ny = _masks(np.array([p.x for p in paulis]), np.array([p.z for p in paulis]))
+    # group terms by X mask; groups in order of first appearance, original order inside a group
+    uniq, first, inv = np.unique(xm, return_index=True, return_inverse=True)
+    g_order = np.argsort(first, kind="stable")
+    g_rank = np.empty_like(g_order)
+    g_rank[g_order] = np.arange(len(g_order))
+    grp_of_term = g_rank[inv.reshape(-1)]
+    perm = np.argsort(grp_of_term, kind="stable")
+    counts = np.bincount(grp_of_term, minlength=len(uniq))
+    grp_ptr = np.zeros(len(uniq) + 1, dtype=np.int32)
+    np.cumsum(counts, out=grp_ptr[1:])
+    grp_x = uniq[g_order]
+
+    def up(a, dt):
+        return torch.from_numpy(np.ascontiguousarray(a).view(dt) if a.dtype != dt else
+                                np.ascontiguousarray(a)).to(dev)
+
+    d_gx = up(grp_x.astype(np.uint64), np.int64)
+    d_gp = up(grp_ptr, np.int32)
+    d_z = up(zm[perm].astype(np.uint64), np.int64)
+    d_ny = up(ny[perm].astype(np.int32), np.int32)
+    d_cf = torch.from_numpy(np.ascontiguousarray(coeffs[perm]).view(np.float64)).to(dev)
+    row_nnz = torch.empty(d, dtype=torch.int32, device=dev)
+    _lib.check(lib.sqd_pauli_project_count(_lib.ptr(keys), d, _lib.ptr(d_gx), _lib.ptr(d_gp),
+                                           len(uniq), _lib.ptr(d_z), _lib.ptr(d_ny), _lib.ptr(d_cf),
+                                           _lib.ptr(row_nnz), st), "sqd_pauli_project_count")
+    row_ptr = torch.empty(d + 1, dtype=torch.int32, device=dev)
+    total = C.c_int(0)
+    _lib.check(lib.sqd_exclusive_scan(_lib.ptr(row_nnz), _lib.ptr(row_ptr), d, C.byref(total), st),
+               "sqd_exclusive_scan")
+    nnz = int(total.value)
+    col = torch.empty(nnz, dtype=torch.int32, device=dev)
+    val = torch.empty(2 * nnz, dtype=torch.float64, device=dev)
+    col_tmp = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
+    val_tmp = torch.empty(max(2 * nnz, 1), dtype=torch.float64, device=dev)
+    if nnz:
+        _lib.check(lib.sqd_pauli_project_fill(_lib.ptr(keys), d, _lib.ptr(d_gx), _lib.ptr(d_gp),
+                                              len(uniq), _lib.ptr(d_z), _lib.ptr(d_ny),
+                                              _lib.ptr(d_cf), _lib.ptr(row_ptr), _lib.ptr(col_tmp),
+                                              _lib.ptr(val_tmp), _lib.ptr(col), _lib.ptr(val), st),
+                   "sqd_pauli_project_fill")
+    return _DeviceCSR(d, row_ptr, col, val)
+
+
+def project_operator_to_subspace(
+    bitstring_matrix: np.ndarray,
+    hamiltonian,
+    *,
+    verbose: bool = False,
+) -> spmatrix:
+    """Project a Pauli operator onto the subspace spanned by the rows of ``bitstring_matrix``.
+
+    As the reference (``qubit.py:78-144``): rows must be unique and sorted ascending by integer value
+    (not checked); the result is a complex128 ``scipy.sparse.csr_matrix`` ``A`` with
+    ``A[source, connected] = amplitude`` -- the TRANSPOSE of the operator's matrix, canonical format,
+    exact zeros dropped.
+    """
+    bitstring_matrix = np.asarray(bitstring_matrix)
+    if bitstring_matrix.shape[1] > 63:
+        raise ValueError(_LEN_ERR)
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    d = bitstring_matrix.shape[0]
+    if d == 0:
+        return csr_matrix((0, 0), dtype="complex128")
+    if verbose:  # pragma: no cover
+        print(f"Projecting {hamiltonian.size} Pauli terms onto {d} configurations on the GPU ...")
+    keys = _keys_device(torch, lib, bitstring_matrix)
+    return _project_device(torch, lib, keys, hamiltonian).to_scipy()
+
+
+def _native_ok(kw: dict) -> bool:
+    if kw.get("k", 6) != 1 or kw.get("which", "LM") != "SA":
+        return False
+    return all(kw.get(key) is None for key in ("sigma", "M", "Minv", "OPinv")) and \
+        kw.get("mode", "normal") == "normal" and kw.get("return_eigenvectors", True)
+
+
+def solve_qubit(
+    bitstring_matrix: np.ndarray,
+    hamiltonian,
+    *,
+    verbose: bool = False,
+    **scipy_kwargs,
+) -> tuple[np.ndarray, np.ndarray]:
+    """Energies and eigenstates of a Pauli Hamiltonian projected into a subspace (``qubit.py:29-75``).
+
+    ``**scipy_kwargs`` has ``scipy.sparse.linalg.eigsh``'s meaning.  ``k=1, which="SA"`` (the usual
+    ground-state call) runs the device-resident Davidson; any other request is served by ``eigsh``
+    itself with the sparse matrix-vector product on the GPU.
+    """
+    bitstring_matrix = np.asarray(bitstring_matrix)
+    if bitstring_matrix.shape[1] > 63:
+        raise ValueError(_LEN_ERR)
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    keys_all = _keys_device(torch, lib, bitstring_matrix)
+    keys = torch.unique(keys_all)  # sorted ascending, duplicates removed (qubit.py:66)
+    d = int(keys.numel())
+    if verbose:  # pragma: no cover
+        print(f"Projecting {hamiltonian.size} Pauli terms onto {d} configurations on the GPU ...")
+    csr = _project_device(torch, lib, keys, hamiltonian)
+    st = _lib.stream_ptr(torch)
+    if verbose:  # pragma: no cover
+        print("Diagonalizing Hamiltonian in the subspace...")
+
+    if _native_ok(scipy_kwargs) and d > 1:
+        tol = float(scipy_kwargs.get("tol", 0) or 0)
+        tol = tol * tol if tol > 0 else 1e-14  # eigsh's tol is a relative residual-like accuracy
+        max_space = int(min(scipy_kwargs.get("ncv") or 20, _lib.MAX_SPACE))
+        max_cycle = int(scipy_kwargs.get("maxiter") or 500)
+        ws_bytes = lib.sqd_csr_davidson_workspace_bytes(d, 1, max_space)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
+        evec = torch.empty(2 * d, dtype=torch.float64, device=keys.device)
+        evals = (C.c_double * 1)()
+        cycles = C.c_int(0)
+        _lib.check(lib.sqd_csr_davidson(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col), _lib.ptr(csr.val),
+                                        1, max_space, max_cycle, tol, _lib.ptr(evec), evals,
+                                        C.byref(cycles), _lib.ptr(ws), ws_bytes, st),
+                   "sqd_csr_davidson")
+        vec = evec.cpu().numpy().view(np.complex128).reshape(d, 1)
+        return np.array([evals[0]]), vec
+
+    # general eigsh request: ARPACK on the host, A @ x on the device
+    x_dev = torch.empty(2 * d, dtype=torch.float64, device=keys.device)
+    y_dev = torch.empty(2 * d, dtype=torch.float64, device=keys.device)
+
+    def matvec(x):
+        xx = np.ascontiguousarray(x, dtype=np.complex128).reshape(-1)
+        x_dev.copy_(torch.from_numpy(xx.view(np.float64)))
+        _lib.check(lib.sqd_csr_matvec_c128(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col),
+                                           _lib.ptr(csr.val), _lib.ptr(x_dev), _lib.ptr(y_dev), st),
+                   "sqd_csr_matvec_c128")
+        return y_dev.cpu().numpy().view(np.complex128)
+
+    if d <= 1 or scipy_kwargs.get("sigma") is not None or scipy_kwargs.get("M") is not None:
+        # shift-invert / generalized problems need a factorisation: hand scipy the explicit matrix
+        return eigsh(csr.to_scipy(), **scipy_kwargs)
+    op = LinearOperator((d, d), matvec=matvec, dtype=np.complex128)
+    return eigsh(op, **scipy_kwargs)

@@ -150,8 +150,12 @@ def test_quadratic_spin_penalty(cuda_lib):
     norb, nel = 6, 3
     h, g = random_integrals(norb, 77)
     sa = _all_strings(norb, nel)
-    # target the triplet (ss = 2) in the Sz = 0 sector -> pyscf's quadratic branch
-    e, state, occ, s2 = fermion.solve_fermion((sa, sa), h, g, spin_sq=2.0, shift=0.5)
+    # target the triplet (ss = 2) in the Sz = 0 sector -> pyscf's quadratic branch.  The default start
+    # vector (lowest closed-shell determinant) is a pure singlet and S^2 commutes with H, so -- as
+    # pyscf's own comment says -- this branch "relies on the quality of the initial guess": pass ci0.
+    ci0 = np.random.default_rng(3).standard_normal((len(sa), len(sa)))
+    e, state, occ, s2 = fermion.solve_fermion((sa, sa), h, g, spin_sq=2.0, shift=0.5, ci0=ci0,
+                                               max_cycle=1000)
     e_ref, c_ref, _, s2_ref, _ = fo.solve_dense(sa, sa, h, g, norb, spin_sq=2.0, shift=0.5)
     assert abs(e - e_ref) < ETOL
     assert abs(s2 - s2_ref) < 1e-6

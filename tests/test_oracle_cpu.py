@@ -1,0 +1,258 @@
+"""CPU-only tests: the oracles against the reference's golden vectors / known answers, and the C-ABI
+library's symbol table.  No compute call touches the GPU here."""
+
+import itertools
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import fermion_oracle as fo
+from oracle import qubit_oracle as qo
+from oracle import recovery_oracle as ro
+from qiskit_addon_sqd_b200._synthetic import PauliSum, PauliTerm, hf_centred_strings, random_integrals
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------------------------------------
+# C-ABI
+# ------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    from qiskit_addon_sqd_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "sqd_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(sqd_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()  # dlopen only
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/sqd_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.sqd_version() == 100
+
+
+def test_product_path_refuses_to_run_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from qiskit_addon_sqd_b200 import configuration_recovery, fermion, qubit
+
+    h, g = random_integrals(4, 0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        fermion.solve_fermion((np.array([3]), np.array([3])), h, g)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        qubit.solve_qubit(np.zeros((2, 3), dtype=bool), PauliSum.from_labels(["XZI"]))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        configuration_recovery.recover_configurations(
+            np.zeros((1, 4), dtype=bool), np.ones(1), (np.ones(2), np.ones(2)), 1, 1, rand_seed=0)
+
+
+def test_product_package_does_not_import_the_oracle():
+    import ast
+
+    pkg = os.path.join(ROOT, "qiskit_addon_sqd_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            tree = ast.parse(open(os.path.join(pkg, fn)).read())
+            for node in ast.walk(tree):
+                names = []
+                if isinstance(node, ast.Import):
+                    names = [a.name for a in node.names]
+                elif isinstance(node, ast.ImportFrom):
+                    names = [node.module or ""]
+                assert not any(n.split(".")[0] == "oracle" for n in names), fn
+
+
+# ------------------------------------------------------------------------------------------------
+# fermion oracle: pinned against an independent Jordan-Wigner construction
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nelec", [(2, 2), (2, 1), (1, 3), (3, 2)])
+def test_fermion_oracle_matches_jordan_wigner(nelec):
+    norb = 4
+    h, g = random_integrals(norb, 1)
+    HJ = fo.jordan_wigner_hamiltonian(h, g, norb)
+    S2J = fo.jordan_wigner_spin_square(norb)
+    SA = sorted(sum(1 << i for i in c) for c in itertools.combinations(range(norb), nelec[0]))
+    SB = sorted(sum(1 << i for i in c) for c in itertools.combinations(range(norb), nelec[1]))
+    rng = np.random.default_rng(5)
+    for trial in range(3):
+        A = SA if trial == 0 else sorted(rng.choice(SA, size=max(1, len(SA) // 2 + 1), replace=False).tolist())
+        B = SB if trial == 0 else sorted(rng.choice(SB, size=max(1, len(SB) // 2), replace=False).tolist())
+        H = fo.projected_hamiltonian(A, B, h, g, norb)
+        S2 = fo.spin_square_matrix(A, B, norb)
+        idx = [fo.jordan_wigner_index(a, b, norb) for a in A for b in B]
+        assert np.abs(H - HJ[np.ix_(idx, idx)]).max() < 1e-13
+        assert np.abs(S2 - S2J[np.ix_(idx, idx)]).max() < 1e-13
+        assert np.abs(fo.make_hdiag(A, B, h, g, norb).reshape(-1) - np.diag(H)).max() < 1e-13
+        assert np.abs(fo.same_spin_matrix_complete(A, h, g, norb) - fo.same_spin_matrix(A, h, g, norb)).max() < 1e-13
+
+
+def test_fermion_oracle_invariants_and_sparse_form():
+    norb = 8
+    h, g = random_integrals(norb, 2)
+    A = hf_centred_strings(norb, 4, 30, 3)
+    B = hf_centred_strings(norb, 3, 20, 4)
+    H = fo.projected_hamiltonian(A, B, h, g, norb)
+    assert np.abs(H - H.T).max() < 1e-13
+    op = fo.SparseProjectedHamiltonian(A, B, h, g, norb)
+    x = np.random.default_rng(0).standard_normal(len(A) * len(B))
+    assert np.abs(op.matvec(x) - H @ x).max() < 1e-12
+    e, c, occ, s2, w0 = fo.solve_dense(A, B, h, g, norb)
+    assert abs(e - w0) < 1e-12 and abs(op.ground_state()[0] - e) < 1e-9
+    assert abs(occ[0].sum() - 4) < 1e-12 and abs(occ[1].sum() - 3) < 1e-12
+    # closed-shell full space: singlet ground state of a spin-free Hamiltonian
+    S = sorted(sum(1 << i for i in c) for c in itertools.combinations(range(5), 2))
+    h5, g5 = random_integrals(5, 9)
+    assert abs(fo.solve_dense(S, S, h5, g5, 5)[3]) < 1e-10
+
+
+# ------------------------------------------------------------------------------------------------
+# qubit oracle: reference known answers (test/test_qubit.py:107-164) and goldens
+# ------------------------------------------------------------------------------------------------
+def test_qubit_oracle_reference_known_answers():
+    bs = np.array([[False, False], [False, True], [True, False], [True, True]])
+    amp, rows, cols = qo.matrix_elements_from_pauli(bs, PauliTerm([False, True], [True, False]))  # "XZ"
+    assert (amp == np.array([1, -1, 1, -1])).all()
+    assert (rows == np.array([0, 1, 2, 3])).all() and (cols == np.array([2, 3, 0, 1])).all()
+    bs7 = np.array([[0, 0, 0, 0], [0, 0, 0, 1], [0, 0, 1, 0], [0, 0, 1, 1], [0, 1, 0, 0], [1, 0, 0, 0],
+                    [1, 1, 0, 0]])
+    ham = PauliSum.from_labels(["XZIY"])
+    amp, rows, cols = qo.matrix_elements_from_pauli(bs7, ham.paulis[0])
+    assert np.allclose(amp, [-1j, 1j]) and list(rows) == [1, 5] and list(cols) == [5, 1]
+    proj = qo.project_operator_to_subspace(bs7, PauliSum.from_labels(["XZIY"], [0.5]))
+    assert proj.shape == (7, 7) and np.allclose(proj.data, [-0.5j, 0.5j])
+    srt = qo.sort_and_remove_duplicates(np.array([[1, 0], [0, 1], [1, 0], [0, 0]], dtype=bool))
+    assert (srt == np.array([[0, 0], [0, 1], [1, 0]], dtype=bool)).all()
+    with pytest.raises(ValueError, match="must have length < 64"):
+        qo.solve_qubit(np.zeros((2, 64), dtype=bool), ham)
+
+
+def _qubit_cases():
+    g = np.load(os.path.join(GOLD, "qubit_golden.npz"))
+    for ci in range(int(g["n_cases"])):
+        yield ci, g
+
+
+@pytest.mark.parametrize("ci", range(5))
+def test_qubit_oracle_matches_reference_golden(ci):
+    g = np.load(os.path.join(GOLD, "qubit_golden.npz"))
+    rows = g[f"c{ci}_rows_in"]
+    srt = qo.sort_and_remove_duplicates(rows)
+    assert np.array_equal(srt, g[f"c{ci}_rows_sorted"])
+    labels = [str(s) for s in g[f"c{ci}_labels"]]
+    op = PauliSum.from_labels(labels, g[f"c{ci}_coeffs"])
+    proj = qo.project_operator_to_subspace(srt, op)
+    proj.sort_indices()
+    assert np.array_equal(proj.indptr, g[f"c{ci}_indptr"])
+    assert np.array_equal(proj.indices, g[f"c{ci}_indices"])
+    assert np.allclose(proj.data, g[f"c{ci}_data"], rtol=0, atol=1e-6)  # reference's complex64 factor
+    for ti in range(4):
+        amp, r, c = qo.matrix_elements_from_pauli(srt, op.paulis[ti])
+        assert np.array_equal(r, g[f"c{ci}_t{ti}_row"]) and np.array_equal(c, g[f"c{ci}_t{ti}_col"])
+        assert np.allclose(amp, g[f"c{ci}_t{ti}_amp"], rtol=0, atol=1e-6)
+    n_terms = len(labels) - 3
+    hop = PauliSum.from_labels(labels[:n_terms], np.real(g[f"c{ci}_coeffs"][:n_terms]))
+    e, _ = qo.solve_qubit(rows, hop, k=1, which="SA")
+    assert abs(e[0] - g[f"c{ci}_e0"][0]) < 1e-6
+
+
+def test_notebook_golden_unique_rows():
+    # docs/guides/project_pauli_operators_onto_hilbert_subspaces.ipynb:61,70-79
+    np.random.seed(22)
+    bts = np.round(np.random.rand(50_000, 22)).astype("int").astype("bool")
+    assert qo.sort_and_remove_duplicates(bts).shape[0] == 49718
+
+
+# ------------------------------------------------------------------------------------------------
+# recovery oracle
+# ------------------------------------------------------------------------------------------------
+def test_pcg64_and_choice_restatement_match_numpy():
+    for seed in range(60):
+        r0 = np.random.default_rng(seed)
+        n = int(r0.integers(2, 64))
+        k = int(r0.integers(1, n + 1))
+        p = r0.random(n)
+        p[r0.random(n) < 0.2] = 0
+        if np.count_nonzero(p) < k:
+            continue
+        p /= p.sum()
+        g1 = np.random.default_rng(seed + 1000)
+        g2 = np.random.default_rng(seed + 1000)
+        expect = g1.choice(n, size=k, replace=False, p=p)
+        s = ro.PCG64Stream.from_generator(g2)
+        got = ro.choice_without_replacement(s, p, k)
+        s.to_generator(g2)
+        assert np.array_equal(expect, got)
+        assert g1.bit_generator.state == g2.bit_generator.state
+    s = ro.PCG64Stream.from_generator(np.random.default_rng(1234))
+    assert np.array_equal(s.random(10), np.random.default_rng(1234).random(10))
+
+
+def test_pairwise_sum_matches_numpy():
+    rng = np.random.default_rng(0)
+    for n in range(1, 65):
+        for _ in range(5):
+            a = rng.random(n) * 10.0 ** rng.integers(-3, 3, n)
+            assert ro.numpy_pairwise_sum(a) == float(np.sum(a)), n
+
+
+def test_recovery_oracle_reference_known_answers():
+    # test/test_configuration_recovery.py:57-135
+    m, p = ro.recover_configurations(np.empty((0, 6)), np.empty((0,)), [False] * 6, 0, 1)
+    assert m.size == 0 and p.size == 0
+    m, p = ro.recover_configurations(np.zeros((1, 4), dtype=bool), np.array([1.0]), [1.0] * 4, 2, 2, 4224)
+    assert m.all() and (p == [1.0]).all()
+    m, p = ro.recover_configurations(np.ones((1, 4), dtype=bool), np.array([1.0]), [0.0] * 4, 0, 0, 4224)
+    assert not m.any()
+    m, p = ro.recover_configurations(np.ones((1, 4), dtype=bool), np.array([1.0]), [0.0, 1.0, 0.0, 0.0],
+                                     0, 1, 4224)
+    assert (m == np.array([[False, True, False, False]])).all()
+    bs = np.random.default_rng(554).integers(2, size=(1, 74), dtype=bool)
+    m, p = ro.recover_configurations(bs, np.array([1.0]), np.zeros(74), 0, 0, 4224)
+    assert not m.any() and m.shape == (1, 74)
+    with pytest.raises(ValueError, match="The numbers of electrons must be specified as non-negative integers."):
+        ro.recover_configurations(np.ones((1, 4), dtype=bool), np.array([1.0]), [0.0] * 4, 0, -1, 4224)
+
+
+@pytest.mark.parametrize("ci", range(6))
+def test_recovery_oracle_matches_reference_golden(ci):
+    g = np.load(os.path.join(GOLD, "recovery_golden.npz"))
+    norb, na, nb, n, seed = (int(v) for v in g[f"c{ci}_meta"])
+    gen = np.random.default_rng(seed)
+    mat, freqs = ro.recover_configurations(g[f"c{ci}_bs"], g[f"c{ci}_probs"],
+                                           (g[f"c{ci}_occ_a"], g[f"c{ci}_occ_b"]), na, nb, gen)
+    assert np.array_equal(mat, g[f"c{ci}_mat"])
+    assert np.array_equal(freqs, g[f"c{ci}_freqs"])  # bit-equal
+    assert np.array_equal(gen.random(4), g[f"c{ci}_next"])
+    assert (mat[:, :norb].sum(1) == nb).all() and (mat[:, norb:].sum(1) == na).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# C oracle (CPU baseline): both sigma algorithms against the dense oracle
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("norb,nea,neb,na,nb", [(6, 3, 3, 15, 12), (8, 4, 3, 30, 21), (7, 2, 5, 12, 9),
+                                                (6, 1, 4, 6, 9)])
+def test_c_oracle_matches_dense_oracle(norb, nea, neb, na, nb):
+    from oracle import sci_cpu
+
+    h, g = random_integrals(norb, norb)
+    A = hf_centred_strings(norb, nea, na, 1)
+    B = hf_centred_strings(norb, neb, nb, 2)
+    H = fo.projected_hamiltonian(A, B, h, g, norb)
+    x = np.random.default_rng(0).standard_normal((len(A), len(B)))
+    ref = (H @ x.reshape(-1)).reshape(x.shape)
+    for algo in (0, 1):  # 0: direct excitation tables, 1: pyscf-style gather/dgemm/scatter
+        assert np.abs(sci_cpu.sigma(A, B, h, g, x, algo) - ref).max() < 1e-12
+    e_ref, c_ref, occ_ref, _, _ = fo.solve_dense(A, B, h, g, norb)
+    for algo in (0, 1):
+        e, amps, occ, info = sci_cpu.solve(A, B, h, g, algo=algo, nthreads=2)
+        assert abs(e - e_ref) < 1e-9 and info["converged"]
+        assert np.allclose(occ[0], occ_ref[0], atol=1e-6)
+    ss = 0.75 if (nea - neb) % 2 else 0.0
+    e_ref = fo.solve_dense(A, B, h, g, norb, spin_sq=ss, shift=0.3)[0]
+    e, _, _, _ = sci_cpu.solve(A, B, h, g, algo=0, spin_sq=ss, shift=0.3, nthreads=2)
+    assert abs(e - e_ref) < 1e-7
