@@ -28,6 +28,7 @@ extern "C" {
 
 #define SQD_B200_VERSION 100
 #define SQD_MAX_SPACE 32 /* largest Davidson subspace the device-side Rayleigh-Ritz supports */
+#define SQD_MAX_LONG_COLUMNS 64 /* beta strings whose single-excitation list is reduced by a whole warp */
 
 int sqd_version(void);
 const char* sqd_last_error(void);
@@ -65,12 +66,14 @@ int sqd_exclusive_scan(const int* d_in, int* d_out, int n, int* h_total, void* s
  *   d_col [nnz]  partner string index (source string s of <t|H|s>, row = target t)
  *   d_val [nnz]  same-spin Hamiltonian element <t| h + 1/2 (pq|rs) |s> (Slater-Condon rules)
  *   d_meta[nnz]  singles: (p*norb+q) | sign_bit<<31 for t = sign * a+_p a_q s ; doubles: 0
+ *   d_pack[nnz]  singles: col | (p*norb+q)<<19 | sign_bit<<31 (one 4-byte load in the hot loop;
+ *                needs n <= 2^19 and norb <= 64); doubles: col
  *   d_diag[n]    <s|H_same-spin|s>
  * d_h: double[norb*norb]; d_g: double[norb^4] chemist order (pq|rs), C-contiguous. */
 int sqd_excitation_fill(const uint64_t* d_strs, int n, int norb, const double* d_h,
                         const double* d_g, const int* d_row_ptr, const int* d_n_single,
-                        uint32_t* d_col, double* d_val, uint32_t* d_meta, double* d_diag,
-                        void* stream);
+                        uint32_t* d_col, double* d_val, uint32_t* d_meta, uint32_t* d_pack,
+                        double* d_diag, void* stream);
 
 /* Opposite-spin tensor with pyscf fix_spin_'s linear penalty folded in:
  *   g_ab[pq*ldg + rs] = (pq|rs) - shift * delta_ps delta_qr       
@@ -104,7 +107,26 @@ typedef struct {
     const uint32_t* col;     /* [nnz] */
     const double* val;       /* [nnz] */
     const uint32_t* meta;    /* [nnz] */
+    const uint32_t* pack;    /* [nnz] */
 } sqd_spin_table;
+
+/* Work decomposition of one sigma build (built once per subspace by sqd_sigma_plan_build).  Rows of the CI
+ * matrix are cut into chunks of bounded cost (one CTA each); a row with several chunks accumulates
+ * per-chunk partial vectors (`part`, n_slots x ldc doubles of caller-owned scratch) that are summed in
+ * chunk order; beta strings with very long excitation lists ("long columns") are reduced by a warp. */
+typedef struct {
+    int n_chunks, n_slots, n_split, n_long;
+    const int* chunk_row;      /* [n_chunks] alpha string index */
+    const int* chunk_beg;      /* [n_chunks] first entry of the alpha table covered */
+    const int* chunk_end;      /* [n_chunks] one past the last entry */
+    const int* chunk_slot;     /* [n_chunks] row of `part`, or -1 when the chunk owns its whole row */
+    const int* split_row;      /* [n_split] rows that have more than one chunk */
+    const int* split_slot_beg; /* [n_split] */
+    const int* split_n;        /* [n_split] */
+    const int* long_idx;       /* [nb] index into long_cols or -1 */
+    const int* long_cols;      /* [n_long] */
+    double* part;              /* [n_slots * ldc] scratch, written by every sigma build */
+} sqd_sigma_plan;
 
 typedef struct {
     sqd_spin_table a, b;     /* alpha strings index rows, beta strings index columns */
@@ -116,7 +138,20 @@ typedef struct {
     const double* Wa;        /* [na*ldg] or NULL */
     const double* Wb;        /* [norb^2*ldc] or NULL */
     int use_same_spin;       /* 1: include table values (Hamiltonian); 0: opposite-spin only (S^2) */
+    sqd_sigma_plan plan;
 } sqd_operator;
+
+/* Build the work plan.  cost_per_chunk: multiple of 4 (a single excitation costs 4, a double 1);
+ * long_threshold: beta strings with more single excitations than this become long columns (at most
+ * SQD_MAX_LONG_COLUMNS); max_chunks: capacity of the d_chunk_* arrays, na + (4*nnz_a)/cost_per_chunk + 1
+ * always suffices.  d_split_*: int[na]; d_long_idx: int[nb]; d_long_cols: int[SQD_MAX_LONG_COLUMNS];
+ * d_counts: int[4] device scratch; h_counts receives {n_chunks, n_slots, n_split, n_long}.
+ * Synchronises the stream. */
+int sqd_sigma_plan_build(const sqd_spin_table* a, const sqd_spin_table* b, int cost_per_chunk,
+                   int long_threshold, int max_chunks, int* d_chunk_row, int* d_chunk_beg,
+                   int* d_chunk_end, int* d_chunk_slot, int* d_split_row, int* d_split_slot_beg,
+                   int* d_split_n, int* d_long_idx, int* d_long_cols, int* d_counts, int* h_counts,
+                   void* stream);
 
 /* Dynamic shared memory the sigma kernel needs for this operator, or <0 if the shape is unsupported. */
 int64_t sqd_sigma_smem_bytes(const sqd_operator* op);

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsqd_b200.so")
 
 MAX_SPACE = 32
+MAX_LONG_COLUMNS = 64
 
 
 class SpinTable(C.Structure):
@@ -25,6 +26,26 @@ class SpinTable(C.Structure):
         ("col", C.c_void_p),
         ("val", C.c_void_p),
         ("meta", C.c_void_p),
+        ("pack", C.c_void_p),
+    ]
+
+
+class SigmaPlan(C.Structure):
+    _fields_ = [
+        ("n_chunks", C.c_int),
+        ("n_slots", C.c_int),
+        ("n_split", C.c_int),
+        ("n_long", C.c_int),
+        ("chunk_row", C.c_void_p),
+        ("chunk_beg", C.c_void_p),
+        ("chunk_end", C.c_void_p),
+        ("chunk_slot", C.c_void_p),
+        ("split_row", C.c_void_p),
+        ("split_slot_beg", C.c_void_p),
+        ("split_n", C.c_void_p),
+        ("long_idx", C.c_void_p),
+        ("long_cols", C.c_void_p),
+        ("part", C.c_void_p),
     ]
 
 
@@ -40,6 +61,7 @@ class Operator(C.Structure):
         ("Wa", C.c_void_p),
         ("Wb", C.c_void_p),
         ("use_same_spin", C.c_int),
+        ("plan", SigmaPlan),
     ]
 
 
@@ -83,7 +105,7 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_check_hamming": (_i, [_vp, _i64, _vp, _pi, _pi, _pi, _vp]),
     "sqd_excitation_count": (_i, [_vp, _i, _vp, _vp, _vp]),
     "sqd_exclusive_scan": (_i, [_vp, _vp, _i, _pi, _vp]),
-    "sqd_excitation_fill": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sqd_excitation_fill": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_make_gab": (_i, [_vp, _i, _d, _i, _vp, _i, _vp]),
     "sqd_opposite_spin_tables": (
         _i,
@@ -91,6 +113,11 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "sqd_sigma_smem_bytes": (_i64, [C.POINTER(Operator)]),
     "sqd_sigma": (_i, [C.POINTER(Operator), _vp, _vp, _vp]),
+    "sqd_sigma_plan_build": (
+        _i,
+        [C.POINTER(SpinTable), C.POINTER(SpinTable), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+         _vp, _vp, _vp, _pi, _vp],
+    ),
     "sqd_davidson_workspace_bytes": (_i64, [_i, _i, _i]),
     "sqd_davidson": (
         _i,

@@ -192,10 +192,13 @@ ortho2_kernel(const DavState* __restrict__ st, const double* __restrict__ V, int
 // ---------------------------------------------------------------------------------------------
 // small (single CTA) steps
 // ---------------------------------------------------------------------------------------------
+// Sum of one row of per-CTA partials by a full warp: lane-strided loads (independent, pipelined) and a
+// fixed xor-shuffle tree -> the same order on every run.  Result on all lanes.
 __device__ __forceinline__ double reduce_partials(const double* partials, int row, int nblk) {
+    const int lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += partials[row * nblk + b];
-    return s;
+    for (int b = lane; b < nblk; b += 32) s += partials[row * nblk + b];
+    return warp_sum(s);
 }
 
 // Rayleigh-Ritz: fold the new Gram column into G, diagonalise G (m x m) by parallel-order Jacobi.
@@ -210,10 +213,12 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
     __shared__ double off_s;
     const int tid = threadIdx.x;
 
-    if (tid < m) {
-        const double g = reduce_partials(partials, tid, nblk);
-        st->G[tid * kMaxS + slot] = g;
-        st->G[slot * kMaxS + tid] = g;
+    for (int row = tid >> 5; row < m; row += blockDim.x >> 5) {
+        const double g = reduce_partials(partials, row, nblk);
+        if ((tid & 31) == 0) {
+            st->G[row * kMaxS + slot] = g;
+            st->G[slot * kMaxS + row] = g;
+        }
     }
     __syncthreads();
     for (int idx = tid; idx < m * m; idx += blockDim.x) {
@@ -320,9 +325,12 @@ __global__ void convergence_kernel(DavState* __restrict__ st, const double* __re
     if (st->status != 0) return;
     __shared__ double p[kMaxS + 2];
     const int tid = threadIdx.x;
-    if (tid < m) p[tid] = reduce_partials(partials, tid, nblk);
-    if (tid == kMaxS) p[kMaxS] = reduce_partials(partials, kMaxS, nblk);
-    if (tid == kMaxS + 1) p[kMaxS + 1] = reduce_partials(partials, kMaxS + 1, nblk);
+    for (int row = tid >> 5; row < kMaxS + 2; row += blockDim.x >> 5) {
+        if (row < m || row >= kMaxS) {
+            const double v = reduce_partials(partials, row, nblk);
+            if ((tid & 31) == 0) p[row] = v;
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         const double rnorm = sqrt(p[kMaxS]);
@@ -348,8 +356,12 @@ __global__ void norm_kernel(DavState* __restrict__ st, const double* __restrict_
     if (st->status != 0) return;
     __shared__ double p[kMaxS + 1];
     const int tid = threadIdx.x;
-    if (tid < m) p[tid] = reduce_partials(partials, tid, nblk);
-    if (tid == kMaxS) p[kMaxS] = reduce_partials(partials, kMaxS, nblk);
+    for (int row = tid >> 5; row < kMaxS + 1; row += blockDim.x >> 5) {
+        if (row < m || row == kMaxS) {
+            const double v = reduce_partials(partials, row, nblk);
+            if ((tid & 31) == 0) p[row] = v;
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         double n2 = p[kMaxS];
@@ -382,11 +394,8 @@ dot_partial_kernel(const double* __restrict__ x, const double* __restrict__ y, i
 }
 
 __global__ void dot_final_kernel(const double* __restrict__ partials, int nblk, double* out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double s = 0.0;
-        for (int b = 0; b < nblk; ++b) s += partials[b];
-        out[0] = s;
-    }
+    const double s = reduce_partials(partials, 0, nblk);  // launched with one warp
+    if (threadIdx.x == 0) out[0] = s;
 }
 
 // y <- alpha * x * (1/sqrt(*norm2) if norm2 else 1)
@@ -539,7 +548,7 @@ occupancy_kernel(const double* __restrict__ wa, const uint64_t* __restrict__ sa,
 }
 
 static inline int red_blocks(int64_t n) {
-    int64_t b = (n + kRedThreads - 1) / kRedThreads;
+    int64_t b = (n + 4 * kRedThreads - 1) / (4 * kRedThreads);
     if (b > kRedBlocks) b = kRedBlocks;
     if (b < 1) b = 1;
     return (int)b;
@@ -659,7 +668,7 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
             residual_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, d_hdiag, n, m,
                                                                 restart, prm->level_shift, ws.X, ws.T,
                                                                 ws.partials);
-            convergence_kernel<<<1, 64, 0, st>>>(ws.state, ws.partials, blocks, m, restart, prm->tol,
+            convergence_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m, restart, prm->tol,
                                                  prm->tol_residual);
             return check_launch("davidson cycle (1)", 4);
         });
@@ -668,7 +677,7 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         rc = dispatch_mv(me, [&](auto mv) {
             constexpr int MV = decltype(mv)::value;
             ortho1_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T, ws.partials);
-            norm_kernel<<<1, 64, 0, st>>>(ws.state, ws.partials, blocks, me, prm->lindep);
+            norm_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, me, prm->lindep);
             ortho2_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T,
                                                               ws.V + (int64_t)me * n);
             return check_launch("davidson cycle (2)", 3);

@@ -189,7 +189,7 @@ __global__ void excitation_fill_kernel(const uint64_t* __restrict__ strs, int n,
                                        const int* __restrict__ row_ptr,
                                        const int* __restrict__ n_single, uint32_t* __restrict__ col,
                                        double* __restrict__ val, uint32_t* __restrict__ meta,
-                                       double* __restrict__ diag) {
+                                       uint32_t* __restrict__ pack, double* __restrict__ diag) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
@@ -214,11 +214,13 @@ __global__ void excitation_fill_kernel(const uint64_t* __restrict__ strs, int n,
             col[o] = (uint32_t)j;
             val[o] = v;
             meta[o] = (uint32_t)(p * norb + q) | (sign < 0 ? 0x80000000u : 0u);
+            pack[o] = (uint32_t)j | ((uint32_t)(p * norb + q) << 19) | (sign < 0 ? 0x80000000u : 0u);
         } else if (pc == 4) {
             const int o = pos2 + __popc(m2 & lt);
             col[o] = (uint32_t)j;
             val[o] = have_ints ? double_element(s, t, norb, g) : 0.0;
             meta[o] = 0u;
+            pack[o] = (uint32_t)j;
         }
         pos1 += __popc(m1);
         pos2 += __popc(m2);
@@ -370,13 +372,14 @@ int sqd_exclusive_scan(const int* d_in, int* d_out, int n, int* h_total, void* s
 
 int sqd_excitation_fill(const uint64_t* d_strs, int n, int norb, const double* d_h,
                         const double* d_g, const int* d_row_ptr, const int* d_n_single,
-                        uint32_t* d_col, double* d_val, uint32_t* d_meta, double* d_diag,
-                        void* stream) {
+                        uint32_t* d_col, double* d_val, uint32_t* d_meta, uint32_t* d_pack,
+                        double* d_diag, void* stream) {
     SQD_REQUIRE(n > 0 && norb > 0 && norb <= 64, "sqd_excitation_fill: need 0 < norb <= 64 (got %d)",
                 norb);
+    SQD_REQUIRE(n <= (1 << 19), "sqd_excitation_fill: at most 2^19 strings per spin (got %d)", n);
     const int wpb = 8;
     excitation_fill_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
-        d_strs, n, norb, d_h, d_g, d_row_ptr, d_n_single, d_col, d_val, d_meta, d_diag);
+        d_strs, n, norb, d_h, d_g, d_row_ptr, d_n_single, d_col, d_val, d_meta, d_pack, d_diag);
     return check_launch("excitation_fill_kernel");
 }
 

@@ -31,6 +31,10 @@ _PYSCF_DEFAULTS = dict(max_cycle=100, max_space=12, lindep=1e-14, level_shift=1e
 # 1e-8 Ha parity bar against any converged solver the default here is tighter.  Passing ``tol=`` gives
 # pyscf's rule (|dE| < tol and |r| < sqrt(tol)) literally.
 _DEFAULT_TOL = 1e-12
+# sigma-build work plan: cost units per CTA (single excitation = 4, double = 1) and the length above
+# which a beta string's single-excitation list is reduced by a whole warp
+_SIGMA_COST_PER_CHUNK = int(__import__("os").environ.get("SQD_SIGMA_CHUNK_COST", "128"))
+_SIGMA_LONG_THRESHOLD = int(__import__("os").environ.get("SQD_SIGMA_LONG_THRESHOLD", "32"))
 _FIX_SPIN_DEFAULT_SHIFT = 0.2  # pyscf.fci.addons.fix_spin_ default, used by solve_sci (fermion.py:715)
 
 
@@ -177,9 +181,13 @@ def bitstring_matrix_to_ci_strs(
     ci_right = np.unique(right_u)
     if not open_shell:
         ci_left = ci_right = np.union1d(ci_left, ci_right)
-    if norb < 64:  # reference returns python ``int`` (int64) below 64 bits, object dtype at 64
-        return ci_right.astype(np.int64), ci_left.astype(np.int64)
-    return ci_right.astype(object), ci_left.astype(object)
+    # reference returns python ``int`` (int64) below 64 bits, object dtype at 64; closed shell returns
+    # the SAME array object for both spins (fermion.py:1032-1035)
+    dt = np.int64 if norb < 64 else object
+    if not open_shell:
+        both = ci_right.astype(dt)
+        return both, both
+    return ci_right.astype(dt), ci_left.astype(dt)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -223,19 +231,21 @@ class _SpinTableDev:
         self.col = torch.empty(m, dtype=torch.int32, device=device)
         self.val = torch.empty(m, dtype=torch.float64, device=device)
         self.meta = torch.empty(m, dtype=torch.int32, device=device)
+        self.pack = torch.empty(m, dtype=torch.int32, device=device)
         self.diag = torch.empty(n, dtype=torch.float64, device=device)
         # ints None: structure-only table (S^2, occupancies) -- the kernel takes NULL integrals
         h, g = (None, None) if ints is None else (ints.h, ints.g)
         _lib.check(lib.sqd_excitation_fill(_lib.ptr(self.strs), n, norb, _lib.ptr(h), _lib.ptr(g),
                                            _lib.ptr(self.row_ptr), _lib.ptr(self.n_single),
                                            _lib.ptr(self.col), _lib.ptr(self.val),
-                                           _lib.ptr(self.meta), _lib.ptr(self.diag), st),
+                                           _lib.ptr(self.meta), _lib.ptr(self.pack),
+                                           _lib.ptr(self.diag), st),
                    "sqd_excitation_fill")
 
     def struct(self) -> _lib.SpinTable:
         return _lib.SpinTable(self.n, _lib.ptr(self.strs), _lib.ptr(self.row_ptr),
                               _lib.ptr(self.n_single), _lib.ptr(self.col), _lib.ptr(self.val),
-                              _lib.ptr(self.meta))
+                              _lib.ptr(self.meta), _lib.ptr(self.pack))
 
 
 class _OperatorDev:
@@ -267,7 +277,7 @@ class _OperatorDev:
             self.Wb = None
         self.struct = _lib.Operator(sub.ta.struct(), sub.tb.struct(), norb, ldc, ldg,
                                     _lib.ptr(self.diag), _lib.ptr(self.gab), _lib.ptr(self.Wa),
-                                    _lib.ptr(self.Wb), 1 if same_spin else 0)
+                                    _lib.ptr(self.Wb), 1 if same_spin else 0, sub.sigma_plan())
         if lib.sqd_sigma_smem_bytes(C.byref(self.struct)) < 0:
             raise ValueError(
                 f"subspace shape (na={na}, nb={nb}, norb={norb}) exceeds the shared-memory row "
@@ -304,8 +314,38 @@ class _Subspace:
         self.tb = self.ta if (same or (ua.shape == ub.shape and np.array_equal(ua, ub))) else \
             _SpinTableDev(torch, lib, ub, ints, norb, self.device, strs_dev[1])
         self._ss_op = None
+        self._plan = None
         self._scratch = torch.empty(4096, dtype=torch.float64, device=self.device)
         self._scalar = torch.empty(8, dtype=torch.float64, device=self.device)
+
+    def sigma_plan(self) -> _lib.SigmaPlan:
+        """Work decomposition of the sigma build (chunks of rows, long columns); built once."""
+        if self._plan is not None:
+            return self._plan
+        torch, lib = self.torch, self.lib
+        dev = self.device
+        cost = int(_SIGMA_COST_PER_CHUNK)
+        max_chunks = self.na + (4 * max(self.ta.nnz, 1)) // cost + 1
+        i32 = dict(dtype=torch.int32, device=dev)
+        bufs = [torch.empty(max_chunks, **i32) for _ in range(4)]
+        split = [torch.empty(self.na, **i32) for _ in range(3)]
+        long_idx = torch.empty(self.nb, **i32)
+        long_cols = torch.empty(_lib.MAX_LONG_COLUMNS, **i32)
+        counts_d = torch.empty(4, **i32)
+        counts = (C.c_int * 4)()
+        ta, tb = self.ta.struct(), self.tb.struct()
+        _lib.check(lib.sqd_sigma_plan_build(C.byref(ta), C.byref(tb), cost, int(_SIGMA_LONG_THRESHOLD),
+                                      max_chunks, *[_lib.ptr(t) for t in bufs],
+                                      *[_lib.ptr(t) for t in split], _lib.ptr(long_idx),
+                                      _lib.ptr(long_cols), _lib.ptr(counts_d), counts,
+                                      _lib.stream_ptr(torch)), "sqd_sigma_plan_build")
+        n_chunks, n_slots, n_split, n_long = (int(v) for v in counts)
+        part = torch.empty(max(n_slots, 1) * self.ldc, dtype=torch.float64, device=dev)
+        self._plan_keep = (bufs, split, long_idx, long_cols, part)
+        self._plan = _lib.SigmaPlan(n_chunks, n_slots, n_split, n_long, *[_lib.ptr(t) for t in bufs],
+                                    *[_lib.ptr(t) for t in split], _lib.ptr(long_idx),
+                                    _lib.ptr(long_cols), _lib.ptr(part))
+        return self._plan
 
     def __enter__(self):
         return self
