@@ -128,6 +128,18 @@ typedef struct {
     double* part;              /* [n_slots * ldc] scratch, written by every sigma build */
 } sqd_sigma_plan;
 
+/* SELL-32 layout of a string list's excitation entries (built by sqd_sell_build): strings sorted by
+ * list length (descending), 32 per slice, entry k of the string at sorted position 32*s+i stored at
+ * slice_ptr[s] + 32*k + i -- a warp reads one coalesced line per step and runs a uniform trip count. */
+typedef struct {
+    int n_slices;            /* ceil(n / 32) */
+    const int* perm;         /* [n] sorted position -> string index */
+    const int* len;          /* [n] list length at each sorted position */
+    const int* slice_ptr;    /* [n_slices + 1] */
+    const uint32_t* pack;    /* same encoding as sqd_spin_table.pack */
+    const double* val;       /* mode 1 only */
+} sqd_sell;
+
 typedef struct {
     sqd_spin_table a, b;     /* alpha strings index rows, beta strings index columns */
     int norb;
@@ -139,7 +151,16 @@ typedef struct {
     const double* Wb;        /* [norb^2*ldc] or NULL */
     int use_same_spin;       /* 1: include table values (Hamiltonian); 0: opposite-spin only (S^2) */
     sqd_sigma_plan plan;
+    sqd_sell bd;             /* beta single excitations (mode 0; long columns have length 0) */
+    sqd_sell bb;             /* every beta entry with its same-spin value (mode 1) */
 } sqd_operator;
+
+/* Build a SELL-32 copy of a table.  mode 0: single excitations only, strings with more than
+ * long_threshold of them get length 0 (they are reduced cooperatively, see sqd_sigma_plan_build);
+ * mode 1: all entries with values.  capacity (entries of d_pack / d_val) >= nnz + 32*n.
+ * d_perm, d_len: int[n]; d_slice_ptr: int[ceil(n/32)+1]. */
+int sqd_sell_build(const sqd_spin_table* t, int mode, int long_threshold, int capacity, int* d_perm,
+                   int* d_len, int* d_slice_ptr, uint32_t* d_pack, double* d_val, void* stream);
 
 /* Build the work plan.  cost_per_chunk: multiple of 4 (a single excitation costs 4, a double 1);
  * long_threshold: beta strings with more single excitations than this become long columns (at most

@@ -49,6 +49,17 @@ class SigmaPlan(C.Structure):
     ]
 
 
+class Sell(C.Structure):
+    _fields_ = [
+        ("n_slices", C.c_int),
+        ("perm", C.c_void_p),
+        ("len", C.c_void_p),
+        ("slice_ptr", C.c_void_p),
+        ("pack", C.c_void_p),
+        ("val", C.c_void_p),
+    ]
+
+
 class Operator(C.Structure):
     _fields_ = [
         ("a", SpinTable),
@@ -62,6 +73,8 @@ class Operator(C.Structure):
         ("Wb", C.c_void_p),
         ("use_same_spin", C.c_int),
         ("plan", SigmaPlan),
+        ("bd", Sell),
+        ("bb", Sell),
     ]
 
 
@@ -113,6 +126,7 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "sqd_sigma_smem_bytes": (_i64, [C.POINTER(Operator)]),
     "sqd_sigma": (_i, [C.POINTER(Operator), _vp, _vp, _vp]),
+    "sqd_sell_build": (_i, [C.POINTER(SpinTable), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_sigma_plan_build": (
         _i,
         [C.POINTER(SpinTable), C.POINTER(SpinTable), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -6,17 +6,25 @@
 // projected operator directly from the in-set excitation tables, O(n_det * links):
 //
 //   sigma[a,b] = diag[a,b] c[a,b]
-//              + sum_{b' in T_b(b)}  ( Hb[b,b'] + [single] sgn_b Wa[a, rs] ) c[a, b']      (phase B)
-//              + sum_{a' in D_a(a)}    Ha[a,a'] c[a', b]                                     (phase C)
-//              + sum_{a' in S_a(a)}  ( Ha[a,a'] + sgn_a Wb[pq, b] ) c[a', b]                 (phase D)
-//              + sum_{a' in S_a(a)} sgn_a sum_{b' in S_b(b)} sgn_b g_ab[pq, rs] c[a', b']    (phase D)
+//              + sum_{b' in T_b(b)}  ( Hb[b,b'] + [single] sgn_b Wa[a, rs] ) c[a, b']      (kernel B)
+//              + sum_{a' in D_a(a)}    Ha[a,a'] c[a', b]                                     (kernel A, phase C)
+//              + sum_{a' in S_a(a)}  ( Ha[a,a'] + sgn_a Wb[pq, b] ) c[a', b]                 (kernel A, phase D)
+//              + sum_{a' in S_a(a)} sgn_a sum_{b' in S_b(b)} sgn_b g_ab[pq, rs] c[a', b']    (kernel A, phase D)
 //
-// S = in-set single excitations, D = in-set doubles, T = S u D.  One CTA owns R rows `a` and every
-// column; a thread owns CPT columns and keeps R*CPT accumulators in registers, so each sigma element
-// is produced by exactly one thread in a fixed order (bit-reproducible, no atomics).
-// The rows c[a,:] and, per alpha single excitation, the row c[a',:] together with the integral row
-// g_ab[pq,:] are staged in shared memory by the bulk-copy engine (cp.async.bulk + mbarrier, SASS
-// UBLKCP), double-buffered so the copy of excitation k+1 overlaps the gathers of excitation k.
+// S = in-set single excitations, D = in-set doubles, T = S u D.
+//
+// Excitation lists are extremely skewed (the Hartree-Fock string has 10-20x the partners of the median
+// string), so the data layout is built for balance:
+//   * beta lists are stored as SELL-32 slices: columns sorted by list length, 32 per slice, entries
+//     interleaved so that a warp reads one coalesced 128-byte line per step and all 32 lanes run the
+//     same trip count (no divergence, no per-thread pointer chasing);
+//   * the few outlier columns ("long columns") are reduced by a whole warp each;
+//   * alpha rows are cut into chunks of bounded cost, one CTA per chunk; rows with several chunks sum
+//     their partial vectors in chunk order.
+// Every sigma element is accumulated in a fixed order by a fixed thread: results are bit-reproducible.
+// Kernel A stages, per alpha single excitation, the row c[a',:] and the integral row g_ab[pq,:] in
+// shared memory with the bulk-copy engine (cp.async.bulk + mbarrier; SASS UBLKCP/SYNCS) through a ring
+// of stages filled by a dedicated producer warp.
 #include "common.cuh"
 #include "../../include/sqd_b200.h"
 
@@ -53,6 +61,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 constexpr int kMaxStages = 8;
 constexpr int kUnroll = 4;
 constexpr int kMaxLong = SQD_MAX_LONG_COLUMNS;
+constexpr int kRowsB = 4;      // rows of c per CTA in kernel B
+constexpr int kWarpsB = 4;     // SELL slices (warps) per CTA in kernel B
 
 // ---------------------------------------------------------------------------------------------------
 // Work decomposition.  The excitation lists are extremely skewed (the Hartree-Fock string of a sampled
@@ -113,7 +123,153 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
     counts[3] = nlong;
 }
 
-// sigma[a,:] = sum over the row's chunk partials, in chunk order
+
+// ---------------------------------------------------------------------------------------------------
+// SELL-32 builder (setup time).  mode 0: single excitations only, columns longer than long_threshold get
+// length 0 (they are handled cooperatively); mode 1: every entry (singles then doubles) with values.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sell_len(const sqd_spin_table& T, int b, int mode, int long_threshold) {
+    if (mode == 0) {
+        const int ns = T.n_single[b];
+        return ns > long_threshold ? 0 : ns;
+    }
+    return T.row_ptr[b + 1] - T.row_ptr[b];
+}
+
+// rank of every column in (length descending, index ascending) order; perm[rank] = column
+__global__ void sell_rank_kernel(const sqd_spin_table T, int mode, int long_threshold,
+                                 int* __restrict__ perm, int* __restrict__ len_sorted) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= T.n) return;
+    const int lb = sell_len(T, b, mode, long_threshold);
+    int rank = 0;
+    for (int o = 0; o < T.n; ++o) {
+        const int lo = sell_len(T, o, mode, long_threshold);
+        rank += (lo > lb) || (lo == lb && o < b);
+    }
+    perm[rank] = b;
+    len_sorted[rank] = lb;
+}
+
+// slice_ptr (exclusive scan of 32 * slice length) by one thread: n/32 slices, setup time
+__global__ void sell_slice_kernel(int n, const int* __restrict__ len_sorted, int* __restrict__ slice_ptr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int ns = (n + 31) / 32;
+    int off = 0;
+    for (int s = 0; s < ns; ++s) {
+        slice_ptr[s] = off;
+        off += 32 * len_sorted[32 * s];  // sorted descending: the first lane of a slice is its longest
+    }
+    slice_ptr[ns] = off;
+}
+
+__global__ void sell_fill_kernel(const sqd_spin_table T, int mode, const int* __restrict__ perm,
+                                 const int* __restrict__ len_sorted, const int* __restrict__ slice_ptr,
+                                 uint32_t* __restrict__ pack, double* __restrict__ val) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = pos >> 5, lane = pos & 31;
+    const int ns = (T.n + 31) / 32;
+    if (s >= ns) return;
+    const int slen = len_sorted[32 * s];
+    const int mylen = pos < T.n ? len_sorted[pos] : 0;
+    const int src = pos < T.n ? T.row_ptr[perm[pos]] : 0;
+    const int base = slice_ptr[s];
+    for (int k = 0; k < slen; ++k) {
+        const bool ok = k < mylen;
+        pack[base + k * 32 + lane] = ok ? T.pack[src + k] : 0u;
+        if (mode == 1) val[base + k * 32 + lane] = ok ? T.val[src + k] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Kernel B:  sigma[a,b] = diag[a,b] c[a,b] + sum_{b'} (Hb[b,b'] + [single] sgn Wa[a,rs]) c[a,b']
+// CTA = kRowsB rows x kWarpsB SELL slices.  The rows of c and of Wa are staged with bulk copies.
+// Writes every element of sigma (pads = 0); kernel A then adds its part.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsB * 32)
+sigma_b_kernel(const SigmaArgs P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (P.done != nullptr && *P.done != 0) return;
+    const sqd_operator& op = P.op;
+    const sqd_sell& L = op.bb;
+    const int na = op.a.n, nb = op.b.n, ldc = op.ldc, ldg = op.ldg;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int a0 = blockIdx.x * kRowsB;
+    const int nrows = min(kRowsB, na - a0);
+    const bool ham = op.use_same_spin != 0;
+    const bool use_wa = op.Wa != nullptr;
+
+    double* Cs = reinterpret_cast<double*>(smem_raw);          // [kRowsB][ldc]
+    double* Ws = Cs + (size_t)kRowsB * ldc;                     // [kRowsB][ldg]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(Ws + (size_t)kRowsB * ldg);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(nrows * (ldc + (use_wa ? ldg : 0)) * sizeof(double));
+        mbar_expect_tx(bar, bytes);
+        for (int r = 0; r < nrows; ++r) {
+            bulk_g2s(Cs + (size_t)r * ldc, P.c + (size_t)(a0 + r) * ldc, (uint32_t)(ldc * sizeof(double)), bar);
+            if (use_wa)
+                bulk_g2s(Ws + (size_t)r * ldg, op.Wa + (size_t)(a0 + r) * ldg,
+                         (uint32_t)(ldg * sizeof(double)), bar);
+        }
+    }
+    const int slice = blockIdx.y * kWarpsB + warp;
+    const int pos = slice * 32 + lane;
+    const int n_slices = L.n_slices;
+    double acc[kRowsB];
+#pragma unroll
+    for (int r = 0; r < kRowsB; ++r) acc[r] = 0.0;
+    mbar_wait_parity(bar, 0);
+    if (slice < n_slices && (ham || use_wa)) {
+        const int base = L.slice_ptr[slice];
+        const int slen = (L.slice_ptr[slice + 1] - base) >> 5;
+        const int mylen = pos < nb ? L.len[pos] : 0;
+        for (int k0 = 0; k0 < slen; k0 += kUnroll) {
+            uint32_t pk[kUnroll];
+            double v[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                const int k = min(k0 + u, slen - 1);
+                pk[u] = __ldg(L.pack + base + k * 32 + lane);
+                v[u] = ham ? __ldg(L.val + base + k * 32 + lane) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; ++u) {
+                if (k0 + u < mylen) {
+                    const uint32_t bp = pk[u] & 0x7ffffu, rs = (pk[u] >> 19) & 0xfffu;
+                    const bool neg = pk[u] >> 31;
+#pragma unroll
+                    for (int r = 0; r < kRowsB; ++r) {
+                        if (r < nrows) {
+                            double coef = v[u];
+                            if (use_wa && rs != 0u) {
+                                const double w = Ws[r * ldg + rs];
+                                coef += neg ? -w : w;
+                            }
+                            acc[r] = fma(coef, Cs[r * ldc + bp], acc[r]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (slice < n_slices && pos < nb) {
+        const int b = L.perm[pos];
+#pragma unroll
+        for (int r = 0; r < kRowsB; ++r)
+            if (r < nrows)
+                P.sigma[(size_t)(a0 + r) * ldc + b] =
+                    fma(op.diag[(size_t)(a0 + r) * ldc + b], Cs[r * ldc + b], acc[r]);
+    } else if (pos >= nb && pos < ldc) {
+        for (int r = 0; r < nrows; ++r) P.sigma[(size_t)(a0 + r) * ldc + pos] = 0.0;  // pads
+    }
+}
+
+// sigma[a,:] += sum over the row's chunk partials, in chunk order
 __global__ void sigma_combine_kernel(const int* __restrict__ done, const sqd_sigma_plan pl, int ldc,
                                      double* __restrict__ sigma) {
     if (done != nullptr && *done != 0) return;
@@ -122,19 +278,25 @@ __global__ void sigma_combine_kernel(const int* __restrict__ done, const sqd_sig
     for (int b = threadIdx.x; b < ldc; b += blockDim.x) {
         double acc = pl.part[(size_t)s0 * ldc + b];
         for (int c = 1; c < k; ++c) acc += pl.part[(size_t)(s0 + c) * ldc + b];
-        sigma[(size_t)a * ldc + b] = acc;
+        sigma[(size_t)a * ldc + b] += acc;
     }
 }
 
-// Warp-specialised: the LAST warp of the CTA is the producer (one lane drives the bulk-copy engine
-// through an NST-deep ring of {c[a',:], g_ab[pq,:]} stages guarded by full/empty mbarriers); all other
-// warps are consumers.  One CTA per chunk.
+// ---------------------------------------------------------------------------------------------------
+// Kernel A: alpha excitations.  One CTA per chunk of one alpha row.  Warp-specialised: the LAST warp is
+// the producer (one lane drives the bulk-copy engine through an NST-deep ring of {c[a',:], g_ab[pq,:]}
+// stages guarded by full/empty mbarriers); all other warps are consumers.
+//   natural mapping  (thread t <-> column t)        : phase C streaming and the c[a',b] terms, coalesced
+//   sorted mapping   (thread t <-> column perm[t])  : the beta-single gathers through SELL slices
+// The two partial results meet in a shared-memory exchange buffer before one coalesced update of sigma.
+// ---------------------------------------------------------------------------------------------------
 template <int CPT>
-__global__ void sigma_kernel(const SigmaArgs P, const int NST) {
+__global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
     const sqd_operator& op = P.op;
     const sqd_sigma_plan& pl = op.plan;
+    const sqd_sell& L = op.bd;
     const int nb = op.b.n, ldc = op.ldc, ldg = op.ldg;
     const int ncons = blockDim.x - 32;  // consumer threads
     const int nwarp_c = ncons >> 5;
@@ -143,31 +305,26 @@ __global__ void sigma_kernel(const SigmaArgs P, const int NST) {
     const int a = pl.chunk_row[blockIdx.x];
     const int cbeg = pl.chunk_beg[blockIdx.x], cend = pl.chunk_end[blockIdx.x];
     const int slot = pl.chunk_slot[blockIdx.x];
-    const int row_beg = op.a.row_ptr[a];
-    const int single_end = row_beg + op.a.n_single[a];
-    const bool first = cbeg == row_beg;          // the first chunk of a row also owns phase B
+    const int single_end = op.a.row_ptr[a] + op.a.n_single[a];
     const int it_beg = min(cbeg, single_end), it_end = min(cend, single_end);   // phase D range
     const int db_beg = max(cbeg, single_end), db_end = max(cend, single_end);   // phase C range
     const int n_items = it_end - it_beg;
     const int n_long = pl.n_long;
+    const bool ham = op.use_same_spin != 0;
 
-    double* Cs = reinterpret_cast<double*>(smem_raw);   // [ldc]   row a of c
-    double* stage = Cs + ldc;                            // NST x ([ldc] row c[a',:] + [ldg] row g_ab[pq,:])
+    double* xbuf = reinterpret_cast<double*>(smem_raw);  // [ldc] exchange sorted -> natural mapping
+    double* stage = xbuf + ldc;                           // NST x ([ldc] row c[a',:] + [ldg] row g_ab[pq,:])
     const int stage_len = ldc + ldg;
-    double* acc_long = stage + (size_t)NST * stage_len;  // [kMaxLong]
+    double* acc_long = stage + (size_t)NST * stage_len;   // [kMaxLong]
     uint64_t* bars = reinterpret_cast<uint64_t*>(acc_long + kMaxLong);
     uint64_t* full = bars;                  // [NST]
     uint64_t* empty = bars + kMaxStages;    // [NST]
-    uint64_t* rows_bar = bars + 2 * kMaxStages;
-
-    const bool ham = op.use_same_spin != 0;
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], nwarp_c);
         }
-        mbar_init(rows_bar, 1);
         mbar_fence_init();
     }
     if (tid < kMaxLong) acc_long[tid] = 0.0;
@@ -176,10 +333,6 @@ __global__ void sigma_kernel(const SigmaArgs P, const int NST) {
     // =========================== producer warp ===========================
     if (tid >= ncons) {
         if (tid == ncons) {
-            if (first) {
-                mbar_expect_tx(rows_bar, (uint32_t)(ldc * sizeof(double)));
-                bulk_g2s(Cs, P.c + (size_t)a * ldc, (uint32_t)(ldc * sizeof(double)), rows_bar);
-            }
             for (int item = 0; item < n_items; ++item) {
                 const int s = item % NST;
                 if (item >= NST) mbar_wait_parity(&empty[s], (uint32_t)(((item / NST) - 1) & 1));
@@ -196,18 +349,21 @@ __global__ void sigma_kernel(const SigmaArgs P, const int NST) {
     }
 
     // =========================== consumer warps ==========================
-    double acc[CPT];
-    int bs_beg[CPT], bs_n[CPT], lidx[CPT];
+    double acc_nat[CPT], acc_srt[CPT];
+    int s_base[CPT], s_len[CPT], my_len[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-        const int b = tid + c * ncons;
-        acc[c] = 0.0;
-        bs_beg[c] = b < nb ? op.b.row_ptr[b] : 0;
-        bs_n[c] = b < nb ? op.b.n_single[b] : 0;
-        lidx[c] = b < nb ? pl.long_idx[b] : -1;
+        acc_nat[c] = 0.0;
+        acc_srt[c] = 0.0;
+        const int pos = tid + c * ncons;
+        const int slice = pos >> 5;
+        const bool ok = slice < L.n_slices;
+        s_base[c] = ok ? L.slice_ptr[slice] : 0;
+        s_len[c] = ok ? (L.slice_ptr[slice + 1] - s_base[c]) >> 5 : 0;
+        my_len[c] = pos < nb ? L.len[pos] : 0;
     }
 
-    // ---- phase C (no shared memory): alpha doubles, coalesced row streaming, kUnroll loads in flight
+    // ---- phase C: alpha doubles, coalesced row streaming, kUnroll loads in flight -------------------
     if (ham) {
         for (int e0 = db_beg; e0 < db_end; e0 += kUnroll) {
             double v[kUnroll];
@@ -226,74 +382,13 @@ __global__ void sigma_kernel(const SigmaArgs P, const int NST) {
 #pragma unroll
                     for (int u = 0; u < kUnroll; ++u) x[u] = __ldg(crow[u] + b);
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) acc[c] = fma(v[u], x[u], acc[c]);
+                    for (int u = 0; u < kUnroll; ++u) acc_nat[c] = fma(v[u], x[u], acc_nat[c]);
                 }
             }
         }
     }
 
-    // ---- phase B (first chunk of the row): diagonal + beta excitations inside the staged row --------
-    if (first) {
-        mbar_wait_parity(rows_bar, 0);
-        const double* wa = op.Wa ? op.Wa + (size_t)a * ldg : nullptr;
-#pragma unroll
-        for (int c = 0; c < CPT; ++c) {
-            const int b = tid + c * ncons;
-            if (b < nb) {
-                acc[c] = fma(op.diag[(size_t)a * ldc + b], Cs[b], acc[c]);
-                if (lidx[c] < 0) {
-                    const int beg = bs_beg[c], ns = bs_n[c], end = op.b.row_ptr[b + 1];
-#pragma unroll 2
-                    for (int e = beg; e < beg + ns; ++e) {
-                        const uint32_t pk = __ldg(op.b.pack + e);
-                        double coef = ham ? __ldg(op.b.val + e) : 0.0;
-                        if (wa) {
-                            const double w = __ldg(wa + ((pk >> 19) & 0xfffu));
-                            coef += (pk >> 31) ? -w : w;
-                        }
-                        acc[c] = fma(coef, Cs[pk & 0x7ffffu], acc[c]);
-                    }
-                    if (ham) {
-                        for (int e0 = beg + ns; e0 < end; e0 += kUnroll) {
-                            uint32_t bp[kUnroll];
-                            double v[kUnroll];
-#pragma unroll
-                            for (int u = 0; u < kUnroll; ++u) {
-                                const int e = min(e0 + u, end - 1);
-                                bp[u] = __ldg(op.b.col + e);
-                                v[u] = (e0 + u < end) ? __ldg(op.b.val + e) : 0.0;
-                            }
-#pragma unroll
-                            for (int u = 0; u < kUnroll; ++u) acc[c] = fma(v[u], Cs[bp[u]], acc[c]);
-                        }
-                    }
-                }
-            }
-        }
-        // long columns: one warp per column, lanes stride the whole list (singles then doubles)
-        for (int li = warp; li < n_long; li += nwarp_c) {
-            const int b = pl.long_cols[li];
-            const int beg = op.b.row_ptr[b], ns = op.b.n_single[b], end = op.b.row_ptr[b + 1];
-            double part = 0.0;
-            for (int e = beg + lane; e < end; e += 32) {
-                const uint32_t pk = __ldg(op.b.pack + e);
-                double coef = ham ? __ldg(op.b.val + e) : 0.0;
-                if (e < beg + ns) {
-                    if (wa) {
-                        const double w = __ldg(wa + ((pk >> 19) & 0xfffu));
-                        coef += (pk >> 31) ? -w : w;
-                    }
-                    part = fma(coef, Cs[pk & 0x7ffffu], part);
-                } else if (ham) {
-                    part = fma(coef, Cs[pk], part);
-                }
-            }
-            part = warp_sum(part);
-            if (lane == 0) acc_long[li] += part;
-        }
-    }
-
-    // ---- phase D: alpha singles through the staged ring, beta singles gathered from shared memory ---
+    // ---- phase D: alpha singles through the staged ring --------------------------------------------
     for (int item = 0; item < n_items; ++item) {
         const int s = item % NST;
         const uint32_t m = __ldg(op.a.meta + it_beg + item);
@@ -302,25 +397,35 @@ __global__ void sigma_kernel(const SigmaArgs P, const int NST) {
         const double va = ham ? __ldg(op.a.val + it_beg + item) : 0.0;
         const double* Cn = stage + (size_t)s * stage_len;
         const double* gs = Cn + ldc;
-        mbar_wait_parity(&full[s], (uint32_t)((item / NST) & 1));
+        // global loads that do not depend on the stage are issued before the wait
+        double wb[CPT];
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int b = tid + c * ncons;
-            if (b < nb) {
-                double sum = 0.0;
-                if (lidx[c] < 0) {
-                    const int e1 = bs_beg[c] + bs_n[c];
-#pragma unroll 4
-                    for (int e = bs_beg[c]; e < e1; ++e) {
-                        const uint32_t pk = __ldg(op.b.pack + e);
-                        const double t = gs[(pk >> 19) & 0xfffu] * Cn[pk & 0x7ffffu];
-                        sum += (pk >> 31) ? -t : t;
+            wb[c] = (op.Wb && b < nb) ? __ldg(op.Wb + (size_t)pq * ldc + b) : 0.0;
+        }
+        mbar_wait_parity(&full[s], (uint32_t)((item / NST) & 1));
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            // sorted mapping: SELL slice, warp-uniform trip count, coalesced loads
+            double sum = 0.0;
+            const uint32_t* src = L.pack + s_base[c] + lane;
+            for (int k0 = 0; k0 < s_len[c]; k0 += kUnroll) {
+                uint32_t pk[kUnroll];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) pk[u] = __ldg(src + min(k0 + u, s_len[c] - 1) * 32);
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    if (k0 + u < my_len[c]) {
+                        const double t = gs[(pk[u] >> 19) & 0xfffu] * Cn[pk[u] & 0x7ffffu];
+                        sum += (pk[u] >> 31) ? -t : t;
                     }
                 }
-                double coef = va;
-                if (op.Wb) coef = fma(sa, __ldg(op.Wb + (size_t)pq * ldc + b), coef);
-                acc[c] += sa * sum + coef * Cn[b];
             }
+            acc_srt[c] = fma(sa, sum, acc_srt[c]);
+            // natural mapping: the c[a', b] terms
+            const int b = tid + c * ncons;
+            if (b < nb) acc_nat[c] = fma(fma(sa, wb[c], va), Cn[b], acc_nat[c]);
         }
         for (int li = warp; li < n_long; li += nwarp_c) {
             const int b = pl.long_cols[li];
@@ -332,22 +437,31 @@ __global__ void sigma_kernel(const SigmaArgs P, const int NST) {
                 part += (pk >> 31) ? -t : t;
             }
             part = warp_sum(part);
-            if (lane == 0) acc_long[li] += sa * part;
+            if (lane == 0) acc_long[li] = fma(sa, part, acc_long[li]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the stage
     }
 
-    // ---- store: fold the cooperatively reduced long columns back into their owner threads ----------
-    if (n_long > 0) asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
-    double* out = slot < 0 ? P.sigma + (size_t)a * ldc : pl.part + (size_t)slot * ldc;
+    // ---- exchange sorted -> natural, then one coalesced update -------------------------------------
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        const int pos = tid + c * ncons;
+        if (pos < nb) xbuf[L.perm[pos]] = acc_srt[c];
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
         const int b = tid + c * ncons;
-        if (b < ldc) {
-            double v = 0.0;
-            if (b < nb) v = acc[c] + (lidx[c] >= 0 ? acc_long[lidx[c]] : 0.0);
-            out[b] = v;
+        if (b < nb) {
+            const int li = pl.long_idx[b];
+            const double v = acc_nat[c] + xbuf[b] + (li >= 0 ? acc_long[li] : 0.0);
+            if (slot < 0)
+                P.sigma[(size_t)a * ldc + b] += v;  // kernel B wrote the element earlier in the stream
+            else
+                pl.part[(size_t)slot * ldc + b] = v;
+        } else if (b < ldc && slot >= 0) {
+            pl.part[(size_t)slot * ldc + b] = 0.0;
         }
     }
 }
@@ -378,9 +492,11 @@ static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
     if (cpt_t == 0) return false;
     auto smem_of = [&](int nst) {
         return (size_t)(ldc + nst * (ldc + op->ldg) + kMaxLong) * sizeof(double) +
-               (2 * kMaxStages + 1) * sizeof(uint64_t);
+               (2 * kMaxStages) * sizeof(uint64_t);
     };
     if (smem_of(2) > 227 * 1024) return false;
+    // kernel B: kRowsB rows of c and of Wa
+    if ((size_t)kRowsB * (ldc + op->ldg) * sizeof(double) + 16 > 227 * 1024) return false;
     // ring depth: as deep as fits in ~56 KB (keeps 4 CTAs per SM resident), at least 2, at most 8
     int nst = 2;
     while (nst < kMaxStages && smem_of(nst + 1) <= 56 * 1024) ++nst;
@@ -391,11 +507,9 @@ static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
     return true;
 }
 
-template <int CPT>
-static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t st) {
-    auto kern = sigma_kernel<CPT>;
-    static bool configured[64] = {false};  // per device: opt in to > 48 KB dynamic shared memory
-    if (pl.smem > 48 * 1024) {
+template <typename K>
+static int opt_in_smem(K kern, size_t smem, bool* configured) {
+    if (smem > 48 * 1024) {
         int dev = 0;
         SQD_CUDA_OK(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !configured[dev]) {
@@ -404,11 +518,28 @@ static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
-    kern<<<args.op.plan.n_chunks, pl.threads + 32, pl.smem, st>>>(args, pl.stages);
-    if (check_launch("sigma_kernel")) return -2;
-    if (args.op.plan.n_split > 0) {
-        sigma_combine_kernel<<<args.op.plan.n_split, 256, 0, st>>>(args.done, args.op.plan, args.op.ldc,
-                                                                  args.sigma);
+    return 0;
+}
+
+template <int CPT>
+static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t st) {
+    const sqd_operator& op = args.op;
+    // kernel B
+    static bool cfg_b[64] = {false};
+    const size_t smem_b = (size_t)kRowsB * (op.ldc + op.ldg) * sizeof(double) + 16;
+    if (opt_in_smem(sigma_b_kernel, smem_b, cfg_b)) return -2;
+    const int n_pos_slices = (op.ldc + 31) / 32;  // slices incl. the pad positions
+    dim3 grid_b((op.a.n + kRowsB - 1) / kRowsB, (n_pos_slices + kWarpsB - 1) / kWarpsB);
+    sigma_b_kernel<<<grid_b, kWarpsB * 32, smem_b, st>>>(args);
+    if (check_launch("sigma_b_kernel")) return -2;
+    // kernel A
+    auto kern = sigma_a_kernel<CPT>;
+    static bool cfg_a[64] = {false};
+    if (opt_in_smem(kern, pl.smem, cfg_a)) return -2;
+    kern<<<op.plan.n_chunks, pl.threads + 32, pl.smem, st>>>(args, pl.stages);
+    if (check_launch("sigma_a_kernel")) return -2;
+    if (op.plan.n_split > 0) {
+        sigma_combine_kernel<<<op.plan.n_split, 256, 0, st>>>(args.done, op.plan, op.ldc, args.sigma);
         return check_launch("sigma_combine_kernel");
     }
     return 0;
@@ -423,6 +554,8 @@ int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sig
                 "sqd_sigma: the operator has no work plan (call sqd_sigma_plan_build first)");
     SQD_REQUIRE(op->plan.n_slots == 0 || op->plan.part != nullptr,
                 "sqd_sigma: the plan needs a partial buffer of n_slots*ldc doubles");
+    SQD_REQUIRE(op->bd.pack != nullptr && op->bb.pack != nullptr,
+                "sqd_sigma: the operator has no SELL tables (call sqd_sell_build first)");
     SQD_REQUIRE(plan_sigma(op, &pl),
                 "sqd_sigma: nb=%d (ldc=%d) with norb=%d does not fit the shared-memory row staging "
                 "(limit: 3*ldc + 2*ldg doubles <= 227 KB, ldc <= 11904)",
@@ -456,10 +589,10 @@ int sqd_sigma(const sqd_operator* op, const double* d_c, double* d_sigma, void* 
 }
 
 int sqd_sigma_plan_build(const sqd_spin_table* a, const sqd_spin_table* b, int cost_per_chunk,
-                   int long_threshold, int max_chunks, int* d_chunk_row, int* d_chunk_beg,
-                   int* d_chunk_end, int* d_chunk_slot, int* d_split_row, int* d_split_slot_beg,
-                   int* d_split_n, int* d_long_idx, int* d_long_cols, int* d_counts, int* h_counts,
-                   void* stream) {
+                         int long_threshold, int max_chunks, int* d_chunk_row, int* d_chunk_beg,
+                         int* d_chunk_end, int* d_chunk_slot, int* d_split_row, int* d_split_slot_beg,
+                         int* d_split_n, int* d_long_idx, int* d_long_cols, int* d_counts,
+                         int* h_counts, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     SQD_REQUIRE(cost_per_chunk >= 4 && cost_per_chunk % 4 == 0,
                 "sqd_sigma_plan_build: cost_per_chunk must be a positive multiple of 4");
@@ -471,6 +604,21 @@ int sqd_sigma_plan_build(const sqd_spin_table* a, const sqd_spin_table* b, int c
     SQD_CUDA_OK(cudaMemcpyAsync(h_counts, d_counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     SQD_CUDA_OK(cudaStreamSynchronize(st));
     return 0;
+}
+
+int sqd_sell_build(const sqd_spin_table* t, int mode, int long_threshold, int capacity, int* d_perm,
+                   int* d_len, int* d_slice_ptr, uint32_t* d_pack, double* d_val, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SQD_REQUIRE(mode == 0 || mode == 1, "sqd_sell_build: mode must be 0 or 1");
+    SQD_REQUIRE(mode == 0 || d_val != nullptr, "sqd_sell_build: mode 1 needs the value array");
+    const int n = t->n;
+    SQD_REQUIRE(n > 0 && capacity >= 32 * n, "sqd_sell_build: capacity must be at least nnz + 32*n");
+    sell_rank_kernel<<<(n + 127) / 128, 128, 0, st>>>(*t, mode, long_threshold, d_perm, d_len);
+    sell_slice_kernel<<<1, 32, 0, st>>>(n, d_len, d_slice_ptr);
+    const int ns = (n + 31) / 32;
+    sell_fill_kernel<<<(ns * 32 + 127) / 128, 128, 0, st>>>(*t, mode, d_perm, d_len, d_slice_ptr, d_pack,
+                                                           d_val);
+    return check_launch("sell kernels", 3);
 }
 
 }  // extern "C"

@@ -215,6 +215,7 @@ class _SpinTableDev:
                  device, strs_dev=None):
         n = len(strs_u64)
         self.n = n
+        self._torch, self._lib, self._sell = torch, lib, {}
         st = _lib.stream_ptr(torch)
         self.strs = strs_dev if strs_dev is not None else \
             torch.from_numpy(strs_u64.view(np.int64).copy()).to(device)
@@ -241,6 +242,28 @@ class _SpinTableDev:
                                            _lib.ptr(self.meta), _lib.ptr(self.pack),
                                            _lib.ptr(self.diag), st),
                    "sqd_excitation_fill")
+
+    def sell(self, mode: int) -> _lib.Sell:
+        """SELL-32 copy of the table (mode 0: singles only, mode 1: all entries + values); cached."""
+        if mode in self._sell:
+            return self._sell[mode][0]
+        torch = self._torch
+        dev = self.strs.device
+        n = self.n
+        cap = self.nnz + 32 * n + 32
+        ns = (n + 31) // 32
+        perm = torch.empty(n, dtype=torch.int32, device=dev)
+        ln = torch.empty(n, dtype=torch.int32, device=dev)
+        sptr = torch.empty(ns + 1, dtype=torch.int32, device=dev)
+        pack = torch.empty(cap, dtype=torch.int32, device=dev)
+        val = torch.empty(cap, dtype=torch.float64, device=dev) if mode == 1 else None
+        t = self.struct()
+        _lib.check(self._lib.sqd_sell_build(C.byref(t), mode, int(_SIGMA_LONG_THRESHOLD), cap,
+                                            _lib.ptr(perm), _lib.ptr(ln), _lib.ptr(sptr), _lib.ptr(pack),
+                                            _lib.ptr(val), _lib.stream_ptr(torch)), "sqd_sell_build")
+        st = _lib.Sell(ns, _lib.ptr(perm), _lib.ptr(ln), _lib.ptr(sptr), _lib.ptr(pack), _lib.ptr(val))
+        self._sell[mode] = (st, (perm, ln, sptr, pack, val))
+        return st
 
     def struct(self) -> _lib.SpinTable:
         return _lib.SpinTable(self.n, _lib.ptr(self.strs), _lib.ptr(self.row_ptr),
@@ -277,7 +300,8 @@ class _OperatorDev:
             self.Wb = None
         self.struct = _lib.Operator(sub.ta.struct(), sub.tb.struct(), norb, ldc, ldg,
                                     _lib.ptr(self.diag), _lib.ptr(self.gab), _lib.ptr(self.Wa),
-                                    _lib.ptr(self.Wb), 1 if same_spin else 0, sub.sigma_plan())
+                                    _lib.ptr(self.Wb), 1 if same_spin else 0, sub.sigma_plan(),
+                                    sub.tb.sell(0), sub.tb.sell(1))
         if lib.sqd_sigma_smem_bytes(C.byref(self.struct)) < 0:
             raise ValueError(
                 f"subspace shape (na={na}, nb={nb}, norb={norb}) exceeds the shared-memory row "
