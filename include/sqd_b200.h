@@ -133,6 +133,7 @@ typedef struct {
  * slice_ptr[s] + 32*k + i -- a warp reads one coalesced line per step and runs a uniform trip count. */
 typedef struct {
     int n_slices;            /* ceil(n / 32) */
+    int n_entries;           /* slice_ptr[n_slices]: stored entries incl. padding */
     const int* perm;         /* [n] sorted position -> string index */
     const int* len;          /* [n] list length at each sorted position */
     const int* slice_ptr;    /* [n_slices + 1] */
@@ -162,9 +163,9 @@ typedef struct {
 int sqd_sell_build(const sqd_spin_table* t, int mode, int long_threshold, int capacity, int* d_perm,
                    int* d_len, int* d_slice_ptr, uint32_t* d_pack, double* d_val, void* stream);
 
-/* Build the work plan.  cost_per_chunk: multiple of 4 (a single excitation costs 4, a double 1);
+/* Build the work plan.  cost_per_chunk: multiple of 16 (a single excitation costs 16, a double 1);
  * long_threshold: beta strings with more single excitations than this become long columns (at most
- * SQD_MAX_LONG_COLUMNS); max_chunks: capacity of the d_chunk_* arrays, na + (4*nnz_a)/cost_per_chunk + 1
+ * SQD_MAX_LONG_COLUMNS); max_chunks: capacity of the d_chunk_* arrays, 2*na + (16*nnz_a)/cost_per_chunk + 1
  * always suffices.  d_split_*: int[na]; d_long_idx: int[nb]; d_long_cols: int[SQD_MAX_LONG_COLUMNS];
  * d_counts: int[4] device scratch; h_counts receives {n_chunks, n_slots, n_split, n_long}.
  * Synchronises the stream. */

@@ -52,6 +52,7 @@ class SigmaPlan(C.Structure):
 class Sell(C.Structure):
     _fields_ = [
         ("n_slices", C.c_int),
+        ("n_entries", C.c_int),
         ("perm", C.c_void_p),
         ("len", C.c_void_p),
         ("slice_ptr", C.c_void_p),

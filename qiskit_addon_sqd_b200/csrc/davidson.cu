@@ -43,7 +43,9 @@ struct DavState {
     int status;  // 0 running, 1 converged, 2 linear dependency, 3 (host) max_cycle
     int cycles;
     double theta, theta_prev, rnorm, tnorm2, inv_norm;
-    double G[kMaxS * kMaxS];
+    int best;
+    double lam[kMaxS];          // eigenvalues of the projected matrix V^T H V
+    double Q[kMaxS * kMaxS];    // its eigenvectors (column j <-> lam[j])
     double y[kMaxS];
     double c1[kMaxS];
     double c2[kMaxS];
@@ -201,45 +203,74 @@ __device__ __forceinline__ double reduce_partials(const double* partials, int ro
     return warp_sum(s);
 }
 
-// Rayleigh-Ritz: fold the new Gram column into G, diagonalise G (m x m) by parallel-order Jacobi.
+// Rayleigh-Ritz.  The eigen-decomposition G = Q diag(lam) Q^T of the previous cycle is kept in the state;
+// appending one basis vector makes the matrix, in the basis [Q, e_new], an ARROWHEAD
+//     [ diag(lam)   z ]        z = Q^T g ,   g = new Gram column
+//     [    z^T      a ]
+// which parallel-order Jacobi (all disjoint pairs of a round rotated at once by one CTA) diagonalises in
+// 2-4 sweeps because |z| shrinks with the residual.
 __global__ void __launch_bounds__(256)
 rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ partials, int nblk, int m,
                      int slot) {
     if (st->status != 0) return;
     __shared__ double A[kMaxS][kMaxS + 1];
-    __shared__ double Q[kMaxS][kMaxS + 1];
+    __shared__ double J[kMaxS][kMaxS + 1];   // accumulated rotations
+    __shared__ double Qo[kMaxS][kMaxS + 1];  // previous eigenvectors, extended by e_new
+    __shared__ double g[kMaxS];
     __shared__ double cs_c[kMaxS / 2], cs_s[kMaxS / 2];
     __shared__ int pr_p[kMaxS / 2], pr_q[kMaxS / 2];
-    __shared__ double off_s;
-    const int tid = threadIdx.x;
+    __shared__ double red_off[8], red_dia[8];
+    __shared__ int stop_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = m - 1;  // dimension of the stored decomposition (slot == d by construction)
 
-    for (int row = tid >> 5; row < m; row += blockDim.x >> 5) {
-        const double g = reduce_partials(partials, row, nblk);
-        if ((tid & 31) == 0) {
-            st->G[row * kMaxS + slot] = g;
-            st->G[slot * kMaxS + row] = g;
-        }
+    for (int row = warp; row < m; row += blockDim.x >> 5) {
+        const double v = reduce_partials(partials, row, nblk);
+        if (lane == 0) g[row] = v;
     }
-    __syncthreads();
     for (int idx = tid; idx < m * m; idx += blockDim.x) {
         const int i = idx / m, j = idx % m;
-        A[i][j] = st->G[i * kMaxS + j];
-        Q[i][j] = i == j ? 1.0 : 0.0;
+        Qo[i][j] = (i < d && j < d) ? st->Q[i * kMaxS + j] : (i == j ? 1.0 : 0.0);
+        J[i][j] = i == j ? 1.0 : 0.0;
+        A[i][j] = (i == j && i < d) ? st->lam[i] : 0.0;
     }
     __syncthreads();
+    if (tid < d) {
+        double z = 0.0;
+        for (int i = 0; i < d; ++i) z = fma(Qo[i][tid], g[i], z);
+        A[tid][d] = z;
+        A[d][tid] = z;
+    }
+    if (tid == 0) A[d][d] = g[d];
+    __syncthreads();
 
-    const int np = (m + 1) / 2;      // pairs per step
-    const int nplayers = 2 * np;     // even
+    const int np = (m + 1) / 2;   // pairs per round
+    const int nplayers = 2 * np;  // even
     for (int sweep = 0; sweep < 30 && m > 1; ++sweep) {
-        // convergence test on the off-diagonal norm
-        if (tid == 0) {
-            double off = 0.0, dia = 0.0;
-            for (int i = 0; i < m; ++i)
-                for (int j = 0; j < m; ++j) (i == j ? dia : off) += A[i][j] * A[i][j];
-            off_s = (off <= 1e-30 * dia || off == 0.0) ? 0.0 : 1.0;
+        // off-diagonal vs diagonal weight, fixed reduction order
+        double off = 0.0, dia = 0.0;
+        for (int idx = tid; idx < m * m; idx += blockDim.x) {
+            const int i = idx / m, j = idx % m;
+            const double v = A[i][j] * A[i][j];
+            if (i == j) dia += v; else off += v;
+        }
+        off = warp_sum(off);
+        dia = warp_sum(dia);
+        if (lane == 0) {
+            red_off[warp] = off;
+            red_dia[warp] = dia;
         }
         __syncthreads();
-        if (off_s == 0.0) break;
+        if (tid == 0) {
+            double o = 0.0, dd = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+                o += red_off[w];
+                dd += red_dia[w];
+            }
+            stop_s = (o <= 1e-26 * dd) ? 1 : 0;
+        }
+        __syncthreads();
+        if (stop_s) break;
         for (int step = 0; step < nplayers - 1; ++step) {
             if (tid < np) {
                 int p, q;
@@ -261,8 +292,10 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
                     if (fabs(apq) > 1e-300) {
                         const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
                         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + t * t);
+                        c = rsqrt(1.0 + t * t);
                         s = t * c;
+                    } else {
+                        q = p;  // nothing to rotate
                     }
                 } else {
                     q = p;  // dummy pair: identity
@@ -273,7 +306,7 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
                 cs_s[tid] = s;
             }
             __syncthreads();
-            // column update: A <- A J, Q <- Q J
+            // column update: A <- A R, J <- J R
             for (int idx = tid; idx < 2 * m * np; idx += blockDim.x) {
                 const int which = idx / (m * np);
                 const int rem = idx % (m * np);
@@ -281,14 +314,14 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
                 const int p = pr_p[k], q = pr_q[k];
                 if (p != q) {
                     const double c = cs_c[k], s = cs_s[k];
-                    double(*M)[kMaxS + 1] = which ? Q : A;
+                    double(*M)[kMaxS + 1] = which ? J : A;
                     const double xp = M[i][p], xq = M[i][q];
                     M[i][p] = c * xp - s * xq;
                     M[i][q] = s * xp + c * xq;
                 }
             }
             __syncthreads();
-            // row update: A <- J^T A
+            // row update: A <- R^T A
             for (int idx = tid; idx < m * np; idx += blockDim.x) {
                 const int j = idx / np, k = idx % np;
                 const int p = pr_p[k], q = pr_q[k];
@@ -302,21 +335,37 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
             __syncthreads();
         }
     }
+    // new decomposition: Q <- [Q 0; 0 1] J, lam <- diag(A)
+    for (int idx = tid; idx < m * m; idx += blockDim.x) {
+        const int i = idx / m, j = idx % m;
+        double v = 0.0;
+        for (int k = 0; k < m; ++k) v = fma(Qo[i][k], J[k][j], v);
+        st->Q[i * kMaxS + j] = v;
+    }
+    if (tid < m) st->lam[tid] = A[tid][tid];
+    __syncthreads();
     if (tid == 0) {
         int best = 0;
         for (int i = 1; i < m; ++i)
             if (A[i][i] < A[best][best]) best = i;
-        // sign: largest component positive
-        int big = 0;
-        for (int i = 1; i < m; ++i)
-            if (fabs(Q[i][best]) > fabs(Q[big][best])) big = i;
-        const double sg = Q[big][best] < 0.0 ? -1.0 : 1.0;
-        double nrm = 0.0;
-        for (int i = 0; i < m; ++i) nrm += Q[i][best] * Q[i][best];
-        nrm = sg / sqrt(nrm);
-        for (int i = 0; i < m; ++i) st->y[i] = Q[i][best] * nrm;
         st->theta_prev = st->theta;
         st->theta = A[best][best];
+        st->best = best;
+    }
+    __syncthreads();
+    // Ritz vector = column `best` of Q, normalised, largest component positive
+    if (tid == 0) {
+        const int best = st->best;
+        double nrm = 0.0;
+        int big = 0;
+        for (int i = 0; i < m; ++i) {
+            const double v = st->Q[i * kMaxS + best];
+            nrm += v * v;
+            if (fabs(v) > fabs(st->Q[big * kMaxS + best])) big = i;
+        }
+        const double sg = st->Q[big * kMaxS + best] < 0.0 ? -1.0 : 1.0;
+        nrm = sg / sqrt(nrm);
+        for (int i = 0; i < m; ++i) st->y[i] = st->Q[i * kMaxS + best] * nrm;
     }
 }
 
@@ -343,7 +392,8 @@ __global__ void convergence_kernel(DavState* __restrict__ st, const double* __re
             double c = 0.0;
             for (int i = 0; i < m; ++i) c += st->y[i] * p[i];
             st->c1[0] = c;
-            st->G[0] = st->theta;
+            st->lam[0] = st->theta;  // the collapsed space is spanned by the Ritz vector alone
+            st->Q[0] = 1.0;
             st->y[0] = 1.0;
         } else {
             for (int i = 0; i < m; ++i) st->c1[i] = p[i];
@@ -426,8 +476,10 @@ __global__ void init_state_kernel(DavState* st) {
         st->tnorm2 = 0.0;
         st->inv_norm = 0.0;
     }
-    for (int i = threadIdx.x; i < kMaxS * kMaxS; i += blockDim.x) st->G[i] = 0.0;
-    for (int i = threadIdx.x; i < kMaxS; i += blockDim.x) st->y[i] = st->c1[i] = st->c2[i] = 0.0;
+    for (int i = threadIdx.x; i < kMaxS * kMaxS; i += blockDim.x) st->Q[i] = 0.0;
+    for (int i = threadIdx.x; i < kMaxS; i += blockDim.x)
+        st->y[i] = st->c1[i] = st->c2[i] = st->lam[i] = 0.0;
+    if (threadIdx.x == 0) st->best = 0;
 }
 
 // argmin over the (na, nb) block of hdiag (pads excluded): stage 1 per-CTA, stage 2 single thread.

@@ -62,7 +62,8 @@ constexpr int kMaxStages = 8;
 constexpr int kUnroll = 4;
 constexpr int kMaxLong = SQD_MAX_LONG_COLUMNS;
 constexpr int kRowsB = 4;      // rows of c per CTA in kernel B
-constexpr int kWarpsB = 4;     // SELL slices (warps) per CTA in kernel B
+constexpr int kWarpsB = 4;     // warps per CTA in kernel B (they split one SELL slice)
+constexpr int kSingleCost = 16;  // plan cost of one alpha single excitation, in units of one double
 
 // ---------------------------------------------------------------------------------------------------
 // Work decomposition.  The excitation lists are extremely skewed (the Hartree-Fock string of a sampled
@@ -81,34 +82,38 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
                                   int* __restrict__ split_slot_beg, int* __restrict__ split_n,
                                   int* __restrict__ long_idx, int* __restrict__ long_cols,
                                   int* __restrict__ counts) {
-    // setup-time, O(na + nb) sequential work: a single thread keeps the order trivially deterministic
+    // setup-time, O(na + nb) sequential work: a single thread keeps the order trivially deterministic.
+    // Two passes: rows that need several chunks are emitted first so that the heaviest CTAs start first.
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int nc = 0, nslots = 0, nsplit = 0;
-    for (int a = 0; a < A.n; ++a) {
-        const int beg = A.row_ptr[a], ns = A.n_single[a], end = A.row_ptr[a + 1];
-        const int nd = end - beg - ns;
-        const int cost = 4 * ns + nd;
-        int k = (cost + cost_per_chunk - 1) / cost_per_chunk;
-        if (k < 1) k = 1;
-        if (nc + k > max_chunks) k = 1;  // cannot happen with the documented bound; stay correct anyway
-        if (k > 1) {
-            split_row[nsplit] = a;
-            split_slot_beg[nsplit] = nslots;
-            split_n[nsplit] = k;
-            ++nsplit;
-        }
-        for (int c = 0; c < k; ++c) {
-            int p0 = c * cost_per_chunk, p1 = (c + 1) * cost_per_chunk;
-            if (k == 1) p1 = cost;
-            if (p0 > cost) p0 = cost;
-            if (p1 > cost) p1 = cost;
-            const int e0 = p0 < 4 * ns ? p0 / 4 : ns + (p0 - 4 * ns);
-            const int e1 = p1 < 4 * ns ? p1 / 4 : ns + (p1 - 4 * ns);
-            chunk_row[nc] = a;
-            chunk_beg[nc] = beg + e0;
-            chunk_end[nc] = beg + e1;
-            chunk_slot[nc] = k > 1 ? nslots++ : -1;
-            ++nc;
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int a = 0; a < A.n; ++a) {
+            const int beg = A.row_ptr[a], ns = A.n_single[a], end = A.row_ptr[a + 1];
+            const int nd = end - beg - ns;
+            const int cost = kSingleCost * ns + nd;
+            int k = (cost + cost_per_chunk - 1) / cost_per_chunk;
+            if (k < 1) k = 1;
+            if ((k > 1) != (pass == 0)) continue;
+            if (nc + k + (A.n - a) > max_chunks && k > 1) k = 1;  // capacity guard, never hit with the documented bound
+            if (k > 1) {
+                split_row[nsplit] = a;
+                split_slot_beg[nsplit] = nslots;
+                split_n[nsplit] = k;
+                ++nsplit;
+            }
+            for (int c = 0; c < k; ++c) {
+                int p0 = c * cost_per_chunk, p1 = (c + 1) * cost_per_chunk;
+                if (k == 1) p1 = cost;
+                if (p0 > cost) p0 = cost;
+                if (p1 > cost) p1 = cost;
+                const int e0 = p0 < kSingleCost * ns ? p0 / kSingleCost : ns + (p0 - kSingleCost * ns);
+                const int e1 = p1 < kSingleCost * ns ? p1 / kSingleCost : ns + (p1 - kSingleCost * ns);
+                chunk_row[nc] = a;
+                chunk_beg[nc] = beg + e0;
+                chunk_end[nc] = beg + e1;
+                chunk_slot[nc] = k > 1 ? nslots++ : -1;
+                ++nc;
+            }
         }
     }
     int nlong = 0;
@@ -183,8 +188,9 @@ __global__ void sell_fill_kernel(const sqd_spin_table T, int mode, const int* __
 
 // ---------------------------------------------------------------------------------------------------
 // Kernel B:  sigma[a,b] = diag[a,b] c[a,b] + sum_{b'} (Hb[b,b'] + [single] sgn Wa[a,rs]) c[a,b']
-// CTA = kRowsB rows x kWarpsB SELL slices.  The rows of c and of Wa are staged with bulk copies.
-// Writes every element of sigma (pads = 0); kernel A then adds its part.
+// CTA = kRowsB rows x ONE SELL slice (32 columns); its kWarpsB warps split the slice's entry range and
+// their partial sums meet in shared memory in warp order.  The rows of c and of Wa are staged with bulk
+// copies.  Writes every element of sigma (pads = 0); kernel A then adds its part.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsB * 32)
 sigma_b_kernel(const SigmaArgs P) {
@@ -198,10 +204,18 @@ sigma_b_kernel(const SigmaArgs P) {
     const int nrows = min(kRowsB, na - a0);
     const bool ham = op.use_same_spin != 0;
     const bool use_wa = op.Wa != nullptr;
+    const int slice = blockIdx.y;
+    const int pos = slice * 32 + lane;
 
     double* Cs = reinterpret_cast<double*>(smem_raw);          // [kRowsB][ldc]
     double* Ws = Cs + (size_t)kRowsB * ldc;                     // [kRowsB][ldg]
-    uint64_t* bar = reinterpret_cast<uint64_t*>(Ws + (size_t)kRowsB * ldg);
+    double* red = Ws + (size_t)kRowsB * ldg;                    // [kWarpsB][kRowsB][32]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(red + kWarpsB * kRowsB * 32);
+    if (slice >= L.n_slices) {  // only pad positions live here
+        if (warp == 0 && pos >= nb && pos < ldc)
+            for (int r = 0; r < nrows; ++r) P.sigma[(size_t)(a0 + r) * ldc + pos] = 0.0;
+        return;
+    }
     if (tid == 0) {
         mbar_init(bar, 1);
         mbar_fence_init();
@@ -217,18 +231,20 @@ sigma_b_kernel(const SigmaArgs P) {
                          (uint32_t)(ldg * sizeof(double)), bar);
         }
     }
-    const int slice = blockIdx.y * kWarpsB + warp;
-    const int pos = slice * 32 + lane;
-    const int n_slices = L.n_slices;
     double acc[kRowsB];
 #pragma unroll
     for (int r = 0; r < kRowsB; ++r) acc[r] = 0.0;
+    const int base = L.slice_ptr[slice];
+    const int slen = (L.slice_ptr[slice + 1] - base) >> 5;
+    const int mylen = pos < nb ? L.len[pos] : 0;
+    // this warp's share of the entry range, a multiple of kUnroll long
+    int per = (slen + kWarpsB - 1) / kWarpsB;
+    per = (per + kUnroll - 1) / kUnroll * kUnroll;
+    const int k_beg = warp * per, k_end = min(slen, k_beg + per);
+    // the table loads do not depend on the staged rows: issue the first batch before the wait
     mbar_wait_parity(bar, 0);
-    if (slice < n_slices && (ham || use_wa)) {
-        const int base = L.slice_ptr[slice];
-        const int slen = (L.slice_ptr[slice + 1] - base) >> 5;
-        const int mylen = pos < nb ? L.len[pos] : 0;
-        for (int k0 = 0; k0 < slen; k0 += kUnroll) {
+    if (ham || use_wa) {
+        for (int k0 = k_beg; k0 < k_end; k0 += kUnroll) {
             uint32_t pk[kUnroll];
             double v[kUnroll];
 #pragma unroll
@@ -257,15 +273,25 @@ sigma_b_kernel(const SigmaArgs P) {
             }
         }
     }
-    if (slice < n_slices && pos < nb) {
-        const int b = L.perm[pos];
 #pragma unroll
-        for (int r = 0; r < kRowsB; ++r)
-            if (r < nrows)
-                P.sigma[(size_t)(a0 + r) * ldc + b] =
-                    fma(op.diag[(size_t)(a0 + r) * ldc + b], Cs[r * ldc + b], acc[r]);
-    } else if (pos >= nb && pos < ldc) {
-        for (int r = 0; r < nrows; ++r) P.sigma[(size_t)(a0 + r) * ldc + pos] = 0.0;  // pads
+    for (int r = 0; r < kRowsB; ++r) red[(warp * kRowsB + r) * 32 + lane] = acc[r];
+    __syncthreads();
+    if (warp == 0) {
+        if (pos < nb) {
+            const int b = L.perm[pos];
+#pragma unroll
+            for (int r = 0; r < kRowsB; ++r) {
+                if (r < nrows) {
+                    double t = red[r * 32 + lane];
+#pragma unroll
+                    for (int w = 1; w < kWarpsB; ++w) t += red[(w * kRowsB + r) * 32 + lane];
+                    P.sigma[(size_t)(a0 + r) * ldc + b] =
+                        fma(op.diag[(size_t)(a0 + r) * ldc + b], Cs[r * ldc + b], t);
+                }
+            }
+        } else if (pos < ldc) {
+            for (int r = 0; r < nrows; ++r) P.sigma[(size_t)(a0 + r) * ldc + pos] = 0.0;  // pads
+        }
     }
 }
 
@@ -290,7 +316,7 @@ __global__ void sigma_combine_kernel(const int* __restrict__ done, const sqd_sig
 //   sorted mapping   (thread t <-> column perm[t])  : the beta-single gathers through SELL slices
 // The two partial results meet in a shared-memory exchange buffer before one coalesced update of sigma.
 // ---------------------------------------------------------------------------------------------------
-template <int CPT>
+template <int CPT, bool STAGE_PACK>
 __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
@@ -319,6 +345,7 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(acc_long + kMaxLong);
     uint64_t* full = bars;                  // [NST]
     uint64_t* empty = bars + kMaxStages;    // [NST]
+    uint32_t* pk_s = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages);  // [n_entries] when staged
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -349,6 +376,14 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
     }
 
     // =========================== consumer warps ==========================
+    // the beta SELL table is re-read for every alpha excitation of the chunk: keep it in shared memory
+    // when it is small enough (decided on the host, STAGE_PACK)
+    const uint32_t* pk_src = L.pack;
+    if (STAGE_PACK && n_items > 0) {
+        for (int i = tid; i < L.n_entries; i += ncons) pk_s[i] = __ldg(L.pack + i);
+        pk_src = pk_s;
+        asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+    }
     double acc_nat[CPT], acc_srt[CPT];
     int s_base[CPT], s_len[CPT], my_len[CPT];
 #pragma unroll
@@ -409,11 +444,11 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
         for (int c = 0; c < CPT; ++c) {
             // sorted mapping: SELL slice, warp-uniform trip count, coalesced loads
             double sum = 0.0;
-            const uint32_t* src = L.pack + s_base[c] + lane;
+            const uint32_t* src = pk_src + s_base[c] + lane;
             for (int k0 = 0; k0 < s_len[c]; k0 += kUnroll) {
                 uint32_t pk[kUnroll];
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) pk[u] = __ldg(src + min(k0 + u, s_len[c] - 1) * 32);
+                for (int u = 0; u < kUnroll; ++u) pk[u] = src[min(k0 + u, s_len[c] - 1) * 32];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
                     if (k0 + u < my_len[c]) {
@@ -468,6 +503,7 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
 
 struct SigmaPlan {
     int CPT, threads, stages;
+    bool stage_pack;
     size_t smem;
 };
 
@@ -490,19 +526,24 @@ static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
     }
     const int cpt_t = cpt <= 1 ? 1 : cpt <= 2 ? 2 : cpt <= 4 ? 4 : cpt <= 8 ? 8 : cpt <= 12 ? 12 : 0;
     if (cpt_t == 0) return false;
+    // beta SELL table staged in shared memory when it costs at most 24 KB
+    const size_t pack_bytes = ((size_t)op->bd.n_entries * 4 + 15) / 16 * 16;
+    const bool stage_pack = op->bd.n_entries > 0 && pack_bytes <= 24 * 1024;
     auto smem_of = [&](int nst) {
         return (size_t)(ldc + nst * (ldc + op->ldg) + kMaxLong) * sizeof(double) +
-               (2 * kMaxStages) * sizeof(uint64_t);
+               (2 * kMaxStages) * sizeof(uint64_t) + (stage_pack ? pack_bytes : 0);
     };
     if (smem_of(2) > 227 * 1024) return false;
-    // kernel B: kRowsB rows of c and of Wa
-    if ((size_t)kRowsB * (ldc + op->ldg) * sizeof(double) + 16 > 227 * 1024) return false;
-    // ring depth: as deep as fits in ~56 KB (keeps 4 CTAs per SM resident), at least 2, at most 8
+    // kernel B: kRowsB rows of c and of Wa + the cross-warp reduction buffer
+    if ((size_t)(kRowsB * (ldc + op->ldg) + kWarpsB * kRowsB * 32) * sizeof(double) + 16 > 227 * 1024)
+        return false;
+    // ring depth: as deep as fits in ~56 KB (keeps 4 CTAs per SM resident), at least 2, at most 6
     int nst = 2;
-    while (nst < kMaxStages && smem_of(nst + 1) <= 56 * 1024) ++nst;
+    while (nst < 6 && smem_of(nst + 1) <= 56 * 1024) ++nst;
     pl->CPT = cpt_t;
     pl->threads = threads;
     pl->stages = nst;
+    pl->stage_pack = stage_pack;
     pl->smem = smem_of(nst);
     return true;
 }
@@ -521,23 +562,30 @@ static int opt_in_smem(K kern, size_t smem, bool* configured) {
     return 0;
 }
 
+template <int CPT, bool STAGE_PACK>
+static int launch_sigma_a(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t st) {
+    auto kern = sigma_a_kernel<CPT, STAGE_PACK>;
+    static bool cfg_a[64] = {false};
+    if (opt_in_smem(kern, pl.smem, cfg_a)) return -2;
+    kern<<<args.op.plan.n_chunks, pl.threads + 32, pl.smem, st>>>(args, pl.stages);
+    return check_launch("sigma_a_kernel");
+}
+
 template <int CPT>
 static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t st) {
     const sqd_operator& op = args.op;
     // kernel B
     static bool cfg_b[64] = {false};
-    const size_t smem_b = (size_t)kRowsB * (op.ldc + op.ldg) * sizeof(double) + 16;
+    const size_t smem_b =
+        (size_t)(kRowsB * (op.ldc + op.ldg) + kWarpsB * kRowsB * 32) * sizeof(double) + 16;
     if (opt_in_smem(sigma_b_kernel, smem_b, cfg_b)) return -2;
     const int n_pos_slices = (op.ldc + 31) / 32;  // slices incl. the pad positions
-    dim3 grid_b((op.a.n + kRowsB - 1) / kRowsB, (n_pos_slices + kWarpsB - 1) / kWarpsB);
+    dim3 grid_b((op.a.n + kRowsB - 1) / kRowsB, n_pos_slices);
     sigma_b_kernel<<<grid_b, kWarpsB * 32, smem_b, st>>>(args);
     if (check_launch("sigma_b_kernel")) return -2;
     // kernel A
-    auto kern = sigma_a_kernel<CPT>;
-    static bool cfg_a[64] = {false};
-    if (opt_in_smem(kern, pl.smem, cfg_a)) return -2;
-    kern<<<op.plan.n_chunks, pl.threads + 32, pl.smem, st>>>(args, pl.stages);
-    if (check_launch("sigma_a_kernel")) return -2;
+    if (pl.stage_pack ? launch_sigma_a<CPT, true>(args, pl, st) : launch_sigma_a<CPT, false>(args, pl, st))
+        return -2;
     if (op.plan.n_split > 0) {
         sigma_combine_kernel<<<op.plan.n_split, 256, 0, st>>>(args.done, op.plan, op.ldc, args.sigma);
         return check_launch("sigma_combine_kernel");
@@ -594,8 +642,8 @@ int sqd_sigma_plan_build(const sqd_spin_table* a, const sqd_spin_table* b, int c
                          int* d_split_n, int* d_long_idx, int* d_long_cols, int* d_counts,
                          int* h_counts, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    SQD_REQUIRE(cost_per_chunk >= 4 && cost_per_chunk % 4 == 0,
-                "sqd_sigma_plan_build: cost_per_chunk must be a positive multiple of 4");
+    SQD_REQUIRE(cost_per_chunk >= kSingleCost && cost_per_chunk % kSingleCost == 0,
+                "sqd_sigma_plan_build: cost_per_chunk must be a positive multiple of %d", kSingleCost);
     SQD_REQUIRE(max_chunks >= a->n, "sqd_sigma_plan_build: max_chunks must be at least the number of rows");
     sigma_plan_kernel<<<1, 32, 0, st>>>(*a, *b, cost_per_chunk, long_threshold, max_chunks, d_chunk_row,
                                         d_chunk_beg, d_chunk_end, d_chunk_slot, d_split_row,

@@ -31,9 +31,9 @@ _PYSCF_DEFAULTS = dict(max_cycle=100, max_space=12, lindep=1e-14, level_shift=1e
 # 1e-8 Ha parity bar against any converged solver the default here is tighter.  Passing ``tol=`` gives
 # pyscf's rule (|dE| < tol and |r| < sqrt(tol)) literally.
 _DEFAULT_TOL = 1e-12
-# sigma-build work plan: cost units per CTA (single excitation = 4, double = 1) and the length above
+# sigma-build work plan: cost units per CTA (single excitation = 16, double = 1) and the length above
 # which a beta string's single-excitation list is reduced by a whole warp
-_SIGMA_COST_PER_CHUNK = int(__import__("os").environ.get("SQD_SIGMA_CHUNK_COST", "128"))
+_SIGMA_COST_PER_CHUNK = int(__import__("os").environ.get("SQD_SIGMA_CHUNK_COST", "256"))
 _SIGMA_LONG_THRESHOLD = int(__import__("os").environ.get("SQD_SIGMA_LONG_THRESHOLD", "32"))
 _FIX_SPIN_DEFAULT_SHIFT = 0.2  # pyscf.fci.addons.fix_spin_ default, used by solve_sci (fermion.py:715)
 
@@ -261,7 +261,9 @@ class _SpinTableDev:
         _lib.check(self._lib.sqd_sell_build(C.byref(t), mode, int(_SIGMA_LONG_THRESHOLD), cap,
                                             _lib.ptr(perm), _lib.ptr(ln), _lib.ptr(sptr), _lib.ptr(pack),
                                             _lib.ptr(val), _lib.stream_ptr(torch)), "sqd_sell_build")
-        st = _lib.Sell(ns, _lib.ptr(perm), _lib.ptr(ln), _lib.ptr(sptr), _lib.ptr(pack), _lib.ptr(val))
+        n_entries = int(sptr[-1].item())
+        st = _lib.Sell(ns, n_entries, _lib.ptr(perm), _lib.ptr(ln), _lib.ptr(sptr), _lib.ptr(pack),
+                       _lib.ptr(val))
         self._sell[mode] = (st, (perm, ln, sptr, pack, val))
         return st
 
@@ -349,7 +351,7 @@ class _Subspace:
         torch, lib = self.torch, self.lib
         dev = self.device
         cost = int(_SIGMA_COST_PER_CHUNK)
-        max_chunks = self.na + (4 * max(self.ta.nnz, 1)) // cost + 1
+        max_chunks = 2 * self.na + (16 * max(self.ta.nnz, 1)) // cost + 1
         i32 = dict(dtype=torch.int32, device=dev)
         bufs = [torch.empty(max_chunks, **i32) for _ in range(4)]
         split = [torch.empty(self.na, **i32) for _ in range(3)]
