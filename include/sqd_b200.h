@@ -28,7 +28,7 @@ extern "C" {
 
 #define SQD_B200_VERSION 100
 #define SQD_MAX_SPACE 32 /* largest Davidson subspace the device-side Rayleigh-Ritz supports */
-#define SQD_MAX_LONG_COLUMNS 64 /* beta strings whose single-excitation list is reduced by a whole warp */
+#define SQD_MAX_LONG_COLUMNS 64 /* capacity of the long-column list (the kernels use the 4 longest) */
 
 int sqd_version(void);
 const char* sqd_last_error(void);
@@ -160,7 +160,7 @@ typedef struct {
  * long_threshold of them get length 0 (they are reduced cooperatively, see sqd_sigma_plan_build);
  * mode 1: all entries with values.  capacity (entries of d_pack / d_val) >= nnz + 32*n.
  * d_perm, d_len: int[n]; d_slice_ptr: int[ceil(n/32)+1]. */
-int sqd_sell_build(const sqd_spin_table* t, int mode, int long_threshold, int capacity, int* d_perm,
+int sqd_sell_build(const sqd_spin_table* t, int mode, const int* d_long_idx, int capacity, int* d_perm,
                    int* d_len, int* d_slice_ptr, uint32_t* d_pack, double* d_val, void* stream);
 
 /* Build the work plan.  cost_per_chunk: multiple of 16 (a single excitation costs 16, a double 1);
@@ -180,6 +180,12 @@ int64_t sqd_sigma_smem_bytes(const sqd_operator* op);
 
 /* d_sigma[a*ldc+b] = sum_{a'b'} <ab|O|a'b'> d_c[a'*ldc+b'];  pads of d_sigma are written as 0. */
 int sqd_sigma(const sqd_operator* op, const double* d_c, double* d_sigma, void* stream);
+
+/* Diagnostics: one sigma build that also records, per CTA of the alpha kernel, 8 values in
+ * d_prof (int64[8 * plan.n_chunks]): clock64() at start / after table staging / after the doubles /
+ * after the singles / at the end, then #singles, #doubles and the SM id. */
+int sqd_sigma_profile(const sqd_operator* op, const double* d_c, double* d_sigma, long long* d_prof,
+                      void* stream);
 
 typedef struct {
     int max_space;       /* <= SQD_MAX_SPACE; pyscf default 12 */

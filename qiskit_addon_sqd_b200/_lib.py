@@ -127,7 +127,8 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "sqd_sigma_smem_bytes": (_i64, [C.POINTER(Operator)]),
     "sqd_sigma": (_i, [C.POINTER(Operator), _vp, _vp, _vp]),
-    "sqd_sell_build": (_i, [C.POINTER(SpinTable), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sqd_sigma_profile": (_i, [C.POINTER(Operator), _vp, _vp, _vp, _vp]),
+    "sqd_sell_build": (_i, [C.POINTER(SpinTable), _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_sigma_plan_build": (
         _i,
         [C.POINTER(SpinTable), C.POINTER(SpinTable), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -25,6 +25,8 @@
 // Kernel A stages, per alpha single excitation, the row c[a',:] and the integral row g_ab[pq,:] in
 // shared memory with the bulk-copy engine (cp.async.bulk + mbarrier; SASS UBLKCP/SYNCS) through a ring
 // of stages filled by a dedicated producer warp.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/sqd_b200.h"
 
@@ -35,23 +37,28 @@ struct SigmaArgs {
     const double* c;
     double* sigma;
     const int* done;  // optional device flag: non-zero -> the launch is a no-op (Davidson finished)
+    long long* prof;  // optional diagnostics: 8 clock64() stamps per kernel-A CTA (sqd_sigma_profile)
 };
 
+// try_wait with a suspend-time hint: a warp whose barrier phase is not complete is parked by the hardware
+// (no issue slots consumed) until the phase completes or ~the hint elapses.  Busy-polling here is
+// poisonous: dozens of waiting warps would take the issue slots of the one warp everybody waits for.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_parity(uint64_t* bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(64);
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -60,7 +67,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 
 constexpr int kMaxStages = 8;
 constexpr int kUnroll = 4;
+constexpr int kUnrollC = 8;   // row loads in flight per thread in phase C
+constexpr int kTileC = 256;   // alpha doubles staged per tile in phase C
 constexpr int kMaxLong = SQD_MAX_LONG_COLUMNS;
+constexpr int kLongA = 4;   // long columns actually used (registers per thread in kernel A)
 constexpr int kRowsB = 4;      // rows of c per CTA in kernel B
 constexpr int kWarpsB = 4;     // warps per CTA in kernel B (they split one SELL slice)
 constexpr int kSingleCost = 16;  // plan cost of one alpha single excitation, in units of one double
@@ -116,11 +126,20 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
             }
         }
     }
+    // long columns: the (at most kLongA) beta strings with the longest single-excitation lists above the
+    // threshold; their links are spread over all threads of a CTA instead of living in one SELL lane
     int nlong = 0;
-    for (int b = 0; b < B.n; ++b) {
-        const bool is_long = B.n_single[b] > long_threshold && nlong < kMaxLong;
-        long_idx[b] = is_long ? nlong : -1;
-        if (is_long) long_cols[nlong++] = b;
+    for (int b = 0; b < B.n; ++b) long_idx[b] = -1;
+    for (int round = 0; round < kLongA; ++round) {
+        int best = -1, best_len = long_threshold;
+        for (int b = 0; b < B.n; ++b)
+            if (long_idx[b] < 0 && B.n_single[b] > best_len) {
+                best = b;
+                best_len = B.n_single[b];
+            }
+        if (best < 0) break;
+        long_idx[best] = nlong;
+        long_cols[nlong++] = best;
     }
     counts[0] = nc;
     counts[1] = nslots;
@@ -133,23 +152,21 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
 // SELL-32 builder (setup time).  mode 0: single excitations only, columns longer than long_threshold get
 // length 0 (they are handled cooperatively); mode 1: every entry (singles then doubles) with values.
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sell_len(const sqd_spin_table& T, int b, int mode, int long_threshold) {
-    if (mode == 0) {
-        const int ns = T.n_single[b];
-        return ns > long_threshold ? 0 : ns;
-    }
+__device__ __forceinline__ int sell_len(const sqd_spin_table& T, int b, int mode,
+                                        const int* __restrict__ long_idx) {
+    if (mode == 0) return (long_idx != nullptr && long_idx[b] >= 0) ? 0 : T.n_single[b];
     return T.row_ptr[b + 1] - T.row_ptr[b];
 }
 
 // rank of every column in (length descending, index ascending) order; perm[rank] = column
-__global__ void sell_rank_kernel(const sqd_spin_table T, int mode, int long_threshold,
+__global__ void sell_rank_kernel(const sqd_spin_table T, int mode, const int* __restrict__ long_idx,
                                  int* __restrict__ perm, int* __restrict__ len_sorted) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= T.n) return;
-    const int lb = sell_len(T, b, mode, long_threshold);
+    const int lb = sell_len(T, b, mode, long_idx);
     int rank = 0;
     for (int o = 0; o < T.n; ++o) {
-        const int lo = sell_len(T, o, mode, long_threshold);
+        const int lo = sell_len(T, o, mode, long_idx);
         rank += (lo > lb) || (lo == lb && o < b);
     }
     perm[rank] = b;
@@ -208,8 +225,8 @@ sigma_b_kernel(const SigmaArgs P) {
     const int pos = slice * 32 + lane;
 
     double* Cs = reinterpret_cast<double*>(smem_raw);          // [kRowsB][ldc]
-    double* Ws = Cs + (size_t)kRowsB * ldc;                     // [kRowsB][ldg]
-    double* red = Ws + (size_t)kRowsB * ldg;                    // [kWarpsB][kRowsB][32]
+    double* red = Cs + (size_t)kRowsB * ldc;                    // [kWarpsB][kRowsB][32]
+    const double* Wg = use_wa ? op.Wa + (size_t)a0 * ldg : nullptr;  // Wa rows: read-only path (L1/L2)
     uint64_t* bar = reinterpret_cast<uint64_t*>(red + kWarpsB * kRowsB * 32);
     if (slice >= L.n_slices) {  // only pad positions live here
         if (warp == 0 && pos >= nb && pos < ldc)
@@ -222,14 +239,9 @@ sigma_b_kernel(const SigmaArgs P) {
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t bytes = (uint32_t)(nrows * (ldc + (use_wa ? ldg : 0)) * sizeof(double));
-        mbar_expect_tx(bar, bytes);
-        for (int r = 0; r < nrows; ++r) {
+        mbar_expect_tx(bar, (uint32_t)(nrows * ldc * sizeof(double)));
+        for (int r = 0; r < nrows; ++r)
             bulk_g2s(Cs + (size_t)r * ldc, P.c + (size_t)(a0 + r) * ldc, (uint32_t)(ldc * sizeof(double)), bar);
-            if (use_wa)
-                bulk_g2s(Ws + (size_t)r * ldg, op.Wa + (size_t)(a0 + r) * ldg,
-                         (uint32_t)(ldg * sizeof(double)), bar);
-        }
     }
     double acc[kRowsB];
 #pragma unroll
@@ -255,19 +267,20 @@ sigma_b_kernel(const SigmaArgs P) {
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                if (k0 + u < mylen) {
-                    const uint32_t bp = pk[u] & 0x7ffffu, rs = (pk[u] >> 19) & 0xfffu;
-                    const bool neg = pk[u] >> 31;
+                // no branches: entries past this lane's list (padding: pack = 0, val = 0) or past this
+                // warp's range are masked by a select
+                const bool valid = (k0 + u < k_end) && (k0 + u < mylen);
+                const uint32_t bp = pk[u] & 0x7ffffu, rs = (pk[u] >> 19) & 0xfffu;
+                const bool neg = pk[u] >> 31;
 #pragma unroll
-                    for (int r = 0; r < kRowsB; ++r) {
-                        if (r < nrows) {
-                            double coef = v[u];
-                            if (use_wa && rs != 0u) {
-                                const double w = Ws[r * ldg + rs];
-                                coef += neg ? -w : w;
-                            }
-                            acc[r] = fma(coef, Cs[r * ldc + bp], acc[r]);
+                for (int r = 0; r < kRowsB; ++r) {
+                    if (r < nrows) {
+                        double coef = v[u];
+                        if (use_wa) {
+                            const double w = __ldg(Wg + (size_t)r * ldg + rs);  // rs = 0 for doubles
+                            coef += (rs != 0u) ? (neg ? -w : w) : 0.0;
                         }
+                        acc[r] = fma(valid ? coef : 0.0, Cs[r * ldc + bp], acc[r]);
                     }
                 }
             }
@@ -341,11 +354,13 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
     double* xbuf = reinterpret_cast<double*>(smem_raw);  // [ldc] exchange sorted -> natural mapping
     double* stage = xbuf + ldc;                           // NST x ([ldc] row c[a',:] + [ldg] row g_ab[pq,:])
     const int stage_len = ldc + ldg;
-    double* acc_long = stage + (size_t)NST * stage_len;   // [kMaxLong]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(acc_long + kMaxLong);
+    double* acc_long = stage + (size_t)NST * stage_len;   // [kLongA][32 warps] (kMaxLong >= 4*32/... sized)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(acc_long + kLongA * 32);
     uint64_t* full = bars;                  // [NST]
     uint64_t* empty = bars + kMaxStages;    // [NST]
-    uint32_t* pk_s = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages);  // [n_entries] when staged
+    double* dval_s = reinterpret_cast<double*>(bars + 2 * kMaxStages);    // [kTileC]
+    uint32_t* dcol_s = reinterpret_cast<uint32_t*>(dval_s + kTileC);      // [kTileC]
+    uint32_t* pk_s = dcol_s + kTileC;                                     // [n_entries] when staged
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -354,7 +369,6 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
         }
         mbar_fence_init();
     }
-    if (tid < kMaxLong) acc_long[tid] = 0.0;
     __syncthreads();
 
     // =========================== producer warp ===========================
@@ -376,13 +390,28 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
     }
 
     // =========================== consumer warps ==========================
+#define SQD_STAMP(k) \
+    if (P.prof != nullptr && tid == 0) P.prof[(size_t)blockIdx.x * 8 + (k)] = clock64();
+    SQD_STAMP(0)
     // the beta SELL table is re-read for every alpha excitation of the chunk: keep it in shared memory
     // when it is small enough (decided on the host, STAGE_PACK)
-    const uint32_t* pk_src = L.pack;
     if (STAGE_PACK && n_items > 0) {
         for (int i = tid; i < L.n_entries; i += ncons) pk_s[i] = __ldg(L.pack + i);
-        pk_src = pk_s;
         asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+    }
+    // long columns: this thread's share of their links lives in registers for the whole chunk
+    uint32_t lpk[kLongA][CPT];
+    double lacc[kLongA];
+#pragma unroll
+    for (int li = 0; li < kLongA; ++li) {
+        lacc[li] = 0.0;
+        const int lb = li < n_long ? pl.long_cols[li] : 0;
+        const int lbeg = op.b.row_ptr[lb], llen = li < n_long ? op.b.n_single[lb] : 0;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+            const int idx = tid + c * ncons;
+            lpk[li][c] = idx < llen ? __ldg(op.b.pack + lbeg + idx) : 0xffffffffu;  // rs=0xfff: never real
+        }
     }
     double acc_nat[CPT], acc_srt[CPT];
     int s_base[CPT], s_len[CPT], my_len[CPT];
@@ -398,33 +427,42 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
         my_len[c] = pos < nb ? L.len[pos] : 0;
     }
 
-    // ---- phase C: alpha doubles, coalesced row streaming, kUnroll loads in flight -------------------
+    SQD_STAMP(1)
+    // ---- phase C: alpha doubles.  The (partner, value) list of the chunk is first copied to shared
+    // memory with coalesced loads, so that the row reads c[a', b] -- the only long-latency accesses left
+    // -- are independent and kUnrollC of them are in flight per thread.
     if (ham) {
-        for (int e0 = db_beg; e0 < db_end; e0 += kUnroll) {
-            double v[kUnroll];
-            const double* crow[kUnroll];
-#pragma unroll
-            for (int u = 0; u < kUnroll; ++u) {
-                const int e = min(e0 + u, db_end - 1);
-                v[u] = (e0 + u < db_end) ? __ldg(op.a.val + e) : 0.0;
-                crow[u] = P.c + (size_t)__ldg(op.a.col + e) * ldc;
+        for (int t0 = db_beg; t0 < db_end; t0 += kTileC) {
+            const int tn = min(kTileC, db_end - t0);
+            asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+            for (int i = tid; i < tn; i += ncons) {
+                dcol_s[i] = __ldg(op.a.col + t0 + i);
+                dval_s[i] = __ldg(op.a.val + t0 + i);
             }
+            asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+            for (int e0 = 0; e0 < tn; e0 += kUnrollC) {
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const int b = tid + c * ncons;
-                if (b < nb) {
-                    double x[kUnroll];
+                for (int c = 0; c < CPT; ++c) {
+                    const int b = tid + c * ncons;
+                    if (b < nb) {
+                        double x[kUnrollC];
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) x[u] = __ldg(crow[u] + b);
+                        for (int u = 0; u < kUnrollC; ++u)
+                            x[u] = __ldg(P.c + (size_t)dcol_s[min(e0 + u, tn - 1)] * ldc + b);
 #pragma unroll
-                    for (int u = 0; u < kUnroll; ++u) acc_nat[c] = fma(v[u], x[u], acc_nat[c]);
+                        for (int u = 0; u < kUnrollC; ++u)
+                            if (e0 + u < tn) acc_nat[c] = fma(dval_s[e0 + u], x[u], acc_nat[c]);
+                    }
                 }
             }
         }
     }
 
+    SQD_STAMP(2)
     // ---- phase D: alpha singles through the staged ring --------------------------------------------
+    long long t_wait = 0, t_pre = 0, t_loop = 0;
     for (int item = 0; item < n_items; ++item) {
+        const long long c0 = P.prof ? clock64() : 0;
         const int s = item % NST;
         const uint32_t m = __ldg(op.a.meta + it_beg + item);
         const uint32_t pq = m & 0x7fffffffu;
@@ -439,22 +477,30 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
             const int b = tid + c * ncons;
             wb[c] = (op.Wb && b < nb) ? __ldg(op.Wb + (size_t)pq * ldc + b) : 0.0;
         }
+        const long long c1 = P.prof ? clock64() : 0;
         mbar_wait_parity(&full[s], (uint32_t)((item / NST) & 1));
+        const long long c2 = P.prof ? clock64() : 0;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
-            // sorted mapping: SELL slice, warp-uniform trip count, coalesced loads
+            // sorted mapping: SELL slice, warp-uniform trip count, coalesced loads, no branches: padded
+            // entries gather element 0 and are masked by a select
             double sum = 0.0;
-            const uint32_t* src = pk_src + s_base[c] + lane;
-            for (int k0 = 0; k0 < s_len[c]; k0 += kUnroll) {
+            const int sl = s_len[c], ml = my_len[c];
+            for (int k0 = 0; k0 < sl; k0 += kUnroll) {
                 uint32_t pk[kUnroll];
-#pragma unroll
-                for (int u = 0; u < kUnroll; ++u) pk[u] = src[min(k0 + u, s_len[c] - 1) * 32];
+                double t[kUnroll];
 #pragma unroll
                 for (int u = 0; u < kUnroll; ++u) {
-                    if (k0 + u < my_len[c]) {
-                        const double t = gs[(pk[u] >> 19) & 0xfffu] * Cn[pk[u] & 0x7ffffu];
-                        sum += (pk[u] >> 31) ? -t : t;
-                    }
+                    const int k = min(k0 + u, sl - 1);
+                    pk[u] = STAGE_PACK ? pk_s[s_base[c] + lane + k * 32] : __ldg(L.pack + s_base[c] + lane + k * 32);
+                }
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u)
+                    t[u] = gs[(pk[u] >> 19) & 0xfffu] * Cn[pk[u] & 0x7ffffu];
+#pragma unroll
+                for (int u = 0; u < kUnroll; ++u) {
+                    const double tv = (pk[u] >> 31) ? -t[u] : t[u];
+                    sum += (k0 + u < ml) ? tv : 0.0;
                 }
             }
             acc_srt[c] = fma(sa, sum, acc_srt[c]);
@@ -462,27 +508,38 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
             const int b = tid + c * ncons;
             if (b < nb) acc_nat[c] = fma(fma(sa, wb[c], va), Cn[b], acc_nat[c]);
         }
-        for (int li = warp; li < n_long; li += nwarp_c) {
-            const int b = pl.long_cols[li];
-            const int beg = op.b.row_ptr[b], e1 = beg + op.b.n_single[b];
-            double part = 0.0;
-            for (int e = beg + lane; e < e1; e += 32) {
-                const uint32_t pk = __ldg(op.b.pack + e);
-                const double t = gs[(pk >> 19) & 0xfffu] * Cn[pk & 0x7ffffu];
-                part += (pk >> 31) ? -t : t;
+#pragma unroll
+        for (int li = 0; li < kLongA; ++li) {
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const uint32_t pk = lpk[li][c];
+                const bool ok = pk != 0xffffffffu;
+                const uint32_t pv = ok ? pk : 0u;
+                const double t = sa * gs[(pv >> 19) & 0xfffu] * Cn[pv & 0x7ffffu];
+                lacc[li] += ok ? ((pv >> 31) ? -t : t) : 0.0;
             }
-            part = warp_sum(part);
-            if (lane == 0) acc_long[li] = fma(sa, part, acc_long[li]);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the stage
+        if (P.prof) {
+            const long long c3 = clock64();
+            t_pre += c1 - c0;
+            t_wait += c2 - c1;
+            t_loop += c3 - c2;
+        }
     }
 
+    SQD_STAMP(3)
     // ---- exchange sorted -> natural, then one coalesced update -------------------------------------
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
         const int pos = tid + c * ncons;
         if (pos < nb) xbuf[L.perm[pos]] = acc_srt[c];
+    }
+#pragma unroll
+    for (int li = 0; li < kLongA; ++li) {
+        const double v = warp_sum(lacc[li]);  // fixed tree inside the warp, fixed warp order below
+        if (lane == 0) acc_long[li * 32 + warp] = v;
     }
     asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
 #pragma unroll
@@ -490,7 +547,9 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
         const int b = tid + c * ncons;
         if (b < nb) {
             const int li = pl.long_idx[b];
-            const double v = acc_nat[c] + xbuf[b] + (li >= 0 ? acc_long[li] : 0.0);
+            double v = acc_nat[c] + xbuf[b];
+            if (li >= 0)
+                for (int w = 0; w < nwarp_c; ++w) v += acc_long[li * 32 + w];
             if (slot < 0)
                 P.sigma[(size_t)a * ldc + b] += v;  // kernel B wrote the element earlier in the stream
             else
@@ -499,6 +558,18 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
             pl.part[(size_t)slot * ldc + b] = 0.0;
         }
     }
+    SQD_STAMP(4)
+    if (P.prof != nullptr && tid == 0) {
+        P.prof[(size_t)blockIdx.x * 8 + 5] = n_items;
+        P.prof[(size_t)blockIdx.x * 8 + 6] = db_end - db_beg;
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        P.prof[(size_t)blockIdx.x * 8 + 7] = smid;
+        P.prof[(size_t)blockIdx.x * 8 + 0] = t_pre;   // diagnostics layout: see tests/gpu_sigma_phases.py
+        P.prof[(size_t)blockIdx.x * 8 + 1] = t_wait;
+        P.prof[(size_t)blockIdx.x * 8 + 4] = t_loop;
+    }
+#undef SQD_STAMP
 }
 
 struct SigmaPlan {
@@ -507,7 +578,16 @@ struct SigmaPlan {
     size_t smem;
 };
 
+// tuning knobs (environment, read once): SQD_SIGMA_STAGES = ring depth (0 = auto),
+// SQD_SIGMA_PACK_BYTES = largest beta SELL table that is staged in shared memory
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
 static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
+    static const int knob_stages = env_int("SQD_SIGMA_STAGES", 0);
+    static const int knob_pack = env_int("SQD_SIGMA_PACK_BYTES", 24 * 1024);
     const int ldc = op->ldc;
     int threads, cpt;
     // `threads` counts the consumer threads; one more warp (the producer) is added at launch
@@ -528,18 +608,19 @@ static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
     if (cpt_t == 0) return false;
     // beta SELL table staged in shared memory when it costs at most 24 KB
     const size_t pack_bytes = ((size_t)op->bd.n_entries * 4 + 15) / 16 * 16;
-    const bool stage_pack = op->bd.n_entries > 0 && pack_bytes <= 24 * 1024;
+    const bool stage_pack = op->bd.n_entries > 0 && pack_bytes <= (size_t)knob_pack;
     auto smem_of = [&](int nst) {
-        return (size_t)(ldc + nst * (ldc + op->ldg) + kMaxLong) * sizeof(double) +
-               (2 * kMaxStages) * sizeof(uint64_t) + (stage_pack ? pack_bytes : 0);
+        return (size_t)(ldc + nst * (ldc + op->ldg) + kLongA * 32) * sizeof(double) +
+               (2 * kMaxStages) * sizeof(uint64_t) + kTileC * 12 + (stage_pack ? pack_bytes : 0);
     };
     if (smem_of(2) > 227 * 1024) return false;
-    // kernel B: kRowsB rows of c and of Wa + the cross-warp reduction buffer
-    if ((size_t)(kRowsB * (ldc + op->ldg) + kWarpsB * kRowsB * 32) * sizeof(double) + 16 > 227 * 1024)
-        return false;
+    // kernel B: kRowsB rows of c + the cross-warp reduction buffer
+    if ((size_t)(kRowsB * ldc + kWarpsB * kRowsB * 32) * sizeof(double) + 16 > 227 * 1024) return false;
     // ring depth: as deep as fits in ~56 KB (keeps 4 CTAs per SM resident), at least 2, at most 6
     int nst = 2;
     while (nst < 6 && smem_of(nst + 1) <= 56 * 1024) ++nst;
+    if (knob_stages >= 2 && knob_stages <= kMaxStages && smem_of(knob_stages) <= 227 * 1024)
+        nst = knob_stages;
     pl->CPT = cpt_t;
     pl->threads = threads;
     pl->stages = nst;
@@ -576,8 +657,7 @@ static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t
     const sqd_operator& op = args.op;
     // kernel B
     static bool cfg_b[64] = {false};
-    const size_t smem_b =
-        (size_t)(kRowsB * (op.ldc + op.ldg) + kWarpsB * kRowsB * 32) * sizeof(double) + 16;
+    const size_t smem_b = (size_t)(kRowsB * op.ldc + kWarpsB * kRowsB * 32) * sizeof(double) + 16;
     if (opt_in_smem(sigma_b_kernel, smem_b, cfg_b)) return -2;
     const int n_pos_slices = (op.ldc + 31) / 32;  // slices incl. the pad positions
     dim3 grid_b((op.a.n + kRowsB - 1) / kRowsB, n_pos_slices);
@@ -592,6 +672,8 @@ static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t
     }
     return 0;
 }
+
+static thread_local long long* g_prof = nullptr;
 
 int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sigma,
                         const int* d_done, cudaStream_t st) {
@@ -608,7 +690,7 @@ int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sig
                 "sqd_sigma: nb=%d (ldc=%d) with norb=%d does not fit the shared-memory row staging "
                 "(limit: 3*ldc + 2*ldg doubles <= 227 KB, ldc <= 11904)",
                 op->b.n, op->ldc, op->norb);
-    SigmaArgs args{*op, d_c, d_sigma, d_done};
+    SigmaArgs args{*op, d_c, d_sigma, d_done, g_prof};
     switch (pl.CPT) {
         case 1: return launch_sigma<1>(args, pl, st);
         case 2: return launch_sigma<2>(args, pl, st);
@@ -636,6 +718,17 @@ int sqd_sigma(const sqd_operator* op, const double* d_c, double* d_sigma, void* 
     return sigma_dispatch_flag(op, d_c, d_sigma, nullptr, (cudaStream_t)stream);
 }
 
+/* diagnostics: one sigma build with 8 clock64() stamps per kernel-A CTA written to d_prof
+ * (int64[8 * n_chunks]: start, after table staging, after phase C, after phase D, end, #singles,
+ * #doubles, SM id) */
+int sqd_sigma_profile(const sqd_operator* op, const double* d_c, double* d_sigma, long long* d_prof,
+                      void* stream) {
+    g_prof = d_prof;
+    const int rc = sigma_dispatch_flag(op, d_c, d_sigma, nullptr, (cudaStream_t)stream);
+    g_prof = nullptr;
+    return rc;
+}
+
 int sqd_sigma_plan_build(const sqd_spin_table* a, const sqd_spin_table* b, int cost_per_chunk,
                          int long_threshold, int max_chunks, int* d_chunk_row, int* d_chunk_beg,
                          int* d_chunk_end, int* d_chunk_slot, int* d_split_row, int* d_split_slot_beg,
@@ -654,14 +747,14 @@ int sqd_sigma_plan_build(const sqd_spin_table* a, const sqd_spin_table* b, int c
     return 0;
 }
 
-int sqd_sell_build(const sqd_spin_table* t, int mode, int long_threshold, int capacity, int* d_perm,
+int sqd_sell_build(const sqd_spin_table* t, int mode, const int* d_long_idx, int capacity, int* d_perm,
                    int* d_len, int* d_slice_ptr, uint32_t* d_pack, double* d_val, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     SQD_REQUIRE(mode == 0 || mode == 1, "sqd_sell_build: mode must be 0 or 1");
     SQD_REQUIRE(mode == 0 || d_val != nullptr, "sqd_sell_build: mode 1 needs the value array");
     const int n = t->n;
     SQD_REQUIRE(n > 0 && capacity >= 32 * n, "sqd_sell_build: capacity must be at least nnz + 32*n");
-    sell_rank_kernel<<<(n + 127) / 128, 128, 0, st>>>(*t, mode, long_threshold, d_perm, d_len);
+    sell_rank_kernel<<<(n + 127) / 128, 128, 0, st>>>(*t, mode, d_long_idx, d_perm, d_len);
     sell_slice_kernel<<<1, 32, 0, st>>>(n, d_len, d_slice_ptr);
     const int ns = (n + 31) / 32;
     sell_fill_kernel<<<(ns * 32 + 127) / 128, 128, 0, st>>>(*t, mode, d_perm, d_len, d_slice_ptr, d_pack,

@@ -243,7 +243,7 @@ class _SpinTableDev:
                                            _lib.ptr(self.diag), st),
                    "sqd_excitation_fill")
 
-    def sell(self, mode: int) -> _lib.Sell:
+    def sell(self, mode: int, long_idx=None) -> _lib.Sell:
         """SELL-32 copy of the table (mode 0: singles only, mode 1: all entries + values); cached."""
         if mode in self._sell:
             return self._sell[mode][0]
@@ -258,7 +258,7 @@ class _SpinTableDev:
         pack = torch.empty(cap, dtype=torch.int32, device=dev)
         val = torch.empty(cap, dtype=torch.float64, device=dev) if mode == 1 else None
         t = self.struct()
-        _lib.check(self._lib.sqd_sell_build(C.byref(t), mode, int(_SIGMA_LONG_THRESHOLD), cap,
+        _lib.check(self._lib.sqd_sell_build(C.byref(t), mode, _lib.ptr(long_idx), cap,
                                             _lib.ptr(perm), _lib.ptr(ln), _lib.ptr(sptr), _lib.ptr(pack),
                                             _lib.ptr(val), _lib.stream_ptr(torch)), "sqd_sell_build")
         n_entries = int(sptr[-1].item())
@@ -303,7 +303,7 @@ class _OperatorDev:
         self.struct = _lib.Operator(sub.ta.struct(), sub.tb.struct(), norb, ldc, ldg,
                                     _lib.ptr(self.diag), _lib.ptr(self.gab), _lib.ptr(self.Wa),
                                     _lib.ptr(self.Wb), 1 if same_spin else 0, sub.sigma_plan(),
-                                    sub.tb.sell(0), sub.tb.sell(1))
+                                    sub.tb.sell(0, sub._plan_keep[2]), sub.tb.sell(1))
         if lib.sqd_sigma_smem_bytes(C.byref(self.struct)) < 0:
             raise ValueError(
                 f"subspace shape (na={na}, nb={nb}, norb={norb}) exceeds the shared-memory row "
