@@ -196,6 +196,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     from concurrent.futures import ThreadPoolExecutor
 
     from qiskit_addon_sqd_b200 import _lib, fermion
+    from qiskit_addon_sqd_b200._dispatch import max_over_ranks
 
     lib = _lib.load()
     dev = torch.device("cuda", local_rank)
@@ -252,10 +253,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         # the host drives K streams from K threads; the device-event span and the wall clock agree to
         # within launch latency -- report the larger so nothing is hidden
         ms = max(ms, wall * 1e3)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), out
+        return max_over_ranks(ms, dev), out
 
     # ---- warm-up (both arms) ----
     for _ in range(args.warmup):
