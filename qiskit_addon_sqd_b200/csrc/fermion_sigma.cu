@@ -5,8 +5,8 @@
 // (N-2)-electron intermediates and dense dgemms, O(n_det * npair^2).  The B200 design applies the
 // projected operator directly from the in-set excitation tables, O(n_det * links):
 //
-//   sigma[a,b] = diag[a,b] c[a,b]
-//              + sum_{b' in T_b(b)}  ( Hb[b,b'] + [single] sgn_b Wa[a, rs] ) c[a, b']      (kernel B)
+//   sigma[a,b] = diag[a,b] c[a,b] + sum_{b' in T_b(b)} Hb[b,b'] c[a, b']                    (kernel B)
+//              + sum_{b' in S_b(b)} sgn_b Wa[a, rs] c[a, b']                                 (kernel A, self item)
 //              + sum_{a' in D_a(a)}    Ha[a,a'] c[a', b]                                     (kernel A, phase C)
 //              + sum_{a' in S_a(a)}  ( Ha[a,a'] + sgn_a Wb[pq, b] ) c[a', b]                 (kernel A, phase D)
 //              + sum_{a' in S_a(a)} sgn_a sum_{b' in S_b(b)} sgn_b g_ab[pq, rs] c[a', b']    (kernel A, phase D)
@@ -70,6 +70,7 @@ constexpr int kUnroll = 4;
 constexpr int kUnrollC = 8;   // row loads in flight per thread in phase C
 constexpr int kTileC = 256;   // alpha doubles staged per tile in phase C
 constexpr int kMaxLong = SQD_MAX_LONG_COLUMNS;
+constexpr uint32_t kPadMarker = 0x7ffffu;  // SELL mode-0 padding entry
 constexpr int kLongA = 4;   // long columns actually used (registers per thread in kernel A)
 constexpr int kRowsB = 4;      // rows of c per CTA in kernel B
 constexpr int kWarpsB = 4;     // warps per CTA in kernel B (they split one SELL slice)
@@ -180,7 +181,9 @@ __global__ void sell_slice_kernel(int n, const int* __restrict__ len_sorted, int
     int off = 0;
     for (int s = 0; s < ns; ++s) {
         slice_ptr[s] = off;
-        off += 32 * len_sorted[32 * s];  // sorted descending: the first lane of a slice is its longest
+        // sorted descending: the first lane of a slice is its longest; lengths are padded to a multiple
+        // of kUnroll so the unrolled gather loops need no tail handling
+        off += 32 * ((len_sorted[32 * s] + kUnroll - 1) / kUnroll * kUnroll);
     }
     slice_ptr[ns] = off;
 }
@@ -192,22 +195,23 @@ __global__ void sell_fill_kernel(const sqd_spin_table T, int mode, const int* __
     const int s = pos >> 5, lane = pos & 31;
     const int ns = (T.n + 31) / 32;
     if (s >= ns) return;
-    const int slen = len_sorted[32 * s];
+    const int base = slice_ptr[s];
+    const int slen = (slice_ptr[s + 1] - base) >> 5;
     const int mylen = pos < T.n ? len_sorted[pos] : 0;
     const int src = pos < T.n ? T.row_ptr[perm[pos]] : 0;
-    const int base = slice_ptr[s];
+    // padding: mode 0 -> marker (partner field all ones, never a valid index); mode 1 -> partner 0, value 0
+    const uint32_t pad = mode == 0 ? kPadMarker : 0u;
     for (int k = 0; k < slen; ++k) {
         const bool ok = k < mylen;
-        pack[base + k * 32 + lane] = ok ? T.pack[src + k] : 0u;
+        pack[base + k * 32 + lane] = ok ? T.pack[src + k] : pad;
         if (mode == 1) val[base + k * 32 + lane] = ok ? T.val[src + k] : 0.0;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Kernel B:  sigma[a,b] = diag[a,b] c[a,b] + sum_{b'} (Hb[b,b'] + [single] sgn Wa[a,rs]) c[a,b']
+// Kernel B:  sigma[a,b] = diag[a,b] c[a,b] + sum_{b'} Hb[b,b'] c[a,b']
 // CTA = kRowsB rows x ONE SELL slice (32 columns); its kWarpsB warps split the slice's entry range and
-// their partial sums meet in shared memory in warp order.  The rows of c and of Wa are staged with bulk
-// copies.  Writes every element of sigma (pads = 0); kernel A then adds its part.
+// their partial sums meet in shared memory in warp order.  The rows of c are staged with bulk copies.  Writes every element of sigma (pads = 0); kernel A then adds its part.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kWarpsB * 32)
 sigma_b_kernel(const SigmaArgs P) {
@@ -215,18 +219,16 @@ sigma_b_kernel(const SigmaArgs P) {
     if (P.done != nullptr && *P.done != 0) return;
     const sqd_operator& op = P.op;
     const sqd_sell& L = op.bb;
-    const int na = op.a.n, nb = op.b.n, ldc = op.ldc, ldg = op.ldg;
+    const int na = op.a.n, nb = op.b.n, ldc = op.ldc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int a0 = blockIdx.x * kRowsB;
     const int nrows = min(kRowsB, na - a0);
     const bool ham = op.use_same_spin != 0;
-    const bool use_wa = op.Wa != nullptr;
     const int slice = blockIdx.y;
     const int pos = slice * 32 + lane;
 
     double* Cs = reinterpret_cast<double*>(smem_raw);          // [kRowsB][ldc]
     double* red = Cs + (size_t)kRowsB * ldc;                    // [kWarpsB][kRowsB][32]
-    const double* Wg = use_wa ? op.Wa + (size_t)a0 * ldg : nullptr;  // Wa rows: read-only path (L1/L2)
     uint64_t* bar = reinterpret_cast<uint64_t*>(red + kWarpsB * kRowsB * 32);
     if (slice >= L.n_slices) {  // only pad positions live here
         if (warp == 0 && pos >= nb && pos < ldc)
@@ -247,42 +249,29 @@ sigma_b_kernel(const SigmaArgs P) {
 #pragma unroll
     for (int r = 0; r < kRowsB; ++r) acc[r] = 0.0;
     const int base = L.slice_ptr[slice];
-    const int slen = (L.slice_ptr[slice + 1] - base) >> 5;
-    const int mylen = pos < nb ? L.len[pos] : 0;
+    const int slen = (L.slice_ptr[slice + 1] - base) >> 5;  // multiple of kUnroll; padding has value 0
     // this warp's share of the entry range, a multiple of kUnroll long
     int per = (slen + kWarpsB - 1) / kWarpsB;
     per = (per + kUnroll - 1) / kUnroll * kUnroll;
-    const int k_beg = warp * per, k_end = min(slen, k_beg + per);
-    // the table loads do not depend on the staged rows: issue the first batch before the wait
+    const int k_beg = min(slen, warp * per), k_end = min(slen, k_beg + per);
     mbar_wait_parity(bar, 0);
-    if (ham || use_wa) {
+    if (ham) {
+        const uint32_t* pp = L.pack + base + lane;
+        const double* vp = L.val + base + lane;
         for (int k0 = k_beg; k0 < k_end; k0 += kUnroll) {
             uint32_t pk[kUnroll];
             double v[kUnroll];
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                const int k = min(k0 + u, slen - 1);
-                pk[u] = __ldg(L.pack + base + k * 32 + lane);
-                v[u] = ham ? __ldg(L.val + base + k * 32 + lane) : 0.0;
+                pk[u] = __ldg(pp + (k0 + u) * 32);
+                v[u] = __ldg(vp + (k0 + u) * 32);
             }
 #pragma unroll
             for (int u = 0; u < kUnroll; ++u) {
-                // no branches: entries past this lane's list (padding: pack = 0, val = 0) or past this
-                // warp's range are masked by a select
-                const bool valid = (k0 + u < k_end) && (k0 + u < mylen);
-                const uint32_t bp = pk[u] & 0x7ffffu, rs = (pk[u] >> 19) & 0xfffu;
-                const bool neg = pk[u] >> 31;
+                const uint32_t bp = pk[u] & 0x7ffffu;
 #pragma unroll
-                for (int r = 0; r < kRowsB; ++r) {
-                    if (r < nrows) {
-                        double coef = v[u];
-                        if (use_wa) {
-                            const double w = __ldg(Wg + (size_t)r * ldg + rs);  // rs = 0 for doubles
-                            coef += (rs != 0u) ? (neg ? -w : w) : 0.0;
-                        }
-                        acc[r] = fma(valid ? coef : 0.0, Cs[r * ldc + bp], acc[r]);
-                    }
-                }
+                for (int r = 0; r < kRowsB; ++r)
+                    if (r < nrows) acc[r] = fma(v[u], Cs[r * ldc + bp], acc[r]);
             }
         }
     }
@@ -371,19 +360,37 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
     }
     __syncthreads();
 
+    // The first chunk of a row also owns the row's "self item": the term
+    //   sum_{b' in S_b(b)} sgn_b Wa[a, rs] c[a, b']
+    // has exactly the shape of an alpha single excitation with a' = a, sgn_a = +1 and the integral row
+    // replaced by Wa[a, :], so it rides the same ring and the same gather loop.
+    const bool self_item = (cbeg == op.a.row_ptr[a]) && (op.Wa != nullptr);
+    const int n_total = n_items + (self_item ? 1 : 0);
+
     // =========================== producer warp ===========================
     if (tid >= ncons) {
         if (tid == ncons) {
-            for (int item = 0; item < n_items; ++item) {
-                const int s = item % NST;
-                if (item >= NST) mbar_wait_parity(&empty[s], (uint32_t)(((item / NST) - 1) & 1));
-                const uint32_t ap = op.a.col[it_beg + item];
-                const uint32_t pq = op.a.meta[it_beg + item] & 0x7fffffffu;
+            int s = 0, round = 0;
+            for (int t = 0; t < n_total; ++t) {
+                if (round > 0) mbar_wait_parity(&empty[s], (uint32_t)((round - 1) & 1));
+                const double* crow;
+                const double* grow;
+                if (self_item && t == 0) {
+                    crow = P.c + (size_t)a * ldc;
+                    grow = op.Wa + (size_t)a * ldg;
+                } else {
+                    const int e = it_beg + t - (self_item ? 1 : 0);
+                    crow = P.c + (size_t)op.a.col[e] * ldc;
+                    grow = op.gab + (size_t)(op.a.meta[e] & 0x7fffffffu) * ldg;
+                }
                 double* dst = stage + (size_t)s * stage_len;
                 mbar_expect_tx(&full[s], (uint32_t)((ldc + ldg) * sizeof(double)));
-                bulk_g2s(dst, P.c + (size_t)ap * ldc, (uint32_t)(ldc * sizeof(double)), &full[s]);
-                bulk_g2s(dst + ldc, op.gab + (size_t)pq * ldg, (uint32_t)(ldg * sizeof(double)),
-                         &full[s]);
+                bulk_g2s(dst, crow, (uint32_t)(ldc * sizeof(double)), &full[s]);
+                bulk_g2s(dst + ldc, grow, (uint32_t)(ldg * sizeof(double)), &full[s]);
+                if (++s == NST) {
+                    s = 0;
+                    ++round;
+                }
             }
         }
         return;
@@ -393,10 +400,18 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
 #define SQD_STAMP(k) \
     if (P.prof != nullptr && tid == 0) P.prof[(size_t)blockIdx.x * 8 + (k)] = clock64();
     SQD_STAMP(0)
-    // the beta SELL table is re-read for every alpha excitation of the chunk: keep it in shared memory
-    // when it is small enough (decided on the host, STAGE_PACK)
-    if (STAGE_PACK && n_items > 0) {
-        for (int i = tid; i < L.n_entries; i += ncons) pk_s[i] = __ldg(L.pack + i);
+    // The beta SELL table is re-read for every alpha excitation of the chunk: when it is small enough
+    // (host decision, STAGE_PACK) it is kept in shared memory, pre-decoded into byte offsets:
+    //   bits 0-15 = 8*b' (into the staged c row), bits 16-30 = 8*rs (into the staged integral row),
+    //   bit 31 = sign; padding entries point at the zero pad of the integral row (rs = norb^2).
+    if (STAGE_PACK && n_total > 0) {
+        const uint32_t zero_slot = (uint32_t)(op.norb * op.norb * 8) << 16;
+        for (int i = tid; i < L.n_entries; i += ncons) {
+            const uint32_t pv = __ldg(L.pack + i);
+            const uint32_t col = pv & 0x7ffffu;
+            pk_s[i] = col == kPadMarker ? zero_slot
+                                        : ((col << 3) | (((pv >> 19) & 0xfffu) << 19) | (pv & 0x80000000u));
+        }
         asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
     }
     // long columns: this thread's share of their links lives in registers for the whole chunk
@@ -459,15 +474,21 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
     }
 
     SQD_STAMP(2)
-    // ---- phase D: alpha singles through the staged ring --------------------------------------------
+    // ---- phase D: alpha singles (and the self item) through the staged ring -------------------------
     long long t_wait = 0, t_pre = 0, t_loop = 0;
-    for (int item = 0; item < n_items; ++item) {
+    int s = 0, round = 0;
+    for (int t = 0; t < n_total; ++t) {
         const long long c0 = P.prof ? clock64() : 0;
-        const int s = item % NST;
-        const uint32_t m = __ldg(op.a.meta + it_beg + item);
-        const uint32_t pq = m & 0x7fffffffu;
-        const double sa = (m >> 31) ? -1.0 : 1.0;
-        const double va = ham ? __ldg(op.a.val + it_beg + item) : 0.0;
+        const bool is_self = self_item && t == 0;
+        const int e = it_beg + t - (self_item ? 1 : 0);
+        double sa = 1.0, va = 0.0;
+        uint32_t pq = 0;
+        if (!is_self) {
+            const uint32_t m = __ldg(op.a.meta + e);
+            pq = m & 0x7fffffffu;
+            sa = (m >> 31) ? -1.0 : 1.0;
+            va = ham ? __ldg(op.a.val + e) : 0.0;
+        }
         const double* Cn = stage + (size_t)s * stage_len;
         const double* gs = Cn + ldc;
         // global loads that do not depend on the stage are issued before the wait
@@ -475,52 +496,74 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
             const int b = tid + c * ncons;
-            wb[c] = (op.Wb && b < nb) ? __ldg(op.Wb + (size_t)pq * ldc + b) : 0.0;
+            wb[c] = (!is_self && op.Wb && b < nb) ? __ldg(op.Wb + (size_t)pq * ldc + b) : 0.0;
         }
         const long long c1 = P.prof ? clock64() : 0;
-        mbar_wait_parity(&full[s], (uint32_t)((item / NST) & 1));
+        mbar_wait_parity(&full[s], (uint32_t)(round & 1));
         const long long c2 = P.prof ? clock64() : 0;
 #pragma unroll
         for (int c = 0; c < CPT; ++c) {
-            // sorted mapping: SELL slice, warp-uniform trip count, coalesced loads, no branches: padded
-            // entries gather element 0 and are masked by a select
+            // sorted mapping: SELL slice, warp-uniform trip count (a multiple of kUnroll), no branches
             double sum = 0.0;
-            const int sl = s_len[c], ml = my_len[c];
-            for (int k0 = 0; k0 < sl; k0 += kUnroll) {
-                uint32_t pk[kUnroll];
-                double t[kUnroll];
+            const int sl = s_len[c];
+            if (STAGE_PACK) {
+                const char* CnB = reinterpret_cast<const char*>(Cn);
+                const char* gsB = reinterpret_cast<const char*>(gs);
+                const uint32_t* src = pk_s + s_base[c] + lane;
+                for (int k0 = 0; k0 < sl; k0 += kUnroll) {
+                    uint32_t pk[kUnroll];
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const int k = min(k0 + u, sl - 1);
-                    pk[u] = STAGE_PACK ? pk_s[s_base[c] + lane + k * 32] : __ldg(L.pack + s_base[c] + lane + k * 32);
+                    for (int u = 0; u < kUnroll; ++u) pk[u] = src[(k0 + u) * 32];
+#pragma unroll
+                    for (int u = 0; u < kUnroll; ++u) {
+                        const double cv = *reinterpret_cast<const double*>(CnB + (pk[u] & 0xffffu));
+                        const double gv = *reinterpret_cast<const double*>(gsB + ((pk[u] >> 16) & 0x7fffu));
+                        // the sign bit of the link goes straight into the sign bit of the integral
+                        const double gsg = __hiloint2double(__double2hiint(gv) ^ (int)(pk[u] & 0x80000000u),
+                                                            __double2loint(gv));
+                        sum = fma(gsg, cv, sum);
+                    }
                 }
+            } else {
+                const int ml = my_len[c];
+                const uint32_t* src = L.pack + s_base[c] + lane;
+                for (int k0 = 0; k0 < sl; k0 += kUnroll) {
+                    uint32_t pk[kUnroll];
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u)
-                    t[u] = gs[(pk[u] >> 19) & 0xfffu] * Cn[pk[u] & 0x7ffffu];
+                    for (int u = 0; u < kUnroll; ++u) pk[u] = __ldg(src + (k0 + u) * 32);
 #pragma unroll
-                for (int u = 0; u < kUnroll; ++u) {
-                    const double tv = (pk[u] >> 31) ? -t[u] : t[u];
-                    sum += (k0 + u < ml) ? tv : 0.0;
+                    for (int u = 0; u < kUnroll; ++u) {
+                        const bool ok = k0 + u < ml;
+                        const uint32_t pv = ok ? pk[u] : 0u;
+                        const double tv = gs[(pv >> 19) & 0xfffu] * Cn[pv & 0x7ffffu];
+                        sum += ok ? ((pv >> 31) ? -tv : tv) : 0.0;
+                    }
                 }
             }
             acc_srt[c] = fma(sa, sum, acc_srt[c]);
-            // natural mapping: the c[a', b] terms
+            // natural mapping: the c[a', b] terms (none for the self item: sa*wb + va == 0 there)
             const int b = tid + c * ncons;
             if (b < nb) acc_nat[c] = fma(fma(sa, wb[c], va), Cn[b], acc_nat[c]);
         }
 #pragma unroll
         for (int li = 0; li < kLongA; ++li) {
+            if (li < n_long) {
 #pragma unroll
-            for (int c = 0; c < CPT; ++c) {
-                const uint32_t pk = lpk[li][c];
-                const bool ok = pk != 0xffffffffu;
-                const uint32_t pv = ok ? pk : 0u;
-                const double t = sa * gs[(pv >> 19) & 0xfffu] * Cn[pv & 0x7ffffu];
-                lacc[li] += ok ? ((pv >> 31) ? -t : t) : 0.0;
+                for (int c = 0; c < CPT; ++c) {
+                    const uint32_t pk = lpk[li][c];
+                    const bool ok = pk != 0xffffffffu;
+                    const uint32_t pv = ok ? pk : 0u;
+                    const double tv = sa * gs[(pv >> 19) & 0xfffu] * Cn[pv & 0x7ffffu];
+                    lacc[li] += ok ? ((pv >> 31) ? -tv : tv) : 0.0;
+                }
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);  // this warp is done with the stage
+        if (++s == NST) {
+            s = 0;
+            ++round;
+        }
         if (P.prof) {
             const long long c3 = clock64();
             t_pre += c1 - c0;
@@ -560,7 +603,7 @@ __global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
     }
     SQD_STAMP(4)
     if (P.prof != nullptr && tid == 0) {
-        P.prof[(size_t)blockIdx.x * 8 + 5] = n_items;
+        P.prof[(size_t)blockIdx.x * 8 + 5] = n_total;
         P.prof[(size_t)blockIdx.x * 8 + 6] = db_end - db_beg;
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -608,7 +651,9 @@ static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
     if (cpt_t == 0) return false;
     // beta SELL table staged in shared memory when it costs at most 24 KB
     const size_t pack_bytes = ((size_t)op->bd.n_entries * 4 + 15) / 16 * 16;
-    const bool stage_pack = op->bd.n_entries > 0 && pack_bytes <= (size_t)knob_pack;
+    const int n2 = op->norb * op->norb;
+    const bool stage_pack = op->bd.n_entries > 0 && pack_bytes <= (size_t)knob_pack && ldc <= 8191 &&
+                            n2 <= 4095 && op->ldg >= n2 + 1;
     auto smem_of = [&](int nst) {
         return (size_t)(ldc + nst * (ldc + op->ldg) + kLongA * 32) * sizeof(double) +
                (2 * kMaxStages) * sizeof(uint64_t) + kTileC * 12 + (stage_pack ? pack_bytes : 0);

@@ -333,7 +333,7 @@ class _Subspace:
         self.strs_a_host, self.strs_b_host = ua, ub
         self.na, self.nb = len(ua), len(ub)
         self.ldc = (self.nb + 1) // 2 * 2
-        self.ldg = (norb * norb + 1) // 2 * 2
+        self.ldg = (norb * norb + 2) // 2 * 2  # even and > norb^2: the pad column is a zero slot for gathers
         self.n_alpha = int(np.bitwise_count(ua[0]))
         self.n_beta = int(np.bitwise_count(ub[0]))
         self.ta = _SpinTableDev(torch, lib, ua, ints, norb, self.device, strs_dev[0])
