@@ -219,11 +219,11 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
     __shared__ double g[kMaxS];
     __shared__ double cs_c[kMaxS / 2], cs_s[kMaxS / 2];
     __shared__ int pr_p[kMaxS / 2], pr_q[kMaxS / 2];
-    __shared__ double red_off[8], red_dia[8];
-    __shared__ int stop_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = m - 1;  // dimension of the stored decomposition (slot == d by construction)
+    (void)slot;
 
+    // all warps: new Gram column and the previous decomposition
     for (int row = warp; row < m; row += blockDim.x >> 5) {
         const double v = reduce_partials(partials, row, nblk);
         if (lane == 0) g[row] = v;
@@ -235,137 +235,119 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
         A[i][j] = (i == j && i < d) ? st->lam[i] : 0.0;
     }
     __syncthreads();
-    if (tid < d) {
+    if (warp != 0) return;
+    // ---- one warp from here on: every phase boundary is a __syncwarp, not a CTA barrier ----
+    for (int j = lane; j < d; j += 32) {
         double z = 0.0;
-        for (int i = 0; i < d; ++i) z = fma(Qo[i][tid], g[i], z);
-        A[tid][d] = z;
-        A[d][tid] = z;
+        for (int i = 0; i < d; ++i) z = fma(Qo[i][j], g[i], z);
+        A[j][d] = z;
+        A[d][j] = z;
     }
-    if (tid == 0) A[d][d] = g[d];
-    __syncthreads();
+    if (lane == 0) A[d][d] = g[d];
+    __syncwarp();
 
     const int np = (m + 1) / 2;   // pairs per round
     const int nplayers = 2 * np;  // even
     for (int sweep = 0; sweep < 30 && m > 1; ++sweep) {
-        // off-diagonal vs diagonal weight, fixed reduction order
         double off = 0.0, dia = 0.0;
-        for (int idx = tid; idx < m * m; idx += blockDim.x) {
+        for (int idx = lane; idx < m * m; idx += 32) {
             const int i = idx / m, j = idx % m;
             const double v = A[i][j] * A[i][j];
             if (i == j) dia += v; else off += v;
         }
         off = warp_sum(off);
         dia = warp_sum(dia);
-        if (lane == 0) {
-            red_off[warp] = off;
-            red_dia[warp] = dia;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            double o = 0.0, dd = 0.0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
-                o += red_off[w];
-                dd += red_dia[w];
-            }
-            stop_s = (o <= 1e-26 * dd) ? 1 : 0;
-        }
-        __syncthreads();
-        if (stop_s) break;
+        if (off <= 1e-26 * dia) break;  // identical on all lanes
         for (int step = 0; step < nplayers - 1; ++step) {
-            if (tid < np) {
+            for (int k = lane; k < np; k += 32) {
                 int p, q;
-                if (tid == 0) {
+                if (k == 0) {
                     p = nplayers - 1;
                     q = step;
                 } else {
-                    p = (step + tid) % (nplayers - 1);
-                    q = (step - tid + (nplayers - 1)) % (nplayers - 1);
+                    p = (step + k) % (nplayers - 1);
+                    q = (step - k + (nplayers - 1)) % (nplayers - 1);
                 }
                 if (p > q) {
                     const int t = p;
                     p = q;
                     q = t;
                 }
-                double c = 1.0, s = 0.0;
+                double c = 1.0, sn = 0.0;
                 if (q < m) {
                     const double apq = A[p][q];
                     if (fabs(apq) > 1e-300) {
                         const double tau = (A[q][q] - A[p][p]) / (2.0 * apq);
                         const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
                         c = rsqrt(1.0 + t * t);
-                        s = t * c;
+                        sn = t * c;
                     } else {
                         q = p;  // nothing to rotate
                     }
                 } else {
                     q = p;  // dummy pair: identity
                 }
-                pr_p[tid] = p;
-                pr_q[tid] = q;
-                cs_c[tid] = c;
-                cs_s[tid] = s;
+                pr_p[k] = p;
+                pr_q[k] = q;
+                cs_c[k] = c;
+                cs_s[k] = sn;
             }
-            __syncthreads();
+            __syncwarp();
             // column update: A <- A R, J <- J R
-            for (int idx = tid; idx < 2 * m * np; idx += blockDim.x) {
+            for (int idx = lane; idx < 2 * m * np; idx += 32) {
                 const int which = idx / (m * np);
                 const int rem = idx % (m * np);
                 const int i = rem / np, k = rem % np;
                 const int p = pr_p[k], q = pr_q[k];
                 if (p != q) {
-                    const double c = cs_c[k], s = cs_s[k];
+                    const double c = cs_c[k], sn = cs_s[k];
                     double(*M)[kMaxS + 1] = which ? J : A;
                     const double xp = M[i][p], xq = M[i][q];
-                    M[i][p] = c * xp - s * xq;
-                    M[i][q] = s * xp + c * xq;
+                    M[i][p] = c * xp - sn * xq;
+                    M[i][q] = sn * xp + c * xq;
                 }
             }
-            __syncthreads();
+            __syncwarp();
             // row update: A <- R^T A
-            for (int idx = tid; idx < m * np; idx += blockDim.x) {
+            for (int idx = lane; idx < m * np; idx += 32) {
                 const int j = idx / np, k = idx % np;
                 const int p = pr_p[k], q = pr_q[k];
                 if (p != q) {
-                    const double c = cs_c[k], s = cs_s[k];
+                    const double c = cs_c[k], sn = cs_s[k];
                     const double xp = A[p][j], xq = A[q][j];
-                    A[p][j] = c * xp - s * xq;
-                    A[q][j] = s * xp + c * xq;
+                    A[p][j] = c * xp - sn * xq;
+                    A[q][j] = sn * xp + c * xq;
                 }
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
-    // new decomposition: Q <- [Q 0; 0 1] J, lam <- diag(A)
-    for (int idx = tid; idx < m * m; idx += blockDim.x) {
+    // new decomposition: Q <- [Q 0; 0 1] J, lam <- diag(A); lowest eigenpair -> theta, y
+    int best = 0;
+    for (int i = 1; i < m; ++i)
+        if (A[i][i] < A[best][best]) best = i;
+    for (int idx = lane; idx < m * m; idx += 32) {
         const int i = idx / m, j = idx % m;
         double v = 0.0;
         for (int k = 0; k < m; ++k) v = fma(Qo[i][k], J[k][j], v);
         st->Q[i * kMaxS + j] = v;
+        if (j == best) g[i] = v;  // g is free now: park the Ritz column there
     }
-    if (tid < m) st->lam[tid] = A[tid][tid];
-    __syncthreads();
-    if (tid == 0) {
-        int best = 0;
-        for (int i = 1; i < m; ++i)
-            if (A[i][i] < A[best][best]) best = i;
-        st->theta_prev = st->theta;
-        st->theta = A[best][best];
-        st->best = best;
-    }
-    __syncthreads();
-    // Ritz vector = column `best` of Q, normalised, largest component positive
-    if (tid == 0) {
-        const int best = st->best;
+    for (int i = lane; i < m; i += 32) st->lam[i] = A[i][i];
+    __syncwarp();
+    if (lane == 0) {
         double nrm = 0.0;
         int big = 0;
         for (int i = 0; i < m; ++i) {
-            const double v = st->Q[i * kMaxS + best];
-            nrm += v * v;
-            if (fabs(v) > fabs(st->Q[big * kMaxS + best])) big = i;
+            nrm += g[i] * g[i];
+            if (fabs(g[i]) > fabs(g[big])) big = i;
         }
-        const double sg = st->Q[big * kMaxS + best] < 0.0 ? -1.0 : 1.0;
+        const double sg = g[big] < 0.0 ? -1.0 : 1.0;
         nrm = sg / sqrt(nrm);
-        for (int i = 0; i < m; ++i) st->y[i] = st->Q[i * kMaxS + best] * nrm;
+        for (int i = 0; i < m; ++i) st->y[i] = g[i] * nrm;
+        st->theta_prev = st->theta;
+        st->theta = A[best][best];
+        st->best = best;
     }
 }
 

@@ -319,7 +319,8 @@ __global__ void sigma_combine_kernel(const int* __restrict__ done, const sqd_sig
 // The two partial results meet in a shared-memory exchange buffer before one coalesced update of sigma.
 // ---------------------------------------------------------------------------------------------------
 template <int CPT, bool STAGE_PACK>
-__global__ void sigma_a_kernel(const SigmaArgs P, const int NST) {
+__global__ void __launch_bounds__(CPT == 1 ? 1024 : 512)
+sigma_a_kernel(const SigmaArgs P, const int NST) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
     const sqd_operator& op = P.op;
@@ -633,22 +634,20 @@ static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
     static const int knob_pack = env_int("SQD_SIGMA_PACK_BYTES", 24 * 1024);
     const int ldc = op->ldc;
     int threads, cpt;
-    // `threads` counts the consumer threads; one more warp (the producer) is added at launch
+    // `threads` counts the consumer threads; one more warp (the producer) is added at launch.  One column
+    // per thread up to 992 columns; beyond that CPT columns per thread with at most 480 consumers (the
+    // register budget of the multi-column instances: __launch_bounds__(512))
     if (ldc <= 992) {
         threads = ((ldc + 31) / 32) * 32;
         if (threads < 32) threads = 32;
         cpt = 1;
-        // fewer, fatter threads once the row is long: keeps more CTAs resident per SM
-        if (ldc > 512) {
-            threads = ((ldc / 2 + 31) / 32) * 32;
-            cpt = 2;
-        }
     } else {
-        threads = 992;
-        cpt = (ldc + threads - 1) / threads;
+        cpt = (ldc + 479) / 480;
+        cpt = cpt <= 2 ? 2 : cpt <= 4 ? 4 : cpt <= 8 ? 8 : cpt <= 12 ? 12 : 0;
+        if (cpt == 0) return false;
+        threads = (((ldc + cpt - 1) / cpt + 31) / 32) * 32;
     }
-    const int cpt_t = cpt <= 1 ? 1 : cpt <= 2 ? 2 : cpt <= 4 ? 4 : cpt <= 8 ? 8 : cpt <= 12 ? 12 : 0;
-    if (cpt_t == 0) return false;
+    const int cpt_t = cpt;
     // beta SELL table staged in shared memory when it costs at most 24 KB
     const size_t pack_bytes = ((size_t)op->bd.n_entries * 4 + 15) / 16 * 16;
     const int n2 = op->norb * op->norb;
@@ -733,7 +732,7 @@ int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sig
                 "sqd_sigma: the operator has no SELL tables (call sqd_sell_build first)");
     SQD_REQUIRE(plan_sigma(op, &pl),
                 "sqd_sigma: nb=%d (ldc=%d) with norb=%d does not fit the shared-memory row staging "
-                "(limit: 3*ldc + 2*ldg doubles <= 227 KB, ldc <= 11904)",
+                "(limits: nb <= 5760 and 3*ldc + 2*ldg doubles <= 227 KB)",
                 op->b.n, op->ldc, op->norb);
     SigmaArgs args{*op, d_c, d_sigma, d_done, g_prof};
     switch (pl.CPT) {

@@ -1,0 +1,137 @@
+"""BASELINE.json's configurations at FULL size, checked through size-independent properties
+(the dense oracle cannot go there) and, where it finishes in seconds, against the C oracle."""
+
+import time
+
+import numpy as np
+import pytest
+
+import bench
+from qiskit_addon_sqd_b200._synthetic import PauliSum, random_pauli_operator
+
+pytestmark = pytest.mark.gpu
+
+
+def _properties(sub, ham, x, e, occ, nelec, tol=1e-6):
+    """Eigen-residual, Rayleigh quotient, Hermiticity of the operator, particle number."""
+    rng = np.random.default_rng(0)
+    hx = sub.apply(ham, x)
+    theta = sub.dot(x, hx) / sub.dot(x, x)
+    assert abs(theta - e) < 1e-9
+    r = hx - theta * x
+    assert float(sub.dot(r, r)) ** 0.5 < tol * 10
+    y = sub.upload_amplitudes(rng.standard_normal((sub.na, sub.nb)))
+    z = sub.upload_amplitudes(rng.standard_normal((sub.na, sub.nb)))
+    hy, hz = sub.apply(ham, y), sub.apply(ham, z)
+    a, b = sub.dot(z, hy), sub.dot(hz, y)
+    assert abs(a - b) < 1e-9 * max(1.0, abs(a))                      # <z|Hy> == <Hz|y>
+    lin = sub.apply(ham, 2.0 * y - 3.0 * z)
+    assert float((lin - (2.0 * hy - 3.0 * hz)).abs().max()) < 1e-9   # linearity
+    assert abs(occ[0].sum() - nelec[0]) < 1e-9 and abs(occ[1].sum() - nelec[1]) < 1e-9
+    assert np.all(occ[0] > -1e-12) and np.all(occ[0] < 1 + 1e-12)
+
+
+@pytest.mark.parametrize("wl,check_oracle", [("c1", True), ("c2", True), ("t", True), ("c4", True), ("c5", False)])
+def test_fermion_configs_full_size(cuda_lib, wl, check_oracle):
+    import torch
+
+    from qiskit_addon_sqd_b200 import fermion
+
+    norb, nelec, h, g, batches = bench.make_batches(wl, 0, 1)
+    sa, sb = batches[0]
+    t0 = time.perf_counter()
+    res = fermion.solve_sci_batch([(sa, sb)], h, g, norb, nelec)[0]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    st = fermion.last_solve_stats()[0]
+    print(f"\n[{wl}] na x nb = {len(sa)} x {len(sb)}, {st.cycles} cycles, {dt * 1e3:.1f} ms end to end, "
+          f"E = {res.energy:.10f}, residual {st.residual:.1e}")
+    assert st.converged == 1
+    sub = fermion._Subspace(sa, sb, norb, h, g)
+    ham = sub.hamiltonian()
+    x = sub.upload_amplitudes(res.sci_state.amplitudes)
+    _properties(sub, ham, x, res.energy, res.orbital_occupancies, nelec)
+    # same call twice -> bit-identical
+    res2 = fermion.solve_sci_batch([(sa, sb)], h, g, norb, nelec)[0]
+    assert res2.energy == res.energy and np.array_equal(res2.sci_state.amplitudes, res.sci_state.amplitudes)
+    if check_oracle:
+        from oracle import sci_cpu
+
+        e_ref, amps_ref, occ_ref, info = sci_cpu.solve(sa, sb, h, g, algo=0, tol=1e-12, max_cycle=200)
+        assert abs(res.energy - e_ref) < 1e-8                         # north_star tolerance (Ha)
+        assert abs(abs(np.vdot(amps_ref, res.sci_state.amplitudes)) - 1) < 1e-6
+        assert np.allclose(res.orbital_occupancies[0], occ_ref[0], atol=1e-6)
+
+
+def test_qubit_config_full_size(cuda_lib):
+    """C3: 40 qubits, 1e4 Pauli terms (2500 X masks x 4 Z masks), 1e5 sampled bitstrings."""
+    from qiskit_addon_sqd_b200 import qubit
+
+    nq, d0 = 40, 100_000
+    rng = np.random.default_rng(103)
+    base = rng.integers(0, 2, nq).astype(bool)
+    rows = np.tile(base, (d0, 1))
+    k = np.minimum(rng.geometric(0.35, d0), 8)
+    for r in range(d0):
+        rows[r, rng.choice(nq, k[r], replace=False)] ^= True
+    x, z, c = random_pauli_operator(nq, 2500, 4, 4, 103)
+    op = PauliSum(x, z, c)
+    t0 = time.perf_counter()
+    srt = qubit.sort_and_remove_duplicates(rows)
+    t1 = time.perf_counter()
+    A = qubit.project_operator_to_subspace(srt, op)
+    t2 = time.perf_counter()
+    e, v = qubit.solve_qubit(rows, op, k=1, which="SA")
+    t3 = time.perf_counter()
+    d = srt.shape[0]
+    print(f"\n[c3] d = {d}, nnz = {A.nnz}, sort {1e3 * (t1 - t0):.0f} ms, project {1e3 * (t2 - t1):.0f} ms, "
+          f"solve_qubit (project + Davidson) {1e3 * (t3 - t2):.0f} ms, E0 = {e[0]:.8f}")
+    keys = (srt.astype(np.int64) * (1 << np.arange(nq - 1, -1, -1, dtype=np.int64))[None, :]).sum(1)
+    assert np.all(np.diff(keys) > 0)                                  # sorted, unique
+    assert A.shape == (d, d) and A.has_canonical_format
+    assert abs(A - A.getH()).max() < 1e-12                            # real-weighted Paulis: Hermitian
+    # brute-force rows: every term applied to a few source states with python integers
+    xm = [sum(1 << q for q in range(nq) if xx[q]) for xx in x]
+    zm = [sum(1 << q for q in range(nq) if zz[q]) for zz in z]
+    ny = [int(np.count_nonzero(xx & zz)) for xx, zz in zip(x, z)]
+    index = {int(kk): i for i, kk in enumerate(keys)}
+    for i in rng.choice(d, 25, replace=False):
+        expect = {}
+        for t in range(len(xm)):
+            j = index.get(int(keys[i]) ^ xm[t])
+            if j is not None:
+                amp = (-1) ** bin(int(keys[i]) & zm[t]).count("1") * (1j) ** ny[t]
+                expect[j] = expect.get(j, 0) + c[t] * amp
+        expect = {j: val for j, val in expect.items() if val != 0}
+        row = A.getrow(int(i))
+        assert sorted(expect) == row.indices.tolist()
+        assert np.allclose([expect[j] for j in row.indices], row.data, atol=1e-12)
+    r = A @ v[:, 0] - e[0] * v[:, 0]
+    assert np.linalg.norm(r) < 1e-5 and abs(np.linalg.norm(v[:, 0]) - 1) < 1e-9
+
+
+def test_recovery_full_size(cuda_lib):
+    """1e5 sampled bitstrings, (30e,30o): exact-stream mode and substream mode."""
+    from oracle import recovery_oracle as ro
+    from qiskit_addon_sqd_b200.configuration_recovery import recover_configurations
+
+    norb, na, nb, n = 30, 15, 15, 100_000
+    rng = np.random.default_rng(7)
+    bs = rng.integers(2, size=(n, 2 * norb), dtype=np.int64).astype(bool)
+    probs = rng.random(n)
+    occ = (rng.random(norb), rng.random(norb))
+    for mode in ("exact", "parallel"):
+        gen = np.random.default_rng(11)
+        t0 = time.perf_counter()
+        mat, freqs = recover_configurations(bs, probs, occ, na, nb, gen, rng_mode=mode)
+        dt = time.perf_counter() - t0
+        print(f"\n[recovery {mode}] {n} rows -> {len(mat)} unique in {dt * 1e3:.0f} ms "
+              f"({dt / n * 1e9:.0f} ns per input bitstring)")
+        assert (mat[:, :norb].sum(1) == nb).all() and (mat[:, norb:].sum(1) == na).all()
+        assert abs(freqs.sum() - 1) < 1e-12 and len(np.unique(mat, axis=0)) == len(mat)
+    # the exact stream is a prefix property: the first rows of a long run equal a short run
+    g1, g2 = np.random.default_rng(5), np.random.default_rng(5)
+    m1, f1 = recover_configurations(bs[:3000], probs[:3000], occ, na, nb, g1)
+    m2, f2 = ro.recover_configurations(bs[:3000], probs[:3000], occ, na, nb, g2)
+    assert np.array_equal(m1, m2) and np.array_equal(f1, f2)
+    assert g1.bit_generator.state == g2.bit_generator.state
