@@ -238,6 +238,13 @@ int sqd_dot(const double* d_x, const double* d_y, int64_t n, double* d_out, doub
 int sqd_occupancies(const double* d_c, const uint64_t* d_strs_a, int na, const uint64_t* d_strs_b,
                     int nb, int ldc, int norb, double* d_occ, double* d_scratch, void* stream);
 
+/* Spin-resolved 1-RDMs  dm1a[p*norb+q] = <c| a+_p a_q |c>, dm1b likewise (pyscf make_rdm1s reached from
+ * fermion.py:117-121, 725-729).  d_dm1: double[2*norb*norb] (alpha block first).  d_workspace:
+ * sqd_rdm1s_workspace_bytes(op) bytes; d_dots: double[max(nnz_a, nnz_b)] scratch. */
+int64_t sqd_rdm1s_workspace_bytes(const sqd_operator* op);
+int sqd_rdm1s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t nnz_b, double* d_dm1,
+              double* d_workspace, double* d_dots, void* stream);
+
 /* ------------------------------------------------------------------------------------------ *
  * Qubit path   (qubit.py:78-300)
  * ------------------------------------------------------------------------------------------ */
@@ -269,14 +276,22 @@ int sqd_pauli_project_fill(const int64_t* d_keys, int64_t d, const uint64_t* d_g
 int sqd_csr_matvec_c128(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col,
                         const double* d_val, const double* d_x, double* d_y, void* stream);
 
-/* Lowest `k` eigenpairs of the Hermitian matrix M = A^T (the reference hands A, the transpose of the
- * operator, to eigsh -- qubit.py:73) by a locked single-vector Davidson, replacing ARPACK.
- * d_evecs: complex128 [k][d] (row = eigenvector); h_evals: double[k]. Synchronises. */
+/* Gershgorin data of a Hermitian CSR matrix: d_diag[i] = Re A_ii and the row's lower bound
+ * d_lower[i] = A_ii - sum_{j != i} |A_ij|  (no eigenvalue of the connected component containing row i
+ * lies below the minimum of d_lower over that component). */
+int sqd_csr_gershgorin(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, const double* d_val,
+                       double* d_diag, double* d_lower, void* stream);
+
+/* Lowest eigenpair (k must be 1) of the Hermitian matrix A -- the matrix the reference hands to eigsh
+ * (qubit.py:73) -- by the device-resident Davidson on the (re, im) embedding, replacing ARPACK.
+ * d_start: complex128[d] start vector or NULL (unit vector at argmin of the diagonal); the iteration
+ * stays inside the connected component(s) the start vector touches.  d_evecs: complex128[d];
+ * h_evals: double[1]; h_cycles / h_residual may be NULL.  Synchronises. */
 int64_t sqd_csr_davidson_workspace_bytes(int64_t d, int k, int max_space);
 int sqd_csr_davidson(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, const double* d_val,
-                     int k, int max_space, int max_cycle, double tol, double* d_evecs,
-                     double* h_evals, int* h_cycles, void* d_workspace, int64_t workspace_bytes,
-                     void* stream);
+                     int k, int max_space, int max_cycle, double tol, const double* d_start,
+                     double* d_evecs, double* h_evals, int* h_cycles, double* h_residual,
+                     void* d_workspace, int64_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * Configuration recovery   (configuration_recovery.py:59-306)

@@ -431,3 +431,16 @@ class SparseProjectedHamiltonian:
         op = LinearOperator((n, n), matvec=self.matvec, dtype=float)
         w, v = eigsh(op, k=1, which="SA", tol=tol)
         return float(w[0]), v[:, 0].reshape(self.na, self.nb)
+
+
+def rdm1s(c: np.ndarray, strs_a, strs_b, norb: int):
+    """Spin-resolved 1-RDMs ``(dm1a, dm1b)``, ``dm1[p, q] = <c| a+_q a_p |c>`` (pyscf's convention,
+    ``make_rdm1s`` reached from ``fermion.py:117-121``)."""
+    c = np.asarray(c)
+    dma = np.zeros((norb, norb))
+    dmb = np.zeros((norb, norb))
+    for (t, s, p, q, sg) in single_excitation_links(strs_a, norb):
+        dma[q, p] += sg * float(c[t] @ c[s])
+    for (t, s, p, q, sg) in single_excitation_links(strs_b, norb):
+        dmb[q, p] += sg * float(c[:, t] @ c[:, s])
+    return dma, dmb

@@ -143,6 +143,8 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_init_guess": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "sqd_dot": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "sqd_occupancies": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "sqd_rdm1s_workspace_bytes": (_i64, [C.POINTER(Operator)]),
+    "sqd_rdm1s": (_i, [C.POINTER(Operator), _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "sqd_bits_to_keys": (_i, [_vp, _i64, _i, _vp, _vp]),
     "sqd_pauli_connect": (_i, [_vp, _i64, _u64, _u64, _vp, _vp, _vp]),
     "sqd_pauli_project_count": (_i, [_vp, _i64, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
@@ -151,8 +153,9 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "sqd_csr_matvec_c128": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_csr_davidson_workspace_bytes": (_i64, [_i64, _i, _i]),
+    "sqd_csr_gershgorin": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_csr_davidson": (
-        _i, [_i64, _vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _pi, _vp, _i64, _vp]
+        _i, [_i64, _vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _pi, _vp, _vp, _i64, _vp]
     ),
     "sqd_recover_workspace_bytes": (_i64, [_i64, _i]),
     "sqd_recover": (

@@ -17,6 +17,7 @@
 //   ortho1/2  : two classical Gram-Schmidt passes (the second fused with normalisation)
 // All reductions are two-stage with a fixed order -> results are bit-reproducible run to run.
 #include <math.h>
+#include <stdlib.h>
 
 #include <functional>
 #include <vector>
@@ -38,12 +39,14 @@ constexpr int kMaxS = SQD_MAX_SPACE;
 constexpr int kRedBlocks = 2 * kNumSMs;  // CTAs of every streaming reduction pass
 constexpr int kRedThreads = 256;
 constexpr int kPartialRows = kMaxS + 4;
+constexpr int kKeep = 4;  // Ritz vectors kept by a thick restart
 
 struct DavState {
     int status;  // 0 running, 1 converged, 2 linear dependency, 3 (host) max_cycle
     int cycles;
     double theta, theta_prev, rnorm, tnorm2, inv_norm;
     int best;
+    int ord[kMaxS];             // eigenvalue order (ascending) of the current decomposition
     double lam[kMaxS];          // eigenvalues of the projected matrix V^T H V
     double Q[kMaxS * kMaxS];    // its eigenvectors (column j <-> lam[j])
     double y[kMaxS];
@@ -86,7 +89,14 @@ residual_kernel(const DavState* __restrict__ st, double* __restrict__ V, double*
     if (st->status != 0) return;
     __shared__ double red[(MV + 2) * (kRedThreads / 32)];
     __shared__ double ys[MV];
+    __shared__ double yk[kKeep][MV];  // thick restart: coefficient columns of the kept Ritz vectors 1..q-1
     if (threadIdx.x < MV) ys[threadIdx.x] = threadIdx.x < m ? st->y[threadIdx.x] : 0.0;
+    if (restart > 1) {
+        for (int idx = threadIdx.x; idx < kKeep * MV; idx += blockDim.x) {
+            const int j = idx / MV, i = idx % MV;
+            yk[j][i] = (j < restart && i < m) ? st->Q[i * kMaxS + st->ord[j]] : 0.0;
+        }
+    }
     __syncthreads();
     const double theta = st->theta;
     double acc[MV + 2];
@@ -94,15 +104,17 @@ residual_kernel(const DavState* __restrict__ st, double* __restrict__ V, double*
     for (int i = 0; i < MV + 2; ++i) acc[i] = 0.0;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
          j += (int64_t)gridDim.x * blockDim.x) {
-        double v[MV];
+        double v[MV], w[MV];
         double x = 0.0, hx = 0.0;
 #pragma unroll
         for (int i = 0; i < MV; ++i) {
             v[i] = 0.0;
+            w[i] = 0.0;
             if (i < m) {
                 v[i] = V[(int64_t)i * n + j];
+                w[i] = W[(int64_t)i * n + j];
                 x = fma(ys[i], v[i], x);
-                hx = fma(ys[i], W[(int64_t)i * n + j], hx);
+                hx = fma(ys[i], w[i], hx);
             }
         }
         const double r = hx - theta * x;
@@ -112,8 +124,20 @@ residual_kernel(const DavState* __restrict__ st, double* __restrict__ V, double*
         X[j] = x;
         T[j] = t;
         if (restart) {
-            V[j] = x;   // slot 0 <- Ritz vector (element-wise, the only reader of V[0][j] is this thread)
-            W[j] = hx;  // slot 0 <- H x
+            // thick restart: the basis collapses onto the `restart` lowest Ritz vectors (element-wise; this
+            // thread is the only reader and writer of element j of every basis vector)
+            V[j] = x;
+            W[j] = hx;
+            for (int k = 1; k < restart; ++k) {
+                double xk = 0.0, hk = 0.0;
+#pragma unroll
+                for (int i = 0; i < MV; ++i) {
+                    xk = fma(yk[k][i], v[i], xk);
+                    hk = fma(yk[k][i], w[i], hk);
+                }
+                V[(int64_t)k * n + j] = xk;
+                W[(int64_t)k * n + j] = hk;
+            }
         }
 #pragma unroll
         for (int i = 0; i < MV; ++i)
@@ -326,6 +350,16 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
     int best = 0;
     for (int i = 1; i < m; ++i)
         if (A[i][i] < A[best][best]) best = i;
+    if (lane == 0) {  // ascending order of the eigenvalues (selection sort, m <= 32)
+        unsigned used = 0u;
+        for (int r = 0; r < m; ++r) {
+            int b = -1;
+            for (int i = 0; i < m; ++i)
+                if (!((used >> i) & 1u) && (b < 0 || A[i][i] < A[b][b])) b = i;
+            used |= 1u << b;
+            st->ord[r] = b;
+        }
+    }
     for (int idx = lane; idx < m * m; idx += 32) {
         const int i = idx / m, j = idx % m;
         double v = 0.0;
@@ -371,12 +405,23 @@ __global__ void convergence_kernel(DavState* __restrict__ st, const double* __re
         if (fabs(st->theta - st->theta_prev) < tol && rnorm < tol_residual) {
             st->status = 1;
         } else if (restart) {
-            double c = 0.0;
-            for (int i = 0; i < m; ++i) c += st->y[i] * p[i];
-            st->c1[0] = c;
-            st->lam[0] = st->theta;  // the collapsed space is spanned by the Ritz vector alone
-            st->Q[0] = 1.0;
-            st->y[0] = 1.0;
+            // the collapsed space is spanned by the `restart` lowest Ritz vectors: projections of t on
+            // them, then the decomposition becomes diagonal
+            double cj[kKeep], lj[kKeep];
+            for (int k = 0; k < restart; ++k) {
+                const int col = st->ord[k];
+                double c = 0.0;
+                for (int i = 0; i < m; ++i) c += (k == 0 ? st->y[i] : st->Q[i * kMaxS + col]) * p[i];
+                cj[k] = c;
+                lj[k] = st->lam[col];
+            }
+            for (int k = 0; k < restart; ++k) {
+                st->c1[k] = cj[k];
+                st->lam[k] = lj[k];
+                st->ord[k] = k;
+                for (int i = 0; i < restart; ++i) st->Q[i * kMaxS + k] = i == k ? 1.0 : 0.0;
+                st->y[k] = k == 0 ? 1.0 : 0.0;
+            }
         } else {
             for (int i = 0; i < m; ++i) st->c1[i] = p[i];
         }
@@ -401,7 +446,9 @@ __global__ void norm_kernel(DavState* __restrict__ st, const double* __restrict_
             st->c2[i] = p[i];
             n2 -= p[i] * p[i];
         }
-        if (!(n2 > lindep)) {
+        // lindep is relative to the size of the correction before orthogonalisation (pyscf tests the
+        // normalised vector); an exactly vanishing correction also ends the iteration
+        if (!(n2 > lindep * st->tnorm2) || !(n2 > 1e-300)) {
             st->status = 2;  // cannot expand the space any further: current Ritz vector is final
             st->inv_norm = 0.0;
         } else {
@@ -459,8 +506,10 @@ __global__ void init_state_kernel(DavState* st) {
         st->inv_norm = 0.0;
     }
     for (int i = threadIdx.x; i < kMaxS * kMaxS; i += blockDim.x) st->Q[i] = 0.0;
-    for (int i = threadIdx.x; i < kMaxS; i += blockDim.x)
+    for (int i = threadIdx.x; i < kMaxS; i += blockDim.x) {
         st->y[i] = st->c1[i] = st->c2[i] = st->lam[i] = 0.0;
+        st->ord[i] = i;
+    }
     if (threadIdx.x == 0) st->best = 0;
 }
 
@@ -520,20 +569,6 @@ __global__ void init_guess_kernel(const double* __restrict__ pval, const int64_t
         // pyscf direct_spin1._get_init_guess: ci0[0][0] += 1e-5; ci0[0][-1] -= 1e-5
         x0[0] += 1e-5;
         x0[(int64_t)(na - 1) * ldc + (nb - 1)] -= 1e-5;
-    }
-}
-
-// x0[j] += scale * u_j, u_j in [-1, 1) from a counter hash: seeds every invariant block of a
-// block-diagonal operator (a unit start vector can never leave its own connected component)
-__global__ void add_noise_kernel(double* __restrict__ x0, int64_t n, double scale) {
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
-         j += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t z = (uint64_t)j * 0x9E3779B97F4A7C15ull + 0xD1B54A32D192ED03ull;
-        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-        z ^= z >> 31;
-        const double u = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
-        x0[j] += scale * u;
     }
 }
 
@@ -693,7 +728,9 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         if (apply(ws.V + (int64_t)slot * n, ws.W + (int64_t)slot * n, ws)) return -2;
         if (prm->profile) SQD_CUDA_OK(cudaEventRecord(ev.back(), st));
         ++sigma_builds;
-        const int restart = (m == M) ? 1 : 0;
+        // thick restart: keep the lowest min(kKeep, M/3) Ritz vectors when the space is full
+        const int q_keep = M / 3 < 1 ? 1 : (M / 3 > kKeep ? kKeep : M / 3);
+        const int restart = (m == M) ? q_keep : 0;
         int rc = dispatch_mv(m, [&](auto mv) {
             constexpr int MV = decltype(mv)::value;
             gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n,
@@ -707,7 +744,7 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
             return check_launch("davidson cycle (1)", 4);
         });
         if (rc) return -2;
-        const int me = restart ? 1 : m;
+        const int me = restart ? restart : m;
         rc = dispatch_mv(me, [&](auto mv) {
             constexpr int MV = decltype(mv)::value;
             ortho1_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T, ws.partials);
@@ -827,9 +864,9 @@ int64_t sqd_csr_davidson_workspace_bytes(int64_t d, int k, int max_space) {
 }
 
 int sqd_csr_davidson(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, const double* d_val,
-                     int k, int max_space, int max_cycle, double tol, double* d_evecs,
-                     double* h_evals, int* h_cycles, void* d_workspace, int64_t ws_bytes,
-                     void* stream) {
+                     int k, int max_space, int max_cycle, double tol, const double* d_start,
+                     double* d_evecs, double* h_evals, int* h_cycles, double* h_residual,
+                     void* d_workspace, int64_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     SQD_REQUIRE(k == 1, "sqd_csr_davidson: only the lowest eigenpair (k=1) runs natively (got k=%d)", k);
     SQD_REQUIRE(d > 0, "sqd_csr_davidson: empty matrix");
@@ -845,12 +882,15 @@ int sqd_csr_davidson(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, 
     double* x0 = (double*)p;
     p += align_up((size_t)n * sizeof(double));
     if (csr_diag_embed(d, d_row_ptr, d_col, d_val, hdiag, st)) return -2;
-    // scratch for the argmin lives in the (not yet used) Davidson workspace
-    if (sqd_init_guess(hdiag, 1, (int)n, (int)n, x0, p, stream)) return -2;
-    // the projected Pauli operator is often block diagonal (disconnected sets of configurations):
-    // give every block a small component, as ARPACK's random start vector does in the reference
-    add_noise_kernel<<<red_blocks(n), kRedThreads, 0, st>>>(x0, n, 0.1 / sqrt((double)n));
-    if (check_launch("add_noise_kernel")) return -2;
+    // start vector: the caller's (complex128[d]) or the unit vector at argmin(diag).  A unit vector never
+    // leaves its own connected component of a block-diagonal operator; the host driver (qubit.py) uses
+    // Gershgorin bounds to decide which other components still have to be searched.
+    if (d_start != nullptr) {
+        SQD_CUDA_OK(cudaMemcpyAsync(x0, d_start, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+        // scratch for the argmin lives in the (not yet used) Davidson workspace
+        if (sqd_init_guess(hdiag, 1, (int)n, (int)n, x0, p, stream)) return -2;
+    }
     sqd_davidson_params prm;
     memset(&prm, 0, sizeof(prm));
     prm.max_space = max_space;
@@ -870,6 +910,7 @@ int sqd_csr_davidson(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, 
     if (rc) return rc;
     h_evals[0] = info.theta;
     if (h_cycles) *h_cycles = info.cycles;
+    if (h_residual) *h_residual = info.residual;
     return 0;
 }
 

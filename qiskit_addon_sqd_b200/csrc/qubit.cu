@@ -164,6 +164,26 @@ __global__ void csr_diag_embed_kernel(int64_t d, const int32_t* __restrict__ row
     out[2 * i + 1] = v;
 }
 
+// Gershgorin data of a Hermitian CSR matrix: diag[i] = Re A_ii, lower[i] = diag[i] - sum_{j != i} |A_ij|
+__global__ void csr_gershgorin_kernel(int64_t d, const int32_t* __restrict__ row_ptr,
+                                      const int32_t* __restrict__ col, const double2* __restrict__ val,
+                                      double* __restrict__ diag, double* __restrict__ lower) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= d) return;
+    double dv = 0.0, r = 0.0;
+    for (int e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) {
+        const double2 a = val[e];
+        if (col[e] == i) dv += a.x; else r += hypot(a.x, a.y);
+    }
+    dv = warp_sum(dv);
+    r = warp_sum(r);
+    if (lane == 0) {
+        diag[i] = dv;
+        lower[i] = dv - r;
+    }
+}
+
 int csr_matvec_flag(const int* d_done, int64_t d, const int32_t* row_ptr, const int32_t* col,
                     const double* val, const double* x, double* y, cudaStream_t st) {
     const int wpb = 8;
@@ -229,6 +249,14 @@ int sqd_pauli_project_fill(const int64_t* d_keys, int64_t d, const uint64_t* d_g
     csr_row_sort_kernel<<<(unsigned)((d + wpb - 1) / wpb), wpb * 32, 0, st>>>(d, d_row_ptr, d_col_tmp,
                                                                             d_val_tmp, d_col, d_val);
     return check_launch("csr_row_sort_kernel");
+}
+
+int sqd_csr_gershgorin(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, const double* d_val,
+                       double* d_diag, double* d_lower, void* stream) {
+    if (d == 0) return 0;
+    csr_gershgorin_kernel<<<(unsigned)((d + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+        d, d_row_ptr, d_col, (const double2*)d_val, d_diag, d_lower);
+    return check_launch("csr_gershgorin_kernel");
 }
 
 int sqd_csr_matvec_c128(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col,

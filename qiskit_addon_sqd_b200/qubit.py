@@ -183,6 +183,63 @@ def project_operator_to_subspace(
     return _project_device(torch, lib, keys, hamiltonian).to_scipy()
 
 
+def _lowest_eigenpair_device(torch, lib, csr: "_DeviceCSR", kw: dict, max_rounds: int = 64):
+    """Lowest eigenpair of the projected operator with the device-resident Davidson.
+
+    The projected matrix is usually block diagonal (sets of configurations no Pauli term connects), and a
+    Davidson run started from a basis state never leaves that state's block.  So: solve from the
+    lowest-diagonal state, mark the block as visited (support of the eigenvector), then use the Gershgorin
+    lower bounds ``A_ii - sum_j |A_ij|`` to find unvisited rows whose block could still hold a lower
+    eigenvalue, and solve from the lowest-diagonal one of those; stop when no candidate is left.  Exact
+    up to the Davidson tolerance; ARPACK's random start vector plays the same role in the reference.
+    """
+    d = csr.d
+    dev = csr.row_ptr.device
+    st = _lib.stream_ptr(torch)
+    tol = float(kw.get("tol", 0) or 0)
+    tol = tol * tol if tol > 0 else 1e-14  # eigsh's tol bounds the relative accuracy of the Ritz value
+    max_space = int(min(kw.get("ncv") or 20, _lib.MAX_SPACE))
+    max_cycle = int(kw.get("maxiter") or 500)
+    diag = torch.empty(d, dtype=torch.float64, device=dev)
+    lower = torch.empty(d, dtype=torch.float64, device=dev)
+    _lib.check(lib.sqd_csr_gershgorin(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col), _lib.ptr(csr.val),
+                                      _lib.ptr(diag), _lib.ptr(lower), st), "sqd_csr_gershgorin")
+    ws_bytes = lib.sqd_csr_davidson_workspace_bytes(d, 1, max_space)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    visited = torch.zeros(d, dtype=torch.bool, device=dev)
+    start = torch.zeros(2 * d, dtype=torch.float64, device=dev)
+    evec = torch.empty(2 * d, dtype=torch.float64, device=dev)
+    best_e, best_vec = None, None
+    v0 = kw.get("v0")
+    row = int(torch.argmin(diag).item())
+    inf = torch.tensor(float("inf"), dtype=torch.float64, device=dev)
+    for rnd in range(max_rounds):
+        start.zero_()
+        if rnd == 0 and v0 is not None:
+            start.copy_(torch.from_numpy(np.ascontiguousarray(v0, dtype=np.complex128).reshape(-1)
+                                         .view(np.float64)))
+        else:
+            start[2 * row] = 1.0
+        evals = (C.c_double * 1)()
+        cycles, resid = C.c_int(0), C.c_double(0.0)
+        _lib.check(lib.sqd_csr_davidson(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col), _lib.ptr(csr.val), 1,
+                                        max_space, max_cycle, tol, _lib.ptr(start), _lib.ptr(evec), evals,
+                                        C.byref(cycles), C.byref(resid), _lib.ptr(ws), ws_bytes, st),
+                   "sqd_csr_davidson")
+        amp2 = evec.view(d, 2).pow(2).sum(dim=1)
+        visited |= amp2 > 1e-20 * amp2.max()
+        visited[row] = True
+        if best_e is None or evals[0] < best_e:
+            best_e, best_vec = float(evals[0]), evec.clone()
+        # unvisited rows whose block might still beat the best eigenvalue found so far
+        cand = torch.where(visited | (lower >= best_e), inf, diag)
+        row = int(torch.argmin(cand).item())
+        if not bool(torch.isfinite(cand[row]).item()):
+            vec = best_vec.cpu().numpy().view(np.complex128)
+            return best_e, vec
+    return None, None
+
+
 def _native_ok(kw: dict) -> bool:
     if kw.get("k", 6) != 1 or kw.get("which", "LM") != "SA":
         return False
@@ -219,21 +276,10 @@ def solve_qubit(
         print("Diagonalizing Hamiltonian in the subspace...")
 
     if _native_ok(scipy_kwargs) and d > 1:
-        tol = float(scipy_kwargs.get("tol", 0) or 0)
-        tol = tol * tol if tol > 0 else 1e-14  # eigsh's tol is a relative residual-like accuracy
-        max_space = int(min(scipy_kwargs.get("ncv") or 20, _lib.MAX_SPACE))
-        max_cycle = int(scipy_kwargs.get("maxiter") or 500)
-        ws_bytes = lib.sqd_csr_davidson_workspace_bytes(d, 1, max_space)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=keys.device)
-        evec = torch.empty(2 * d, dtype=torch.float64, device=keys.device)
-        evals = (C.c_double * 1)()
-        cycles = C.c_int(0)
-        _lib.check(lib.sqd_csr_davidson(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col), _lib.ptr(csr.val),
-                                        1, max_space, max_cycle, tol, _lib.ptr(evec), evals,
-                                        C.byref(cycles), _lib.ptr(ws), ws_bytes, st),
-                   "sqd_csr_davidson")
-        vec = evec.cpu().numpy().view(np.complex128).reshape(d, 1)
-        return np.array([evals[0]]), vec
+        e0, vec = _lowest_eigenpair_device(torch, lib, csr, scipy_kwargs)
+        if vec is not None:
+            return np.array([e0]), vec.reshape(d, 1)
+        # (the search did not settle within its round budget: let ARPACK drive the GPU matvec below)
 
     # general eigsh request: ARPACK on the host, A @ x on the device
     x_dev = torch.empty(2 * d, dtype=torch.float64, device=keys.device)

@@ -254,3 +254,23 @@ def test_state_methods_and_npz_roundtrip(cuda_lib, tmp_path):
     assert np.array_equal(st2.amplitudes, state.amplitudes) and st2.nelec == state.nelec
     with pytest.raises(ValueError, match=r"'amplitudes' shape must be \(2, 2\) but got \(3, 2\)"):
         fermion.SCIState(np.zeros((3, 2)), np.array([1, 2]), np.array([1, 2]), 2, (1, 1))
+
+
+def test_rdm1_matches_oracle(cuda_lib):
+    from qiskit_addon_sqd_b200 import fermion
+
+    norb = 8
+    h, g = random_integrals(norb, 12)
+    sa = hf_centred_strings(norb, 4, 30, 1)
+    sb = hf_centred_strings(norb, 3, 21, 2)
+    e, state, occ, s2 = fermion.solve_fermion((sa, sb), h, g)
+    dma, dmb = state.rdm(rank=1, spin_summed=False)
+    ra, rb = fo.rdm1s(state.amplitudes, sa, sb, norb)
+    assert np.abs(dma - ra).max() < 1e-12 and np.abs(dmb - rb).max() < 1e-12
+    assert np.allclose(np.diagonal(dma), occ[0], atol=1e-12) and np.allclose(np.diagonal(dmb), occ[1], atol=1e-12)
+    assert abs(np.trace(dma) - 4) < 1e-10 and abs(np.trace(dmb) - 3) < 1e-10
+    assert np.abs(state.rdm(rank=1, spin_summed=True) - (ra + rb)).max() < 1e-12
+    with pytest.raises(NotImplementedError):
+        state.rdm(rank=3)
+    res = fermion.solve_sci((sa, sb), h, g, norb, (4, 3), compute_rdms=True)
+    assert np.abs(res.rdm1 - (ra + rb)).max() < 1e-6

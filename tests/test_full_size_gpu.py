@@ -71,7 +71,7 @@ def test_qubit_config_full_size(cuda_lib):
     rng = np.random.default_rng(103)
     base = rng.integers(0, 2, nq).astype(bool)
     rows = np.tile(base, (d0, 1))
-    k = np.minimum(rng.geometric(0.35, d0), 8)
+    k = np.minimum(rng.geometric(0.18, d0) + 1, 14)
     for r in range(d0):
         rows[r, rng.choice(nq, k[r], replace=False)] ^= True
     x, z, c = random_pauli_operator(nq, 2500, 4, 4, 103)
