@@ -181,6 +181,10 @@ int64_t sqd_sigma_smem_bytes(const sqd_operator* op);
 /* d_sigma[a*ldc+b] = sum_{a'b'} <ab|O|a'b'> d_c[a'*ldc+b'];  pads of d_sigma are written as 0. */
 int sqd_sigma(const sqd_operator* op, const double* d_c, double* d_sigma, void* stream);
 
+/* As sqd_sigma, restricted to rows [row_begin, row_end) of sigma; other rows are left untouched. */
+int sqd_sigma_rows(const sqd_operator* op, const double* d_c, double* d_sigma, int row_begin,
+                   int row_end, void* stream);
+
 /* Diagnostics: one sigma build that also records, per CTA of the alpha kernel, 8 values in
  * d_prof (int64[8 * plan.n_chunks]): clock64() at start / after table staging / after the doubles /
  * after the singles / at the end, then #singles, #doubles and the SM id. */
@@ -199,6 +203,10 @@ typedef struct {
     const sqd_operator* ss_op; /* NULL unless the quadratic form is requested */
     double ss_shift, ss_value;
     int profile;         /* != 0: bracket every operator application with CUDA events (measurement) */
+    /* one diagonalisation sharded over GPUs: NULL, or a communicator from sqd_nccl_init; this rank then
+     * builds rows [row_begin, row_end) of every sigma vector and the blocks are all-reduced (sum) */
+    void* nccl_comm;
+    int row_begin, row_end;
 } sqd_davidson_params;
 
 typedef struct {
@@ -225,6 +233,17 @@ int sqd_davidson(const sqd_operator* op, const double* d_hdiag, const double* d_
 /* pyscf direct_spin1._get_init_guess: e_argmin(hdiag), +1e-5 on element 0 and -1e-5 on the last. */
 int sqd_init_guess(const double* d_hdiag, int na, int nb, int ldc, double* d_x0, void* d_scratch,
                    void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Multi-GPU exchange for one sharded diagonalisation (the K-batches mode needs no collective).
+ * NCCL is resolved with dlopen at first use.  Bootstrap: rank 0 calls sqd_nccl_unique_id and ships the
+ * 128 bytes to the other ranks by any means (the Python host uses torch.distributed); every rank then
+ * calls sqd_nccl_init with its CUDA device current.
+ * ------------------------------------------------------------------------------------------ */
+int sqd_nccl_unique_id(char* h_id128);
+int sqd_nccl_init(const char* h_id128, int rank, int world, void** comm_out);
+int sqd_nccl_destroy(void* comm);
+int sqd_allreduce_sum_f64(void* comm, double* d_buf, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * Expectation values   (fermion.py:821-830: make_rdm1s diagonals, energy, spin_square)

@@ -92,6 +92,9 @@ class DavidsonParams(C.Structure):
         ("ss_shift", C.c_double),
         ("ss_value", C.c_double),
         ("profile", C.c_int),
+        ("nccl_comm", C.c_void_p),
+        ("row_begin", C.c_int),
+        ("row_end", C.c_int),
     ]
 
 
@@ -127,6 +130,11 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "sqd_sigma_smem_bytes": (_i64, [C.POINTER(Operator)]),
     "sqd_sigma": (_i, [C.POINTER(Operator), _vp, _vp, _vp]),
+    "sqd_sigma_rows": (_i, [C.POINTER(Operator), _vp, _vp, _i, _i, _vp]),
+    "sqd_nccl_unique_id": (_i, [C.c_char_p]),
+    "sqd_nccl_init": (_i, [C.c_char_p, _i, _i, C.POINTER(C.c_void_p)]),
+    "sqd_nccl_destroy": (_i, [_vp]),
+    "sqd_allreduce_sum_f64": (_i, [_vp, _vp, _i64, _vp]),
     "sqd_sigma_profile": (_i, [C.POINTER(Operator), _vp, _vp, _vp, _vp]),
     "sqd_sell_build": (_i, [C.POINTER(SpinTable), _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_sigma_plan_build": (

@@ -30,6 +30,9 @@ namespace sqd {
 
 int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sigma,
                         const int* d_done, cudaStream_t st);
+int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
+                        int row_begin, int row_end, cudaStream_t st);
+int nccl_allreduce_sum_f64(void* comm, double* buf, int64_t n, cudaStream_t st);
 int csr_matvec_flag(const int* d_done, int64_t d, const int32_t* row_ptr, const int32_t* col,
                     const double* val, const double* x, double* y, cudaStream_t st);
 int csr_diag_embed(int64_t d, const int32_t* row_ptr, const int32_t* col, const double* val,
@@ -672,7 +675,15 @@ static void carve(void* base, int64_t n, int max_space, Workspace* ws) {
 static int apply_operator(const sqd_operator* op, const sqd_davidson_params* prm, const double* v,
                           double* w, Workspace& ws, int64_t n, cudaStream_t st) {
     const int* done = &ws.state->status;
-    if (sigma_dispatch_flag(op, v, w, done, st)) return -2;
+    if (prm->nccl_comm != nullptr) {
+        // sharded build: this rank owns rows [row_begin, row_end) of sigma; the other rows are zero and
+        // the blocks meet in an all-reduce over NVLink.  Every rank runs the identical enqueue sequence.
+        SQD_CUDA_OK(cudaMemsetAsync(w, 0, (size_t)n * sizeof(double), st));
+        if (sigma_dispatch_rows(op, v, w, done, prm->row_begin, prm->row_end, st)) return -2;
+        if (nccl_allreduce_sum_f64(prm->nccl_comm, w, n, st)) return -2;
+    } else if (sigma_dispatch_flag(op, v, w, done, st)) {
+        return -2;
+    }
     if (prm->ss_op) {
         // w += shift * (S^2 - ss)^2 v   (pyscf fix_spin_, quadratic branch)
         const int blocks = red_blocks(n);

@@ -38,6 +38,7 @@ struct SigmaArgs {
     double* sigma;
     const int* done;  // optional device flag: non-zero -> the launch is a no-op (Davidson finished)
     long long* prof;  // optional diagnostics: 8 clock64() stamps per kernel-A CTA (sqd_sigma_profile)
+    int row_begin, row_end;  // rows of sigma this launch owns (sharded builds); other rows are untouched
 };
 
 // try_wait with a suspend-time hint: a warp whose barrier phase is not complete is parked by the hardware
@@ -221,8 +222,8 @@ sigma_b_kernel(const SigmaArgs P) {
     const sqd_sell& L = op.bb;
     const int na = op.a.n, nb = op.b.n, ldc = op.ldc;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int a0 = blockIdx.x * kRowsB;
-    const int nrows = min(kRowsB, na - a0);
+    const int a0 = P.row_begin + blockIdx.x * kRowsB;
+    const int nrows = min(kRowsB, min(na, P.row_end) - a0);
     const bool ham = op.use_same_spin != 0;
     const int slice = blockIdx.y;
     const int pos = slice * 32 + lane;
@@ -299,10 +300,11 @@ sigma_b_kernel(const SigmaArgs P) {
 
 // sigma[a,:] += sum over the row's chunk partials, in chunk order
 __global__ void sigma_combine_kernel(const int* __restrict__ done, const sqd_sigma_plan pl, int ldc,
-                                     double* __restrict__ sigma) {
+                                     double* __restrict__ sigma, int row_begin, int row_end) {
     if (done != nullptr && *done != 0) return;
     const int j = blockIdx.x;
     const int a = pl.split_row[j], s0 = pl.split_slot_beg[j], k = pl.split_n[j];
+    if (a < row_begin || a >= row_end) return;
     for (int b = threadIdx.x; b < ldc; b += blockDim.x) {
         double acc = pl.part[(size_t)s0 * ldc + b];
         for (int c = 1; c < k; ++c) acc += pl.part[(size_t)(s0 + c) * ldc + b];
@@ -332,6 +334,7 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     const int a = pl.chunk_row[blockIdx.x];
+    if (a < P.row_begin || a >= P.row_end) return;  // sharded build: another rank owns this row
     const int cbeg = pl.chunk_beg[blockIdx.x], cend = pl.chunk_end[blockIdx.x];
     const int slot = pl.chunk_slot[blockIdx.x];
     const int single_end = op.a.row_ptr[a] + op.a.n_single[a];
@@ -704,14 +707,17 @@ static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t
     const size_t smem_b = (size_t)(kRowsB * op.ldc + kWarpsB * kRowsB * 32) * sizeof(double) + 16;
     if (opt_in_smem(sigma_b_kernel, smem_b, cfg_b)) return -2;
     const int n_pos_slices = (op.ldc + 31) / 32;  // slices incl. the pad positions
-    dim3 grid_b((op.a.n + kRowsB - 1) / kRowsB, n_pos_slices);
+    const int rows_owned = args.row_end - args.row_begin;
+    if (rows_owned <= 0) return 0;
+    dim3 grid_b((rows_owned + kRowsB - 1) / kRowsB, n_pos_slices);
     sigma_b_kernel<<<grid_b, kWarpsB * 32, smem_b, st>>>(args);
     if (check_launch("sigma_b_kernel")) return -2;
     // kernel A
     if (pl.stage_pack ? launch_sigma_a<CPT, true>(args, pl, st) : launch_sigma_a<CPT, false>(args, pl, st))
         return -2;
     if (op.plan.n_split > 0) {
-        sigma_combine_kernel<<<op.plan.n_split, 256, 0, st>>>(args.done, op.plan, op.ldc, args.sigma);
+        sigma_combine_kernel<<<op.plan.n_split, 256, 0, st>>>(args.done, op.plan, op.ldc, args.sigma,
+                                                              args.row_begin, args.row_end);
         return check_launch("sigma_combine_kernel");
     }
     return 0;
@@ -719,8 +725,16 @@ static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t
 
 static thread_local long long* g_prof = nullptr;
 
+int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
+                        int row_begin, int row_end, cudaStream_t st);
+
 int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sigma,
                         const int* d_done, cudaStream_t st) {
+    return sigma_dispatch_rows(op, d_c, d_sigma, d_done, 0, op->a.n, st);
+}
+
+int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
+                        int row_begin, int row_end, cudaStream_t st) {
     SigmaPlan pl;
     SQD_REQUIRE(op->ldc % 2 == 0 && op->ldg % 2 == 0 && op->ldc >= op->b.n,
                 "sqd_sigma: ldc/ldg must be even and ldc >= nb");
@@ -734,7 +748,8 @@ int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sig
                 "sqd_sigma: nb=%d (ldc=%d) with norb=%d does not fit the shared-memory row staging "
                 "(limits: nb <= 5760 and 3*ldc + 2*ldg doubles <= 227 KB)",
                 op->b.n, op->ldc, op->norb);
-    SigmaArgs args{*op, d_c, d_sigma, d_done, g_prof};
+    SQD_REQUIRE(row_begin >= 0 && row_end <= op->a.n && row_begin <= row_end, "sqd_sigma: bad row range");
+    SigmaArgs args{*op, d_c, d_sigma, d_done, g_prof, row_begin, row_end};
     switch (pl.CPT) {
         case 1: return launch_sigma<1>(args, pl, st);
         case 2: return launch_sigma<2>(args, pl, st);
@@ -760,6 +775,11 @@ int64_t sqd_sigma_smem_bytes(const sqd_operator* op) {
 
 int sqd_sigma(const sqd_operator* op, const double* d_c, double* d_sigma, void* stream) {
     return sigma_dispatch_flag(op, d_c, d_sigma, nullptr, (cudaStream_t)stream);
+}
+
+int sqd_sigma_rows(const sqd_operator* op, const double* d_c, double* d_sigma, int row_begin,
+                   int row_end, void* stream) {
+    return sigma_dispatch_rows(op, d_c, d_sigma, nullptr, row_begin, row_end, (cudaStream_t)stream);
 }
 
 /* diagnostics: one sigma build with 8 clock64() stamps per kernel-A CTA written to d_prof

@@ -437,7 +437,8 @@ class _Subspace:
 
     # -- eigensolver -------------------------------------------------------------------------
     def ground_state(self, op: _OperatorDev, *, tol, tol_residual, max_cycle, max_space, lindep,
-                     level_shift, ci0=None, quad_penalty=None, check_every=4, profile=False):
+                     level_shift, ci0=None, quad_penalty=None, check_every=4, profile=False,
+                     shard=None):
         torch, lib = self.torch, self.lib
         st = _lib.stream_ptr(torch)
         n = self.na * self.ldc
@@ -460,6 +461,8 @@ class _Subspace:
             prm.ss_op = C.pointer(ss_op.struct)
             prm.ss_shift = float(shift)
             prm.ss_value = float(ss)
+        if shard is not None:
+            prm.nccl_comm, prm.row_begin, prm.row_end = shard
         info = _lib.DavidsonInfo()
         _lib.check(lib.sqd_davidson(C.byref(op.struct), _lib.ptr(op.diag), _lib.ptr(x0), _lib.ptr(x),
                                     _lib.ptr(ws), ws_bytes, C.byref(prm), C.byref(info), st),
@@ -527,7 +530,7 @@ def last_solve_stats() -> list[SolveStats]:
 
 def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq, shift, opts,
                      want_spin: bool, want_rdm: bool, *, strs_dev=(None, None), download: bool = True,
-                     profile: bool = False):
+                     profile: bool = False, shard_group=None):
     """Ground state of H projected on A x B.  Returns dict of results (host arrays; with
     ``download=False`` the amplitudes stay on the device as a padded ``(na, ldc)`` tensor)."""
     sub = _Subspace(strs_a, strs_b, norb, None, None, ints=ints, strs_dev=strs_dev)
@@ -544,7 +547,10 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
         ham = sub.hamiltonian()
         quad = (sub.spin_operator(), float(shift), float(spin_sq))
         lin_shift = 0.0
-    x, info = sub.ground_state(ham, tol=opts["tol"], tol_residual=opts["tol_residual"],
+    shard = None
+    if shard_group is not None:
+        shard = shard_group.row_range(sub)
+    x, info = sub.ground_state(ham, shard=shard, tol=opts["tol"], tol_residual=opts["tol_residual"],
                                max_cycle=opts["max_cycle"], max_space=opts["max_space"],
                                lindep=opts["lindep"], level_shift=opts["level_shift"],
                                ci0=opts.get("ci0"), quad_penalty=quad, profile=profile)
@@ -678,6 +684,80 @@ def solve_sci_batch(
         out.append(SCIResult(r["energy"], state, orbital_occupancies=r["occupancies"],
                              rdm1=r["rdm1"], rdm2=r["rdm2"]))
     return out
+
+
+class ShardGroup:
+    """NCCL communicator for ONE diagonalisation sharded over the ranks of ``torch.distributed``.
+
+    Rank 0 creates the NCCL unique id, ``torch.distributed`` (any backend) ships its 128 bytes, every
+    rank joins with its current CUDA device.  Rows of the CI matrix are split into contiguous blocks of
+    equal estimated sigma-build cost (the Hartree-Fock end of the string list is much heavier).
+    """
+
+    def __init__(self):
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()):
+            raise RuntimeError("ShardGroup needs an initialised torch.distributed process group")
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        lib = _lib.load()
+        buf = C.create_string_buffer(128)
+        if self.rank == 0:
+            _lib.check(lib.sqd_nccl_unique_id(buf), "sqd_nccl_unique_id")
+        box = [buf.raw if self.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self._comm = C.c_void_p()
+        _lib.check(lib.sqd_nccl_init(box[0], self.rank, self.world, C.byref(self._comm)),
+                   "sqd_nccl_init")
+
+    def row_range(self, sub: "_Subspace") -> tuple[int, int, int]:
+        ns = sub.ta.n_single.cpu().numpy().astype(np.int64)
+        ptr = sub.ta.row_ptr.cpu().numpy().astype(np.int64)
+        nd = np.diff(ptr) - ns
+        # per-row cost: alpha singles (gather loops), alpha doubles (row streaming), beta part (fixed)
+        cost = 16 * (ns + 1) + nd + max(1, sub.tb.nnz // max(sub.nb, 1))
+        cum = np.concatenate([[0], np.cumsum(cost)])
+        bounds = [int(np.searchsorted(cum, cum[-1] * r / self.world)) for r in range(self.world + 1)]
+        bounds[0], bounds[-1] = 0, sub.na
+        return self._comm.value, bounds[self.rank], bounds[self.rank + 1]
+
+    def close(self):
+        if self._comm:
+            _lib.load().sqd_nccl_destroy(self._comm)
+            self._comm = C.c_void_p()
+
+
+def solve_sci_sharded(
+    ci_strings: tuple[np.ndarray, np.ndarray],
+    one_body_tensor: np.ndarray,
+    two_body_tensor: np.ndarray,
+    norb: int,
+    nelec: tuple[int, int],
+    *,
+    group: ShardGroup,
+    spin_sq: float | None = None,
+    **kwargs,
+) -> SCIResult:
+    """One large diagonalisation with the sigma build sharded over the ranks of ``group``.
+
+    SPMD, like the reference's MPI mode (``fermion.py:316-324``): every rank calls this with the same
+    arguments and gets the same ``SCIResult``.  Vectors are replicated, rank r builds its block of rows of
+    sigma and the blocks are summed with an NCCL all-reduce over NVLink (BASELINE.json config 5).
+    """
+    torch = _lib.require_cuda()
+    one_body_tensor = np.asarray(one_body_tensor)
+    two_body_tensor = np.asarray(two_body_tensor)
+    norb, _ = one_body_tensor.shape
+    shift = float(kwargs.pop("shift", _FIX_SPIN_DEFAULT_SHIFT))
+    opts = _solver_options(kwargs)
+    _tls.stats = []
+    ints = _DeviceIntegrals(torch, one_body_tensor, two_body_tensor,
+                            torch.device("cuda", torch.cuda.current_device()))
+    r = _solve_on_device(ci_strings[0], ci_strings[1], norb, ints, spin_sq, shift, opts, want_spin=False,
+                         want_rdm=False, shard_group=group)
+    state = SCIState(amplitudes=r["amplitudes"], ci_strs_a=np.asarray(ci_strings[0]),
+                     ci_strs_b=np.asarray(ci_strings[1]), norb=norb, nelec=tuple(nelec))
+    return SCIResult(r["energy"], state, orbital_occupancies=r["occupancies"])
 
 
 def solve_fermion(
