@@ -166,8 +166,9 @@ def workload_config(args, world: int) -> dict:
                     f"{args.batches} subspaces x {na}x{nb}={na * nb} dets per GPU per step, HF-centred strings",
         "batches_per_gpu": args.batches, "na": na, "nb": nb, "norb": norb, "nelec": [nea, neb],
         "davidson": {"tol": 1e-12, "max_space": 12, "max_cycle": 100},
-        "l2": "working set (< 40 MB per subspace) is L2-resident by design of the path; no flush "
-              "between steps -- every step rebuilds its tables and vectors from the resident inputs",
+        "l2": "no explicit flush: the %d concurrent subspaces of a step hold ~%d MB of Davidson vectors, "
+              "integrals and tables (> 126 MB L2), and every step rebuilds its tables and vectors from the "
+              "resident inputs" % (args.batches, 35 * args.batches),
         "parallelism": f"{world} x independent ranks, no data-path collective",
     }
 
@@ -228,8 +229,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             main.wait_stream(s)
         return res
 
+    # host inputs of the end-to-end arm live in pinned memory (numpy views of pinned tensors)
+    h_pin = torch.from_numpy(h).pin_memory().numpy()
+    g_pin = torch.from_numpy(g).pin_memory().numpy()
+    batches_pin = [(torch.from_numpy(a.copy()).pin_memory().numpy(), torch.from_numpy(b.copy()).pin_memory().numpy())
+                   for a, b in batches]
+
     def e2e_step():
-        return fermion.solve_sci_batch(batches, h, g, norb, nelec)
+        return fermion.solve_sci_batch(batches_pin, h_pin, g_pin, norb, nelec)
 
     def barrier():
         torch.cuda.synchronize()
@@ -319,7 +326,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "roofline": {
             "kernel": "sigma_kernel (CI sigma-vector build inside the Davidson loop)",
             "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "peak_source": peak_src, "traffic": None,
+            "frac": achieved / peak_gbs, "peak_source": peak_src, "traffic": ncu_traffic(),
             "bytes_per_launch": sig_bytes, "ms_per_launch": sig_ms,
             "share_of_davidson_loop": sig_share, "davidson_loop_ms": dav_ms,
             "note": "algorithmic bytes = 16 n_det + 8 norb^4 + 12 nnz + 8 links (SURVEY 8d); the working "
@@ -335,6 +342,20 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the alpha sigma kernel from the committed `ncu --set full` capture
+    (profiles/r1_sigma_a_ncu_raw_c4.txt); null when the summary is not there."""
+    path = os.path.join(ROOT, "profiles", "r1_sigma_a_ncu_raw_c4.txt")
+    if not os.path.exists(path):
+        return None
+    tot = 0.0
+    for ln in open(path):
+        if ln.startswith(("dram__bytes_read.sum", "dram__bytes_write.sum")):
+            val, unit = ln.split("=")[1].split()[:2]
+            tot += float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+    return tot
 
 
 def cpu_baseline(args, batches, h, g, res_dev) -> dict:

@@ -522,6 +522,26 @@ class SolveStats:
 
 
 _tls = threading.local()
+_pool_lock = threading.Lock()
+_pool: ThreadPoolExecutor | None = None
+_streams: dict[tuple[int, int], object] = {}
+
+
+def _worker_pool() -> ThreadPoolExecutor:
+    """Host threads that drive the concurrent subspaces (created once; ctypes calls release the GIL)."""
+    global _pool
+    with _pool_lock:
+        if _pool is None:
+            _pool = ThreadPoolExecutor(max_workers=16, thread_name_prefix="sqd-b200")
+        return _pool
+
+
+def _stream_for(torch, device: int, slot: int):
+    with _pool_lock:
+        key = (device, slot)
+        if key not in _streams:
+            _streams[key] = torch.cuda.Stream(device=device)
+        return _streams[key]
 
 
 def last_solve_stats() -> list[SolveStats]:
@@ -564,15 +584,12 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
         s2 = sub.spin_square(x)
     energy = e_pen - lin_shift * (s2 - float(spin_sq)) if lin_shift != 0.0 else e_pen
     occ = sub.occupancies(x)
-    if download:
-        amps = sub.download_amplitudes(x)
-        # eigenvector sign: pyscf's is whatever LAPACK returns for the small problem; fix the
-        # convention "largest-magnitude amplitude positive" so that results are reproducible.
-        k = np.unravel_index(np.argmax(np.abs(amps)), amps.shape)
-        if amps[k] < 0:
-            amps = -amps
-    else:
-        amps = x.reshape(sub.na, sub.ldc)
+    # eigenvector sign: pyscf's is whatever LAPACK returns for the small problem; fix the convention
+    # "largest-magnitude amplitude positive" (first such element) so that results are reproducible.
+    kmax = int(x.abs().argmax().item())
+    if float(x[kmax].item()) < 0:
+        x = -x
+    amps = sub.download_amplitudes(x) if download else x.reshape(sub.na, sub.ldc)
     rdm1 = rdm2 = None
     if want_rdm:
         from ._rdm import subspace_rdms
@@ -580,7 +597,8 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
         rdm1, rdm2 = subspace_rdms(sub, x)
     stats = SolveStats(info.cycles, info.sigma_builds, info.converged, info.residual, info.theta,
                        sub.na * sub.nb, sub.ta.nnz, sub.tb.nnz,
-                       int(sub.ta.n_single.sum().item()), int(sub.tb.n_single.sum().item()),
+                       int(sub.ta.n_single.sum().item()) if profile else 0,
+                       int(sub.tb.n_single.sum().item()) if profile else 0,
                        info.sigma_ms, info.total_ms, sub.na, sub.nb, norb)
     if not hasattr(_tls, "stats"):
         _tls.stats = []
@@ -659,7 +677,7 @@ def solve_sci_batch(
         d = dev_list[k % len(dev_list)]
         with torch.cuda.device(d):
             it = get_ints(d)
-            stream = torch.cuda.Stream(device=d) if K > 1 else torch.cuda.current_stream()
+            stream = _stream_for(torch, d, k // len(dev_list)) if K > 1 else torch.cuda.current_stream()
             if K > 1:
                 stream.wait_stream(torch.cuda.default_stream(d))
             with torch.cuda.stream(stream):
@@ -673,8 +691,7 @@ def solve_sci_batch(
         raw = [work(0)]
     else:
         # ctypes releases the GIL during every sqd_* call, so the K host threads overlap
-        with ThreadPoolExecutor(max_workers=min(K, 16)) as pool:
-            raw = list(pool.map(work, range(K)))
+        raw = list(_worker_pool().map(work, range(K)))
     _tls.stats = [r["stats"] for r in raw]
 
     out = []
