@@ -235,6 +235,55 @@ int sqd_init_guess(const double* d_hdiag, int na, int nb, int ldc, double* d_x0,
                    void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
+ * One-call subspace solve: everything below the Python signature of fermion.py:solve_sci (:711-740)
+ *   kernel_fixed_space (tables, hdiag, initial guess, Davidson) -> make_rdm1s diagonals -> energy of the
+ *   bare Hamiltonian -> spin_square -> optional make_rdm1 / make_rdm2.
+ * The host thread stays inside this call from the first kernel to the last read-back, so K subspaces
+ * solved by K host threads (one stream each) do not serialise on the interpreter lock.  Scratch memory
+ * is taken from the device's stream-ordered pool (cudaMallocAsync) and returned before the call ends.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    int norb, na, nb;            /* strings sorted ascending, unique, equal popcount per list */
+    int n_alpha, n_beta;         /* electrons per spin (popcount of the strings) */
+    const uint64_t* d_strs_a;    /* [na] device */
+    const uint64_t* d_strs_b;    /* [nb] device; the same pointer as d_strs_a shares one table */
+    const double* d_h;           /* [norb^2] device */
+    const double* d_g;           /* [norb^4] device, chemist order (pq|rs) */
+    int penalty;                 /* 0: none; 1: pyscf fix_spin_(ss=spin_sq, shift) -- the linear form when
+                                    spin_sq < sz(sz+1)+0.1, else the quadratic form */
+    double spin_sq, shift;
+    int want_spin;               /* also return <S^2> when no penalty is requested */
+    int max_space, max_cycle;    /* Davidson, see sqd_davidson_params */
+    double tol, tol_residual, lindep, level_shift;
+    int check_every;
+    const double* d_ci0;         /* NULL, or start vector (na, nb) row-major on the device */
+    int cost_per_chunk, long_threshold; /* sigma work plan, 0 = defaults (256, 64) */
+    int profile;                 /* time the operator applications with CUDA events; count singles */
+    void* nccl_comm;             /* NULL, or sharded build (see sqd_davidson_params) */
+    int row_begin, row_end;      /* rows of sigma this rank builds; row_begin < 0: split the rows into
+                                    shard_world contiguous blocks of equal estimated cost, take block
+                                    shard_rank */
+    int shard_rank, shard_world;
+} sqd_solve_params;
+
+typedef struct {
+    double energy;               /* <x|H|x> of the bare Hamiltonian (fermion.py:730-732) */
+    double spin_square;          /* <x|S^2|x> when have_spin_square */
+    int have_spin_square;
+    double occ_a[64], occ_b[64]; /* diagonals of the spin 1-RDMs (fermion.py:725-726) */
+    sqd_davidson_info info;
+    int64_t nnz_a, nnz_b;        /* entries of the two excitation tables */
+    int64_t singles_a, singles_b;/* profile != 0: single excitations among them, else -1 */
+    int ldc;                     /* row stride of d_x */
+} sqd_solve_result;
+
+/* d_x: double[na * ldc], ldc = nb rounded up to even, receives the normalised ground state (pad columns
+ * zero; sign: first element of largest magnitude positive).  d_rdm1: NULL or double[norb^2] (pyscf
+ * make_rdm1).  d_rdm2: NULL or double[norb^4] (pyscf make_rdm2, dm2[p,q,r,s] = <p+ r+ s q>). */
+int sqd_solve_subspace(const sqd_solve_params* params, double* d_x, double* d_rdm1, double* d_rdm2,
+                       sqd_solve_result* h_result, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
  * Multi-GPU exchange for one sharded diagonalisation (the K-batches mode needs no collective).
  * NCCL is resolved with dlopen at first use.  Bootstrap: rank 0 calls sqd_nccl_unique_id and ships the
  * 128 bytes to the other ranks by any means (the Python host uses torch.distributed); every rank then
@@ -252,6 +301,15 @@ int sqd_allreduce_sum_f64(void* comm, double* d_buf, int64_t n, void* stream);
 int sqd_dot(const double* d_x, const double* d_y, int64_t n, double* d_out, double* d_scratch,
             void* stream);
 
+/* Sign convention of a returned eigenvector (fermion.py:837-845 hands pyscf's vector through as is; its
+ * sign is LAPACK's): flip d_x in place so that its first element of largest magnitude is positive.
+ * d_scratch: at least 4096 doubles. */
+int sqd_fix_sign(double* d_x, int64_t n, void* d_scratch, void* stream);
+
+/* Small (<= 16 KB) device -> host read-back through a per-thread pinned staging buffer followed by a
+ * stream synchronisation; never blocks the launches of other host threads. */
+int sqd_read_back(void* h_dst, const void* d_src, int64_t bytes, void* stream);
+
 /* occ_a[p] = sum_{a: p in a} sum_b c[a,b]^2, occ_b[p] likewise.  d_occ: double[2*norb] (alpha first).
  * d_scratch: double[na + nb]. */
 int sqd_occupancies(const double* d_c, const uint64_t* d_strs_a, int na, const uint64_t* d_strs_b,
@@ -263,6 +321,15 @@ int sqd_occupancies(const double* d_c, const uint64_t* d_strs_a, int na, const u
 int64_t sqd_rdm1s_workspace_bytes(const sqd_operator* op);
 int sqd_rdm1s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t nnz_b, double* d_dm1,
               double* d_workspace, double* d_dots, void* stream);
+
+/* Spin-separated 2-RDMs in pyscf's convention  dm2[p,q,r,s] = <c| p+ r+ s q |c>  (selected_ci.make_rdm2s:
+ * (alpha,alpha), (alpha,beta), (beta,beta) blocks), reached from fermion.py:117-128 (SCIState.rdm) and
+ * fermion.py:728-729, 825-826 (energy from RDMs, SCIResult.rdm2).  Each output is double[norb^4],
+ * C-order [p][q][r][s]; for the opposite-spin block p,q are alpha and r,s beta orbitals.  nnz_a / nnz_b =
+ * entries of the excitation tables.  Deterministic (no atomics). */
+int64_t sqd_rdm2s_workspace_bytes(const sqd_operator* op, int64_t nnz_a, int64_t nnz_b);
+int sqd_rdm2s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t nnz_b, double* d_dm2aa,
+              double* d_dm2ab, double* d_dm2bb, void* d_workspace, int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * Qubit path   (qubit.py:78-300)

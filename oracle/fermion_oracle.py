@@ -444,3 +444,53 @@ def rdm1s(c: np.ndarray, strs_a, strs_b, norb: int):
     for (t, s, p, q, sg) in single_excitation_links(strs_b, norb):
         dmb[q, p] += sg * float(c[:, t] @ c[:, s])
     return dma, dmb
+
+
+def rdm2s(c: np.ndarray, strs_a, strs_b, norb: int):
+    """Spin-separated 2-RDMs ``(dm2aa, dm2ab, dm2bb)`` in pyscf's convention
+    ``dm2[p, q, r, s] = <c| p^+ r^+ s q |c>`` (``selected_ci.make_rdm2s``, reached from
+    ``fermion.py:117-128`` and ``:728-729``); for ``dm2ab`` p, q are alpha and r, s beta orbitals.
+
+    Brute force on the 2*norb spin-orbital occupation strings (alpha modes first, then beta: the
+    determinant ordering of SURVEY Appendix B.1), operator by operator with ``annihilate`` / ``create``
+    -- independent of the excitation-table construction the CUDA kernels use.  Small cases only."""
+    c = np.asarray(c, dtype=float)
+    sa = [int(x) for x in strs_a]
+    sb = [int(x) for x in strs_b]
+    index = {(a | (b << norb)): (i, j) for i, a in enumerate(sa) for j, b in enumerate(sb)}
+    out = {k: np.zeros((norb,) * 4) for k in ("aa", "ab", "bb")}
+    off = {"a": 0, "b": norb}
+    for det, (i, j) in index.items():
+        ck = c[i, j]
+        if ck == 0.0:
+            continue
+        for key in ("aa", "ab", "bb"):
+            o1, o2 = off[key[0]], off[key[1]]   # spin of (p, q) and of (r, s)
+            for q in range(norb):
+                r1 = annihilate(q + o1, det)
+                if r1 is None:
+                    continue
+                for s in range(norb):
+                    r2 = annihilate(s + o2, r1[1])
+                    if r2 is None:
+                        continue
+                    for r in range(norb):
+                        r3 = create(r + o2, r2[1])
+                        if r3 is None:
+                            continue
+                        for p in range(norb):
+                            r4 = create(p + o1, r3[1])
+                            if r4 is None:
+                                continue
+                            tgt = index.get(r4[1])
+                            if tgt is None:
+                                continue
+                            sign = r1[0] * r2[0] * r3[0] * r4[0]
+                            out[key][p, q, r, s] += sign * c[tgt] * ck
+    return out["aa"], out["ab"], out["bb"]
+
+
+def rdm2(c: np.ndarray, strs_a, strs_b, norb: int) -> np.ndarray:
+    """Spin-summed 2-RDM (pyscf ``make_rdm2``): ``aa + bb + ab + ab.transpose(2, 3, 0, 1)``."""
+    aa, ab, bb = rdm2s(c, strs_a, strs_b, norb)
+    return aa + bb + ab + ab.transpose(2, 3, 0, 1)

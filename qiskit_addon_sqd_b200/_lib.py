@@ -110,6 +110,42 @@ class DavidsonInfo(C.Structure):
     ]
 
 
+class SolveParams(C.Structure):
+    """``sqd_solve_params`` of include/sqd_b200.h."""
+
+    _fields_ = [
+        ("norb", C.c_int), ("na", C.c_int), ("nb", C.c_int),
+        ("n_alpha", C.c_int), ("n_beta", C.c_int),
+        ("d_strs_a", C.c_void_p), ("d_strs_b", C.c_void_p),
+        ("d_h", C.c_void_p), ("d_g", C.c_void_p),
+        ("penalty", C.c_int), ("spin_sq", C.c_double), ("shift", C.c_double),
+        ("want_spin", C.c_int),
+        ("max_space", C.c_int), ("max_cycle", C.c_int),
+        ("tol", C.c_double), ("tol_residual", C.c_double), ("lindep", C.c_double),
+        ("level_shift", C.c_double),
+        ("check_every", C.c_int),
+        ("d_ci0", C.c_void_p),
+        ("cost_per_chunk", C.c_int), ("long_threshold", C.c_int),
+        ("profile", C.c_int),
+        ("nccl_comm", C.c_void_p),
+        ("row_begin", C.c_int), ("row_end", C.c_int),
+        ("shard_rank", C.c_int), ("shard_world", C.c_int),
+    ]
+
+
+class SolveResult(C.Structure):
+    """``sqd_solve_result`` of include/sqd_b200.h."""
+
+    _fields_ = [
+        ("energy", C.c_double), ("spin_square", C.c_double), ("have_spin_square", C.c_int),
+        ("occ_a", C.c_double * 64), ("occ_b", C.c_double * 64),
+        ("info", DavidsonInfo),
+        ("nnz_a", C.c_int64), ("nnz_b", C.c_int64),
+        ("singles_a", C.c_int64), ("singles_b", C.c_int64),
+        ("ldc", C.c_int),
+    ]
+
+
 _vp, _i, _i64, _u64, _d = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double
 _pi = C.POINTER(C.c_int)
 
@@ -148,11 +184,18 @@ SIGNATURES: dict[str, tuple] = {
         [C.POINTER(Operator), _vp, _vp, _vp, _vp, _i64, C.POINTER(DavidsonParams),
          C.POINTER(DavidsonInfo), _vp],
     ),
+    "sqd_solve_subspace": (
+        _i, [C.POINTER(SolveParams), _vp, _vp, _vp, C.POINTER(SolveResult), _vp]
+    ),
     "sqd_init_guess": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "sqd_dot": (_i, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "sqd_occupancies": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "sqd_fix_sign": (_i, [_vp, _i64, _vp, _vp]),
+    "sqd_read_back": (_i, [_vp, _vp, _i64, _vp]),
     "sqd_rdm1s_workspace_bytes": (_i64, [C.POINTER(Operator)]),
     "sqd_rdm1s": (_i, [C.POINTER(Operator), _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "sqd_rdm2s_workspace_bytes": (_i64, [C.POINTER(Operator), _i64, _i64]),
+    "sqd_rdm2s": (_i, [C.POINTER(Operator), _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "sqd_bits_to_keys": (_i, [_vp, _i64, _i, _vp, _vp]),
     "sqd_pauli_connect": (_i, [_vp, _i64, _u64, _u64, _vp, _vp, _vp]),
     "sqd_pauli_project_count": (_i, [_vp, _i64, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
@@ -226,3 +269,39 @@ def ptr(t) -> int:
 
 def stream_ptr(torch) -> int:
     return torch.cuda.current_stream().cuda_stream
+
+
+def read_back(torch, t):
+    """Small device tensor -> numpy array through the library's per-thread pinned staging buffer
+    (``sqd_read_back``); synchronises the current stream.  Unlike ``tensor.cpu()`` / ``.item()`` it never
+    copies into pageable memory, which would stall the launches of the other solver threads."""
+    import numpy as np
+
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    buf = (C.c_char * max(nbytes, 1))()
+    check(load().sqd_read_back(C.addressof(buf), ptr(t), nbytes, stream_ptr(torch)), "sqd_read_back")
+    dt = {torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}[t.dtype]
+    return np.frombuffer(buf, dtype=dt, count=t.numel()).copy()
+
+
+_pinned_cache = threading.local()
+
+
+def download(torch, t):
+    """Large device tensor -> fresh numpy array, staged through a per-thread pinned buffer that is
+    reused between calls (asynchronous copy + stream synchronisation, then one host memcpy)."""
+    import numpy as np
+
+    t = t.contiguous()
+    n = t.numel()
+    cache = getattr(_pinned_cache, "bufs", None)
+    if cache is None:
+        cache = _pinned_cache.bufs = {}
+    buf = cache.get(t.dtype)
+    if buf is None or buf.numel() < n:
+        buf = cache[t.dtype] = torch.empty(max(n, 1 << 16), dtype=t.dtype, pin_memory=True)
+    view = buf[:n]
+    view.copy_(t.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return np.array(view.numpy(), copy=True).reshape(tuple(t.shape))

@@ -29,6 +29,21 @@ int check_launch(const char* what, int n_launched) {
     return 0;
 }
 
+static thread_local void* g_pinned = nullptr;
+constexpr size_t kPinnedBytes = 16 * 1024;
+
+int read_back(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+    if (bytes > kPinnedBytes) {
+        set_error("read_back: %zu bytes exceed the pinned staging buffer", bytes);
+        return -1;
+    }
+    if (g_pinned == nullptr) SQD_CUDA_OK(cudaHostAlloc(&g_pinned, kPinnedBytes, cudaHostAllocPortable));
+    SQD_CUDA_OK(cudaMemcpyAsync(g_pinned, d_src, bytes, cudaMemcpyDeviceToHost, st));
+    SQD_CUDA_OK(cudaStreamSynchronize(st));
+    memcpy(h_dst, g_pinned, bytes);
+    return 0;
+}
+
 }  // namespace sqd
 
 extern "C" {

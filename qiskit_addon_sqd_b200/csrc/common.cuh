@@ -10,6 +10,10 @@ namespace sqd {
 // ---- error plumbing (C-ABI: 0 = ok, <0 = error, message via sqd_last_error) ------------------
 void set_error(const char* fmt, ...);
 int check_launch(const char* what, int n_launched = 1);  // also counts kernel launches
+// Small device -> host read-back through a per-thread PINNED staging buffer, then a stream sync.  A copy
+// into pageable memory makes the runtime hold a context-wide lock until the stream has drained, which
+// stalls the launches of every other host thread (one thread per concurrent subspace solve).
+int read_back(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st);
 
 #define SQD_CUDA_OK(expr)                                                              \
     do {                                                                               \

@@ -575,6 +575,67 @@ __global__ void init_guess_kernel(const double* __restrict__ pval, const int64_t
     }
 }
 
+// Sign convention of the returned eigenvector: the first element of largest magnitude is positive
+// (pyscf's sign is whatever LAPACK returns for the small problem).  Stage 1 per CTA, stage 2 one thread,
+// stage 3 flips the vector when needed -- no host round trip.
+__global__ void __launch_bounds__(kRedThreads)
+absmax_partial_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ pval,
+                      int64_t* __restrict__ pidx) {
+    __shared__ double sv[kRedThreads];
+    __shared__ int64_t si[kRedThreads];
+    double best = -1.0;
+    int64_t bi = -1;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (int64_t)gridDim.x * blockDim.x) {
+        const double v = fabs(x[k]);
+        if (v > best) {  // k ascends per thread: ties keep the lowest index
+            best = v;
+            bi = k;
+        }
+    }
+    sv[threadIdx.x] = best;
+    si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = kRedThreads / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const double v2 = sv[threadIdx.x + o];
+            const int64_t i2 = si[threadIdx.x + o];
+            if (i2 >= 0 && (v2 > sv[threadIdx.x] || si[threadIdx.x] < 0 ||
+                            (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x]))) {
+                sv[threadIdx.x] = v2;
+                si[threadIdx.x] = i2;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        pval[blockIdx.x] = sv[0];
+        pidx[blockIdx.x] = si[0];
+    }
+}
+
+__global__ void sign_flag_kernel(const double* __restrict__ pval, int64_t* __restrict__ pidx, int nblk,
+                                 const double* __restrict__ x) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double best = -1.0;
+        int64_t bi = -1;
+        for (int b = 0; b < nblk; ++b)
+            if (pidx[b] >= 0 && (pval[b] > best || (pval[b] == best && pidx[b] < bi))) {
+                best = pval[b];
+                bi = pidx[b];
+            }
+        pidx[kRedBlocks] = (bi >= 0 && x[bi] < 0.0) ? 1 : 0;  // flag slot after the partial indices
+    }
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+flip_kernel(double* __restrict__ x, int64_t n, const int64_t* __restrict__ flag) {
+    if (*flag == 0) return;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (int64_t)gridDim.x * blockDim.x)
+        x[k] = -x[k];
+}
+
 // row / column weights of c^2 and orbital occupancies
 __global__ void row_weight_kernel(const double* __restrict__ c, int na, int nb, int ldc,
                                   double* __restrict__ wa) {
@@ -711,7 +772,6 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
     carve(d_workspace, n, M, &ws);
     const int blocks = red_blocks(n);
     const int check_every = prm->check_every > 0 ? prm->check_every : 4;
-
     init_state_kernel<<<1, 256, 0, st>>>(ws.state);
     // V_0 = x0 / |x0|
     dot_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_x0, d_x0, n, ws.partials);
@@ -768,9 +828,7 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         m = me + 1;
         slot = me;
         if ((cycle + 1) % check_every == 0 || cycle + 1 == prm->max_cycle) {
-            SQD_CUDA_OK(cudaMemcpyAsync(&status, &ws.state->status, sizeof(int),
-                                        cudaMemcpyDeviceToHost, st));
-            SQD_CUDA_OK(cudaStreamSynchronize(st));
+            if (read_back(&status, &ws.state->status, sizeof(int), st)) return -2;
             if (status != 0) {
                 ++cycle;
                 break;
@@ -778,10 +836,9 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         }
     }
     DavState hs;
-    SQD_CUDA_OK(cudaMemcpyAsync(&hs, ws.state, sizeof(DavState), cudaMemcpyDeviceToHost, st));
     SQD_CUDA_OK(cudaMemcpyAsync(d_x, ws.X, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (prm->profile) SQD_CUDA_OK(cudaEventRecord(ev_end, st));
-    SQD_CUDA_OK(cudaStreamSynchronize(st));
+    if (read_back(&hs, ws.state, sizeof(DavState), st)) return -2;
     double sigma_ms = 0.0, total_ms = 0.0;
     if (prm->profile) {
         // only cycles that ran before the device-side stop flag was raised did real work
@@ -844,6 +901,23 @@ int sqd_init_guess(const double* d_hdiag, int na, int nb, int ldc, double* d_x0,
     argmin_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_hdiag, na, nb, ldc, pval, pidx);
     init_guess_kernel<<<1, 32, 0, st>>>(pval, pidx, blocks, na, nb, ldc, d_x0);
     return check_launch("init_guess kernels", 2);
+}
+
+int sqd_fix_sign(double* d_x, int64_t n, void* d_scratch, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SQD_REQUIRE(n > 0, "sqd_fix_sign: empty vector");
+    const int blocks = red_blocks(n);
+    double* pval = (double*)d_scratch;
+    int64_t* pidx = (int64_t*)(pval + kRedBlocks);
+    absmax_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_x, n, pval, pidx);
+    sign_flag_kernel<<<1, 32, 0, st>>>(pval, pidx, blocks, d_x);
+    flip_kernel<<<blocks, kRedThreads, 0, st>>>(d_x, n, pidx + kRedBlocks);
+    return check_launch("fix_sign kernels", 3);
+}
+
+int sqd_read_back(void* h_dst, const void* d_src, int64_t bytes, void* stream) {
+    SQD_REQUIRE(bytes >= 0, "sqd_read_back: negative size");
+    return read_back(h_dst, d_src, (size_t)bytes, (cudaStream_t)stream);
 }
 
 int sqd_occupancies(const double* d_c, const uint64_t* d_strs_a, int na, const uint64_t* d_strs_b,

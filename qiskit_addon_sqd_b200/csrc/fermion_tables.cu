@@ -333,16 +333,15 @@ int sqd_check_hamming(const uint64_t* d_strs, int64_t n, int* d_scratch2, int* h
     check_hamming_kernel<<<blocks, 256, 0, st>>>(d_strs, n, d_scratch2);
     if (check_launch("check_hamming_kernel")) return -2;
     int bad = 0;
-    SQD_CUDA_OK(cudaMemcpyAsync(&bad, d_scratch2, sizeof(int), cudaMemcpyDeviceToHost, st));
-    SQD_CUDA_OK(cudaStreamSynchronize(st));
+    if (read_back(&bad, d_scratch2, sizeof(int), st)) return -2;
     uint64_t s0 = 0, sb = 0;
-    SQD_CUDA_OK(cudaMemcpy(&s0, d_strs, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (read_back(&s0, d_strs, sizeof(uint64_t), st)) return -2;
     *h_weight0 = __builtin_popcountll(s0);
     if (bad == 0x7fffffff) {
         *h_bad_index = -1;
         *h_weight_bad = *h_weight0;
     } else {
-        SQD_CUDA_OK(cudaMemcpy(&sb, d_strs + bad, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        if (read_back(&sb, d_strs + bad, sizeof(uint64_t), st)) return -2;
         *h_bad_index = bad;
         *h_weight_bad = __builtin_popcountll(sb);
     }
@@ -364,8 +363,7 @@ int sqd_exclusive_scan(const int* d_in, int* d_out, int n, int* h_total, void* s
     exclusive_scan_kernel<<<1, 1024, 0, st>>>(d_in, d_out, n);
     if (check_launch("exclusive_scan_kernel")) return -2;
     if (h_total) {
-        SQD_CUDA_OK(cudaMemcpyAsync(h_total, d_out + n, sizeof(int), cudaMemcpyDeviceToHost, st));
-        SQD_CUDA_OK(cudaStreamSynchronize(st));
+        if (read_back(h_total, d_out + n, sizeof(int), st)) return -2;
     }
     return 0;
 }

@@ -71,6 +71,329 @@ rdm1_collect_kernel(const sqd_spin_table T, int norb, const double* __restrict__
     if (threadIdx.x == 0) dm1[p * norb + q] = acc[0];
 }
 
+
+// ============================================================================================
+// Two-particle reduced density matrices, pyscf convention  dm2[p,q,r,s] = <c| p+ r+ s q |c>
+// (selected_ci.make_rdm2s / make_rdm2, reached from fermion.py:117-128 and :728-729, :825-826).
+//
+// pyscf resolves the same-spin blocks through (N-2)-electron intermediates (SCIrdm2_aaaa) and the
+// opposite-spin block through t1a^T t1b dgemms (FCItdm12kern_ab).  Here every block comes straight from
+// the in-set excitation tables:
+//   same spin   : every ordered pair (t, s) of strings that differ by 0, 1 or 2 orbitals contributes
+//                 <x[t,:], x[s,:]> to a fixed, disjoint family of cells --
+//                   identical strings  -> [p,p,r,r] and [p,r,r,p]          (rdm2_diag_kernel)
+//                   single excitation  -> [p,q,j,j] [j,j,p,q] [p,j,j,q] [j,q,p,j], j a spectator
+//                                                                            (rdm2_singles_kernel)
+//                   double excitation  -> the four antisymmetric images of [a1,i1,a2,i2]
+//                                                                            (rdm2_doubles_kernel)
+//   opposite    : dm2ab[pq,rs] = sum_{(a<-a',pq)} sum_{(b<-b',rs)} sgn_a sgn_b c[a,b] c[a',b'] with the
+//                 single-excitation lists (diagonal p=q included) grouped by orbital pair.
+// No atomics: every cell is accumulated by one thread in table order, so the result is bit-reproducible.
+// ============================================================================================
+
+constexpr uint32_t kNotDouble = 0xffffffffu;
+
+// dots[e] = <x[row(e),:], x[col(e),:]> for EVERY entry; roww[i] = |x[i,:]|^2;
+// dinfo[e] = a1 | a2<<6 | i1<<12 | i2<<18 | parity<<31 for doubles (target = (-1)^parity a1+ a2+ i2 i1 source,
+// i1<i2 holes of the source, a1<a2 particles of the target), kNotDouble for singles
+__global__ void pair_dots_kernel(const sqd_spin_table T, const double* __restrict__ x, int ncols, int ldx,
+                                 double* __restrict__ dots, double* __restrict__ roww,
+                                 uint32_t* __restrict__ dinfo) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= T.n) return;
+    const double* xi = x + (size_t)i * ldx;
+    double w = 0.0;
+    for (int b = lane; b < ncols; b += 32) w = fma(xi[b], xi[b], w);
+    w = warp_sum(w);
+    if (lane == 0) roww[i] = w;
+    const int beg = T.row_ptr[i], ns = T.n_single[i], end = T.row_ptr[i + 1];
+    const uint64_t t = T.strs[i];
+    for (int e = beg; e < end; ++e) {
+        const int j = (int)T.col[e];
+        const double* xj = x + (size_t)j * ldx;
+        double d = 0.0;
+        for (int b = lane; b < ncols; b += 32) d = fma(xi[b], xj[b], d);
+        d = warp_sum(d);
+        if (lane == 0) {
+            dots[e] = d;
+            uint32_t info = kNotDouble;
+            if (e >= beg + ns) {
+                const uint64_t s = T.strs[j];
+                const uint64_t xo = s ^ t;
+                uint64_t holes = xo & s, parts = xo & t;
+                const int i1 = lowbit64(holes);
+                holes &= holes - 1;
+                const int i2 = lowbit64(holes);
+                const int a1 = lowbit64(parts);
+                parts &= parts - 1;
+                const int a2 = lowbit64(parts);
+                int par = popc64(s & below_mask(i1));
+                uint64_t u = s ^ (1ull << i1);
+                par += popc64(u & below_mask(i2));
+                u ^= (1ull << i2);
+                par += popc64(u & below_mask(a2));
+                u |= (1ull << a2);
+                par += popc64(u & below_mask(a1));
+                info = (uint32_t)a1 | ((uint32_t)a2 << 6) | ((uint32_t)i1 << 12) | ((uint32_t)i2 << 18) |
+                       ((uint32_t)(par & 1) << 31);
+            }
+            dinfo[e] = info;
+        }
+    }
+}
+
+constexpr int kD2Threads = 256;
+constexpr int kD2Cap = 2048;
+
+// One CTA per row [P,Q,:,:] of the same-spin dm2.  Writes the WHOLE row (zeros included), so it runs
+// before the singles / diagonal kernels, which then overwrite their own (disjoint) cells.
+__global__ void __launch_bounds__(kD2Threads)
+rdm2_doubles_kernel(const uint32_t* __restrict__ dinfo, const double* __restrict__ dots, int nnz, int norb,
+                    double* __restrict__ dm2) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n2 = norb * norb;
+    double* acc = reinterpret_cast<double*>(smem_raw);   // [n2]
+    double* lval = acc + n2;                              // [kD2Cap]
+    int* lcell = reinterpret_cast<int*>(lval + kD2Cap);   // [kD2Cap]
+    __shared__ int wcnt[kD2Threads / 32];
+    __shared__ int list_n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = blockIdx.x / norb, Q = blockIdx.x % norb;
+    for (int c = tid; c < n2; c += kD2Threads) acc[c] = 0.0;
+    if (tid == 0) list_n = 0;
+    __syncthreads();
+    auto flush = [&]() {
+        const int ln = list_n;
+        for (int k = 0; k < ln; ++k) {
+            const int c = lcell[k];
+            if ((c & (kD2Threads - 1)) == tid) acc[c] += lval[k];  // cell owner: fixed thread, list order
+        }
+        __syncthreads();
+        if (tid == 0) list_n = 0;
+        __syncthreads();
+    };
+    if (P != Q) {
+        for (int e0 = 0; e0 < nnz; e0 += kD2Threads) {
+            const int e = e0 + tid;
+            bool match = false;
+            int cell = 0;
+            double val = 0.0;
+            if (e < nnz) {
+                const uint32_t info = __ldg(dinfo + e);
+                if (info != kNotDouble) {
+                    const int a1 = info & 63, a2 = (info >> 6) & 63, i1 = (info >> 12) & 63,
+                              i2 = (info >> 18) & 63;
+                    const int pa = P == a1 ? 0 : (P == a2 ? 1 : -1);
+                    const int qi = Q == i1 ? 0 : (Q == i2 ? 1 : -1);
+                    if (pa >= 0 && qi >= 0) {
+                        // [a1,i1,a2,i2] carries the table phase; swapping the creators or the
+                        // annihilators flips the sign
+                        const int R = pa ? a1 : a2, S = qi ? i1 : i2;
+                        const int neg = (int)(info >> 31) ^ pa ^ qi;
+                        const double d = __ldg(dots + e);
+                        match = true;
+                        cell = R * norb + S;
+                        val = neg ? -d : d;
+                    }
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, match);
+            if (lane == 0) wcnt[warp] = __popc(bal);
+            __syncthreads();
+            int woff = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kD2Threads / 32; ++w) {
+                if (w < warp) woff += wcnt[w];
+                total += wcnt[w];
+            }
+            if (list_n + total > kD2Cap) flush();  // uniform decision; flush ends with a barrier
+            const int base = list_n;
+            if (match) {
+                const int o = base + woff + __popc(bal & ((1u << lane) - 1u));
+                lcell[o] = cell;
+                lval[o] = val;
+            }
+            __syncthreads();
+            if (tid == 0) list_n = base + total;
+            __syncthreads();
+        }
+        flush();
+    }
+    double* row = dm2 + (size_t)blockIdx.x * n2;
+    for (int c = tid; c < n2; c += kD2Threads) row[c] = acc[c];
+}
+
+// One warp per (p,q), p != q; lane j (and j+32) owns the spectator orbital j.
+__global__ void __launch_bounds__(128)
+rdm2_singles_kernel(const sqd_spin_table T, const double* __restrict__ dots, int norb,
+                    double* __restrict__ dm2) {
+    const int lane = threadIdx.x & 31;
+    const int pq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int n2 = norb * norb;
+    if (pq >= n2) return;
+    const int p = pq / norb, q = pq % norb;
+    if (p == q) return;
+    double g0 = 0.0, g1 = 0.0;
+    for (int i = 0; i < T.n; ++i) {
+        const int beg = T.row_ptr[i], ns = T.n_single[i];
+        for (int e = beg; e < beg + ns; ++e) {
+            const uint32_t m = __ldg(T.meta + e);
+            if ((int)(m & 0x7fffffffu) == pq) {
+                // target strs[i] = sgn * p+ q source; spectators = occupied orbitals of the source but q
+                const uint64_t src = T.strs[T.col[e]] & ~(1ull << q);
+                const double d = (m >> 31) ? -__ldg(dots + e) : __ldg(dots + e);
+                if ((src >> lane) & 1ull) g0 += d;
+                if ((src >> (lane + 32)) & 1ull) g1 += d;
+                break;  // at most one source per (target, p, q)
+            }
+        }
+    }
+    const size_t n1 = norb, n3 = (size_t)n2 * norb;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int j = lane + 32 * half;
+        const double g = half ? g1 : g0;
+        if (j < norb && j != p && j != q) {
+            dm2[p * n3 + q * (size_t)n2 + j * n1 + j] = g;    // <p+ j+ j q>
+            dm2[j * n3 + j * (size_t)n2 + p * n1 + q] = g;    // <j+ p+ q j>
+            dm2[p * n3 + j * (size_t)n2 + j * n1 + q] = -g;   // <p+ j+ q j>
+            dm2[j * n3 + q * (size_t)n2 + p * n1 + j] = -g;   // <j+ p+ j q>
+        }
+    }
+}
+
+// dm2[p,p,r,r] = sum_{s: p,r in s} |x[s,:]|^2 = -dm2[p,r,r,p]   (p != r); one CTA per p, thread r
+__global__ void __launch_bounds__(64)
+rdm2_diag_kernel(const sqd_spin_table T, const double* __restrict__ roww, int norb,
+                 double* __restrict__ dm2) {
+    const int p = blockIdx.x, r = threadIdx.x;
+    if (r >= norb || r == p) return;
+    const uint64_t need = (1ull << p) | (1ull << r);
+    double acc = 0.0;
+    for (int i = 0; i < T.n; ++i)
+        if ((T.strs[i] & need) == need) acc += roww[i];
+    const size_t n1 = norb, n2 = n1 * n1, n3 = n2 * n1;
+    dm2[p * n3 + p * n2 + r * n1 + r] = acc;
+    dm2[p * n3 + r * n2 + r * n1 + p] = -acc;
+}
+
+// ---- single-excitation lists grouped by orbital pair (diagonal p == q included) ---------------
+// entry = {target index, source index | sign << 31}
+__device__ __forceinline__ bool group_probe(const sqd_spin_table& T, int i, int p, int q, int pq,
+                                            uint32_t* colsign) {
+    if (p == q) {
+        *colsign = (uint32_t)i;
+        return (T.strs[i] >> p) & 1ull;
+    }
+    const int beg = T.row_ptr[i], ns = T.n_single[i];
+    for (int e = beg; e < beg + ns; ++e) {
+        const uint32_t m = __ldg(T.meta + e);
+        if ((int)(m & 0x7fffffffu) == pq) {
+            *colsign = T.col[e] | (m & 0x80000000u);
+            return true;
+        }
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(256)
+group_count_kernel(const sqd_spin_table T, int norb, int* __restrict__ cnt) {
+    __shared__ int red[8];
+    const int pq = blockIdx.x, p = pq / norb, q = pq % norb;
+    int c = 0;
+    uint32_t dummy;
+    for (int i = threadIdx.x; i < T.n; i += blockDim.x) c += group_probe(T, i, p, q, pq, &dummy) ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        cnt[pq] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+group_fill_kernel(const sqd_spin_table T, int norb, const int* __restrict__ ptr, int2* __restrict__ ent) {
+    __shared__ int wcnt[8];
+    const int pq = blockIdx.x, p = pq / norb, q = pq % norb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int base = ptr[pq];
+    for (int i0 = 0; i0 < T.n; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        uint32_t cs = 0;
+        const bool hit = i < T.n && group_probe(T, i, p, q, pq, &cs);
+        const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            if (w < warp) woff += wcnt[w];
+            total += wcnt[w];
+        }
+        if (hit) ent[base + woff + __popc(bal & ((1u << lane) - 1u))] = make_int2(i, (int)cs);
+        base += total;
+        __syncthreads();
+    }
+}
+
+// One CTA per row [p,q,:,:] of dm2ab.  For every alpha entry (a <- a') of the pair the rows c[a,:] and
+// c[a',:] are staged in shared memory; thread rs walks the beta group rs (off-diagonal groups are a few
+// entries long), the long diagonal groups rs = rr are reduced by one warp each.
+__global__ void __launch_bounds__(256)
+rdm2_ab_kernel(const double* __restrict__ c, int nb, int ldc, int norb, const int* __restrict__ ptr_a,
+               const int2* __restrict__ ent_a, const int* __restrict__ ptr_b,
+               const int2* __restrict__ ent_b, double* __restrict__ dm2ab) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n2 = norb * norb;
+    double* X = reinterpret_cast<double*>(smem_raw);  // c[a ,:]  (bra)
+    double* Y = X + ldc;                                // c[a',:]  (ket)
+    double* acc = Y + ldc;                              // [n2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int pq = blockIdx.x;
+    for (int k = tid; k < n2; k += blockDim.x) acc[k] = 0.0;
+    const int ea_beg = ptr_a[pq], ea_end = ptr_a[pq + 1];
+    for (int ea = ea_beg; ea < ea_end; ++ea) {
+        const int2 A = ent_a[ea];
+        const int a = A.x, a1 = A.y & 0x7fffffff;
+        const double sa = A.y < 0 ? -1.0 : 1.0;
+        __syncthreads();
+        for (int b = tid; b < nb; b += blockDim.x) {
+            X[b] = c[(size_t)a * ldc + b];
+            Y[b] = c[(size_t)a1 * ldc + b];
+        }
+        __syncthreads();
+        // off-diagonal beta pairs: one thread per rs
+        for (int rs = tid; rs < n2; rs += blockDim.x) {
+            if (rs / norb == rs % norb) continue;
+            double s = 0.0;
+            for (int eb = ptr_b[rs]; eb < ptr_b[rs + 1]; ++eb) {
+                const int2 B = ent_b[eb];
+                const double t = X[B.x] * Y[B.y & 0x7fffffff];
+                s += B.y < 0 ? -t : t;
+            }
+            acc[rs] = fma(sa, s, acc[rs]);
+        }
+        // diagonal beta pairs: one warp per r
+        for (int r = warp; r < norb; r += nwarp) {
+            const int rs = r * norb + r;
+            double s = 0.0;
+            for (int eb = ptr_b[rs] + lane; eb < ptr_b[rs + 1]; eb += 32) {
+                const int bb = ent_b[eb].x;
+                s = fma(X[bb], Y[bb], s);
+            }
+            s = warp_sum(s);
+            if (lane == 0) acc[rs] = fma(sa, s, acc[rs]);
+        }
+    }
+    __syncthreads();
+    double* row = dm2ab + (size_t)pq * n2;
+    for (int k = tid; k < n2; k += blockDim.x) row[k] = acc[k];
+}
+
 }  // namespace sqd
 
 using namespace sqd;
@@ -103,6 +426,96 @@ int sqd_rdm1s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t 
     link_dots_kernel<<<(nb + 7) / 8, 256, 0, st>>>(op->b, ct, na, ldt, d_dots, rw_b);
     rdm1_collect_kernel<<<norb * norb, 256, 0, st>>>(op->b, norb, d_dots, rw_b, d_dm1 + norb * norb);
     return check_launch("rdm1s kernels", 5);
+}
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+int64_t sqd_rdm2s_workspace_bytes(const sqd_operator* op, int64_t nnz_a, int64_t nnz_b) {
+    const int64_t na = op->a.n, nb = op->b.n, norb = op->norb, n2 = norb * norb;
+    const int64_t ldt = (na + 1) / 2 * 2;
+    const int64_t nnz = nnz_a > nnz_b ? nnz_a : nnz_b;
+    size_t b = 0;
+    b += al256((size_t)nb * ldt * sizeof(double));          // c^T
+    b += al256((size_t)(na + nb) * sizeof(double));         // row weights
+    b += al256((size_t)(nnz + 1) * sizeof(double));         // dots
+    b += al256((size_t)(nnz + 1) * sizeof(uint32_t));       // dinfo
+    b += 4 * al256((size_t)(n2 + 1) * sizeof(int));         // cnt/ptr for both spins
+    b += al256((size_t)(nnz_a + na * norb + 1) * sizeof(int2));
+    b += al256((size_t)(nnz_b + nb * norb + 1) * sizeof(int2));
+    return (int64_t)b;
+}
+
+static int rdm2_same_spin(const sqd_spin_table& T, int64_t nnz, const double* x, int ncols, int ldx,
+                          int norb, double* dots, double* roww, uint32_t* dinfo, double* dm2,
+                          cudaStream_t st) {
+    const int n2 = norb * norb;
+    pair_dots_kernel<<<(T.n + 7) / 8, 256, 0, st>>>(T, x, ncols, ldx, dots, roww, dinfo);
+    const size_t smem = (size_t)n2 * sizeof(double) + kD2Cap * (sizeof(double) + sizeof(int));
+    static bool cfg[64] = {false};
+    if (smem > 48 * 1024) {
+        int dev = 0;
+        SQD_CUDA_OK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !cfg[dev]) {
+            SQD_CUDA_OK(cudaFuncSetAttribute(rdm2_doubles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(227 * 1024)));
+            if (dev >= 0 && dev < 64) cfg[dev] = true;
+        }
+    }
+    rdm2_doubles_kernel<<<n2, kD2Threads, smem, st>>>(dinfo, dots, (int)nnz, norb, dm2);
+    rdm2_singles_kernel<<<(n2 + 3) / 4, 128, 0, st>>>(T, dots, norb, dm2);
+    rdm2_diag_kernel<<<norb, 64, 0, st>>>(T, roww, norb, dm2);
+    return check_launch("rdm2 same-spin kernels", 4);
+}
+
+int sqd_rdm2s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t nnz_b, double* d_dm2aa,
+              double* d_dm2ab, double* d_dm2bb, void* d_workspace, int64_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int na = op->a.n, nb = op->b.n, ldc = op->ldc, norb = op->norb, n2 = norb * norb;
+    const int ldt = (na + 1) / 2 * 2;
+    SQD_REQUIRE(norb >= 1 && norb <= 64, "sqd_rdm2s: norb must be in [1, 64]");
+    SQD_REQUIRE(ws_bytes >= sqd_rdm2s_workspace_bytes(op, nnz_a, nnz_b), "sqd_rdm2s: workspace too small");
+    const int64_t nnz = nnz_a > nnz_b ? nnz_a : nnz_b;
+    char* p = (char*)d_workspace;
+    double* ct = (double*)p;        p += al256((size_t)nb * ldt * sizeof(double));
+    double* roww = (double*)p;      p += al256((size_t)(na + nb) * sizeof(double));
+    double* dots = (double*)p;      p += al256((size_t)(nnz + 1) * sizeof(double));
+    uint32_t* dinfo = (uint32_t*)p; p += al256((size_t)(nnz + 1) * sizeof(uint32_t));
+    int* cnt_a = (int*)p;           p += al256((size_t)(n2 + 1) * sizeof(int));
+    int* ptr_a = (int*)p;           p += al256((size_t)(n2 + 1) * sizeof(int));
+    int* cnt_b = (int*)p;           p += al256((size_t)(n2 + 1) * sizeof(int));
+    int* ptr_b = (int*)p;           p += al256((size_t)(n2 + 1) * sizeof(int));
+    int2* ent_a = (int2*)p;         p += al256((size_t)(nnz_a + (int64_t)na * norb + 1) * sizeof(int2));
+    int2* ent_b = (int2*)p;
+    // same spin, alpha: rows of c
+    if (rdm2_same_spin(op->a, nnz_a, d_c, nb, ldc, norb, dots, roww, dinfo, d_dm2aa, st)) return -2;
+    // same spin, beta: rows of c^T
+    dim3 tb(32, 8), tg((nb + 31) / 32, (na + 31) / 32);
+    transpose_kernel<<<tg, tb, 0, st>>>(d_c, na, nb, ldc, ct, ldt);
+    if (check_launch("transpose_kernel")) return -2;
+    if (rdm2_same_spin(op->b, nnz_b, ct, na, ldt, norb, dots, roww + na, dinfo, d_dm2bb, st)) return -2;
+    // opposite spin
+    group_count_kernel<<<n2, 256, 0, st>>>(op->a, norb, cnt_a);
+    group_count_kernel<<<n2, 256, 0, st>>>(op->b, norb, cnt_b);
+    if (check_launch("group_count_kernel", 2)) return -2;
+    if (sqd_exclusive_scan(cnt_a, ptr_a, n2, nullptr, stream)) return -2;
+    if (sqd_exclusive_scan(cnt_b, ptr_b, n2, nullptr, stream)) return -2;
+    group_fill_kernel<<<n2, 256, 0, st>>>(op->a, norb, ptr_a, ent_a);
+    group_fill_kernel<<<n2, 256, 0, st>>>(op->b, norb, ptr_b, ent_b);
+    const size_t smem_ab = (size_t)(2 * ldc + n2) * sizeof(double);
+    SQD_REQUIRE(smem_ab <= 227 * 1024, "sqd_rdm2s: nb=%d, norb=%d do not fit the shared-memory row staging",
+                nb, norb);
+    static bool cfg_ab[64] = {false};
+    if (smem_ab > 48 * 1024) {
+        int dev = 0;
+        SQD_CUDA_OK(cudaGetDevice(&dev));
+        if (dev < 0 || dev >= 64 || !cfg_ab[dev]) {
+            SQD_CUDA_OK(cudaFuncSetAttribute(rdm2_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(227 * 1024)));
+            if (dev >= 0 && dev < 64) cfg_ab[dev] = true;
+        }
+    }
+    rdm2_ab_kernel<<<n2, 256, smem_ab, st>>>(d_c, nb, ldc, norb, ptr_a, ent_a, ptr_b, ent_b, d_dm2ab);
+    return check_launch("rdm2 opposite-spin kernels", 3);
 }
 
 }  // extern "C"

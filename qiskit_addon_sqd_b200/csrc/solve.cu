@@ -1,0 +1,402 @@
+// One-call ground state of the Hamiltonian projected on a product subspace A x B.
+//
+// Replaces the whole body of qiskit_addon_sqd/fermion.py:solve_sci (:711-740) below the Python
+// signature: kernel_fixed_space (link tables, hdiag, initial guess, Davidson), make_rdm1s diagonals,
+// the energy of the bare Hamiltonian, spin_square and -- on request -- make_rdm1 / make_rdm2.
+//
+// Why one call: a batch of K subspaces is solved by K host threads (one CUDA stream each).  Driving the
+// ~40 set-up steps of one solve from Python serialises the K threads on the interpreter lock and leaves
+// every stream idle most of the time; here the host thread stays inside C from the first kernel to the
+// last read-back.  Scratch memory comes from the device's stream-ordered pool (cudaMallocAsync) and is
+// returned before the call ends; results are written to caller-owned buffers.
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/sqd_b200.h"
+
+namespace sqd {
+
+struct Pool {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    bool failed = false;
+    explicit Pool(cudaStream_t s) : st(s) {}
+    template <typename T>
+    T* get(size_t n) {
+        void* p = nullptr;
+        const size_t bytes = (n > 0 ? n : 1) * sizeof(T);
+        if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) {
+            set_error("sqd_solve_subspace: cudaMallocAsync of %zu bytes failed: %s", bytes,
+                      cudaGetErrorString(cudaGetLastError()));
+            failed = true;
+            return nullptr;
+        }
+        ptrs.push_back(p);
+        return (T*)p;
+    }
+    ~Pool() {
+        for (void* p : ptrs) cudaFreeAsync(p, st);
+    }
+};
+
+// keep freed blocks in the pool instead of returning them to the driver at every synchronisation
+static int configure_pool() {
+    static bool done[64] = {};
+    int dev = 0;
+    SQD_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !done[dev]) {
+        cudaMemPool_t pool;
+        SQD_CUDA_OK(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long thr = ~0ull;
+        SQD_CUDA_OK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+        done[dev] = true;
+    }
+    return 0;
+}
+
+static int read_back_large(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+    const size_t step = 8 * 1024;
+    for (size_t o = 0; o < bytes; o += step) {
+        const size_t k = bytes - o < step ? bytes - o : step;
+        if (read_back((char*)h_dst + o, (const char*)d_src + o, k, st)) return -2;
+    }
+    return 0;
+}
+
+struct TableBufs {
+    int* n_single;
+    int* n_total;
+    int* row_ptr;
+    uint32_t *col, *meta, *pack;
+    double *val, *diag;
+    int nnz;
+};
+
+static int table_count(Pool& P, const uint64_t* strs, int n, TableBufs* T) {
+    T->n_single = P.get<int>(n);
+    T->n_total = P.get<int>(n);
+    T->row_ptr = P.get<int>(n + 1);
+    if (P.failed) return -2;
+    if (sqd_excitation_count(strs, n, T->n_single, T->n_total, P.st)) return -2;
+    return sqd_exclusive_scan(T->n_total, T->row_ptr, n, nullptr, P.st);
+}
+
+static int table_fill(Pool& P, const uint64_t* strs, int n, int norb, const double* h, const double* g,
+                      TableBufs* T, sqd_spin_table* out) {
+    const size_t m = T->nnz > 0 ? T->nnz : 1;
+    T->col = P.get<uint32_t>(m);
+    T->meta = P.get<uint32_t>(m);
+    T->pack = P.get<uint32_t>(m);
+    T->val = P.get<double>(m);
+    T->diag = P.get<double>(n);
+    if (P.failed) return -2;
+    if (sqd_excitation_fill(strs, n, norb, h, g, T->row_ptr, T->n_single, T->col, T->val, T->meta, T->pack,
+                            T->diag, P.st))
+        return -2;
+    *out = sqd_spin_table{n, strs, T->row_ptr, T->n_single, T->col, T->val, T->meta, T->pack};
+    return 0;
+}
+
+struct SellBufs {
+    int *perm, *len, *slice_ptr;
+    uint32_t* pack;
+    double* val;
+    int cap;
+};
+
+static int sell_launch(Pool& P, const sqd_spin_table& T, int64_t nnz, int mode, const int* long_idx,
+                       SellBufs* S) {
+    const int n = T.n;
+    S->cap = (int)(nnz + 36 * (int64_t)n + 256);
+    S->perm = P.get<int>(n);
+    S->len = P.get<int>(n);
+    S->slice_ptr = P.get<int>((n + 31) / 32 + 1);
+    S->pack = P.get<uint32_t>(S->cap);
+    S->val = mode == 1 ? P.get<double>(S->cap) : nullptr;
+    if (P.failed) return -2;
+    return sqd_sell_build(&T, mode, long_idx, S->cap, S->perm, S->len, S->slice_ptr, S->pack, S->val, P.st);
+}
+
+// gab, Wa, Wb and diag of one operator over tables / plan / SELL copies that are already built
+static int operator_build(Pool& P, const sqd_solve_params* prm, const sqd_operator& base, int mode,
+                          double shift, double diag_const, bool same_spin, bool with_w, const double* da,
+                          const double* db, sqd_operator* out) {
+    const int norb = base.norb, na = base.a.n, nb = base.b.n, ldc = base.ldc, ldg = base.ldg;
+    const int n2 = norb * norb;
+    double* gab = P.get<double>((size_t)n2 * ldg);
+    double* Wa = with_w ? P.get<double>((size_t)na * ldg) : nullptr;
+    double* Wb = P.get<double>((size_t)n2 * ldc);
+    double* diag = P.get<double>((size_t)na * ldc);
+    if (P.failed) return -2;
+    if (sqd_make_gab(mode == 0 ? prm->d_g : nullptr, norb, shift, mode, gab, ldg, P.st)) return -2;
+    if (sqd_opposite_spin_tables(base.a.strs, na, base.b.strs, nb, norb, gab, ldg, same_spin ? da : nullptr,
+                                 same_spin ? db : nullptr, diag_const, same_spin ? 1e300 : 0.0, Wa, Wb, diag,
+                                 ldc, P.st))
+        return -2;
+    *out = base;
+    out->diag = diag;
+    out->gab = gab;
+    out->Wa = Wa;
+    out->Wb = with_w ? Wb : nullptr;
+    out->use_same_spin = same_spin ? 1 : 0;
+    return 0;
+}
+
+__global__ void rdm2_spin_sum_kernel(double* __restrict__ aa, const double* __restrict__ ab,
+                                     const double* __restrict__ bb, int norb) {
+    // pyscf make_rdm2: dm2aa + dm2bb + dm2ab + dm2ab.transpose(2,3,0,1), accumulated into the aa block
+    const int64_t n2 = (int64_t)norb * norb, n4 = n2 * n2;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t pq = i / n2, rs = i % n2;
+        aa[i] = aa[i] + bb[i] + ab[i] + ab[rs * n2 + pq];
+    }
+}
+
+__global__ void rdm1_spin_sum_kernel(const double* __restrict__ dm1, int norb, double* __restrict__ out) {
+    // sqd_rdm1s stores <p+ q>; pyscf's make_rdm1 is dm1[p,q] = <q+ p>: transpose while adding the spins
+    const int n2 = norb * norb;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const int p = i / norb, q = i % norb;
+        out[i] = dm1[q * norb + p] + dm1[n2 + q * norb + p];
+    }
+}
+
+}  // namespace sqd
+
+using namespace sqd;
+
+extern "C" {
+
+int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1, double* d_rdm2,
+                       sqd_solve_result* h_res, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int norb = prm->norb, na = prm->na, nb = prm->nb;
+    SQD_REQUIRE(norb >= 1 && norb <= 64, "sqd_solve_subspace: norb must be in [1, 64] (got %d)", norb);
+    SQD_REQUIRE(na > 0 && nb > 0, "sqd_solve_subspace: empty string list");
+    SQD_REQUIRE(prm->d_h != nullptr && prm->d_g != nullptr && d_x != nullptr && h_res != nullptr,
+                "sqd_solve_subspace: missing integrals or output buffers");
+    if (configure_pool()) return -2;
+    const int ldc = (nb + 1) / 2 * 2;
+    const int ldg = (norb * norb + 2) / 2 * 2;
+    const int64_t n = (int64_t)na * ldc;
+    const bool same = prm->d_strs_b == prm->d_strs_a && na == nb;
+    Pool P(st);
+
+    // ---- excitation tables (one synchronisation: the two entry counts) ----
+    TableBufs Ta{}, Tb{};
+    if (table_count(P, prm->d_strs_a, na, &Ta)) return -2;
+    if (!same && table_count(P, prm->d_strs_b, nb, &Tb)) return -2;
+    int* pair = P.get<int>(2);
+    if (P.failed) return -2;
+    SQD_CUDA_OK(cudaMemcpyAsync(pair, Ta.row_ptr + na, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    SQD_CUDA_OK(cudaMemcpyAsync(pair + 1, (same ? Ta.row_ptr + na : Tb.row_ptr + nb), sizeof(int),
+                                cudaMemcpyDeviceToDevice, st));
+    int h_pair[2];
+    if (read_back(h_pair, pair, sizeof(h_pair), st)) return -2;
+    Ta.nnz = h_pair[0];
+    Tb.nnz = h_pair[1];
+    sqd_spin_table ta{}, tb{};
+    if (table_fill(P, prm->d_strs_a, na, norb, prm->d_h, prm->d_g, &Ta, &ta)) return -2;
+    if (same) {
+        tb = ta;
+        Tb = Ta;
+    } else if (table_fill(P, prm->d_strs_b, nb, norb, prm->d_h, prm->d_g, &Tb, &tb)) {
+        return -2;
+    }
+
+    // ---- work plan and SELL copies (one synchronisation: their sizes) ----
+    const int cost = prm->cost_per_chunk > 0 ? prm->cost_per_chunk : 256;
+    const int long_thr = prm->long_threshold > 0 ? prm->long_threshold : 64;
+    const int max_chunks = 2 * na + (int)((16 * (int64_t)(Ta.nnz > 0 ? Ta.nnz : 1)) / cost) + 1;
+    int* chunk[4];
+    for (auto& c : chunk) c = P.get<int>(max_chunks);
+    int* split[3];
+    for (auto& c : split) c = P.get<int>(na);
+    int* long_idx = P.get<int>(nb);
+    int* long_cols = P.get<int>(SQD_MAX_LONG_COLUMNS);
+    int* counts = P.get<int>(8);
+    if (P.failed) return -2;
+    if (sqd_sigma_plan_build(&ta, &tb, cost, long_thr, max_chunks, chunk[0], chunk[1], chunk[2], chunk[3],
+                             split[0], split[1], split[2], long_idx, long_cols, counts, nullptr, st))
+        return -2;
+    SellBufs S0{}, S1{};
+    if (sell_launch(P, tb, Tb.nnz, 0, long_idx, &S0)) return -2;
+    if (sell_launch(P, tb, Tb.nnz, 1, nullptr, &S1)) return -2;
+    const int nsl = (nb + 31) / 32;
+    SQD_CUDA_OK(cudaMemcpyAsync(counts + 5, S0.slice_ptr + nsl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    SQD_CUDA_OK(cudaMemcpyAsync(counts + 6, S1.slice_ptr + nsl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    int hc[8];
+    if (read_back(hc, counts, 7 * sizeof(int), st)) return -2;  // hc[4] unused
+    double* part = P.get<double>((size_t)(hc[1] > 0 ? hc[1] : 1) * ldc);
+    if (P.failed) return -2;
+
+    sqd_operator base{};
+    base.a = ta;
+    base.b = tb;
+    base.norb = norb;
+    base.ldc = ldc;
+    base.ldg = ldg;
+    base.plan = sqd_sigma_plan{hc[0], hc[1], hc[2], hc[3], chunk[0], chunk[1], chunk[2], chunk[3],
+                               split[0], split[1], split[2], long_idx, long_cols, part};
+    base.bd = sqd_sell{nsl, hc[5], S0.perm, S0.len, S0.slice_ptr, S0.pack, nullptr};
+    base.bb = sqd_sell{nsl, hc[6], S1.perm, S1.len, S1.slice_ptr, S1.pack, S1.val};
+
+    // ---- operators ----
+    const int n_alpha = prm->n_alpha, n_beta = prm->n_beta;
+    const double sz = 0.5 * (n_alpha > n_beta ? n_alpha - n_beta : n_beta - n_alpha);
+    const double szz = 0.5 * (n_alpha - n_beta);
+    const bool have_ss = prm->penalty != 0;
+    const bool linear = have_ss && prm->spin_sq < sz * (sz + 1.0) + 0.1;  // pyscf fix_spin_ branches
+    const bool quad = have_ss && !linear;
+    const double lin_shift = linear ? prm->shift : 0.0;
+    sqd_operator ham{}, s2op{};
+    if (operator_build(P, prm, base, 0, lin_shift,
+                       lin_shift * (szz * (szz + 1.0) + n_beta - prm->spin_sq), true, true, Ta.diag, Tb.diag,
+                       &ham))
+        return -2;
+    const bool need_s2 = have_ss || prm->want_spin;
+    if (need_s2 && operator_build(P, prm, base, 1, 0.0, szz * (szz + 1.0) + n_beta, false, false, nullptr,
+                                  nullptr, &s2op))
+        return -2;
+
+    // ---- Davidson ----
+    const int M = prm->max_space < 2 ? 2 : (prm->max_space > SQD_MAX_SPACE ? SQD_MAX_SPACE : prm->max_space);
+    const int64_t ws_bytes = sqd_davidson_workspace_bytes(na, ldc, M);
+    void* ws = P.get<char>((size_t)ws_bytes);
+    double* x0 = P.get<double>(n);
+    double* scratch = P.get<double>(4096);
+    if (P.failed) return -2;
+    if (prm->d_ci0 != nullptr) {
+        SQD_CUDA_OK(cudaMemsetAsync(x0, 0, n * sizeof(double), st));
+        SQD_CUDA_OK(cudaMemcpy2DAsync(x0, (size_t)ldc * sizeof(double), prm->d_ci0, (size_t)nb * sizeof(double),
+                                      (size_t)nb * sizeof(double), na, cudaMemcpyDeviceToDevice, st));
+    } else if (sqd_init_guess(ham.diag, na, nb, ldc, x0, scratch, st)) {
+        return -2;
+    }
+    sqd_davidson_params dp{};
+    dp.max_space = M;
+    dp.max_cycle = prm->max_cycle;
+    dp.tol = prm->tol;
+    dp.tol_residual = prm->tol_residual;
+    dp.lindep = prm->lindep;
+    dp.level_shift = prm->level_shift;
+    dp.check_every = prm->check_every > 0 ? prm->check_every : 4;
+    dp.profile = prm->profile;
+    if (quad) {
+        dp.ss_op = &s2op;
+        dp.ss_shift = prm->shift;
+        dp.ss_value = prm->spin_sq;
+    }
+    dp.nccl_comm = prm->nccl_comm;
+    dp.row_begin = prm->row_begin;
+    dp.row_end = prm->row_end;
+    std::vector<int> h_ns, h_ptr;
+    if (prm->profile || (prm->nccl_comm != nullptr && prm->row_begin < 0)) {
+        h_ns.resize(na);
+        h_ptr.resize(na + 1);
+        if (read_back_large(h_ns.data(), Ta.n_single, (size_t)na * sizeof(int), st)) return -2;
+        if (read_back_large(h_ptr.data(), Ta.row_ptr, (size_t)(na + 1) * sizeof(int), st)) return -2;
+    }
+    if (prm->nccl_comm != nullptr && prm->row_begin < 0) {
+        // per-row cost: alpha singles (gather loops), alpha doubles (row streaming), beta part (fixed);
+        // the Hartree-Fock end of the string list is much heavier than the tail
+        SQD_REQUIRE(prm->shard_world >= 1 && prm->shard_rank >= 0 && prm->shard_rank < prm->shard_world,
+                    "sqd_solve_subspace: bad shard rank/world");
+        std::vector<long long> cum(na + 1, 0);
+        const long long beta = Tb.nnz / (nb > 0 ? nb : 1) > 1 ? Tb.nnz / nb : 1;
+        for (int a = 0; a < na; ++a) {
+            const long long ns = h_ns[a], nd = (long long)(h_ptr[a + 1] - h_ptr[a]) - ns;
+            cum[a + 1] = cum[a] + 16 * (ns + 1) + nd + beta;
+        }
+        auto bound = [&](int r) {
+            if (r <= 0) return 0;
+            if (r >= prm->shard_world) return na;
+            const double target = (double)cum[na] * r / prm->shard_world;
+            int lo = 0;
+            while (lo < na && (double)cum[lo] < target) ++lo;
+            return lo;
+        };
+        dp.row_begin = bound(prm->shard_rank);
+        dp.row_end = bound(prm->shard_rank + 1);
+    }
+    sqd_davidson_info info{};
+    if (sqd_davidson(&ham, ham.diag, x0, d_x, ws, ws_bytes, &dp, &info, st)) return -2;
+
+    // ---- expectation values: everything lands in one small buffer, read back once ----
+    // res = [<x|x>, <x|Hx>, -, <x|S^2 x>, -,-,-,-, occ_a[norb], occ_b[norb]]
+    double* res = P.get<double>(8 + 2 * norb);
+    double* hx = P.get<double>(n);
+    double* occ_scratch = P.get<double>(na + nb);
+    if (P.failed) return -2;
+    SQD_CUDA_OK(cudaMemsetAsync(res, 0, (8 + 2 * norb) * sizeof(double), st));
+    if (sqd_sigma(&ham, d_x, hx, st)) return -2;
+    if (sqd_dot(d_x, d_x, n, res, scratch, st)) return -2;
+    if (sqd_dot(d_x, hx, n, res + 1, scratch, st)) return -2;
+    if (need_s2) {
+        if (sqd_sigma(&s2op, d_x, hx, st)) return -2;
+        if (sqd_dot(d_x, hx, n, res + 3, scratch, st)) return -2;
+    }
+    if (sqd_occupancies(d_x, ta.strs, na, tb.strs, nb, ldc, norb, res + 8, occ_scratch, st)) return -2;
+    if (sqd_fix_sign(d_x, n, scratch, st)) return -2;
+
+    // ---- reduced density matrices (optional; spin-summed, pyscf conventions) ----
+    if (d_rdm1 != nullptr || d_rdm2 != nullptr) {
+        sqd_operator rop = base;  // the RDM kernels only read the tables
+        if (d_rdm1 != nullptr) {
+            double* dm1 = P.get<double>(2 * (size_t)norb * norb);
+            double* w1 = (double*)P.get<char>((size_t)sqd_rdm1s_workspace_bytes(&rop) + 16);
+            const int64_t mx = Ta.nnz > Tb.nnz ? Ta.nnz : Tb.nnz;
+            double* dots = P.get<double>((size_t)(mx > 0 ? mx : 1));
+            if (P.failed) return -2;
+            if (sqd_rdm1s(&rop, d_x, Ta.nnz, Tb.nnz, dm1, w1, dots, st)) return -2;
+            rdm1_spin_sum_kernel<<<(norb * norb + 255) / 256, 256, 0, st>>>(dm1, norb, d_rdm1);
+            if (check_launch("rdm1_spin_sum_kernel")) return -2;
+        }
+        if (d_rdm2 != nullptr) {
+            const int64_t n4 = (int64_t)norb * norb * norb * norb;
+            const int64_t wb = sqd_rdm2s_workspace_bytes(&rop, Ta.nnz, Tb.nnz);
+            void* w2 = P.get<char>((size_t)wb);
+            double* abbb = P.get<double>(2 * (size_t)n4);
+            if (P.failed) return -2;
+            if (sqd_rdm2s(&rop, d_x, Ta.nnz, Tb.nnz, d_rdm2, abbb, abbb + n4, w2, wb, st)) return -2;
+            rdm2_spin_sum_kernel<<<kNumSMs * 4, 256, 0, st>>>(d_rdm2, abbb, abbb + n4, norb);
+            if (check_launch("rdm2_spin_sum_kernel")) return -2;
+        }
+    }
+
+    double hr[8 + 128];
+    if (read_back(hr, res, (8 + 2 * norb) * sizeof(double), st)) return -2;
+    const double xx = hr[0];
+    const double e_pen = hr[1] / xx;
+    const double s2 = need_s2 ? hr[3] / xx : 0.0;
+    h_res->energy = linear ? e_pen - lin_shift * (s2 - prm->spin_sq) : e_pen;
+    h_res->spin_square = s2;
+    h_res->have_spin_square = need_s2 ? 1 : 0;
+    for (int p = 0; p < norb; ++p) {
+        h_res->occ_a[p] = hr[8 + p];
+        h_res->occ_b[p] = hr[8 + norb + p];
+    }
+    h_res->info = info;
+    h_res->nnz_a = Ta.nnz;
+    h_res->nnz_b = Tb.nnz;
+    h_res->ldc = ldc;
+    // singles of each table (diagnostics for the byte model of the bench): not read back on the hot path
+    h_res->singles_a = h_res->singles_b = -1;
+    if (prm->profile) {
+        long long sa = 0, sb = 0;
+        for (int a = 0; a < na; ++a) sa += h_ns[a];
+        if (same) {
+            sb = sa;
+        } else {
+            std::vector<int> h_nb(nb);
+            if (read_back_large(h_nb.data(), Tb.n_single, (size_t)nb * sizeof(int), st)) return -2;
+            for (int b = 0; b < nb; ++b) sb += h_nb[b];
+        }
+        h_res->singles_a = sa;
+        h_res->singles_b = sb;
+    }
+    return 0;
+}
+
+}  // extern "C"

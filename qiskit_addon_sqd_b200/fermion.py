@@ -261,7 +261,7 @@ class _SpinTableDev:
         _lib.check(self._lib.sqd_sell_build(C.byref(t), mode, _lib.ptr(long_idx), cap,
                                             _lib.ptr(perm), _lib.ptr(ln), _lib.ptr(sptr), _lib.ptr(pack),
                                             _lib.ptr(val), _lib.stream_ptr(torch)), "sqd_sell_build")
-        n_entries = int(sptr[-1].item())
+        n_entries = int(_lib.read_back(torch, sptr[-1:])[0])
         st = _lib.Sell(ns, n_entries, _lib.ptr(perm), _lib.ptr(ln), _lib.ptr(sptr), _lib.ptr(pack),
                        _lib.ptr(val))
         self._sell[mode] = (st, (perm, ln, sptr, pack, val))
@@ -358,14 +358,14 @@ class _Subspace:
         long_idx = torch.empty(self.nb, **i32)
         long_cols = torch.empty(_lib.MAX_LONG_COLUMNS, **i32)
         counts_d = torch.empty(4, **i32)
-        counts = (C.c_int * 4)()
+        counts = (C.c_int * 8)()
         ta, tb = self.ta.struct(), self.tb.struct()
         _lib.check(lib.sqd_sigma_plan_build(C.byref(ta), C.byref(tb), cost, int(_SIGMA_LONG_THRESHOLD),
                                       max_chunks, *[_lib.ptr(t) for t in bufs],
                                       *[_lib.ptr(t) for t in split], _lib.ptr(long_idx),
                                       _lib.ptr(long_cols), _lib.ptr(counts_d), counts,
                                       _lib.stream_ptr(torch)), "sqd_sigma_plan_build")
-        n_chunks, n_slots, n_split, n_long = (int(v) for v in counts)
+        n_chunks, n_slots, n_split, n_long = (int(v) for v in counts[:4])
         part = torch.empty(max(n_slots, 1) * self.ldc, dtype=torch.float64, device=dev)
         self._plan_keep = (bufs, split, long_idx, long_cols, part)
         self._plan = _lib.SigmaPlan(n_chunks, n_slots, n_split, n_long, *[_lib.ptr(t) for t in bufs],
@@ -406,7 +406,7 @@ class _Subspace:
         return c.reshape(-1)
 
     def download_amplitudes(self, c) -> np.ndarray:
-        return c.reshape(self.na, self.ldc)[:, : self.nb].contiguous().cpu().numpy()
+        return _lib.download(self.torch, c.reshape(self.na, self.ldc)[:, : self.nb])
 
     def apply(self, op: _OperatorDev, c, out=None):
         out = self.new_vector() if out is None else out
@@ -417,7 +417,7 @@ class _Subspace:
     def dot(self, x, y) -> float:
         _lib.check(self.lib.sqd_dot(_lib.ptr(x), _lib.ptr(y), x.numel(), _lib.ptr(self._scalar),
                                     _lib.ptr(self._scratch), _lib.stream_ptr(self.torch)), "sqd_dot")
-        return float(self._scalar[0].item())
+        return float(_lib.read_back(self.torch, self._scalar[:1])[0])
 
     # -- observables -------------------------------------------------------------------------
     def spin_square(self, c) -> float:
@@ -432,7 +432,7 @@ class _Subspace:
                                             _lib.ptr(self.tb.strs), self.nb, self.ldc, self.norb,
                                             _lib.ptr(occ), _lib.ptr(scratch),
                                             _lib.stream_ptr(torch)), "sqd_occupancies")
-        o = occ.cpu().numpy()
+        o = _lib.read_back(torch, occ)
         return o[: self.norb].copy(), o[self.norb:].copy()
 
     # -- eigensolver -------------------------------------------------------------------------
@@ -551,60 +551,73 @@ def last_solve_stats() -> list[SolveStats]:
 def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq, shift, opts,
                      want_spin: bool, want_rdm: bool, *, strs_dev=(None, None), download: bool = True,
                      profile: bool = False, shard_group=None):
-    """Ground state of H projected on A x B.  Returns dict of results (host arrays; with
-    ``download=False`` the amplitudes stay on the device as a padded ``(na, ldc)`` tensor)."""
-    sub = _Subspace(strs_a, strs_b, norb, None, None, ints=ints, strs_dev=strs_dev)
-    sz = 0.5 * abs(sub.n_alpha - sub.n_beta)
-    quad = None
-    if spin_sq is None:
-        ham = sub.hamiltonian()
-        lin_shift = 0.0
-    elif spin_sq < sz * (sz + 1.0) + 0.1:
-        # pyscf fix_spin_: H + shift (S^2 - ss), folded into the opposite-spin integrals
-        ham = sub.hamiltonian(penalty_shift=float(shift), penalty_ss=float(spin_sq))
-        lin_shift = float(shift)
-    else:
-        ham = sub.hamiltonian()
-        quad = (sub.spin_operator(), float(shift), float(spin_sq))
-        lin_shift = 0.0
-    shard = None
+    """Ground state of H projected on A x B: ONE call into the library (``sqd_solve_subspace``), so the
+    host thread does not touch the interpreter between the first kernel and the last read-back.
+    Returns dict of results (host arrays; with ``download=False`` the amplitudes stay on the device as a
+    padded ``(na, ldc)`` tensor)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if norb > 64 or norb < 1:
+        raise ValueError("qiskit_addon_sqd_b200 supports 1..64 spatial orbitals.")
+    same = strs_a is strs_b
+    ua = _as_uint64(strs_a)
+    ub = ua if same else _as_uint64(strs_b)
+    if ua.size == 0 or ub.size == 0:
+        raise ValueError("The subspace must contain at least one alpha and one beta string.")
+    same = same or (ua.shape == ub.shape and np.array_equal(ua, ub))
+    na, nb = len(ua), len(ub)
+    ldc = (nb + 1) // 2 * 2
+    da = strs_dev[0] if strs_dev[0] is not None else torch.from_numpy(ua.view(np.int64).copy()).to(dev)
+    db = da if same else (strs_dev[1] if strs_dev[1] is not None
+                          else torch.from_numpy(ub.view(np.int64).copy()).to(dev))
+    n_alpha, n_beta = int(np.bitwise_count(ua[0])), int(np.bitwise_count(ub[0]))
+    x = torch.empty(na * ldc, dtype=torch.float64, device=dev)
+    rdm1_d = torch.empty(norb * norb, dtype=torch.float64, device=dev) if want_rdm else None
+    rdm2_d = torch.empty(norb**4, dtype=torch.float64, device=dev) if want_rdm else None
+    ci0 = opts.get("ci0")
+    ci0_d = None
+    if ci0 is not None:
+        ci0_d = torch.from_numpy(np.ascontiguousarray(ci0, dtype=np.float64).reshape(na, nb)).to(dev)
+    prm = _lib.SolveParams()
+    prm.norb, prm.na, prm.nb, prm.n_alpha, prm.n_beta = norb, na, nb, n_alpha, n_beta
+    prm.d_strs_a, prm.d_strs_b = _lib.ptr(da), _lib.ptr(db)
+    prm.d_h, prm.d_g = _lib.ptr(ints.h), _lib.ptr(ints.g)
+    prm.penalty = 0 if spin_sq is None else 1
+    prm.spin_sq = 0.0 if spin_sq is None else float(spin_sq)
+    prm.shift = float(shift)
+    prm.want_spin = 1 if want_spin else 0
+    prm.max_space = int(min(max(2, opts["max_space"]), _lib.MAX_SPACE))
+    prm.max_cycle = int(opts["max_cycle"])
+    prm.tol, prm.tol_residual = float(opts["tol"]), float(opts["tol_residual"])
+    prm.lindep, prm.level_shift = float(opts["lindep"]), float(opts["level_shift"])
+    prm.check_every = 4
+    prm.d_ci0 = _lib.ptr(ci0_d) or None
+    prm.cost_per_chunk, prm.long_threshold = int(_SIGMA_COST_PER_CHUNK), int(_SIGMA_LONG_THRESHOLD)
+    prm.profile = 1 if profile else 0
     if shard_group is not None:
-        shard = shard_group.row_range(sub)
-    x, info = sub.ground_state(ham, shard=shard, tol=opts["tol"], tol_residual=opts["tol_residual"],
-                               max_cycle=opts["max_cycle"], max_space=opts["max_space"],
-                               lindep=opts["lindep"], level_shift=opts["level_shift"],
-                               ci0=opts.get("ci0"), quad_penalty=quad, profile=profile)
-    # energy = <x|H_bare|x>  (reference computes it from the RDMs and ignores the solver's eigenvalue,
-    # fermion.py:806-809, 824-827)
-    hx = sub.apply(ham, x)
-    xx = sub.dot(x, x)
-    e_pen = sub.dot(x, hx) / xx
-    s2 = None
-    if lin_shift != 0.0 or want_spin:
-        s2 = sub.spin_square(x)
-    energy = e_pen - lin_shift * (s2 - float(spin_sq)) if lin_shift != 0.0 else e_pen
-    occ = sub.occupancies(x)
-    # eigenvector sign: pyscf's is whatever LAPACK returns for the small problem; fix the convention
-    # "largest-magnitude amplitude positive" (first such element) so that results are reproducible.
-    kmax = int(x.abs().argmax().item())
-    if float(x[kmax].item()) < 0:
-        x = -x
-    amps = sub.download_amplitudes(x) if download else x.reshape(sub.na, sub.ldc)
+        # rows are split inside the call into blocks of equal estimated sigma-build cost
+        prm.nccl_comm, prm.row_begin, prm.row_end = shard_group._comm.value, -1, -1
+        prm.shard_rank, prm.shard_world = shard_group.rank, shard_group.world
+    res = _lib.SolveResult()
+    _lib.check(lib.sqd_solve_subspace(C.byref(prm), _lib.ptr(x), _lib.ptr(rdm1_d), _lib.ptr(rdm2_d),
+                                      C.byref(res), _lib.stream_ptr(torch)), "sqd_solve_subspace")
+    info = res.info
+    occ = (np.array(res.occ_a[:norb]), np.array(res.occ_b[:norb]))
+    s2 = float(res.spin_square) if res.have_spin_square else None
+    amps = _lib.download(torch, x.reshape(na, ldc)[:, :nb]) if download else x.reshape(na, ldc)
     rdm1 = rdm2 = None
     if want_rdm:
-        from ._rdm import subspace_rdms
-
-        rdm1, rdm2 = subspace_rdms(sub, x)
+        rdm1 = _lib.download(torch, rdm1_d).reshape(norb, norb)
+        rdm2 = _lib.download(torch, rdm2_d).reshape((norb,) * 4)
     stats = SolveStats(info.cycles, info.sigma_builds, info.converged, info.residual, info.theta,
-                       sub.na * sub.nb, sub.ta.nnz, sub.tb.nnz,
-                       int(sub.ta.n_single.sum().item()) if profile else 0,
-                       int(sub.tb.n_single.sum().item()) if profile else 0,
-                       info.sigma_ms, info.total_ms, sub.na, sub.nb, norb)
+                       na * nb, int(res.nnz_a), int(res.nnz_b), max(int(res.singles_a), 0),
+                       max(int(res.singles_b), 0), info.sigma_ms, info.total_ms, na, nb, norb)
     if not hasattr(_tls, "stats"):
         _tls.stats = []
     _tls.stats.append(stats)
-    return dict(energy=float(energy), amplitudes=amps, occupancies=occ, spin_square=s2,
-                nelec=(sub.n_alpha, sub.n_beta), rdm1=rdm1, rdm2=rdm2, stats=stats)
+    return dict(energy=float(res.energy), amplitudes=amps, occupancies=occ, spin_square=s2,
+                nelec=(n_alpha, n_beta), rdm1=rdm1, rdm2=rdm2, stats=stats)
 
 
 def solve_sci(
@@ -619,8 +632,10 @@ def solve_sci(
 ) -> SCIResult:
     """Diagonalize the Hamiltonian in the subspace defined by CI strings (reference ``fermion.py:684-742``).
 
-    Extra keyword ``compute_rdms`` (default ``False``): also fill ``SCIResult.rdm1/rdm2`` (spin-summed)
-    as the reference does; the SQD loop never reads them (``fermion.py:577-622``).
+    As in the reference (``fermion.py:728-740``) the result carries the spin-summed ``rdm1`` and ``rdm2``.
+    Extra keyword ``compute_rdms=False`` skips them (the SQD loop never reads them, ``fermion.py:577-622``);
+    the energy does not depend on it -- it is the Rayleigh quotient of the bare Hamiltonian, which equals
+    the reference's RDM contraction (``fermion.py:730-732``).
     """
     return solve_sci_batch([ci_strings], one_body_tensor, two_body_tensor, norb, nelec,
                            spin_sq=spin_sq, **kwargs)[0]
@@ -649,7 +664,7 @@ def solve_sci_batch(
     two_body_tensor = np.asarray(two_body_tensor)
     norb, _ = one_body_tensor.shape  # as the reference: norb comes from the tensor (fermion.py:711)
     devices = kwargs.pop("devices", None)
-    want_rdm = bool(kwargs.pop("compute_rdms", False))
+    want_rdm = bool(kwargs.pop("compute_rdms", True))
     shift = float(kwargs.pop("shift", _FIX_SPIN_DEFAULT_SHIFT))
     opts = _solver_options(kwargs)
     if devices is None:
@@ -726,17 +741,6 @@ class ShardGroup:
         self._comm = C.c_void_p()
         _lib.check(lib.sqd_nccl_init(box[0], self.rank, self.world, C.byref(self._comm)),
                    "sqd_nccl_init")
-
-    def row_range(self, sub: "_Subspace") -> tuple[int, int, int]:
-        ns = sub.ta.n_single.cpu().numpy().astype(np.int64)
-        ptr = sub.ta.row_ptr.cpu().numpy().astype(np.int64)
-        nd = np.diff(ptr) - ns
-        # per-row cost: alpha singles (gather loops), alpha doubles (row streaming), beta part (fixed)
-        cost = 16 * (ns + 1) + nd + max(1, sub.tb.nnz // max(sub.nb, 1))
-        cum = np.concatenate([[0], np.cumsum(cost)])
-        bounds = [int(np.searchsorted(cum, cum[-1] * r / self.world)) for r in range(self.world + 1)]
-        bounds[0], bounds[-1] = 0, sub.na
-        return self._comm.value, bounds[self.rank], bounds[self.rank + 1]
 
     def close(self):
         if self._comm:

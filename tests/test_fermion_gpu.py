@@ -272,8 +272,57 @@ def test_rdm1_matches_oracle(cuda_lib):
     assert np.abs(state.rdm(rank=1, spin_summed=True) - (ra + rb)).max() < 1e-12
     with pytest.raises(NotImplementedError):
         state.rdm(rank=3)
-    res = fermion.solve_sci((sa, sb), h, g, norb, (4, 3), compute_rdms=True)
+    res = fermion.solve_sci((sa, sb), h, g, norb, (4, 3))
     assert np.abs(res.rdm1 - (ra + rb)).max() < 1e-6
+
+
+@pytest.mark.parametrize("norb,nea,neb,na,nb", [(5, 2, 3, 7, 6), (6, 3, 3, 14, 14), (6, 1, 4, 5, 9), (7, 4, 2, 20, 12)])
+def test_rdm2_matches_oracle(cuda_lib, norb, nea, neb, na, nb):
+    """dm2aa / dm2ab / dm2bb (pyscf convention <p+ r+ s q>) against the operator-by-operator brute force,
+    plus the reference's own energy formula (fermion.py:730-732) and the spin-summed form."""
+    from qiskit_addon_sqd_b200 import fermion
+
+    h, g = random_integrals(norb, 31 + norb)
+    sa = hf_centred_strings(norb, nea, na, 1)
+    sb = hf_centred_strings(norb, neb, nb, 2)
+    e, state, occ, s2 = fermion.solve_fermion((sa, sb), h, g, open_shell=True)
+    aa, ab, bb = state.rdm(rank=2, spin_summed=False)
+    raa, rab, rbb = fo.rdm2s(state.amplitudes, sa, sb, norb)
+    assert np.abs(aa - raa).max() < 1e-12
+    assert np.abs(bb - rbb).max() < 1e-12
+    assert np.abs(ab - rab).max() < 1e-12
+    dm2 = state.rdm(rank=2, spin_summed=True)
+    assert np.abs(dm2 - (raa + rbb + rab + rab.transpose(2, 3, 0, 1))).max() < 1e-12
+    dm1 = state.rdm(rank=1, spin_summed=True)
+    e_rdm = np.einsum("pr,pr->", dm1, h) + 0.5 * np.einsum("prqs,prqs->", dm2, g)
+    assert abs(e_rdm - e) < 1e-10
+    # traces: N(N-1) pairs
+    n = nea + neb
+    assert abs(np.einsum("pprr->", dm2) - n * (n - 1)) < 1e-10
+
+
+def test_solve_sci_returns_rdms_like_the_reference(cuda_lib):
+    """fermion.py:728-740: SCIResult carries the spin-summed rdm1 and rdm2 and the energy equals their
+    contraction with the integrals."""
+    from qiskit_addon_sqd_b200 import fermion
+
+    norb = 10
+    h, g = random_integrals(norb, 5)
+    sa = hf_centred_strings(norb, 5, 60, 1)
+    sb = hf_centred_strings(norb, 4, 45, 2)
+    res = fermion.solve_sci((sa, sb), h, g, norb, (5, 4))
+    assert res.rdm1.shape == (norb,) * 2 and res.rdm2.shape == (norb,) * 4
+    e_rdm = np.einsum("pr,pr->", res.rdm1, h) + 0.5 * np.einsum("prqs,prqs->", res.rdm2, g)
+    assert abs(e_rdm - res.energy) < 1e-9
+    # symmetries of a real state: dm2[p,q,r,s] = dm2[q,p,s,r] = dm2[r,s,p,q]
+    assert np.abs(res.rdm2 - res.rdm2.transpose(1, 0, 3, 2)).max() < 1e-12
+    assert np.abs(res.rdm2 - res.rdm2.transpose(2, 3, 0, 1)).max() < 1e-12
+    # bit-reproducible (no atomics)
+    res2 = fermion.solve_sci((sa, sb), h, g, norb, (5, 4))
+    assert np.array_equal(res.rdm2, res2.rdm2) and np.array_equal(res.rdm1, res2.rdm1)
+    # opt-out used by throughput-oriented callers
+    res3 = fermion.solve_sci((sa, sb), h, g, norb, (5, 4), compute_rdms=False)
+    assert res3.rdm1 is None and res3.rdm2 is None and res3.energy == res.energy
 
 
 def test_sigma_row_blocks_sum_to_full_sigma(cuda_lib):
