@@ -326,10 +326,12 @@ int sqd_rdm1s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t 
  * (alpha,alpha), (alpha,beta), (beta,beta) blocks), reached from fermion.py:117-128 (SCIState.rdm) and
  * fermion.py:728-729, 825-826 (energy from RDMs, SCIResult.rdm2).  Each output is double[norb^4],
  * C-order [p][q][r][s]; for the opposite-spin block p,q are alpha and r,s beta orbitals.  nnz_a / nnz_b =
- * entries of the excitation tables.  Deterministic (no atomics). */
+ * entries of the excitation tables.  d_dm1: NULL, or double[2*norb^2] that receives the spin 1-RDMs in
+ * the layout of sqd_rdm1s (they share the row-pair dot products).  Deterministic (no atomics). */
 int64_t sqd_rdm2s_workspace_bytes(const sqd_operator* op, int64_t nnz_a, int64_t nnz_b);
 int sqd_rdm2s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t nnz_b, double* d_dm2aa,
-              double* d_dm2ab, double* d_dm2bb, void* d_workspace, int64_t ws_bytes, void* stream);
+              double* d_dm2ab, double* d_dm2bb, double* d_dm1, void* d_workspace, int64_t ws_bytes,
+              void* stream);
 
 /* ------------------------------------------------------------------------------------------ *
  * Qubit path   (qubit.py:78-300)

@@ -195,7 +195,7 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_rdm1s_workspace_bytes": (_i64, [C.POINTER(Operator)]),
     "sqd_rdm1s": (_i, [C.POINTER(Operator), _vp, _i64, _i64, _vp, _vp, _vp, _vp]),
     "sqd_rdm2s_workspace_bytes": (_i64, [C.POINTER(Operator), _i64, _i64]),
-    "sqd_rdm2s": (_i, [C.POINTER(Operator), _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sqd_rdm2s": (_i, [C.POINTER(Operator), _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "sqd_bits_to_keys": (_i, [_vp, _i64, _i, _vp, _vp]),
     "sqd_pauli_connect": (_i, [_vp, _i64, _u64, _u64, _vp, _vp, _vp]),
     "sqd_pauli_project_count": (_i, [_vp, _i64, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
@@ -305,3 +305,4 @@ def download(torch, t):
     view.copy_(t.reshape(-1), non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return np.array(view.numpy(), copy=True).reshape(tuple(t.shape))
+

@@ -39,7 +39,7 @@ def subspace_rdm2s_device(sub, c):
     ws_bytes = lib.sqd_rdm2s_workspace_bytes(C.byref(op.struct), sub.ta.nnz, sub.tb.nnz)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=sub.device)
     _lib.check(lib.sqd_rdm2s(C.byref(op.struct), _lib.ptr(c), sub.ta.nnz, sub.tb.nnz, _lib.ptr(out[0]),
-                             _lib.ptr(out[1]), _lib.ptr(out[2]), _lib.ptr(ws), ws_bytes,
+                             _lib.ptr(out[1]), _lib.ptr(out[2]), None, _lib.ptr(ws), ws_bytes,
                              _lib.stream_ptr(torch)), "sqd_rdm2s")
     return out[0], out[1], out[2]
 

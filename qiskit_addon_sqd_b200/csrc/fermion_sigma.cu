@@ -320,8 +320,8 @@ __global__ void sigma_combine_kernel(const int* __restrict__ done, const sqd_sig
 //   sorted mapping   (thread t <-> column perm[t])  : the beta-single gathers through SELL slices
 // The two partial results meet in a shared-memory exchange buffer before one coalesced update of sigma.
 // ---------------------------------------------------------------------------------------------------
-template <int CPT, bool STAGE_PACK>
-__global__ void __launch_bounds__(CPT == 1 ? 1024 : 512)
+template <int CPT, bool STAGE_PACK, int TB, int MINB>
+__global__ void __launch_bounds__(TB, MINB)
 sigma_a_kernel(const SigmaArgs P, const int NST) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
@@ -684,19 +684,35 @@ static int opt_in_smem(K kern, size_t smem, bool* configured) {
         if (dev < 0 || dev >= 64 || !configured[dev]) {
             SQD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(227 * 1024)));
+            // as many CTAs per SM as the registers allow: do not let a smaller carve-out cap them
+            SQD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared));
             if (dev >= 0 && dev < 64) configured[dev] = true;
         }
     }
     return 0;
 }
 
-template <int CPT, bool STAGE_PACK>
-static int launch_sigma_a(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t st) {
-    auto kern = sigma_a_kernel<CPT, STAGE_PACK>;
+template <int CPT, bool STAGE_PACK, int TB, int MINB>
+static int launch_sigma_a_tb(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t st) {
+    auto kern = sigma_a_kernel<CPT, STAGE_PACK, TB, MINB>;
     static bool cfg_a[64] = {false};
     if (opt_in_smem(kern, pl.smem, cfg_a)) return -2;
     kern<<<args.op.plan.n_chunks, pl.threads + 32, pl.smem, st>>>(args, pl.stages);
     return check_launch("sigma_a_kernel");
+}
+
+// CTAs of at most 384 threads are compiled under a register cap that lets three of them share an SM
+template <int CPT, bool STAGE_PACK>
+static int launch_sigma_a(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t st) {
+    if constexpr (CPT == 1) {
+        static const int knob_minb = env_int("SQD_SIGMA_MINB", 1);
+        if (pl.threads + 32 <= 384 && knob_minb == 3)
+            return launch_sigma_a_tb<1, STAGE_PACK, 384, 3>(args, pl, st);
+        return launch_sigma_a_tb<1, STAGE_PACK, 1024, 1>(args, pl, st);
+    } else {
+        return launch_sigma_a_tb<CPT, STAGE_PACK, 512, 1>(args, pl, st);
+    }
 }
 
 template <int CPT>

@@ -93,24 +93,37 @@ rdm1_collect_kernel(const sqd_spin_table T, int norb, const double* __restrict__
 
 constexpr uint32_t kNotDouble = 0xffffffffu;
 
-// dots[e] = <x[row(e),:], x[col(e),:]> for EVERY entry; roww[i] = |x[i,:]|^2;
-// dinfo[e] = a1 | a2<<6 | i1<<12 | i2<<18 | parity<<31 for doubles (target = (-1)^parity a1+ a2+ i2 i1 source,
-// i1<i2 holes of the source, a1<a2 particles of the target), kNotDouble for singles
-__global__ void pair_dots_kernel(const sqd_spin_table T, const double* __restrict__ x, int ncols, int ldx,
-                                 double* __restrict__ dots, double* __restrict__ roww,
-                                 uint32_t* __restrict__ dinfo) {
+// erow[e] = row of table entry e (one warp per row)
+__global__ void entry_rows_kernel(const sqd_spin_table T, int* __restrict__ erow) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= T.n) return;
+    for (int e = T.row_ptr[i] + lane; e < T.row_ptr[i + 1]; e += 32) erow[e] = i;
+}
+
+__global__ void row_norms_kernel(const double* __restrict__ x, int nrows, int ncols, int ldx,
+                                 double* __restrict__ roww) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= nrows) return;
     const double* xi = x + (size_t)i * ldx;
     double w = 0.0;
     for (int b = lane; b < ncols; b += 32) w = fma(xi[b], xi[b], w);
     w = warp_sum(w);
     if (lane == 0) roww[i] = w;
-    const int beg = T.row_ptr[i], ns = T.n_single[i], end = T.row_ptr[i + 1];
-    const uint64_t t = T.strs[i];
-    for (int e = beg; e < end; ++e) {
-        const int j = (int)T.col[e];
+}
+
+// One warp per table entry e (grid-stride): dots[e] = <x[row(e),:], x[col(e),:]> (fixed shuffle tree);
+// dinfo[e] = a1 | a2<<6 | i1<<12 | i2<<18 | parity<<31 for doubles (target = (-1)^parity a1+ a2+ i2 i1
+// source, i1<i2 holes of the source, a1<a2 particles of the target), kNotDouble for singles
+__global__ void __launch_bounds__(256)
+pair_dots_kernel(const sqd_spin_table T, const int* __restrict__ erow, int nnz, const double* __restrict__ x,
+                 int ncols, int ldx, double* __restrict__ dots, uint32_t* __restrict__ dinfo) {
+    const int lane = threadIdx.x & 31;
+    const int nwarp = gridDim.x * (blockDim.x >> 5);
+    for (int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < nnz; e += nwarp) {
+        const int i = erow[e], j = (int)T.col[e];
+        const double* xi = x + (size_t)i * ldx;
         const double* xj = x + (size_t)j * ldx;
         double d = 0.0;
         for (int b = lane; b < ncols; b += 32) d = fma(xi[b], xj[b], d);
@@ -118,8 +131,8 @@ __global__ void pair_dots_kernel(const sqd_spin_table T, const double* __restric
         if (lane == 0) {
             dots[e] = d;
             uint32_t info = kNotDouble;
-            if (e >= beg + ns) {
-                const uint64_t s = T.strs[j];
+            if (e >= T.row_ptr[i] + T.n_single[i]) {
+                const uint64_t s = T.strs[j], t = T.strs[i];
                 const uint64_t xo = s ^ t;
                 uint64_t holes = xo & s, parts = xo & t;
                 const int i1 = lowbit64(holes);
@@ -224,9 +237,11 @@ rdm2_doubles_kernel(const uint32_t* __restrict__ dinfo, const double* __restrict
     for (int c = tid; c < n2; c += kD2Threads) row[c] = acc[c];
 }
 
-// One warp per (p,q), p != q; lane j (and j+32) owns the spectator orbital j.
+// One warp per (p,q), p != q; lane j (and j+32) owns the spectator orbital j.  The single excitations
+// with this orbital pair come from the grouped list (ent / ent_e), in table order.
 __global__ void __launch_bounds__(128)
-rdm2_singles_kernel(const sqd_spin_table T, const double* __restrict__ dots, int norb,
+rdm2_singles_kernel(const sqd_spin_table T, const int* __restrict__ gptr, const int2* __restrict__ ent,
+                    const int* __restrict__ ent_e, const double* __restrict__ dots, int norb,
                     double* __restrict__ dm2) {
     const int lane = threadIdx.x & 31;
     const int pq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -235,19 +250,14 @@ rdm2_singles_kernel(const sqd_spin_table T, const double* __restrict__ dots, int
     const int p = pq / norb, q = pq % norb;
     if (p == q) return;
     double g0 = 0.0, g1 = 0.0;
-    for (int i = 0; i < T.n; ++i) {
-        const int beg = T.row_ptr[i], ns = T.n_single[i];
-        for (int e = beg; e < beg + ns; ++e) {
-            const uint32_t m = __ldg(T.meta + e);
-            if ((int)(m & 0x7fffffffu) == pq) {
-                // target strs[i] = sgn * p+ q source; spectators = occupied orbitals of the source but q
-                const uint64_t src = T.strs[T.col[e]] & ~(1ull << q);
-                const double d = (m >> 31) ? -__ldg(dots + e) : __ldg(dots + e);
-                if ((src >> lane) & 1ull) g0 += d;
-                if ((src >> (lane + 32)) & 1ull) g1 += d;
-                break;  // at most one source per (target, p, q)
-            }
-        }
+    for (int k = gptr[pq]; k < gptr[pq + 1]; ++k) {
+        const int2 E = ent[k];
+        // target strs[E.x] = sgn * p+ q source; spectators = occupied orbitals of the source but q
+        const uint64_t src = T.strs[E.y & 0x7fffffff] & ~(1ull << q);
+        const double d0 = dots[ent_e[k]];
+        const double d = E.y < 0 ? -d0 : d0;
+        if ((src >> lane) & 1ull) g0 += d;
+        if ((src >> (lane + 32)) & 1ull) g1 += d;
     }
     const size_t n1 = norb, n3 = (size_t)n2 * norb;
 #pragma unroll
@@ -281,7 +291,8 @@ rdm2_diag_kernel(const sqd_spin_table T, const double* __restrict__ roww, int no
 // ---- single-excitation lists grouped by orbital pair (diagonal p == q included) ---------------
 // entry = {target index, source index | sign << 31}
 __device__ __forceinline__ bool group_probe(const sqd_spin_table& T, int i, int p, int q, int pq,
-                                            uint32_t* colsign) {
+                                            uint32_t* colsign, int* entry) {
+    *entry = -1;
     if (p == q) {
         *colsign = (uint32_t)i;
         return (T.strs[i] >> p) & 1ull;
@@ -291,6 +302,7 @@ __device__ __forceinline__ bool group_probe(const sqd_spin_table& T, int i, int 
         const uint32_t m = __ldg(T.meta + e);
         if ((int)(m & 0x7fffffffu) == pq) {
             *colsign = T.col[e] | (m & 0x80000000u);
+            *entry = e;
             return true;
         }
     }
@@ -303,7 +315,9 @@ group_count_kernel(const sqd_spin_table T, int norb, int* __restrict__ cnt) {
     const int pq = blockIdx.x, p = pq / norb, q = pq % norb;
     int c = 0;
     uint32_t dummy;
-    for (int i = threadIdx.x; i < T.n; i += blockDim.x) c += group_probe(T, i, p, q, pq, &dummy) ? 1 : 0;
+    int dummy_e;
+    for (int i = threadIdx.x; i < T.n; i += blockDim.x)
+        c += group_probe(T, i, p, q, pq, &dummy, &dummy_e) ? 1 : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
@@ -316,7 +330,8 @@ group_count_kernel(const sqd_spin_table T, int norb, int* __restrict__ cnt) {
 }
 
 __global__ void __launch_bounds__(256)
-group_fill_kernel(const sqd_spin_table T, int norb, const int* __restrict__ ptr, int2* __restrict__ ent) {
+group_fill_kernel(const sqd_spin_table T, int norb, const int* __restrict__ ptr, int2* __restrict__ ent,
+                  int* __restrict__ ent_e) {
     __shared__ int wcnt[8];
     const int pq = blockIdx.x, p = pq / norb, q = pq % norb;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -324,7 +339,8 @@ group_fill_kernel(const sqd_spin_table T, int norb, const int* __restrict__ ptr,
     for (int i0 = 0; i0 < T.n; i0 += 256) {
         const int i = i0 + threadIdx.x;
         uint32_t cs = 0;
-        const bool hit = i < T.n && group_probe(T, i, p, q, pq, &cs);
+        int en = -1;
+        const bool hit = i < T.n && group_probe(T, i, p, q, pq, &cs, &en);
         const uint32_t bal = __ballot_sync(0xffffffffu, hit);
         if (lane == 0) wcnt[warp] = __popc(bal);
         __syncthreads();
@@ -334,26 +350,87 @@ group_fill_kernel(const sqd_spin_table T, int norb, const int* __restrict__ ptr,
             if (w < warp) woff += wcnt[w];
             total += wcnt[w];
         }
-        if (hit) ent[base + woff + __popc(bal & ((1u << lane) - 1u))] = make_int2(i, (int)cs);
+        if (hit) {
+            const int o = base + woff + __popc(bal & ((1u << lane) - 1u));
+            ent[o] = make_int2(i, (int)cs);
+            ent_e[o] = en;
+        }
         base += total;
         __syncthreads();
     }
 }
 
-// One CTA per row [p,q,:,:] of dm2ab.  For every alpha entry (a <- a') of the pair the rows c[a,:] and
-// c[a',:] are staged in shared memory; thread rs walks the beta group rs (off-diagonal groups are a few
-// entries long), the long diagonal groups rs = rr are reduced by one warp each.
+// acc[rs] += sa * sum_{(b <- b', rs)} sgn_b X[b] Y[b'] for every beta pair rs: off-diagonal groups (a few
+// entries each) by one thread per rs, the long diagonal groups rs = rr by one warp each.  Every acc[rs]
+// has exactly one writer.
+__device__ __forceinline__ void ab_accumulate(const double* X, const double* Y, double sa, int norb,
+                                              const int* __restrict__ ptr_b, const int2* __restrict__ ent_b,
+                                              double* acc, bool overwrite) {
+    const int n2 = norb * norb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    for (int rs = tid; rs < n2; rs += blockDim.x) {
+        if (rs / norb == rs % norb) continue;
+        double s = 0.0;
+        for (int eb = ptr_b[rs]; eb < ptr_b[rs + 1]; ++eb) {
+            const int2 B = ent_b[eb];
+            const double t = X[B.x] * Y[B.y & 0x7fffffff];
+            s += B.y < 0 ? -t : t;
+        }
+        acc[rs] = overwrite ? sa * s : fma(sa, s, acc[rs]);
+    }
+    for (int r = warp; r < norb; r += nwarp) {
+        const int rs = r * norb + r;
+        double s = 0.0;
+        for (int eb = ptr_b[rs] + lane; eb < ptr_b[rs + 1]; eb += 32) {
+            const int bb = ent_b[eb].x;
+            s = fma(X[bb], Y[bb], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) acc[rs] = overwrite ? sa * s : fma(sa, s, acc[rs]);
+    }
+}
+
+// Diagonal alpha pairs: dm2ab[pp, rs] = sum_{a: p in a} T[a][rs] with the per-row beta transition
+// T[a][rs] = sum_{(b <- b', rs)} sgn_b c[a,b] c[a,b'].  One CTA per alpha string builds its T row ...
+__global__ void __launch_bounds__(256)
+rdm2_ab_rows_kernel(const double* __restrict__ c, int nb, int ldc, int norb, const int* __restrict__ ptr_b,
+                    const int2* __restrict__ ent_b, double* __restrict__ Trows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* X = reinterpret_cast<double*>(smem_raw);
+    const int a = blockIdx.x;
+    for (int b = threadIdx.x; b < nb; b += blockDim.x) X[b] = c[(size_t)a * ldc + b];
+    __syncthreads();
+    ab_accumulate(X, X, 1.0, norb, ptr_b, ent_b, Trows + (size_t)a * norb * norb, true);
+}
+
+// ... and the rows are added in string order (one thread per rs, fixed order -> reproducible)
+__global__ void __launch_bounds__(256)
+rdm2_ab_diag_kernel(const uint64_t* __restrict__ strs_a, int na, int norb, const double* __restrict__ Trows,
+                    double* __restrict__ dm2ab) {
+    const int n2 = norb * norb;
+    const int p = blockIdx.x;
+    const int rs = blockIdx.y * blockDim.x + threadIdx.x;
+    if (rs >= n2) return;
+    double acc = 0.0;
+    for (int a = 0; a < na; ++a)
+        if ((strs_a[a] >> p) & 1ull) acc += Trows[(size_t)a * n2 + rs];
+    dm2ab[(size_t)(p * norb + p) * n2 + rs] = acc;
+}
+
+// Off-diagonal alpha pairs: one CTA per row [p,q,:,:] of dm2ab (p != q).  For every alpha excitation
+// (a <- a') of the pair the rows c[a,:] and c[a',:] are staged in shared memory.
 __global__ void __launch_bounds__(256)
 rdm2_ab_kernel(const double* __restrict__ c, int nb, int ldc, int norb, const int* __restrict__ ptr_a,
                const int2* __restrict__ ent_a, const int* __restrict__ ptr_b,
                const int2* __restrict__ ent_b, double* __restrict__ dm2ab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n2 = norb * norb;
+    const int pq = blockIdx.x;
+    if (pq / norb == pq % norb) return;  // written by rdm2_ab_diag_kernel
     double* X = reinterpret_cast<double*>(smem_raw);  // c[a ,:]  (bra)
     double* Y = X + ldc;                                // c[a',:]  (ket)
     double* acc = Y + ldc;                              // [n2]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const int pq = blockIdx.x;
+    const int tid = threadIdx.x;
     for (int k = tid; k < n2; k += blockDim.x) acc[k] = 0.0;
     const int ea_beg = ptr_a[pq], ea_end = ptr_a[pq + 1];
     for (int ea = ea_beg; ea < ea_end; ++ea) {
@@ -366,28 +443,7 @@ rdm2_ab_kernel(const double* __restrict__ c, int nb, int ldc, int norb, const in
             Y[b] = c[(size_t)a1 * ldc + b];
         }
         __syncthreads();
-        // off-diagonal beta pairs: one thread per rs
-        for (int rs = tid; rs < n2; rs += blockDim.x) {
-            if (rs / norb == rs % norb) continue;
-            double s = 0.0;
-            for (int eb = ptr_b[rs]; eb < ptr_b[rs + 1]; ++eb) {
-                const int2 B = ent_b[eb];
-                const double t = X[B.x] * Y[B.y & 0x7fffffff];
-                s += B.y < 0 ? -t : t;
-            }
-            acc[rs] = fma(sa, s, acc[rs]);
-        }
-        // diagonal beta pairs: one warp per r
-        for (int r = warp; r < norb; r += nwarp) {
-            const int rs = r * norb + r;
-            double s = 0.0;
-            for (int eb = ptr_b[rs] + lane; eb < ptr_b[rs + 1]; eb += 32) {
-                const int bb = ent_b[eb].x;
-                s = fma(X[bb], Y[bb], s);
-            }
-            s = warp_sum(s);
-            if (lane == 0) acc[rs] = fma(sa, s, acc[rs]);
-        }
+        ab_accumulate(X, Y, sa, norb, ptr_b, ent_b, acc, false);
     }
     __syncthreads();
     double* row = dm2ab + (size_t)pq * n2;
@@ -428,9 +484,11 @@ int sqd_rdm1s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t 
     return check_launch("rdm1s kernels", 5);
 }
 
+}  // extern "C"
+
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-int64_t sqd_rdm2s_workspace_bytes(const sqd_operator* op, int64_t nnz_a, int64_t nnz_b) {
+extern "C" int64_t sqd_rdm2s_workspace_bytes(const sqd_operator* op, int64_t nnz_a, int64_t nnz_b) {
     const int64_t na = op->a.n, nb = op->b.n, norb = op->norb, n2 = norb * norb;
     const int64_t ldt = (na + 1) / 2 * 2;
     const int64_t nnz = nnz_a > nnz_b ? nnz_a : nnz_b;
@@ -439,36 +497,52 @@ int64_t sqd_rdm2s_workspace_bytes(const sqd_operator* op, int64_t nnz_a, int64_t
     b += al256((size_t)(na + nb) * sizeof(double));         // row weights
     b += al256((size_t)(nnz + 1) * sizeof(double));         // dots
     b += al256((size_t)(nnz + 1) * sizeof(uint32_t));       // dinfo
+    b += al256((size_t)(nnz + 1) * sizeof(int));            // entry -> row
     b += 4 * al256((size_t)(n2 + 1) * sizeof(int));         // cnt/ptr for both spins
-    b += al256((size_t)(nnz_a + na * norb + 1) * sizeof(int2));
-    b += al256((size_t)(nnz_b + nb * norb + 1) * sizeof(int2));
+    b += al256((size_t)(nnz_a + na * norb + 1) * sizeof(int2)) + al256((size_t)(nnz_a + na * norb + 1) * sizeof(int));
+    b += al256((size_t)(nnz_b + nb * norb + 1) * sizeof(int2)) + al256((size_t)(nnz_b + nb * norb + 1) * sizeof(int));
+    b += al256((size_t)na * n2 * sizeof(double));           // per-row beta transitions
     return (int64_t)b;
 }
 
-static int rdm2_same_spin(const sqd_spin_table& T, int64_t nnz, const double* x, int ncols, int ldx,
-                          int norb, double* dots, double* roww, uint32_t* dinfo, double* dm2,
-                          cudaStream_t st) {
-    const int n2 = norb * norb;
-    pair_dots_kernel<<<(T.n + 7) / 8, 256, 0, st>>>(T, x, ncols, ldx, dots, roww, dinfo);
-    const size_t smem = (size_t)n2 * sizeof(double) + kD2Cap * (sizeof(double) + sizeof(int));
-    static bool cfg[64] = {false};
+template <typename K>
+static int big_smem(K kern, size_t smem, bool* cfg) {
     if (smem > 48 * 1024) {
         int dev = 0;
         SQD_CUDA_OK(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !cfg[dev]) {
-            SQD_CUDA_OK(cudaFuncSetAttribute(rdm2_doubles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(227 * 1024)));
+            SQD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
             if (dev >= 0 && dev < 64) cfg[dev] = true;
         }
     }
-    rdm2_doubles_kernel<<<n2, kD2Threads, smem, st>>>(dinfo, dots, (int)nnz, norb, dm2);
-    rdm2_singles_kernel<<<(n2 + 3) / 4, 128, 0, st>>>(T, dots, norb, dm2);
-    rdm2_diag_kernel<<<norb, 64, 0, st>>>(T, roww, norb, dm2);
-    return check_launch("rdm2 same-spin kernels", 4);
+    return 0;
 }
 
-int sqd_rdm2s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t nnz_b, double* d_dm2aa,
-              double* d_dm2ab, double* d_dm2bb, void* d_workspace, int64_t ws_bytes, void* stream) {
+// same-spin block of dm2 (+ the spin's dm1 when asked) for table T over the rows of x
+static int rdm2_same_spin(const sqd_spin_table& T, int64_t nnz, const double* x, int ncols, int ldx,
+                          int norb, const int* gptr, const int2* ent, const int* ent_e, int* erow,
+                          double* dots, double* roww, uint32_t* dinfo, double* dm2, double* dm1,
+                          cudaStream_t st) {
+    const int n2 = norb * norb;
+    row_norms_kernel<<<(T.n + 7) / 8, 256, 0, st>>>(x, T.n, ncols, ldx, roww);
+    if (nnz > 0) {
+        entry_rows_kernel<<<(T.n + 7) / 8, 256, 0, st>>>(T, erow);
+        const int blocks = (int)((nnz + 7) / 8 < kNumSMs * 8 ? (nnz + 7) / 8 : kNumSMs * 8);
+        pair_dots_kernel<<<blocks, 256, 0, st>>>(T, erow, (int)nnz, x, ncols, ldx, dots, dinfo);
+    }
+    const size_t smem = (size_t)n2 * sizeof(double) + kD2Cap * (sizeof(double) + sizeof(int));
+    static bool cfg[64] = {false};
+    if (big_smem(rdm2_doubles_kernel, smem, cfg)) return -2;
+    rdm2_doubles_kernel<<<n2, kD2Threads, smem, st>>>(dinfo, dots, (int)nnz, norb, dm2);
+    rdm2_singles_kernel<<<(n2 + 3) / 4, 128, 0, st>>>(T, gptr, ent, ent_e, dots, norb, dm2);
+    rdm2_diag_kernel<<<norb, 64, 0, st>>>(T, roww, norb, dm2);
+    if (dm1 != nullptr) rdm1_collect_kernel<<<n2, 256, 0, st>>>(T, norb, dots, roww, dm1);
+    return check_launch("rdm2 same-spin kernels", 7);
+}
+
+extern "C" int sqd_rdm2s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t nnz_b,
+                         double* d_dm2aa, double* d_dm2ab, double* d_dm2bb, double* d_dm1,
+                         void* d_workspace, int64_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int na = op->a.n, nb = op->b.n, ldc = op->ldc, norb = op->norb, n2 = norb * norb;
     const int ldt = (na + 1) / 2 * 2;
@@ -480,42 +554,46 @@ int sqd_rdm2s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t 
     double* roww = (double*)p;      p += al256((size_t)(na + nb) * sizeof(double));
     double* dots = (double*)p;      p += al256((size_t)(nnz + 1) * sizeof(double));
     uint32_t* dinfo = (uint32_t*)p; p += al256((size_t)(nnz + 1) * sizeof(uint32_t));
+    int* erow = (int*)p;            p += al256((size_t)(nnz + 1) * sizeof(int));
     int* cnt_a = (int*)p;           p += al256((size_t)(n2 + 1) * sizeof(int));
     int* ptr_a = (int*)p;           p += al256((size_t)(n2 + 1) * sizeof(int));
     int* cnt_b = (int*)p;           p += al256((size_t)(n2 + 1) * sizeof(int));
     int* ptr_b = (int*)p;           p += al256((size_t)(n2 + 1) * sizeof(int));
     int2* ent_a = (int2*)p;         p += al256((size_t)(nnz_a + (int64_t)na * norb + 1) * sizeof(int2));
-    int2* ent_b = (int2*)p;
-    // same spin, alpha: rows of c
-    if (rdm2_same_spin(op->a, nnz_a, d_c, nb, ldc, norb, dots, roww, dinfo, d_dm2aa, st)) return -2;
-    // same spin, beta: rows of c^T
-    dim3 tb(32, 8), tg((nb + 31) / 32, (na + 31) / 32);
-    transpose_kernel<<<tg, tb, 0, st>>>(d_c, na, nb, ldc, ct, ldt);
-    if (check_launch("transpose_kernel")) return -2;
-    if (rdm2_same_spin(op->b, nnz_b, ct, na, ldt, norb, dots, roww + na, dinfo, d_dm2bb, st)) return -2;
-    // opposite spin
+    int* ente_a = (int*)p;          p += al256((size_t)(nnz_a + (int64_t)na * norb + 1) * sizeof(int));
+    int2* ent_b = (int2*)p;         p += al256((size_t)(nnz_b + (int64_t)nb * norb + 1) * sizeof(int2));
+    int* ente_b = (int*)p;          p += al256((size_t)(nnz_b + (int64_t)nb * norb + 1) * sizeof(int));
+    double* Trows = (double*)p;
+    // single-excitation lists grouped by orbital pair, both spins
     group_count_kernel<<<n2, 256, 0, st>>>(op->a, norb, cnt_a);
     group_count_kernel<<<n2, 256, 0, st>>>(op->b, norb, cnt_b);
     if (check_launch("group_count_kernel", 2)) return -2;
     if (sqd_exclusive_scan(cnt_a, ptr_a, n2, nullptr, stream)) return -2;
     if (sqd_exclusive_scan(cnt_b, ptr_b, n2, nullptr, stream)) return -2;
-    group_fill_kernel<<<n2, 256, 0, st>>>(op->a, norb, ptr_a, ent_a);
-    group_fill_kernel<<<n2, 256, 0, st>>>(op->b, norb, ptr_b, ent_b);
+    group_fill_kernel<<<n2, 256, 0, st>>>(op->a, norb, ptr_a, ent_a, ente_a);
+    group_fill_kernel<<<n2, 256, 0, st>>>(op->b, norb, ptr_b, ent_b, ente_b);
+    if (check_launch("group_fill_kernel", 2)) return -2;
+    // same spin, alpha: rows of c
+    if (rdm2_same_spin(op->a, nnz_a, d_c, nb, ldc, norb, ptr_a, ent_a, ente_a, erow, dots, roww, dinfo,
+                       d_dm2aa, d_dm1, st))
+        return -2;
+    // same spin, beta: rows of c^T
+    dim3 tb(32, 8), tg((nb + 31) / 32, (na + 31) / 32);
+    transpose_kernel<<<tg, tb, 0, st>>>(d_c, na, nb, ldc, ct, ldt);
+    if (check_launch("transpose_kernel")) return -2;
+    if (rdm2_same_spin(op->b, nnz_b, ct, na, ldt, norb, ptr_b, ent_b, ente_b, erow, dots, roww + na, dinfo,
+                       d_dm2bb, d_dm1 ? d_dm1 + n2 : nullptr, st))
+        return -2;
+    // opposite spin
+    const size_t smem_rows = (size_t)ldc * sizeof(double);
     const size_t smem_ab = (size_t)(2 * ldc + n2) * sizeof(double);
     SQD_REQUIRE(smem_ab <= 227 * 1024, "sqd_rdm2s: nb=%d, norb=%d do not fit the shared-memory row staging",
                 nb, norb);
-    static bool cfg_ab[64] = {false};
-    if (smem_ab > 48 * 1024) {
-        int dev = 0;
-        SQD_CUDA_OK(cudaGetDevice(&dev));
-        if (dev < 0 || dev >= 64 || !cfg_ab[dev]) {
-            SQD_CUDA_OK(cudaFuncSetAttribute(rdm2_ab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(227 * 1024)));
-            if (dev >= 0 && dev < 64) cfg_ab[dev] = true;
-        }
-    }
+    static bool cfg_rows[64] = {false}, cfg_ab[64] = {false};
+    if (big_smem(rdm2_ab_rows_kernel, smem_rows, cfg_rows)) return -2;
+    if (big_smem(rdm2_ab_kernel, smem_ab, cfg_ab)) return -2;
+    rdm2_ab_rows_kernel<<<na, 256, smem_rows, st>>>(d_c, nb, ldc, norb, ptr_b, ent_b, Trows);
+    rdm2_ab_diag_kernel<<<dim3(norb, (n2 + 255) / 256), 256, 0, st>>>(op->a.strs, na, norb, Trows, d_dm2ab);
     rdm2_ab_kernel<<<n2, 256, smem_ab, st>>>(d_c, nb, ldc, norb, ptr_a, ent_a, ptr_b, ent_b, d_dm2ab);
     return check_launch("rdm2 opposite-spin kernels", 3);
 }
-
-}  // extern "C"

@@ -343,25 +343,27 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
     // ---- reduced density matrices (optional; spin-summed, pyscf conventions) ----
     if (d_rdm1 != nullptr || d_rdm2 != nullptr) {
         sqd_operator rop = base;  // the RDM kernels only read the tables
-        if (d_rdm1 != nullptr) {
-            double* dm1 = P.get<double>(2 * (size_t)norb * norb);
-            double* w1 = (double*)P.get<char>((size_t)sqd_rdm1s_workspace_bytes(&rop) + 16);
-            const int64_t mx = Ta.nnz > Tb.nnz ? Ta.nnz : Tb.nnz;
-            double* dots = P.get<double>((size_t)(mx > 0 ? mx : 1));
-            if (P.failed) return -2;
-            if (sqd_rdm1s(&rop, d_x, Ta.nnz, Tb.nnz, dm1, w1, dots, st)) return -2;
-            rdm1_spin_sum_kernel<<<(norb * norb + 255) / 256, 256, 0, st>>>(dm1, norb, d_rdm1);
-            if (check_launch("rdm1_spin_sum_kernel")) return -2;
-        }
+        // the 1-RDMs share the row-pair dot products of the 2-RDM pass when both are wanted
+        double* dm1 = d_rdm1 != nullptr ? P.get<double>(2 * (size_t)norb * norb) : nullptr;
         if (d_rdm2 != nullptr) {
             const int64_t n4 = (int64_t)norb * norb * norb * norb;
             const int64_t wb = sqd_rdm2s_workspace_bytes(&rop, Ta.nnz, Tb.nnz);
             void* w2 = P.get<char>((size_t)wb);
             double* abbb = P.get<double>(2 * (size_t)n4);
             if (P.failed) return -2;
-            if (sqd_rdm2s(&rop, d_x, Ta.nnz, Tb.nnz, d_rdm2, abbb, abbb + n4, w2, wb, st)) return -2;
+            if (sqd_rdm2s(&rop, d_x, Ta.nnz, Tb.nnz, d_rdm2, abbb, abbb + n4, dm1, w2, wb, st)) return -2;
             rdm2_spin_sum_kernel<<<kNumSMs * 4, 256, 0, st>>>(d_rdm2, abbb, abbb + n4, norb);
             if (check_launch("rdm2_spin_sum_kernel")) return -2;
+        } else {
+            double* w1 = (double*)P.get<char>((size_t)sqd_rdm1s_workspace_bytes(&rop) + 16);
+            const int64_t mx = Ta.nnz > Tb.nnz ? Ta.nnz : Tb.nnz;
+            double* dots = P.get<double>((size_t)(mx > 0 ? mx : 1));
+            if (P.failed) return -2;
+            if (sqd_rdm1s(&rop, d_x, Ta.nnz, Tb.nnz, dm1, w1, dots, st)) return -2;
+        }
+        if (d_rdm1 != nullptr) {
+            rdm1_spin_sum_kernel<<<(norb * norb + 255) / 256, 256, 0, st>>>(dm1, norb, d_rdm1);
+            if (check_launch("rdm1_spin_sum_kernel")) return -2;
         }
     }
 

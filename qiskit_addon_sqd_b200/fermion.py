@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import time
 import warnings
 from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
@@ -519,6 +520,7 @@ class SolveStats:
     na: int = 0
     nb: int = 0
     norb: int = 0
+    host_ms: tuple = ()     # host wall time of (preparation, library call, downloads)
 
 
 _tls = threading.local()
@@ -555,6 +557,7 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
     host thread does not touch the interpreter between the first kernel and the last read-back.
     Returns dict of results (host arrays; with ``download=False`` the amplitudes stay on the device as a
     padded ``(na, ldc)`` tensor)."""
+    t_host0 = time.perf_counter()
     torch = _lib.require_cuda()
     lib = _lib.load()
     dev = torch.device("cuda", torch.cuda.current_device())
@@ -600,19 +603,23 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
         prm.nccl_comm, prm.row_begin, prm.row_end = shard_group._comm.value, -1, -1
         prm.shard_rank, prm.shard_world = shard_group.rank, shard_group.world
     res = _lib.SolveResult()
+    t_host1 = time.perf_counter()
     _lib.check(lib.sqd_solve_subspace(C.byref(prm), _lib.ptr(x), _lib.ptr(rdm1_d), _lib.ptr(rdm2_d),
                                       C.byref(res), _lib.stream_ptr(torch)), "sqd_solve_subspace")
+    t_host2 = time.perf_counter()
     info = res.info
     occ = (np.array(res.occ_a[:norb]), np.array(res.occ_b[:norb]))
     s2 = float(res.spin_square) if res.have_spin_square else None
     amps = _lib.download(torch, x.reshape(na, ldc)[:, :nb]) if download else x.reshape(na, ldc)
     rdm1 = rdm2 = None
     if want_rdm:
-        rdm1 = _lib.download(torch, rdm1_d).reshape(norb, norb)
-        rdm2 = _lib.download(torch, rdm2_d).reshape((norb,) * 4)
+        rdm1 = _lib.download(torch, rdm1_d.reshape(norb, norb))
+        rdm2 = _lib.download(torch, rdm2_d.reshape((norb,) * 4))
+    t_host3 = time.perf_counter()
     stats = SolveStats(info.cycles, info.sigma_builds, info.converged, info.residual, info.theta,
                        na * nb, int(res.nnz_a), int(res.nnz_b), max(int(res.singles_a), 0),
-                       max(int(res.singles_b), 0), info.sigma_ms, info.total_ms, na, nb, norb)
+                       max(int(res.singles_b), 0), info.sigma_ms, info.total_ms, na, nb, norb,
+                       (1e3 * (t_host1 - t_host0), 1e3 * (t_host2 - t_host1), 1e3 * (t_host3 - t_host2)))
     if not hasattr(_tls, "stats"):
         _tls.stats = []
     _tls.stats.append(stats)
