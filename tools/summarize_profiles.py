@@ -31,18 +31,22 @@ for row in csv.DictReader(lines):
 tot = sum(v[1] for v in agg.values())
 with open(os.path.join(out, f"{tag}_launch_summary_{wl}.md"), "w") as f:
     f.write(f"# ncu launch list summary ({tag}, workload {wl})\n\n"
-            "Command: `ncu --metrics gpu__time_duration.sum --clock-control none python "
-            f"tests/gpu_profile_driver.py {wl} 2` (two full `solve_sci` calls, single stream; per-launch times "
-            "are serialised and cold-cache: compare shares).\n\n"
+            "Command: `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py "
+            f"--workload {wl} --steps 1 --warmup 3 --no-cpu-baseline` (the bench command itself; ncu serialises "
+            "the 8 solver threads at ~0.3 s per launch, so the list is the launches recorded before the capture "
+            "was stopped -- whole steps of 8 solves each, set-up kernels included; every launch runs cold-cache: "
+            "compare shares, not absolute times).\n\n"
             "| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write(f"| `{k}` | {v[0]} | {v[1]:.1f} | {v[1] / v[0]:.2f} | {100 * v[1] / tot:.1f}% |\n")
     f.write(f"\nTotal device time: {tot:.1f} us\n")
-rep = os.path.join(root, "gpurun_out", f"prof_sigma_{wl}.ncu-rep")
-if os.path.exists(rep):
+for kname, rep in (("sigma_a", os.path.join(root, "gpurun_out", f"prof_sigma_{wl}.ncu-rep")),
+                   ("sigma_b", os.path.join(root, "gpurun_out", f"prof_sigmab_{wl}.ncu-rep"))):
+    if not os.path.exists(rep):
+        continue
     txt = subprocess.run(["ncu", "-i", rep, "--page", "details"], capture_output=True, text=True).stdout
     keep = [l for l in txt.splitlines() if not l.strip().startswith(("OPT", "INF")) or "Est." in l]
-    open(os.path.join(out, f"{tag}_sigma_a_ncu_details_{wl}.txt"), "w").write("\n".join(keep) + "\n")
+    open(os.path.join(out, f"{tag}_{kname}_ncu_details_{wl}.txt"), "w").write("\n".join(keep) + "\n")
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     want = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -50,7 +54,7 @@ if os.path.exists(rep):
             "sm__inst_executed.avg.per_cycle_active", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
             "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
             "sm__warps_active.avg.pct_of_peak_sustained_active", "lts__t_sectors.sum")
-    with open(os.path.join(out, f"{tag}_sigma_a_ncu_raw_{wl}.txt"), "w") as f:
+    with open(os.path.join(out, f"{tag}_{kname}_ncu_raw_{wl}.txt"), "w") as f:
         for w in want:
             for i, h in enumerate(rows[0]):
                 if h == w:

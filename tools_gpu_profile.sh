@@ -1,9 +1,18 @@
 #!/bin/bash
+# ncu evidence (run under gpurun, ONE GPU).  Numbers printed by these runs are never bench values.
+#   1. launch list of the bench command itself; ncu serialises the 8 solver threads (~0.3 s per launch),
+#      so the capture is bounded: skip the first step, record the next $NL launches (about one step)
+#   2. full captures of the two sigma kernels inside a real single-stream solve
 mkdir -p gpurun_out
 WL=${1:-c4}
-# launch list: every kernel of one warm solve with its device time
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${WL}.csv python tests/gpu_profile_driver.py $WL 2 > gpurun_out/launches_${WL}.out 2>&1
-# full capture of the sigma kernel (skip the first solve's launches)
-ncu --set full --clock-control none --import-source on -k regex:sigma_a_kernel -s 20 -c 1 -f -o gpurun_out/prof_sigma_${WL} python tests/gpu_profile_driver.py $WL 2 > gpurun_out/prof_sigma_${WL}.out 2>&1
+NL=${2:-1200}
+if [ "$NL" -gt 0 ]; then
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 2800 -c $NL --csv \
+    --log-file gpurun_out/launches_${WL}.csv \
+    python bench.py --workload $WL --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/launches_${WL}.out 2>&1
+fi
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:sigma_a_kernel -s 20 -c 1 -f \
+    -o gpurun_out/prof_sigma_${WL} python tests/gpu_profile_driver.py $WL 2 > gpurun_out/prof_sigma_${WL}.out 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:sigma_b_kernel -s 20 -c 1 -f \
+    -o gpurun_out/prof_sigmab_${WL} python tests/gpu_profile_driver.py $WL 2 > gpurun_out/prof_sigmab_${WL}.out 2>&1
 ls -la gpurun_out | tail -8
-tail -3 gpurun_out/launches_${WL}.out
