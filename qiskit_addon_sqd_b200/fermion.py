@@ -725,6 +725,186 @@ def solve_sci_batch(
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# the self-consistent SQD loop (reference fermion.py:204-640)
+# ------------------------------------------------------------------------------------------------
+def _first_occurrences(values: np.ndarray) -> np.ndarray:
+    """Distinct values in order of first appearance (reference ``fermion.py:465-469``)."""
+    _, first = np.unique(values, return_index=True)
+    return values[np.sort(first)]
+
+
+def _by_descending(keys: np.ndarray) -> np.ndarray:
+    """Permutation used by the reference wherever it ranks strings: numpy's default argsort, reversed."""
+    return np.argsort(keys)[::-1]
+
+
+class _SQDRun:
+    """State of one ``diagonalize_fermionic_hamiltonian`` call: the loop-invariant inputs plus what one
+    configuration-recovery iteration hands to the next (occupancies, reference result, carry-over
+    strings).  ``strings_for_iteration`` is the first half of an iteration (reference
+    ``_prepare_ci_strings``, ``fermion.py:472-560``), ``digest`` the second (``_process_sci_results``,
+    ``fermion.py:563-640``)."""
+
+    def __init__(self, raw_bitstrings, raw_probs, norb, nelec, samples_per_batch, num_batches,
+                 symmetrize_spin, include, max_dims, energy_tol, occupancies_tol, carryover_threshold,
+                 rng, occupancies):
+        self.bits, self.probs = raw_bitstrings, raw_probs
+        self.norb = norb
+        self.n_alpha, self.n_beta = nelec
+        self.samples_per_batch, self.num_batches = samples_per_batch, num_batches
+        self.symmetric = symmetrize_spin
+        self.include_a, self.include_b = include
+        self.max_dim_a, self.max_dim_b = max_dims
+        self.energy_tol, self.occupancies_tol = energy_tol, occupancies_tol
+        self.carryover_threshold = carryover_threshold
+        self.rng = rng
+        self.occupancies = occupancies
+        self.reference = None            # result the next iteration is compared with
+        self.best = None
+        self.carry_a = np.array([], dtype=np.int64)
+        self.carry_b = np.array([], dtype=np.int64)
+
+    # -- first half: noisy samples -> K pairs of sorted string lists ------------------------------
+    def strings_for_iteration(self) -> list[tuple[np.ndarray, np.ndarray]]:
+        from .configuration_recovery import recover_configurations
+        from .counts import bitstring_matrix_to_integers
+        from .subsampling import postselect_by_hamming_right_and_left, subsample
+
+        if self.occupancies is None:
+            rows, probs = postselect_by_hamming_right_and_left(
+                self.bits, self.probs, hamming_right=self.n_alpha, hamming_left=self.n_beta)
+            if not rows.size:
+                raise ValueError(
+                    "The input bit array did not contain any valid bitstrings. "
+                    "Either pass a bit array that contains at least one valid bitstring "
+                    "(with the correct right and left Hamming weights), or specify a value for initial_occupancies."
+                )
+        else:
+            rows, probs = recover_configurations(self.bits, self.probs, self.occupancies, self.n_alpha,
+                                                 self.n_beta, rand_seed=self.rng)
+        out = []
+        for batch in subsample(rows, probs, samples_per_batch=self.samples_per_batch,
+                               num_batches=self.num_batches, rand_seed=self.rng):
+            halves = []
+            for cols in (batch[:, self.norb:], batch[:, : self.norb]):   # alpha = right half, beta = left
+                halves.append(np.unique(bitstring_matrix_to_integers(cols), return_counts=True))
+            (str_a, cnt_a), (str_b, cnt_b) = halves
+            if self.symmetric:
+                pooled = np.concatenate((str_a, str_b))[_by_descending(np.concatenate((cnt_a, cnt_b)))]
+                ranked = np.concatenate((self.include_a, self.include_b, self.carry_a, pooled))
+                list_a = list_b = _first_occurrences(ranked)[: self.max_dim_a]
+                list_a.sort()
+            else:
+                list_a = _first_occurrences(np.concatenate(
+                    (self.include_a, self.carry_a, str_a[_by_descending(cnt_a)])))[: self.max_dim_a]
+                list_b = _first_occurrences(np.concatenate(
+                    (self.include_b, self.carry_b, str_b[_by_descending(cnt_b)])))[: self.max_dim_b]
+                list_a.sort()
+                list_b.sort()
+            out.append((list_a, list_b))
+        return out
+
+    # -- second half: K results -> best / converged / carry-over ----------------------------------
+    def digest(self, results: list[SCIResult]) -> bool:
+        """Returns True when the loop has converged."""
+        winner = min(results, key=lambda r: r.energy)
+        if self.best is None or winner.energy < self.best.energy:
+            self.best = winner
+        if self.reference is not None and abs(self.reference.energy - winner.energy) < self.energy_tol:
+            drift = np.ravel(self.occupancies) - np.ravel(winner.orbital_occupancies)
+            if np.linalg.norm(drift, ord=np.inf) < self.occupancies_tol:
+                return True
+        self.reference = winner
+        self.occupancies = winner.orbital_occupancies
+        # strings of every determinant whose |amplitude| exceeds the threshold, ranked by marginal weight
+        state = winner.sci_state
+        magnitude = np.abs(state.amplitudes.reshape(-1))
+        order = np.argsort(magnitude)
+        big = order[np.searchsorted(magnitude, self.carryover_threshold, sorter=order):]
+        rows, cols = np.divmod(big, state.amplitudes.shape[1])
+        rows, cols = np.unique(rows), np.unique(cols)
+        weight_a = np.sum(np.abs(state.amplitudes[rows]) ** 2, axis=1)
+        weight_b = np.sum(np.abs(state.amplitudes[:, cols]) ** 2, axis=0)
+        keep_a, keep_b = state.ci_strs_a[rows], state.ci_strs_b[cols]
+        if self.symmetric:
+            pooled = np.concatenate((keep_a, keep_b))[_by_descending(np.concatenate((weight_a, weight_b)))]
+            self.carry_a = self.carry_b = _first_occurrences(pooled)
+        else:
+            self.carry_a, self.carry_b = keep_a[_by_descending(weight_a)], keep_b[_by_descending(weight_b)]
+        return False
+
+
+def diagonalize_fermionic_hamiltonian(
+    one_body_tensor: np.ndarray,
+    two_body_tensor: np.ndarray,
+    bit_array,
+    samples_per_batch: int,
+    norb: int,
+    nelec: tuple[int, int],
+    *,
+    num_batches: int = 1,
+    energy_tol: float = 1e-8,
+    occupancies_tol: float = 1e-5,
+    max_iterations: int = 100,
+    sci_solver=None,
+    symmetrize_spin: bool = False,
+    max_dim: int | tuple[int, int] | None = None,
+    include_configurations=None,
+    initial_occupancies: tuple[np.ndarray, np.ndarray] | None = None,
+    carryover_threshold: float = 1e-4,
+    callback=None,
+    seed: int | np.random.Generator | None = None,
+) -> SCIResult:
+    """Sample-based quantum diagonalisation: the self-consistent configuration-recovery loop (reference
+    ``fermion.py:204-462``, same arguments, same error messages, same use of the random generator).
+
+    Per iteration: configuration recovery on the GPU (``recover_configurations``; Hamming post-selection
+    on the first pass without ``initial_occupancies``) -> ``subsample`` -> string lists ->
+    ``sci_solver`` (default: ``solve_sci_batch``, the K subspaces solved concurrently on the GPU) ->
+    best energy / convergence / carry-over.  ``bit_array`` is duck-typed (``.array``, ``.num_bits``,
+    ``.num_shots``), so qiskit is not needed.  Single process: the reference's optional MPI broadcast
+    (``fermion.py:429, 451``) has no counterpart here -- shard the K subspaces with
+    ``solve_sci_batch(devices=...)`` or one process per GPU instead.
+    """
+    from .counts import bit_array_to_arrays
+
+    if max_iterations < 1:
+        raise ValueError("Maximum number of iterations must be at least 1.")
+    n_alpha, n_beta = nelec
+    if symmetrize_spin and n_alpha != n_beta:
+        raise ValueError(
+            "Spin symmetrization is only possible if the numbers of alpha and beta "
+            f"electrons are equal. Instead, got {n_alpha} and {n_beta}."
+        )
+    dims = max_dim if isinstance(max_dim, tuple) else (max_dim, max_dim)
+    if symmetrize_spin and dims[0] != dims[1]:
+        raise ValueError(
+            "When requesting spin symmetrization, the maximum dimension must be "
+            "the same for both spin alpha and spin beta. "
+            f"Instead, got {dims[0]} and {dims[1]}"
+        )
+    if include_configurations is None:
+        include = (np.array([], dtype=int), np.array([], dtype=int))
+    elif isinstance(include_configurations, tuple):
+        include = include_configurations
+    else:
+        include = (include_configurations, include_configurations)
+    include = (np.unique(include[0]), np.unique(include[1]))
+    solver = solve_sci_batch if sci_solver is None else sci_solver
+    raw_bitstrings, raw_probs = bit_array_to_arrays(bit_array)
+    run = _SQDRun(raw_bitstrings, raw_probs, norb, (n_alpha, n_beta), samples_per_batch, num_batches,
+                  symmetrize_spin, include, dims, energy_tol, occupancies_tol, carryover_threshold,
+                  np.random.default_rng(seed), initial_occupancies)
+    for _ in range(max_iterations):
+        results = solver(run.strings_for_iteration(), one_body_tensor, two_body_tensor, norb, nelec)
+        if callback is not None:
+            callback(results)
+        if run.digest(results):
+            break
+    return cast(SCIResult, run.best)
+
+
 class ShardGroup:
     """NCCL communicator for ONE diagonalisation sharded over the ranks of ``torch.distributed``.
 

@@ -6,8 +6,10 @@ Run in the build container only (needs /root/reference):
 
 qiskit and jax are not installed here; ``oracle/shims`` provides the few names the reference imports
 (``qiskit.quantum_info.{Pauli,SparsePauliOp}``, ``qiskit.primitives.BitArray``,
-``qiskit.utils.deprecation.deprecate_func`` and a numpy-backed ``jax``).  ``fermion.py`` cannot be
-imported (pyscf absent), so no fermion golden exists -- see ``oracle/fermion_oracle.py``.
+``qiskit.utils.deprecation.deprecate_func`` and a numpy-backed ``jax``).  pyscf is absent too: ``oracle/shims/pyscf``
+stands in for ``pyscf.fci.selected_ci`` with the dense CPU oracle, which lets the reference's own
+``fermion.py`` run -- its SQD loop, string handling and result conventions are the reference's code, only
+the eigen-solver arithmetic is the oracle's (``sqd_loop_golden.npz``).
 The outputs are committed as small ``.npz`` fixtures next to this script.
 """
 
@@ -131,8 +133,65 @@ def recovery_goldens():
     print("recovery goldens:", len(out), "arrays")
 
 
+def loop_goldens():
+    """The reference's ``diagonalize_fermionic_hamiltonian`` (unmodified source) on small noisy samples."""
+    import functools
+    import math
+
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import qiskit_addon_sqd.fermion as ref_fermion  # whole package: fermion.py imports through the pyscf shim
+    from qiskit.primitives import BitArray  # shim
+    from qiskit_addon_sqd_b200._synthetic import hf_centred_strings, random_integrals
+
+    from make_golden_cases import LOOP_CASES
+
+    shapes = [dict(norb=6, nelec=(3, 3), shots=1500, noise=0.08),
+              dict(norb=7, nelec=(3, 2), shots=1200, noise=0.05),
+              dict(norb=5, nelec=(2, 2), shots=800, noise=0.10)]
+    cases = [dict(shape, **extra) for shape, extra in zip(shapes, LOOP_CASES)]
+    out = {"n_cases": np.array(len(cases))}
+    for ci, case in enumerate(cases):
+        norb, nelec = case["norb"], case["nelec"]
+        h, g = random_integrals(norb, 50 + ci)
+        rng = np.random.default_rng(900 + ci)
+        pool_a = hf_centred_strings(norb, nelec[0], min(14, math.comb(norb, nelec[0])), 10 + ci)
+        pool_b = hf_centred_strings(norb, nelec[1], min(14, math.comb(norb, nelec[1])), 20 + ci)
+        wa = np.exp(-0.5 * np.arange(len(pool_a)))
+        wb = np.exp(-0.5 * np.arange(len(pool_b)))
+        ia = rng.choice(len(pool_a), case["shots"], p=wa / wa.sum())
+        ib = rng.choice(len(pool_b), case["shots"], p=wb / wb.sum())
+        bits = np.zeros((case["shots"], 2 * norb), dtype=bool)
+        for k in range(norb):   # columns: [b_{N-1} .. b_0, a_{N-1} .. a_0]
+            bits[:, norb - 1 - k] = (pool_b[ib].astype(np.uint64) >> np.uint64(k)) & np.uint64(1)
+            bits[:, 2 * norb - 1 - k] = (pool_a[ia].astype(np.uint64) >> np.uint64(k)) & np.uint64(1)
+        bits ^= rng.random(bits.shape) < case["noise"]
+        bit_array = BitArray.from_bool_array(bits)
+        kw = dict(case["kw"])
+        if ci == 1:
+            kw["initial_occupancies"] = (np.linspace(0.9, 0.1, norb), np.linspace(0.8, 0.05, norb))
+        history = []
+        solver = functools.partial(ref_fermion.solve_sci_batch, spin_sq=case["spin_sq"])
+        best = ref_fermion.diagonalize_fermionic_hamiltonian(
+            h, g, bit_array, norb=norb, nelec=nelec, sci_solver=solver, callback=history.append, **kw)
+        out[f"c{ci}_meta"] = np.array([norb, nelec[0], nelec[1], len(history), kw["num_batches"]])
+        out[f"c{ci}_packed"] = bit_array.array.reshape(case["shots"], -1)
+        out[f"c{ci}_best_energy"] = np.array(best.energy)
+        out[f"c{ci}_best_occ"] = np.array(best.orbital_occupancies)
+        for it, results in enumerate(history):
+            for k, r in enumerate(results):
+                out[f"c{ci}_i{it}_b{k}_a"] = np.asarray(r.sci_state.ci_strs_a, dtype=np.int64)
+                out[f"c{ci}_i{it}_b{k}_b"] = np.asarray(r.sci_state.ci_strs_b, dtype=np.int64)
+                out[f"c{ci}_i{it}_b{k}_e"] = np.array(r.energy)
+                out[f"c{ci}_i{it}_b{k}_occ"] = np.array(r.orbital_occupancies)
+        print(f"loop case {ci}: {len(history)} iterations, best energy {best.energy:.10f}, dims",
+              [tuple(r.sci_state.amplitudes.shape) for r in history[-1]])
+    np.savez_compressed(os.path.join(HERE, "sqd_loop_golden.npz"), **out)
+
+
 if __name__ == "__main__":
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         qubit_goldens()
         recovery_goldens()
+        loop_goldens()

@@ -1,0 +1,149 @@
+"""The SQD loop (`fermion.diagonalize_fermionic_hamiltonian`), `counts` and `subsampling` mirrors against
+goldens produced by the reference's own, unmodified loop (`tests/golden/make_golden.py::loop_goldens`).
+
+CPU tests drive OUR loop logic with oracle stand-ins for the two GPU steps (dense solver, recovery
+restatement) and demand the reference's strings in every iteration; the GPU test runs the product path.
+"""
+
+import functools
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import fermion_oracle as fo
+from oracle import recovery_oracle as ro
+from qiskit_addon_sqd_b200._synthetic import random_integrals
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+sys.path.insert(0, GOLD)
+from make_golden_cases import LOOP_CASES  # noqa: E402
+
+
+class PackedBits:
+    """Duck-typed stand-in for qiskit's BitArray (`.array`, `.num_bits`, `.num_shots`)."""
+
+    def __init__(self, packed: np.ndarray, num_bits: int):
+        self.array, self.num_bits, self.num_shots = packed, num_bits, packed.shape[0]
+
+
+def _load_case(ci):
+    z = np.load(os.path.join(GOLD, "sqd_loop_golden.npz"))
+    norb, nea, neb, n_iter, n_batches = (int(v) for v in z[f"c{ci}_meta"])
+    h, g = random_integrals(norb, 50 + ci)
+    kw = dict(LOOP_CASES[ci]["kw"])
+    if ci == 1:
+        kw["initial_occupancies"] = (np.linspace(0.9, 0.1, norb), np.linspace(0.8, 0.05, norb))
+    return z, norb, (nea, neb), n_iter, n_batches, h, g, kw, PackedBits(z[f"c{ci}_packed"], 2 * norb)
+
+
+def _check_history(z, ci, history, n_iter, n_batches, etol, otol):
+    assert len(history) == n_iter
+    for it, results in enumerate(history):
+        assert len(results) == n_batches
+        for k, r in enumerate(results):
+            # string lists: bit-exact, every iteration (recovery + subsampling + ordering + carry-over)
+            assert np.array_equal(np.asarray(r.sci_state.ci_strs_a), z[f"c{ci}_i{it}_b{k}_a"]), (it, k)
+            assert np.array_equal(np.asarray(r.sci_state.ci_strs_b), z[f"c{ci}_i{it}_b{k}_b"]), (it, k)
+            assert abs(r.energy - float(z[f"c{ci}_i{it}_b{k}_e"])) < etol, (it, k)
+            assert np.abs(np.array(r.orbital_occupancies) - z[f"c{ci}_i{it}_b{k}_occ"]).max() < otol
+
+
+def _oracle_solver(ci_strings, h, g, norb, nelec, *, spin_sq=None):
+    from qiskit_addon_sqd_b200.fermion import SCIResult, SCIState
+
+    out = []
+    for sa, sb in ci_strings:
+        if spin_sq is None:
+            e, c, occ, _s2, _ = fo.solve_dense(sa, sb, h, g, norb)
+        else:
+            e, c, occ, _s2, _ = fo.solve_dense(sa, sb, h, g, norb, spin_sq=spin_sq, shift=0.2)
+        out.append(SCIResult(e, SCIState(c, np.asarray(sa), np.asarray(sb), norb, tuple(nelec)),
+                             orbital_occupancies=occ))
+    return out
+
+
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_loop_logic_matches_reference_loop_on_cpu(ci, monkeypatch):
+    from qiskit_addon_sqd_b200 import configuration_recovery, fermion
+
+    z, norb, nelec, n_iter, n_batches, h, g, kw, bits = _load_case(ci)
+    monkeypatch.setattr(configuration_recovery, "recover_configurations", ro.recover_configurations)
+    history = []
+    solver = functools.partial(_oracle_solver, spin_sq=LOOP_CASES[ci]["spin_sq"])
+    best = fermion.diagonalize_fermionic_hamiltonian(h, g, bits, norb=norb, nelec=nelec, sci_solver=solver,
+                                                     callback=history.append, **kw)
+    _check_history(z, ci, history, n_iter, n_batches, 1e-10, 1e-9)
+    assert abs(best.energy - float(z[f"c{ci}_best_energy"])) < 1e-10
+
+
+def test_loop_argument_errors_are_the_reference_messages():
+    from qiskit_addon_sqd_b200 import fermion
+
+    h, g = random_integrals(4, 1)
+    bits = PackedBits(np.zeros((3, 1), dtype=np.uint8), 8)
+    with pytest.raises(ValueError, match="Maximum number of iterations must be at least 1."):
+        fermion.diagonalize_fermionic_hamiltonian(h, g, bits, 2, 4, (2, 2), max_iterations=0)
+    with pytest.raises(ValueError, match="Spin symmetrization is only possible"):
+        fermion.diagonalize_fermionic_hamiltonian(h, g, bits, 2, 4, (2, 1), symmetrize_spin=True)
+    with pytest.raises(ValueError, match="the maximum dimension must be"):
+        fermion.diagonalize_fermionic_hamiltonian(h, g, bits, 2, 4, (2, 2), symmetrize_spin=True, max_dim=(3, 4))
+    with pytest.raises(ValueError, match="did not contain any valid bitstrings"):
+        fermion.diagonalize_fermionic_hamiltonian(h, g, bits, 2, 4, (2, 2), sci_solver=_oracle_solver)
+
+
+def test_counts_and_subsampling_known_answers():
+    """Known answers of the reference's own tests (test_subsampling.py:53-75, test_counts.py) and docs
+    (select_open_closed_shell.ipynb: counts -> integers)."""
+    from qiskit_addon_sqd_b200 import counts, subsampling
+
+    mat = np.array([[1, 0, 1, 0], [0, 1, 1, 0], [1, 1, 0, 0], [1, 0, 0, 1]], dtype=bool)
+    p = np.array([0.1, 0.2, 0.3, 0.4])
+    rows, probs = subsampling.postselect_by_hamming_right_and_left(mat, p, hamming_right=1, hamming_left=1)
+    assert np.array_equal(rows, mat[[0, 1, 3]]) and np.allclose(probs, np.array([0.1, 0.2, 0.4]) / 0.7)
+    assert p[0] == 0.1  # input untouched
+    with pytest.raises(ValueError, match="non-negative integer"):
+        subsampling.postselect_by_hamming_right_and_left(mat, p, hamming_right=-1, hamming_left=1)
+    with pytest.raises(ValueError, match="must be even"):
+        subsampling.postselect_by_hamming_right_and_left(mat[:, :3], p, hamming_right=1, hamming_left=1)
+    assert all(b.size == 0 for b in subsampling.subsample(np.zeros((0, 4), dtype=bool), np.zeros(0), 2, 3))
+    with pytest.raises(ValueError, match="Samples per batch"):
+        subsampling.subsample(mat, p, 0, 1)
+    with pytest.raises(ValueError, match="number of batches"):
+        subsampling.subsample(mat, p, 1, 0)
+    # fewer rows than requested: whole input, generator untouched
+    gen = np.random.default_rng(3)
+    full = subsampling.subsample(mat, p, 9, 2, gen)
+    assert len(full) == 2 and np.array_equal(full[0], mat) and gen.random() == np.random.default_rng(3).random()
+    # the generator stream is numpy's weighted choice
+    g1, g2 = np.random.default_rng(11), np.random.default_rng(11)
+    got = subsampling.subsample(mat, p, 2, 3, g1)
+    want = [mat[g2.choice(np.arange(4), 2, replace=False, p=p)] for _ in range(3)]
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    # integers: big-endian, int64 below 64 bits, Python ints from 64 bits on (test_fermion.py:344-360)
+    assert counts.bitstring_matrix_to_integers(np.array([[0, 0, 0, 1, 0, 0, 1, 0]], dtype=bool)).tolist() == [18]
+    wide = np.zeros((1, 64), dtype=bool)
+    wide[0, 0] = wide[0, -1] = True
+    out = counts.bitstring_matrix_to_integers(wide)
+    assert out.dtype == object and out[0] == (1 << 63) + 1
+    arr = PackedBits(np.array([[0b00010010], [0b01001000], [0b00010010], [0b00010001]], dtype=np.uint8), 8)
+    rows, probs = counts.bit_array_to_arrays(arr)
+    assert counts.bitstring_matrix_to_integers(rows).tolist() == [17, 18, 72] and probs.tolist() == [0.25, 0.5, 0.25]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ci", [0, 1, 2])
+def test_loop_on_gpu_matches_reference_loop(ci):
+    """Product path: GPU configuration recovery + GPU subspace solves inside our loop reproduce the
+    reference loop's string lists exactly and its energies to 1e-8 Ha in every iteration."""
+    from qiskit_addon_sqd_b200 import fermion
+
+    z, norb, nelec, n_iter, n_batches, h, g, kw, bits = _load_case(ci)
+    history = []
+    solver = functools.partial(fermion.solve_sci_batch, spin_sq=LOOP_CASES[ci]["spin_sq"])
+    best = fermion.diagonalize_fermionic_hamiltonian(h, g, bits, norb=norb, nelec=nelec, sci_solver=solver,
+                                                     callback=history.append, **kw)
+    _check_history(z, ci, history, n_iter, n_batches, 1e-8, 1e-6)
+    assert abs(best.energy - float(z[f"c{ci}_best_energy"])) < 1e-8
+    assert np.abs(np.array(best.orbital_occupancies) - z[f"c{ci}_best_occ"]).max() < 1e-6
