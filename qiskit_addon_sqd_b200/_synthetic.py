@@ -122,3 +122,40 @@ class PauliSum:
     @property
     def size(self) -> int:
         return len(self.paulis)
+
+
+class PackedBitArray:
+    """Minimal stand-in for ``qiskit.primitives.BitArray`` (what the SQD loop reads: ``.array`` uint8
+    ``(shots, bytes)`` big-endian left-padded, ``.num_bits``, ``.num_shots``)."""
+
+    def __init__(self, array: np.ndarray, num_bits: int):
+        self.array = np.ascontiguousarray(array, dtype=np.uint8)
+        self.num_bits = int(num_bits)
+        self.num_shots = int(self.array.shape[0])
+
+    @classmethod
+    def from_bool_array(cls, bits: np.ndarray) -> "PackedBitArray":
+        bits = np.asarray(bits, dtype=bool)
+        pad = (-bits.shape[1]) % 8
+        return cls(np.packbits(np.pad(bits, ((0, 0), (pad, 0))), axis=1), bits.shape[1])
+
+
+def noisy_samples(norb: int, nelec: tuple[int, int], shots: int, n_strings: int, noise: float,
+                  seed: int) -> PackedBitArray:
+    """Synthetic measurement record for the SQD loop: alpha/beta strings drawn from HF-centred pools with
+    exponentially decaying weights, columns ``[b_{N-1}..b_0, a_{N-1}..a_0]``, every bit then flipped with
+    probability ``noise`` (so that configuration recovery has something to repair)."""
+    import math
+
+    rng = np.random.default_rng(seed)
+    pools = [hf_centred_strings(norb, ne, min(n_strings, math.comb(norb, ne)), seed + 1 + s)
+             for s, ne in enumerate(nelec)]
+    bits = np.zeros((shots, 2 * norb), dtype=bool)
+    for spin, pool in enumerate(pools):
+        w = np.exp(-4.0 * np.arange(len(pool)) / len(pool))
+        pick = pool[rng.choice(len(pool), shots, p=w / w.sum())].astype(np.uint64)
+        first = norb if spin == 0 else 0   # alpha on the right
+        for k in range(norb):
+            bits[:, first + norb - 1 - k] = (pick >> np.uint64(k)) & np.uint64(1)
+    bits ^= rng.random(bits.shape) < noise
+    return PackedBitArray.from_bool_array(bits)

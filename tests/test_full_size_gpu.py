@@ -135,3 +135,50 @@ def test_recovery_full_size(cuda_lib):
     m2, f2 = ro.recover_configurations(bs[:3000], probs[:3000], occ, na, nb, g2)
     assert np.array_equal(m1, m2) and np.array_equal(f1, f2)
     assert g1.bit_generator.state == g2.bit_generator.state
+
+
+def test_sqd_loop_config2_full_size(cuda_lib):
+    """BASELINE.json configs[1]: (10e,16o), 5 batches of ~1e4 determinants, 3 configuration-recovery
+    iterations on one GPU -- the whole loop through the drop-in entry point.  Synthetic integrals and a
+    synthetic noisy measurement record (no pyscf / N2 integrals offline)."""
+    import functools
+
+    from qiskit_addon_sqd_b200 import fermion
+    from qiskit_addon_sqd_b200._synthetic import noisy_samples, random_integrals
+
+    norb, nelec = 16, (5, 5)
+    h, g = random_integrals(norb, 102)
+    record = noisy_samples(norb, nelec, shots=10_000, n_strings=400, noise=0.04, seed=202)
+    solver = functools.partial(fermion.solve_sci_batch, spin_sq=0.0)
+
+    def run():
+        history = []
+        t0 = time.perf_counter()
+        best = fermion.diagonalize_fermionic_hamiltonian(
+            h, g, record, samples_per_batch=300, norb=norb, nelec=nelec, num_batches=5, max_iterations=3,
+            max_dim=100, sci_solver=solver, symmetrize_spin=True, callback=history.append, seed=5)
+        return best, history, time.perf_counter() - t0
+
+    run()  # warm-up (allocator pools, module loads)
+    best, history, dt = run()
+    best2, history2, _ = run()
+    assert len(history) == 3 and all(len(r) == 5 for r in history)
+    dims = [r.sci_state.amplitudes.shape for it in history for r in it]
+    assert all(d[0] <= 100 and d[1] <= 100 for d in dims) and max(d[0] * d[1] for d in dims) == 10_000
+    for it in history:
+        for r in it:
+            sa = np.asarray(r.sci_state.ci_strs_a)
+            assert np.all(np.diff(sa) > 0) and np.all(np.bitwise_count(sa.astype(np.uint64)) == 5)
+            assert abs(r.orbital_occupancies[0].sum() - 5) < 1e-9 and abs(r.orbital_occupancies[1].sum() - 5) < 1e-9
+            assert abs(np.linalg.norm(r.sci_state.amplitudes) - 1.0) < 1e-9
+            e_rdm = np.einsum("pr,pr->", r.rdm1, h) + 0.5 * np.einsum("prqs,prqs->", r.rdm2, g)
+            assert abs(e_rdm - r.energy) < 1e-8      # the reference's own energy formula (fermion.py:730-732)
+    lowest = [min(r.energy for r in it) for it in history]
+    assert best.energy == min(lowest)
+    assert lowest[-1] <= lowest[0] + 1e-9            # carry-over + recovery do not lose the best state
+    # same seed -> same strings, energies, amplitudes (reference test_fermion.py:285-342)
+    assert best2.energy == best.energy and np.array_equal(best2.sci_state.amplitudes, best.sci_state.amplitudes)
+    assert all(np.array_equal(a.sci_state.ci_strs_a, b.sci_state.ci_strs_a)
+               for x, y in zip(history, history2) for a, b in zip(x, y))
+    print(f"\nconfig 2 loop: 3 iterations x 5 subspaces of <= 1e4 dets in {dt*1e3:.1f} ms, "
+          f"best energy per iteration {np.round(lowest, 8).tolist()}")
