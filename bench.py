@@ -214,8 +214,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ints = fermion._DeviceIntegrals(torch, h, g, dev)
     strs_dev = [(torch.from_numpy(a.astype(np.uint64).view(np.int64)).to(dev),
                  torch.from_numpy(b.astype(np.uint64).view(np.int64)).to(dev)) for a, b in batches]
-    streams = [torch.cuda.Stream(device=dev) for _ in range(K)]
-    pool = ThreadPoolExecutor(max_workers=K)
+    # the same streams and host threads as the library's own batch driver: the stream-ordered memory pool
+    # and the per-thread pinned staging buffers are then shared by the two arms
+    streams = [fermion._stream_for(torch, local_rank, k) for k in range(K)]
+    pool = fermion._worker_pool()
 
     def device_step(profile=False):
         main = torch.cuda.current_stream()
@@ -225,7 +227,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 streams[k].wait_stream(main)
                 r = fermion._solve_on_device(batches[k][0], batches[k][1], norb, ints, None, 0.2, opts,
                                              want_spin=False, want_rdm=False, strs_dev=strs_dev[k],
-                                             download=False, profile=profile)
+                                             download=False, profile=profile, throughput=K > 1)
                 return r
 
         res = list(pool.map(work, range(K)))
@@ -279,7 +281,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         e2e_loop_step()
 
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not args.no_clock_sampler:
         sampler.start()
     lib.sqd_launch_count(1)
     ms_dev, res_dev = timed(device_step, args.steps)
@@ -417,6 +419,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=2, help="subspaces per step on the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-pyscf-style", action="store_true")
+    ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics: do not poll nvidia-smi")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

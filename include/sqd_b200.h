@@ -154,6 +154,7 @@ typedef struct {
     sqd_sigma_plan plan;
     sqd_sell bd;             /* beta single excitations (mode 0; long columns have length 0) */
     sqd_sell bb;             /* every beta entry with its same-spin value (mode 1) */
+    int throughput_mode;     /* see sqd_solve_params.throughput_mode */
 } sqd_operator;
 
 /* Build a SELL-32 copy of a table.  mode 0: single excitations only, strings with more than
@@ -264,6 +265,9 @@ typedef struct {
                                     shard_world contiguous blocks of equal estimated cost, take block
                                     shard_rank */
     int shard_rank, shard_world;
+    int throughput_mode;         /* != 0: this solve shares the GPU with others (one stream each): the sigma
+                                    kernel is launched under a register cap that lets three of its CTAs
+                                    share an SM -- slower alone, faster in aggregate */
 } sqd_solve_params;
 
 typedef struct {

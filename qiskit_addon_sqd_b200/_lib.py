@@ -76,6 +76,7 @@ class Operator(C.Structure):
         ("plan", SigmaPlan),
         ("bd", Sell),
         ("bb", Sell),
+        ("throughput_mode", C.c_int),
     ]
 
 
@@ -130,6 +131,7 @@ class SolveParams(C.Structure):
         ("nccl_comm", C.c_void_p),
         ("row_begin", C.c_int), ("row_end", C.c_int),
         ("shard_rank", C.c_int), ("shard_world", C.c_int),
+        ("throughput_mode", C.c_int),
     ]
 
 

@@ -706,9 +706,13 @@ static int launch_sigma_a_tb(const SigmaArgs& args, const SigmaPlan& pl, cudaStr
 template <int CPT, bool STAGE_PACK>
 static int launch_sigma_a(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t st) {
     if constexpr (CPT == 1) {
-        static const int knob_minb = env_int("SQD_SIGMA_MINB", 1);
+        // SQD_SIGMA_MINB overrides the choice made from the operator's throughput_mode (1 or 3 CTAs per SM)
+        static const int knob_env = env_int("SQD_SIGMA_MINB", 0);
+        const int knob_minb = knob_env > 0 ? knob_env : (args.op.throughput_mode ? 3 : 1);
         if (pl.threads + 32 <= 384 && knob_minb == 3)
             return launch_sigma_a_tb<1, STAGE_PACK, 384, 3>(args, pl, st);
+        if (pl.threads + 32 <= 384 && knob_minb == 4)
+            return launch_sigma_a_tb<1, STAGE_PACK, 384, 4>(args, pl, st);
         return launch_sigma_a_tb<1, STAGE_PACK, 1024, 1>(args, pl, st);
     } else {
         return launch_sigma_a_tb<CPT, STAGE_PACK, 512, 1>(args, pl, st);

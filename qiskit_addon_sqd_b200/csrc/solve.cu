@@ -237,6 +237,7 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
     base.norb = norb;
     base.ldc = ldc;
     base.ldg = ldg;
+    base.throughput_mode = prm->throughput_mode;
     base.plan = sqd_sigma_plan{hc[0], hc[1], hc[2], hc[3], chunk[0], chunk[1], chunk[2], chunk[3],
                                split[0], split[1], split[2], long_idx, long_cols, part};
     base.bd = sqd_sell{nsl, hc[5], S0.perm, S0.len, S0.slice_ptr, S0.pack, nullptr};

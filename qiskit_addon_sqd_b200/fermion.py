@@ -304,7 +304,7 @@ class _OperatorDev:
         self.struct = _lib.Operator(sub.ta.struct(), sub.tb.struct(), norb, ldc, ldg,
                                     _lib.ptr(self.diag), _lib.ptr(self.gab), _lib.ptr(self.Wa),
                                     _lib.ptr(self.Wb), 1 if same_spin else 0, sub.sigma_plan(),
-                                    sub.tb.sell(0, sub._plan_keep[2]), sub.tb.sell(1))
+                                    sub.tb.sell(0, sub._plan_keep[2]), sub.tb.sell(1), 0)
         if lib.sqd_sigma_smem_bytes(C.byref(self.struct)) < 0:
             raise ValueError(
                 f"subspace shape (na={na}, nb={nb}, norb={norb}) exceeds the shared-memory row "
@@ -552,7 +552,7 @@ def last_solve_stats() -> list[SolveStats]:
 
 def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq, shift, opts,
                      want_spin: bool, want_rdm: bool, *, strs_dev=(None, None), download: bool = True,
-                     profile: bool = False, shard_group=None):
+                     profile: bool = False, shard_group=None, throughput: bool = False):
     """Ground state of H projected on A x B: ONE call into the library (``sqd_solve_subspace``), so the
     host thread does not touch the interpreter between the first kernel and the last read-back.
     Returns dict of results (host arrays; with ``download=False`` the amplitudes stay on the device as a
@@ -598,6 +598,7 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
     prm.d_ci0 = _lib.ptr(ci0_d) or None
     prm.cost_per_chunk, prm.long_threshold = int(_SIGMA_COST_PER_CHUNK), int(_SIGMA_LONG_THRESHOLD)
     prm.profile = 1 if profile else 0
+    prm.throughput_mode = 1 if throughput else 0
     if shard_group is not None:
         # rows are split inside the call into blocks of equal estimated sigma-build cost
         prm.nccl_comm, prm.row_begin, prm.row_end = shard_group._comm.value, -1, -1
@@ -685,43 +686,131 @@ def solve_sci_batch(
     if K == 0:
         return []
 
-    ints = {d: None for d in dev_list}
-    ints_lock = threading.Lock()
-
-    def get_ints(d):
-        with ints_lock:
-            if ints[d] is None:
-                ints[d] = _DeviceIntegrals(torch, one_body_tensor, two_body_tensor,
-                                           torch.device("cuda", d))
-            return ints[d]
+    # One upload, K library calls, one download per device.  Everything the interpreter has to do for a
+    # subspace happens here, on the calling thread, before / after the solves; a worker thread only makes
+    # the `sqd_solve_subspace` call (ctypes drops the interpreter lock for its whole duration), so the K
+    # solves overlap instead of queueing on the lock.
+    lib = _lib.load()
+    if norb > 64 or norb < 1:
+        raise ValueError("qiskit_addon_sqd_b200 supports 1..64 spatial orbitals.")
+    jobs: list[dict] = []
+    per_device: dict[int, list[int]] = {d: [] for d in dev_list}
+    for k, (strs_a, strs_b) in enumerate(ci_strings):
+        same = strs_a is strs_b
+        ua = _as_uint64(strs_a)
+        ub = ua if same else _as_uint64(strs_b)
+        if ua.size == 0 or ub.size == 0:
+            raise ValueError("The subspace must contain at least one alpha and one beta string.")
+        same = same or (ua.shape == ub.shape and np.array_equal(ua, ub))
+        d = dev_list[k % len(dev_list)]
+        per_device[d].append(k)
+        jobs.append(dict(ua=ua, ub=ub, same=same, na=len(ua), nb=len(ub), ldc=(len(ub) + 1) // 2 * 2,
+                         device=d, slot=len(per_device[d]) - 1))
+    n2, n4 = norb * norb, norb**4
+    keep = {}
+    for d, ks in per_device.items():
+        if not ks:
+            continue
+        with torch.cuda.device(d):
+            dev = torch.device("cuda", d)
+            ints = _DeviceIntegrals(torch, one_body_tensor, two_body_tensor, dev)
+            # strings of every subspace of this device in one array -> one host-to-device copy
+            parts, off = [], 0
+            for k in ks:
+                j = jobs[k]
+                j["off_a"] = off
+                parts.append(j["ua"])
+                off += j["na"]
+                if j["same"]:
+                    j["off_b"] = j["off_a"]
+                else:
+                    j["off_b"] = off
+                    parts.append(j["ub"])
+                    off += j["nb"]
+            strs_d = torch.from_numpy(np.concatenate(parts).view(np.int64)).to(dev)
+            x_off, tot = [], 0
+            for k in ks:
+                x_off.append(tot)
+                tot += jobs[k]["na"] * jobs[k]["ldc"]
+            x_d = torch.empty(tot, dtype=torch.float64, device=dev)
+            rdm1_d = torch.empty(len(ks) * n2, dtype=torch.float64, device=dev) if want_rdm else None
+            rdm2_d = torch.empty(len(ks) * n4, dtype=torch.float64, device=dev) if want_rdm else None
+            ci0 = opts.get("ci0")
+            for i, k in enumerate(ks):
+                j = jobs[k]
+                prm = _lib.SolveParams()
+                prm.norb, prm.na, prm.nb = norb, j["na"], j["nb"]
+                prm.n_alpha, prm.n_beta = int(np.bitwise_count(j["ua"][0])), int(np.bitwise_count(j["ub"][0]))
+                prm.d_strs_a = strs_d.data_ptr() + 8 * j["off_a"]
+                prm.d_strs_b = strs_d.data_ptr() + 8 * j["off_b"]
+                prm.d_h, prm.d_g = _lib.ptr(ints.h), _lib.ptr(ints.g)
+                prm.penalty = 0 if spin_sq is None else 1
+                prm.spin_sq = 0.0 if spin_sq is None else float(spin_sq)
+                prm.shift = shift
+                prm.max_space = int(min(max(2, opts["max_space"]), _lib.MAX_SPACE))
+                prm.max_cycle = int(opts["max_cycle"])
+                prm.tol, prm.tol_residual = float(opts["tol"]), float(opts["tol_residual"])
+                prm.lindep, prm.level_shift = float(opts["lindep"]), float(opts["level_shift"])
+                prm.check_every = 4
+                if ci0 is not None:
+                    j["ci0_d"] = torch.from_numpy(
+                        np.ascontiguousarray(ci0, dtype=np.float64).reshape(j["na"], j["nb"])).to(dev)
+                    prm.d_ci0 = j["ci0_d"].data_ptr()
+                prm.cost_per_chunk, prm.long_threshold = int(_SIGMA_COST_PER_CHUNK), int(_SIGMA_LONG_THRESHOLD)
+                prm.throughput_mode = 1 if K > 1 else 0
+                j["prm"], j["res"] = prm, _lib.SolveResult()
+                j["x_ptr"] = x_d.data_ptr() + 8 * x_off[i]
+                j["x_off"] = x_off[i]
+                j["rdm1_ptr"] = rdm1_d.data_ptr() + 8 * i * n2 if want_rdm else None
+                j["rdm2_ptr"] = rdm2_d.data_ptr() + 8 * i * n4 if want_rdm else None
+                j["n_alpha"], j["n_beta"] = prm.n_alpha, prm.n_beta
+            keep[d] = (ints, strs_d, x_d, rdm1_d, rdm2_d)
 
     def work(k: int):
-        d = dev_list[k % len(dev_list)]
+        j = jobs[k]
+        d = j["device"]
         with torch.cuda.device(d):
-            it = get_ints(d)
-            stream = _stream_for(torch, d, k // len(dev_list)) if K > 1 else torch.cuda.current_stream()
+            stream = _stream_for(torch, d, j["slot"]) if K > 1 else torch.cuda.current_stream()
             if K > 1:
-                stream.wait_stream(torch.cuda.default_stream(d))
+                stream.wait_stream(torch.cuda.current_stream())
+            rc = lib.sqd_solve_subspace(C.byref(j["prm"]), j["x_ptr"], j["rdm1_ptr"], j["rdm2_ptr"],
+                                        C.byref(j["res"]), stream.cuda_stream)
+            if rc:
+                return rc, lib.sqd_last_error()   # the error string is per host thread
+            # results come back on the worker's own stream through its pinned staging buffer, so the K
+            # device-to-host copies and the K host copies overlap
+            _ints, _strs, x_d, rdm1_d, rdm2_d = keep[d]
+            na, nb, ldc, i = j["na"], j["nb"], j["ldc"], j["slot"]
             with torch.cuda.stream(stream):
-                strs_a, strs_b = ci_strings[k]
-                res = _solve_on_device(strs_a, strs_b, norb, it, spin_sq, shift, opts,
-                                       want_spin=False, want_rdm=want_rdm)
-                stream.synchronize()
-            return res
+                j["amps"] = _lib.download(torch, x_d[j["x_off"]: j["x_off"] + na * ldc].view(na, ldc)[:, :nb])
+                if want_rdm:
+                    j["rdm1"] = _lib.download(torch, rdm1_d[i * n2: (i + 1) * n2].view(norb, norb))
+                    j["rdm2"] = _lib.download(torch, rdm2_d[i * n4: (i + 1) * n4].view((norb,) * 4))
+        return 0, None
 
     if K == 1:
-        raw = [work(0)]
+        status = [work(0)]
     else:
-        # ctypes releases the GIL during every sqd_* call, so the K host threads overlap
-        raw = list(_worker_pool().map(work, range(K)))
-    _tls.stats = [r["stats"] for r in raw]
+        status = list(_worker_pool().map(work, range(K)))
+    for rc, err in status:
+        if rc:
+            raise _lib.SqdCudaError(f"sqd_solve_subspace failed ({rc}): {err.decode() if err else ''}")
 
-    out = []
-    for (strs_a, strs_b), r in zip(ci_strings, raw):
-        state = SCIState(amplitudes=r["amplitudes"], ci_strs_a=np.asarray(strs_a),
-                         ci_strs_b=np.asarray(strs_b), norb=norb, nelec=tuple(nelec))
-        out.append(SCIResult(r["energy"], state, orbital_occupancies=r["occupancies"],
-                             rdm1=r["rdm1"], rdm2=r["rdm2"]))
+    out, stats = [], []
+    for k, (strs_a, strs_b) in enumerate(ci_strings):
+        j = jobs[k]
+        res, info = j["res"], j["res"].info
+        na, nb = j["na"], j["nb"]
+        amps = j["amps"]
+        occ = (np.array(res.occ_a[:norb]), np.array(res.occ_b[:norb]))
+        state = SCIState(amplitudes=amps, ci_strs_a=np.asarray(strs_a), ci_strs_b=np.asarray(strs_b),
+                         norb=norb, nelec=tuple(nelec))
+        out.append(SCIResult(float(res.energy), state, orbital_occupancies=occ,
+                             rdm1=j.get("rdm1"), rdm2=j.get("rdm2")))
+        stats.append(SolveStats(info.cycles, info.sigma_builds, info.converged, info.residual, info.theta,
+                                na * nb, int(res.nnz_a), int(res.nnz_b), 0, 0, info.sigma_ms,
+                                info.total_ms, na, nb, norb))
+    _tls.stats = stats
     return out
 
 
