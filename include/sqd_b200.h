@@ -208,6 +208,10 @@ typedef struct {
      * builds rows [row_begin, row_end) of every sigma vector and the blocks are all-reduced (sum) */
     void* nccl_comm;
     int row_begin, row_end;
+    /* 0: the lowest Ritz pair comes from the secular equation on the main stream and the full
+     * Rayleigh-Ritz decomposition runs on a side stream (shortest critical path of ONE solve);
+     * != 0: one Rayleigh-Ritz kernel on the main stream (fewer launches when many solves share the GPU) */
+    int single_stream_ritz;
 } sqd_davidson_params;
 
 typedef struct {

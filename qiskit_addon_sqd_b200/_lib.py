@@ -96,6 +96,7 @@ class DavidsonParams(C.Structure):
         ("nccl_comm", C.c_void_p),
         ("row_begin", C.c_int),
         ("row_end", C.c_int),
+        ("single_stream_ritz", C.c_int),
     ]
 
 

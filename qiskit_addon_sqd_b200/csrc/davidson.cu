@@ -55,6 +55,7 @@ struct DavState {
     double y[kMaxS];
     double c1[kMaxS];
     double c2[kMaxS];
+    double gcol[kMaxS];         // newest column of V^T H V (reduced once, read by both Rayleigh-Ritz kernels)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -230,6 +231,126 @@ __device__ __forceinline__ double reduce_partials(const double* partials, int ro
     return warp_sum(s);
 }
 
+// Lowest Ritz pair only -- the one thing the rest of the cycle waits for.  In the eigenbasis of the
+// previous cycle the projected matrix is the arrowhead [diag(lam) z; z^T a]; its lowest eigenvalue is the
+// root below the smallest pole of the secular function
+//     f(mu) = a - mu - sum_j z_j^2 / (lam_j - mu)          (strictly decreasing there),
+// found with the origin shifted to that pole (tau = mu - p0, so the differences lam_j - mu keep full
+// relative accuracy) by a safeguarded Newton iteration on tau * f(tau), and the eigenvector is
+// [z_j / (mu - lam_j); 1].  Directions with z_j = 0 decouple (their eigenpair is (lam_j, e_j)).
+// The full decomposition for the NEXT cycle is rebuilt by rayleigh_ritz_kernel on a side stream, off the
+// critical path.
+__global__ void __launch_bounds__(256)
+ritz_lowest_kernel(DavState* __restrict__ st, const double* __restrict__ partials, int nblk, int m) {
+    if (st->status != 0) return;
+    __shared__ double g[kMaxS];
+    __shared__ double v[kMaxS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = m - 1;
+    for (int row = warp; row < m; row += blockDim.x >> 5) {
+        const double s = reduce_partials(partials, row, nblk);
+        if (lane == 0) {
+            g[row] = s;
+            st->gcol[row] = s;
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const double a = g[d];
+    // lane j < d owns pole j (kMaxS <= 32)
+    double pj = 0.0, zj = 0.0;
+    if (lane < d) {
+        pj = st->lam[lane];
+        for (int i = 0; i < d; ++i) zj = fma(st->Q[i * kMaxS + lane], g[i], zj);
+    }
+    double scale = fmax(fabs(a), fmax(fabs(pj), fabs(zj)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, o));
+    const bool active = lane < d && fabs(zj) > 1e-15 * scale;
+    const double big = 1e300;
+    // smallest active pole (ties: lowest lane), smallest decoupled pole
+    double pa = active ? pj : big, pd = (lane < d && !active) ? pj : big;
+    int ia = active ? lane : 99, id = (lane < d && !active) ? lane : 99;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double pa2 = __shfl_xor_sync(0xffffffffu, pa, o), pd2 = __shfl_xor_sync(0xffffffffu, pd, o);
+        const int ia2 = __shfl_xor_sync(0xffffffffu, ia, o), id2 = __shfl_xor_sync(0xffffffffu, id, o);
+        if (pa2 < pa || (pa2 == pa && ia2 < ia)) { pa = pa2; ia = ia2; }
+        if (pd2 < pd || (pd2 == pd && id2 < id)) { pd = pd2; id = id2; }
+    }
+    double mu, vj = 0.0, vd = 0.0;  // eigenvector in the [Q, e_new] basis: vj on lane j, vd for e_new
+    if (ia == 99) {
+        // nothing couples to the new direction: the matrix is already diagonal
+        mu = fmin(a, pd);
+        if (a <= pd) vd = 1.0; else vj = lane == id ? 1.0 : 0.0;
+    } else {
+        const double p0 = pa, c0 = a - p0;
+        const double dj = pj - p0;               // >= 0 on active lanes, exactly 0 on lane ia
+        const double z2 = active ? zj * zj : 0.0;
+        const bool at0 = active && dj == 0.0;      // poles that coincide with p0 act as one
+        const double z0sq = warp_sum(at0 ? z2 : 0.0);
+        // start: two-term model  c + z0^2/tau - tau = 0  with the other poles frozen at tau = 0
+        double c = (active && !at0) ? z2 / dj : 0.0;
+        c = c0 - warp_sum(c);
+        const double rt = sqrt(c * c + 4.0 * z0sq);
+        double tau = c > 0.0 ? -2.0 * z0sq / (c + rt) : 0.5 * (c - rt);
+        double zn = warp_sum(z2);
+        double lo = -(fabs(c0) + sqrt(zn)) * (1.0 + 1e-12) - 1e-300, hi = 0.0;  // f(lo) > 0 > f(hi^-)
+        if (!(tau > lo && tau < hi)) tau = 0.5 * lo;
+        for (int it = 0; it < 80; ++it) {
+            // f and f' at tau
+            const double den = dj - tau;                      // > 0
+            const double t = active ? z2 / den : 0.0;
+            const double f = c0 - tau - warp_sum(t);
+            const double fp = -1.0 - warp_sum(active ? t / den : 0.0);
+            if (f > 0.0) lo = tau; else hi = tau;
+            if (f == 0.0) break;
+            // Newton on h(tau) = tau f(tau): nearly linear when the origin pole dominates
+            const double h = tau * f, hp = f + tau * fp;
+            double next = tau - h / hp;
+            if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);   // safeguard: bisection
+            const double step = fabs(next - tau);
+            tau = next;
+            if (step <= 4.4e-16 * fabs(tau) || hi - lo <= 4.4e-16 * fabs(lo)) break;
+        }
+        mu = p0 + tau;
+        if (pd < mu) {
+            // a decoupled direction lies even lower
+            mu = pd;
+            vj = lane == id ? 1.0 : 0.0;
+        } else {
+            vj = active ? zj / (tau - dj) : 0.0;   // z_j / (mu - lam_j)
+            vd = 1.0;
+        }
+    }
+    // back to the V basis: y_i = sum_j Q[i][j] v_j (i < d), y_d = vd
+    if (lane < kMaxS) v[lane] = vj;
+    __syncwarp();
+    double yi = 0.0;
+    if (lane < d) {
+        for (int j = 0; j < d; ++j) yi = fma(st->Q[lane * kMaxS + j], v[j], yi);
+    } else if (lane == d) {
+        yi = vd;
+    }
+    const double nrm2 = warp_sum(yi * yi);
+    // sign: the component of largest magnitude (first such) is positive
+    double mag = lane < m ? fabs(yi) : -1.0;
+    int who = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double m2 = __shfl_xor_sync(0xffffffffu, mag, o);
+        const int w2 = __shfl_xor_sync(0xffffffffu, who, o);
+        if (m2 > mag || (m2 == mag && w2 < who)) { mag = m2; who = w2; }
+    }
+    const double lead = __shfl_sync(0xffffffffu, yi, who);
+    const double f = (lead < 0.0 ? -1.0 : 1.0) / sqrt(nrm2);
+    if (lane < m) st->y[lane] = yi * f;
+    if (lane == 0) {
+        st->theta_prev = st->theta;
+        st->theta = mu;
+    }
+}
+
 // Rayleigh-Ritz.  The eigen-decomposition G = Q diag(lam) Q^T of the previous cycle is kept in the state;
 // appending one basis vector makes the matrix, in the basis [Q, e_new], an ARROWHEAD
 //     [ diag(lam)   z ]        z = Q^T g ,   g = new Gram column
@@ -238,7 +359,7 @@ __device__ __forceinline__ double reduce_partials(const double* partials, int ro
 // 2-4 sweeps because |z| shrinks with the residual.
 __global__ void __launch_bounds__(256)
 rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ partials, int nblk, int m,
-                     int slot) {
+                     int publish) {
     if (st->status != 0) return;
     __shared__ double A[kMaxS][kMaxS + 1];
     __shared__ double J[kMaxS][kMaxS + 1];   // accumulated rotations
@@ -247,13 +368,18 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
     __shared__ double cs_c[kMaxS / 2], cs_s[kMaxS / 2];
     __shared__ int pr_p[kMaxS / 2], pr_q[kMaxS / 2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = m - 1;  // dimension of the stored decomposition (slot == d by construction)
-    (void)slot;
+    const int d = m - 1;  // dimension of the stored decomposition
 
-    // all warps: new Gram column and the previous decomposition
-    for (int row = warp; row < m; row += blockDim.x >> 5) {
-        const double v = reduce_partials(partials, row, nblk);
-        if (lane == 0) g[row] = v;
+    // new Gram column and the previous decomposition.  publish == 0: ritz_lowest_kernel has reduced the
+    // column and published the lowest pair, this kernel runs beside the main stream; publish != 0: this
+    // kernel is the whole Rayleigh-Ritz step (one launch fewer when the GPU is shared by many solves)
+    if (publish) {
+        for (int row = warp; row < m; row += blockDim.x >> 5) {
+            const double v = reduce_partials(partials, row, nblk);
+            if (lane == 0) g[row] = v;
+        }
+    } else {
+        for (int row = tid; row < m; row += blockDim.x) g[row] = st->gcol[row];
     }
     for (int idx = tid; idx < m * m; idx += blockDim.x) {
         const int i = idx / m, j = idx % m;
@@ -371,6 +497,8 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
         if (j == best) g[i] = v;  // g is free now: park the Ritz column there
     }
     for (int i = lane; i < m; i += 32) st->lam[i] = A[i][i];
+    if (lane == 0) st->best = best;
+    if (!publish) return;  // the lowest Ritz pair (theta, y) was published by ritz_lowest_kernel
     __syncwarp();
     if (lane == 0) {
         double nrm = 0.0;
@@ -384,7 +512,6 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
         for (int i = 0; i < m; ++i) st->y[i] = g[i] * nrm;
         st->theta_prev = st->theta;
         st->theta = A[best][best];
-        st->best = best;
     }
 }
 
@@ -681,7 +808,9 @@ occupancy_kernel(const double* __restrict__ wa, const uint64_t* __restrict__ sa,
 }
 
 static inline int red_blocks(int64_t n) {
-    int64_t b = (n + 4 * kRedThreads - 1) / (4 * kRedThreads);
+    static const int per_thread = getenv("SQD_RED_PER_THREAD") ? atoi(getenv("SQD_RED_PER_THREAD")) : 4;
+    const int64_t chunk = (int64_t)(per_thread > 0 ? per_thread : 4) * kRedThreads;
+    int64_t b = (n + chunk - 1) / chunk;
     if (b > kRedBlocks) b = kRedBlocks;
     if (b < 1) b = 1;
     return (int)b;
@@ -761,6 +890,34 @@ static int apply_operator(const sqd_operator* op, const sqd_davidson_params* prm
 
 using ApplyFn = std::function<int(const double*, double*, Workspace&)>;
 
+// Side stream of a host thread: the full Rayleigh-Ritz decomposition of cycle k runs there, concurrently
+// with the residual / orthogonalisation / next sigma build of the main stream, and is joined before the
+// Rayleigh-Ritz step of cycle k+1 (or before the residual kernel of a restart cycle).
+struct SideStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int dev = -1;
+};
+static thread_local SideStream g_side;
+
+static int side_stream(SideStream** out) {
+    int dev = 0;
+    SQD_CUDA_OK(cudaGetDevice(&dev));
+    if (g_side.s == nullptr || g_side.dev != dev) {
+        if (g_side.s != nullptr) {
+            cudaStreamDestroy(g_side.s);
+            cudaEventDestroy(g_side.ev_fork);
+            cudaEventDestroy(g_side.ev_join);
+        }
+        SQD_CUDA_OK(cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking));
+        SQD_CUDA_OK(cudaEventCreateWithFlags(&g_side.ev_fork, cudaEventDisableTiming));
+        SQD_CUDA_OK(cudaEventCreateWithFlags(&g_side.ev_join, cudaEventDisableTiming));
+        g_side.dev = dev;
+    }
+    *out = &g_side;
+    return 0;
+}
+
 static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag, const double* d_x0,
                          double* d_x, void* d_workspace, int64_t ws_bytes,
                          const sqd_davidson_params* prm, sqd_davidson_info* h_info, cudaStream_t st) {
@@ -786,6 +943,9 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         SQD_CUDA_OK(cudaEventCreate(&ev_end));
         SQD_CUDA_OK(cudaEventRecord(ev_begin, st));
     }
+    SideStream* side = nullptr;
+    if (side_stream(&side)) return -2;
+    bool full_pending = false;
     int m = 1, slot = 0, status = 0, cycle = 0, sigma_builds = 0;
     for (; cycle < prm->max_cycle; ++cycle) {
         if (prm->profile) {
@@ -806,13 +966,30 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
             constexpr int MV = decltype(mv)::value;
             gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n,
                                                             m, ws.partials);
-            rayleigh_ritz_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m, slot);
+            if (prm->single_stream_ritz) {
+                // many solves share the GPU: their streams hide each other's latency, one launch is cheaper
+                rayleigh_ritz_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m, 1);
+            } else {
+                // lowest Ritz pair on the main stream; the full decomposition (needed by the next cycle,
+                // and by this one only when it restarts) on the side stream
+                if (full_pending) SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));
+                ritz_lowest_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m);
+                SQD_CUDA_OK(cudaEventRecord(side->ev_fork, st));
+                SQD_CUDA_OK(cudaStreamWaitEvent(side->s, side->ev_fork, 0));
+                rayleigh_ritz_kernel<<<1, 256, 0, side->s>>>(ws.state, ws.partials, blocks, m, 0);
+                SQD_CUDA_OK(cudaEventRecord(side->ev_join, side->s));
+                full_pending = true;
+                if (restart) {
+                    SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));
+                    full_pending = false;
+                }
+            }
             residual_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, d_hdiag, n, m,
                                                                 restart, prm->level_shift, ws.X, ws.T,
                                                                 ws.partials);
             convergence_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m, restart, prm->tol,
                                                  prm->tol_residual);
-            return check_launch("davidson cycle (1)", 4);
+            return check_launch("davidson cycle (1)", 5);
         });
         if (rc) return -2;
         const int me = restart ? restart : m;
@@ -836,6 +1013,7 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         }
     }
     DavState hs;
+    if (full_pending) SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));  // nothing outlives the call
     SQD_CUDA_OK(cudaMemcpyAsync(d_x, ws.X, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (prm->profile) SQD_CUDA_OK(cudaEventRecord(ev_end, st));
     if (read_back(&hs, ws.state, sizeof(DavState), st)) return -2;

@@ -284,6 +284,7 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
     dp.level_shift = prm->level_shift;
     dp.check_every = prm->check_every > 0 ? prm->check_every : 4;
     dp.profile = prm->profile;
+    dp.single_stream_ritz = prm->throughput_mode;
     if (quad) {
         dp.ss_op = &s2op;
         dp.ss_shift = prm->shift;
