@@ -320,6 +320,33 @@ __global__ void sigma_combine_kernel(const int* __restrict__ done, const sqd_sig
 //   sorted mapping   (thread t <-> column perm[t])  : the beta-single gathers through SELL slices
 // The two partial results meet in a shared-memory exchange buffer before one coalesced update of sigma.
 // ---------------------------------------------------------------------------------------------------
+struct ChunkInfo {
+    int a, slot, it_beg, db_beg, db_end, n_total;
+    bool self_item, owned;
+};
+
+__device__ __forceinline__ ChunkInfo load_chunk(const SigmaArgs& P, int chunk) {
+    const sqd_operator& op = P.op;
+    const sqd_sigma_plan& pl = op.plan;
+    ChunkInfo c;
+    c.a = pl.chunk_row[chunk];
+    c.owned = c.a >= P.row_begin && c.a < P.row_end;  // sharded build: another rank may own this row
+    const int cbeg = pl.chunk_beg[chunk], cend = pl.chunk_end[chunk];
+    c.slot = pl.chunk_slot[chunk];
+    const int single_end = op.a.row_ptr[c.a] + op.a.n_single[c.a];
+    c.it_beg = min(cbeg, single_end);                                 // phase D range
+    const int it_end = min(cend, single_end);
+    c.db_beg = max(cbeg, single_end);                                 // phase C range
+    c.db_end = max(cend, single_end);
+    // The first chunk of a row also owns the row's "self item": the term
+    //   sum_{b' in S_b(b)} sgn_b Wa[a, rs] c[a, b']
+    // has exactly the shape of an alpha single excitation with a' = a, sgn_a = +1 and the integral row
+    // replaced by Wa[a, :], so it rides the same ring and the same gather loop.
+    c.self_item = (cbeg == op.a.row_ptr[c.a]) && (op.Wa != nullptr);
+    c.n_total = (it_end - c.it_beg) + (c.self_item ? 1 : 0);
+    return c;
+}
+
 template <int CPT, bool STAGE_PACK, int TB, int MINB>
 __global__ void __launch_bounds__(TB, MINB)
 sigma_a_kernel(const SigmaArgs P, const int NST) {
@@ -333,14 +360,6 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
     const int nwarp_c = ncons >> 5;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    const int a = pl.chunk_row[blockIdx.x];
-    if (a < P.row_begin || a >= P.row_end) return;  // sharded build: another rank owns this row
-    const int cbeg = pl.chunk_beg[blockIdx.x], cend = pl.chunk_end[blockIdx.x];
-    const int slot = pl.chunk_slot[blockIdx.x];
-    const int single_end = op.a.row_ptr[a] + op.a.n_single[a];
-    const int it_beg = min(cbeg, single_end), it_end = min(cend, single_end);   // phase D range
-    const int db_beg = max(cbeg, single_end), db_end = max(cend, single_end);   // phase C range
-    const int n_items = it_end - it_beg;
     const int n_long = pl.n_long;
     const bool ham = op.use_same_spin != 0;
 
@@ -364,36 +383,33 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
     }
     __syncthreads();
 
-    // The first chunk of a row also owns the row's "self item": the term
-    //   sum_{b' in S_b(b)} sgn_b Wa[a, rs] c[a, b']
-    // has exactly the shape of an alpha single excitation with a' = a, sgn_a = +1 and the integral row
-    // replaced by Wa[a, :], so it rides the same ring and the same gather loop.
-    const bool self_item = (cbeg == op.a.row_ptr[a]) && (op.Wa != nullptr);
-    const int n_total = n_items + (self_item ? 1 : 0);
-
     // =========================== producer warp ===========================
     if (tid >= ncons) {
         if (tid == ncons) {
-            int s = 0, round = 0;
-            for (int t = 0; t < n_total; ++t) {
-                if (round > 0) mbar_wait_parity(&empty[s], (uint32_t)((round - 1) & 1));
-                const double* crow;
-                const double* grow;
-                if (self_item && t == 0) {
-                    crow = P.c + (size_t)a * ldc;
-                    grow = op.Wa + (size_t)a * ldg;
-                } else {
-                    const int e = it_beg + t - (self_item ? 1 : 0);
-                    crow = P.c + (size_t)op.a.col[e] * ldc;
-                    grow = op.gab + (size_t)(op.a.meta[e] & 0x7fffffffu) * ldg;
-                }
-                double* dst = stage + (size_t)s * stage_len;
-                mbar_expect_tx(&full[s], (uint32_t)((ldc + ldg) * sizeof(double)));
-                bulk_g2s(dst, crow, (uint32_t)(ldc * sizeof(double)), &full[s]);
-                bulk_g2s(dst + ldc, grow, (uint32_t)(ldg * sizeof(double)), &full[s]);
-                if (++s == NST) {
-                    s = 0;
-                    ++round;
+            int s = 0, round = 0;  // ring position: runs on across the chunks of this CTA
+            for (int chunk = blockIdx.x; chunk < pl.n_chunks; chunk += gridDim.x) {
+                const ChunkInfo ck = load_chunk(P, chunk);
+                if (!ck.owned) continue;
+                for (int t = 0; t < ck.n_total; ++t) {
+                    if (round > 0) mbar_wait_parity(&empty[s], (uint32_t)((round - 1) & 1));
+                    const double* crow;
+                    const double* grow;
+                    if (ck.self_item && t == 0) {
+                        crow = P.c + (size_t)ck.a * ldc;
+                        grow = op.Wa + (size_t)ck.a * ldg;
+                    } else {
+                        const int e = ck.it_beg + t - (ck.self_item ? 1 : 0);
+                        crow = P.c + (size_t)op.a.col[e] * ldc;
+                        grow = op.gab + (size_t)(op.a.meta[e] & 0x7fffffffu) * ldg;
+                    }
+                    double* dst = stage + (size_t)s * stage_len;
+                    mbar_expect_tx(&full[s], (uint32_t)((ldc + ldg) * sizeof(double)));
+                    bulk_g2s(dst, crow, (uint32_t)(ldc * sizeof(double)), &full[s]);
+                    bulk_g2s(dst + ldc, grow, (uint32_t)(ldg * sizeof(double)), &full[s]);
+                    if (++s == NST) {
+                        s = 0;
+                        ++round;
+                    }
                 }
             }
         }
@@ -402,13 +418,12 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
 
     // =========================== consumer warps ==========================
 #define SQD_STAMP(k) \
-    if (P.prof != nullptr && tid == 0) P.prof[(size_t)blockIdx.x * 8 + (k)] = clock64();
-    SQD_STAMP(0)
+    if (P.prof != nullptr && tid == 0) P.prof[(size_t)chunk * 8 + (k)] = clock64();
     // The beta SELL table is re-read for every alpha excitation of the chunk: when it is small enough
     // (host decision, STAGE_PACK) it is kept in shared memory, pre-decoded into byte offsets:
     //   bits 0-15 = 8*b' (into the staged c row), bits 16-30 = 8*rs (into the staged integral row),
     //   bit 31 = sign; padding entries point at the zero pad of the integral row (rs = norb^2).
-    if (STAGE_PACK && n_total > 0) {
+    if (STAGE_PACK) {
         const uint32_t zero_slot = (uint32_t)(op.norb * op.norb * 8) << 16;
         for (int i = tid; i < L.n_entries; i += ncons) {
             const uint32_t pv = __ldg(L.pack + i);
@@ -432,18 +447,35 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
             lpk[li][c] = idx < llen ? __ldg(op.b.pack + lbeg + idx) : 0xffffffffu;  // rs=0xfff: never real
         }
     }
-    double acc_nat[CPT], acc_srt[CPT];
     int s_base[CPT], s_len[CPT], my_len[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
-        acc_nat[c] = 0.0;
-        acc_srt[c] = 0.0;
         const int pos = tid + c * ncons;
         const int slice = pos >> 5;
         const bool ok = slice < L.n_slices;
         s_base[c] = ok ? L.slice_ptr[slice] : 0;
         s_len[c] = ok ? (L.slice_ptr[slice + 1] - s_base[c]) >> 5 : 0;
         my_len[c] = pos < nb ? L.len[pos] : 0;
+    }
+
+    // Persistent CTA: the grid is capped at what is resident at once and every CTA walks the chunk list
+    // with stride gridDim.x, so a sigma build never leaves CTAs waiting in the hardware queue in front of
+    // the kernels of the other solves that share the GPU.
+    int s = 0, round = 0;
+    for (int chunk = blockIdx.x; chunk < pl.n_chunks; chunk += gridDim.x) {
+    const ChunkInfo ck = load_chunk(P, chunk);
+    if (!ck.owned) continue;
+    const int a = ck.a, slot = ck.slot, it_beg = ck.it_beg, db_beg = ck.db_beg, db_end = ck.db_end;
+    const int n_total = ck.n_total;
+    const bool self_item = ck.self_item;
+    SQD_STAMP(0)
+    double acc_nat[CPT], acc_srt[CPT];
+#pragma unroll
+    for (int li = 0; li < kLongA; ++li) lacc[li] = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+        acc_nat[c] = 0.0;
+        acc_srt[c] = 0.0;
     }
 
     SQD_STAMP(1)
@@ -480,7 +512,6 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
     SQD_STAMP(2)
     // ---- phase D: alpha singles (and the self item) through the staged ring -------------------------
     long long t_wait = 0, t_pre = 0, t_loop = 0;
-    int s = 0, round = 0;
     for (int t = 0; t < n_total; ++t) {
         const long long c0 = P.prof ? clock64() : 0;
         const bool is_self = self_item && t == 0;
@@ -607,15 +638,18 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
     }
     SQD_STAMP(4)
     if (P.prof != nullptr && tid == 0) {
-        P.prof[(size_t)blockIdx.x * 8 + 5] = n_total;
-        P.prof[(size_t)blockIdx.x * 8 + 6] = db_end - db_beg;
+        P.prof[(size_t)chunk * 8 + 5] = n_total;
+        P.prof[(size_t)chunk * 8 + 6] = db_end - db_beg;
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        P.prof[(size_t)blockIdx.x * 8 + 7] = smid;
-        P.prof[(size_t)blockIdx.x * 8 + 0] = t_pre;   // diagnostics layout: see tests/gpu_sigma_phases.py
-        P.prof[(size_t)blockIdx.x * 8 + 1] = t_wait;
-        P.prof[(size_t)blockIdx.x * 8 + 4] = t_loop;
+        P.prof[(size_t)chunk * 8 + 7] = smid;
+        P.prof[(size_t)chunk * 8 + 0] = t_pre;   // diagnostics layout: see tests/gpu_sigma_phases.py
+        P.prof[(size_t)chunk * 8 + 1] = t_wait;
+        P.prof[(size_t)chunk * 8 + 4] = t_loop;
     }
+    // xbuf / acc_long are reused by the next chunk
+    asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
+    }  // chunk loop
 #undef SQD_STAMP
 }
 
@@ -698,7 +732,17 @@ static int launch_sigma_a_tb(const SigmaArgs& args, const SigmaPlan& pl, cudaStr
     auto kern = sigma_a_kernel<CPT, STAGE_PACK, TB, MINB>;
     static bool cfg_a[64] = {false};
     if (opt_in_smem(kern, pl.smem, cfg_a)) return -2;
-    kern<<<args.op.plan.n_chunks, pl.threads + 32, pl.smem, st>>>(args, pl.stages);
+    // grid = the CTAs that are resident at once (occupancy query, cached per kernel instance and shape)
+    static thread_local int cached_key = -1, cached_ctas = 0;
+    const int key = (pl.threads + 32) * 1024 + (int)(pl.smem / 256);
+    if (key != cached_key) {
+        int per_sm = 0;
+        SQD_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, pl.threads + 32, pl.smem));
+        cached_ctas = (per_sm > 0 ? per_sm : 1) * kNumSMs;
+        cached_key = key;
+    }
+    const int grid = args.op.plan.n_chunks < cached_ctas ? args.op.plan.n_chunks : cached_ctas;
+    kern<<<grid, pl.threads + 32, pl.smem, st>>>(args, pl.stages);
     return check_launch("sigma_a_kernel");
 }
 
