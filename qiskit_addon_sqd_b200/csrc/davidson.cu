@@ -966,7 +966,9 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
             constexpr int MV = decltype(mv)::value;
             gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n,
                                                             m, ws.partials);
-            if (prm->single_stream_ritz) {
+            static const int knob_side = getenv("SQD_RITZ_SIDE") ? atoi(getenv("SQD_RITZ_SIDE")) : -1;
+            const bool one_kernel = knob_side >= 0 ? knob_side == 0 : prm->single_stream_ritz != 0;
+            if (one_kernel) {
                 // many solves share the GPU: their streams hide each other's latency, one launch is cheaper
                 rayleigh_ritz_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m, 1);
             } else {
