@@ -98,6 +98,30 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
     // Two passes: rows that need several chunks are emitted first so that the heaviest CTAs start first.
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int nc = 0, nslots = 0, nsplit = 0;
+    // Order of the chunk list = order in which the persistent CTAs of kernel A pick their work: rows that
+    // need several chunks first (every such chunk is full), then the single-chunk rows by descending cost
+    // (counting sort into 64 cost classes, row order inside a class) -- the heaviest CTAs start first and
+    // the snake assignment of kernel A pairs a heavy chunk with a light one.
+    constexpr int kClasses = 64;
+    int class_pos[kClasses + 1];
+    for (int k = 0; k <= kClasses; ++k) class_pos[k] = 0;
+    int n_multi_chunks = 0;
+    for (int a = 0; a < A.n; ++a) {
+        const int beg = A.row_ptr[a], ns = A.n_single[a], end = A.row_ptr[a + 1];
+        const int cost = kSingleCost * ns + (end - beg - ns);
+        int k = (cost + cost_per_chunk - 1) / cost_per_chunk;
+        if (k < 1) k = 1;
+        if (k > 1) {
+            n_multi_chunks += k;
+        } else {
+            int cls = (int)(((long long)cost * kClasses) / (cost_per_chunk + 1));
+            cls = kClasses - 1 - (cls < kClasses ? cls : kClasses - 1);  // class 0 = most expensive
+            ++class_pos[cls + 1];
+        }
+    }
+    bool capped = n_multi_chunks + A.n > max_chunks;  // capacity guard, never hit with the documented bound
+    for (int k = 0; k < kClasses; ++k) class_pos[k + 1] += class_pos[k];
+    const int single_base = capped ? 0 : n_multi_chunks;
     for (int pass = 0; pass < 2; ++pass) {
         for (int a = 0; a < A.n; ++a) {
             const int beg = A.row_ptr[a], ns = A.n_single[a], end = A.row_ptr[a + 1];
@@ -105,8 +129,8 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
             const int cost = kSingleCost * ns + nd;
             int k = (cost + cost_per_chunk - 1) / cost_per_chunk;
             if (k < 1) k = 1;
+            if (capped) k = 1;
             if ((k > 1) != (pass == 0)) continue;
-            if (nc + k + (A.n - a) > max_chunks && k > 1) k = 1;  // capacity guard, never hit with the documented bound
             if (k > 1) {
                 split_row[nsplit] = a;
                 split_slot_beg[nsplit] = nslots;
@@ -120,10 +144,16 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
                 if (p1 > cost) p1 = cost;
                 const int e0 = p0 < kSingleCost * ns ? p0 / kSingleCost : ns + (p0 - kSingleCost * ns);
                 const int e1 = p1 < kSingleCost * ns ? p1 / kSingleCost : ns + (p1 - kSingleCost * ns);
-                chunk_row[nc] = a;
-                chunk_beg[nc] = beg + e0;
-                chunk_end[nc] = beg + e1;
-                chunk_slot[nc] = k > 1 ? nslots++ : -1;
+                int at = nc;
+                if (k == 1 && !capped) {
+                    int cls = (int)(((long long)cost * kClasses) / (cost_per_chunk + 1));
+                    cls = kClasses - 1 - (cls < kClasses ? cls : kClasses - 1);
+                    at = single_base + class_pos[cls]++;
+                }
+                chunk_row[at] = a;
+                chunk_beg[at] = beg + e0;
+                chunk_end[at] = beg + e1;
+                chunk_slot[at] = k > 1 ? nslots++ : -1;
                 ++nc;
             }
         }
@@ -320,6 +350,12 @@ __global__ void sigma_combine_kernel(const int* __restrict__ done, const sqd_sig
 //   sorted mapping   (thread t <-> column perm[t])  : the beta-single gathers through SELL slices
 // The two partial results meet in a shared-memory exchange buffer before one coalesced update of sigma.
 // ---------------------------------------------------------------------------------------------------
+// Chunk of round k for this CTA: even rounds walk the (cost-descending) list forwards, odd rounds
+// backwards, so the CTA that got the heaviest chunk of one round gets the lightest of the next.
+__device__ __forceinline__ int snake_chunk(int k) {
+    return (k & 1) ? (k + 1) * (int)gridDim.x - 1 - (int)blockIdx.x : k * (int)gridDim.x + (int)blockIdx.x;
+}
+
 struct ChunkInfo {
     int a, slot, it_beg, db_beg, db_end, n_total;
     bool self_item, owned;
@@ -387,7 +423,9 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
     if (tid >= ncons) {
         if (tid == ncons) {
             int s = 0, round = 0;  // ring position: runs on across the chunks of this CTA
-            for (int chunk = blockIdx.x; chunk < pl.n_chunks; chunk += gridDim.x) {
+            for (int k = 0; k * (int)gridDim.x < pl.n_chunks; ++k) {
+                const int chunk = snake_chunk(k);
+                if (chunk >= pl.n_chunks) continue;
                 const ChunkInfo ck = load_chunk(P, chunk);
                 if (!ck.owned) continue;
                 for (int t = 0; t < ck.n_total; ++t) {
@@ -459,10 +497,12 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
     }
 
     // Persistent CTA: the grid is capped at what is resident at once and every CTA walks the chunk list
-    // with stride gridDim.x, so a sigma build never leaves CTAs waiting in the hardware queue in front of
+    // in snake order, so a sigma build never leaves CTAs waiting in the hardware queue in front of
     // the kernels of the other solves that share the GPU.
     int s = 0, round = 0;
-    for (int chunk = blockIdx.x; chunk < pl.n_chunks; chunk += gridDim.x) {
+    for (int k = 0; k * (int)gridDim.x < pl.n_chunks; ++k) {
+    const int chunk = snake_chunk(k);
+    if (chunk >= pl.n_chunks) continue;
     const ChunkInfo ck = load_chunk(P, chunk);
     if (!ck.owned) continue;
     const int a = ck.a, slot = ck.slot, it_beg = ck.it_beg, db_beg = ck.db_beg, db_end = ck.db_end;
