@@ -74,7 +74,7 @@ constexpr int kMaxLong = SQD_MAX_LONG_COLUMNS;
 constexpr uint32_t kPadMarker = 0x7ffffu;  // SELL mode-0 padding entry
 constexpr int kLongA = 4;   // long columns actually used (registers per thread in kernel A)
 constexpr int kRowsB = 4;      // rows of c per CTA in kernel B
-constexpr int kWarpsB = 4;     // warps per CTA in kernel B (they split one SELL slice)
+constexpr int kWarpsB = 8;     // warps per CTA in kernel B (they split one SELL slice)
 constexpr int kSingleCost = 16;  // plan cost of one alpha single excitation, in units of one double
 
 // ---------------------------------------------------------------------------------------------------
