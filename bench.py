@@ -317,6 +317,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     sig_ms = np.mean([s.sigma_ms / max(s.cycles, 1) for s in stats_prof])
     sig_bytes = np.mean([sigma_algorithmic_bytes(s) for s in stats_prof])
     achieved = sig_bytes / (sig_ms * 1e-3) / 1e9
+    # applied matrix elements per sigma build: opposite-spin (links+diagonal of both spins), same-spin doubles
+    # and singles of each spin against every string of the other, operator diagonal
+    applied = np.mean([(s.singles_a + s.na) * (s.singles_b + s.nb) + (s.nnz_a - s.singles_a) * s.nb
+                       + (s.nnz_b - s.singles_b) * s.na + s.singles_a * s.nb + s.singles_b * s.na + s.n_det
+                       for s in stats_prof])
     dav_ms = np.mean([s.davidson_ms for s in stats_prof])
     sig_share = np.mean([s.sigma_ms / max(s.davidson_ms, 1e-9) for s in stats_prof])
     cycles = [s.cycles for s in [r["stats"] for r in res_dev]]
@@ -348,6 +353,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
             "frac": achieved / peak_gbs, "peak_source": peak_src, "traffic": ncu_traffic(),
             "bytes_per_launch": sig_bytes, "ms_per_launch": sig_ms,
+            "gflops": 2.0 * applied / (sig_ms * 1e-3) / 1e9, "matrix_elements_per_launch": applied,
+            "dram_gbs_from_ncu_traffic": (ncu_traffic() or 0.0) / (sig_ms * 1e-3) / 1e9,
             "share_of_davidson_loop": sig_share, "davidson_loop_ms": dav_ms,
             "note": "algorithmic bytes = 16 n_det + 8 norb^4 + 12 nnz + 8 links (SURVEY 8d); the working "
                     "set is L2-resident, the kernel is bound by shared-memory gathers and FP64 FMA "
@@ -365,17 +372,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
 
 def ncu_traffic():
-    """DRAM bytes per launch of the alpha sigma kernel from the committed `ncu --set full` capture
-    (profiles/r1_sigma_a_ncu_raw_c4.txt); null when the summary is not there."""
-    path = os.path.join(ROOT, "profiles", "r1_sigma_a_ncu_raw_c4.txt")
-    if not os.path.exists(path):
-        return None
-    tot = 0.0
-    for ln in open(path):
-        if ln.startswith(("dram__bytes_read.sum", "dram__bytes_write.sum")):
-            val, unit = ln.split("=")[1].split()[:2]
-            tot += float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
-    return tot
+    """DRAM bytes per sigma build (kernel A + kernel B) from the committed `ncu --set full` captures
+    (profiles/r1_sigma_{a,b}_ncu_raw_c4.txt); null when the summaries are not there."""
+    tot, found = 0.0, False
+    for k in ("a", "b"):
+        path = os.path.join(ROOT, "profiles", f"r1_sigma_{k}_ncu_raw_c4.txt")
+        if not os.path.exists(path):
+            continue
+        found = True
+        for ln in open(path):
+            if ln.startswith(("dram__bytes_read.sum", "dram__bytes_write.sum")):
+                val, unit = ln.split("=")[1].split()[:2]
+                tot += float(val) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+    return tot if found else None
 
 
 def cpu_baseline(args, batches, h, g, res_dev) -> dict:
