@@ -352,3 +352,80 @@ def test_sigma_row_blocks_sum_to_full_sigma(cuda_lib):
         assert float(blk[:lo].abs().max() if lo else 0.0) == 0.0 and float(blk[hi:].abs().max() if hi < sub.na else 0.0) == 0.0
         total += part
     assert torch.equal(total, full)
+
+
+def test_solve_subspace_c_abi_direct(cuda_lib):
+    """`sqd_solve_subspace` called the way a non-Python host would: raw device pointers in, caller-owned
+    buffers out.  Checked against the dense oracle incl. the linear and quadratic spin penalties."""
+    import ctypes as C
+
+    import torch
+
+    from qiskit_addon_sqd_b200 import _lib
+
+    norb, nea, neb = 7, 3, 2
+    h, g = random_integrals(norb, 77)
+    sa = hf_centred_strings(norb, nea, 18, 1)
+    sb = hf_centred_strings(norb, neb, 15, 2)
+    dev = torch.device("cuda")
+    d_sa = torch.from_numpy(sa.astype(np.uint64).view(np.int64)).to(dev)
+    d_sb = torch.from_numpy(sb.astype(np.uint64).view(np.int64)).to(dev)
+    d_h, d_g = torch.from_numpy(h).to(dev), torch.from_numpy(g).to(dev)
+    na, nb = len(sa), len(sb)
+    ldc = (nb + 1) // 2 * 2
+    for spin_sq in (None, 0.75, 3.75):   # none / linear branch (sz(sz+1)+0.1 = 0.85) / quadratic branch
+        x = torch.full((na * ldc,), float("nan"), dtype=torch.float64, device=dev)
+        dm1 = torch.empty(norb**2, dtype=torch.float64, device=dev)
+        dm2 = torch.empty(norb**4, dtype=torch.float64, device=dev)
+        prm = _lib.SolveParams()
+        prm.norb, prm.na, prm.nb, prm.n_alpha, prm.n_beta = norb, na, nb, nea, neb
+        prm.d_strs_a, prm.d_strs_b = d_sa.data_ptr(), d_sb.data_ptr()
+        prm.d_h, prm.d_g = d_h.data_ptr(), d_g.data_ptr()
+        prm.penalty = 0 if spin_sq is None else 1
+        prm.spin_sq, prm.shift = (0.0 if spin_sq is None else spin_sq), 0.3
+        prm.want_spin = 1
+        prm.max_space, prm.max_cycle = 12, 100
+        prm.tol, prm.tol_residual, prm.lindep, prm.level_shift = 1e-12, 1e-6, 1e-14, 1e-4
+        res = _lib.SolveResult()
+        _lib.check(cuda_lib.sqd_solve_subspace(C.byref(prm), x.data_ptr(), dm1.data_ptr(), dm2.data_ptr(),
+                                               C.byref(res), torch.cuda.current_stream().cuda_stream))
+        if spin_sq is None:
+            e_ref, c_ref, occ_ref, s2_ref, _ = fo.solve_dense(sa, sb, h, g, norb)
+        else:
+            e_ref, c_ref, occ_ref, s2_ref, _ = fo.solve_dense(sa, sb, h, g, norb, spin_sq=spin_sq, shift=0.3)
+        assert res.ldc == ldc and res.info.converged == 1
+        assert abs(res.energy - e_ref) < ETOL
+        assert res.have_spin_square == 1 and abs(res.spin_square - s2_ref) < 1e-6
+        amps = x.cpu().numpy().reshape(na, ldc)
+        assert np.all(amps[:, nb:] == 0.0)                       # pad columns stay zero
+        assert np.abs(amps[:, :nb] - c_ref).max() < 1e-6         # same sign convention as the oracle
+        assert np.allclose(np.array(res.occ_a[:norb]), occ_ref[0], atol=1e-7)
+        assert np.allclose(np.array(res.occ_b[:norb]), occ_ref[1], atol=1e-7)
+        r1 = dm1.cpu().numpy().reshape(norb, norb)
+        r2 = dm2.cpu().numpy().reshape((norb,) * 4)
+        e_rdm = np.einsum("pr,pr->", r1, h) + 0.5 * np.einsum("prqs,prqs->", r2, g)
+        assert abs(e_rdm - res.energy) < 1e-9                    # fermion.py:730-732
+    # error convention: <0 and a message, no exception across the C boundary
+    prm.norb = 65
+    assert cuda_lib.sqd_solve_subspace(C.byref(prm), x.data_ptr(), None, None, C.byref(res), None) < 0
+    assert b"norb" in cuda_lib.sqd_last_error()
+
+
+def test_fix_sign_and_read_back(cuda_lib):
+    import ctypes as C
+
+    import torch
+
+    from qiskit_addon_sqd_b200 import _lib
+
+    x = torch.tensor([0.1, -0.7, 0.7, 0.2], dtype=torch.float64, device="cuda")
+    scratch = torch.empty(4096, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(cuda_lib.sqd_fix_sign(x.data_ptr(), 4, scratch.data_ptr(), st))
+    assert x.cpu().tolist() == [-0.1, 0.7, -0.7, -0.2]            # first largest |x| becomes positive
+    _lib.check(cuda_lib.sqd_fix_sign(x.data_ptr(), 4, scratch.data_ptr(), st))
+    assert x.cpu().tolist() == [-0.1, 0.7, -0.7, -0.2]            # idempotent
+    out = (C.c_double * 4)()
+    _lib.check(cuda_lib.sqd_read_back(out, x.data_ptr(), 32, st))
+    assert list(out) == [-0.1, 0.7, -0.7, -0.2]
+    assert cuda_lib.sqd_read_back(out, x.data_ptr(), 1 << 20, st) < 0   # larger than the staging buffer

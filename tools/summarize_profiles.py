@@ -2,7 +2,7 @@
 
     python tools/summarize_profiles.py r1 c4
 
-Inputs (written by tools_gpu_profile.sh on the GPU box):
+Inputs (written by tools/gpu_profile.sh on the GPU box):
   gpurun_out/launches_<wl>.csv        ncu --metrics gpu__time_duration.sum --clock-control none
   gpurun_out/prof_sigma_<wl>.ncu-rep  ncu --set full --clock-control none --import-source on (sigma_a)
 """
