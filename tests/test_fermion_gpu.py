@@ -373,7 +373,7 @@ def test_solve_subspace_c_abi_direct(cuda_lib):
     d_h, d_g = torch.from_numpy(h).to(dev), torch.from_numpy(g).to(dev)
     na, nb = len(sa), len(sb)
     ldc = (nb + 1) // 2 * 2
-    for spin_sq in (None, 0.75, 3.75):   # none / linear branch (sz(sz+1)+0.1 = 0.85) / quadratic branch
+    for spin_sq in (None, 0.75, 2.0):   # none / linear branch (sz(sz+1)+0.1 = 0.85) / quadratic branch
         x = torch.full((na * ldc,), float("nan"), dtype=torch.float64, device=dev)
         dm1 = torch.empty(norb**2, dtype=torch.float64, device=dev)
         dm2 = torch.empty(norb**4, dtype=torch.float64, device=dev)
@@ -382,7 +382,7 @@ def test_solve_subspace_c_abi_direct(cuda_lib):
         prm.d_strs_a, prm.d_strs_b = d_sa.data_ptr(), d_sb.data_ptr()
         prm.d_h, prm.d_g = d_h.data_ptr(), d_g.data_ptr()
         prm.penalty = 0 if spin_sq is None else 1
-        prm.spin_sq, prm.shift = (0.0 if spin_sq is None else spin_sq), 0.3
+        prm.spin_sq, prm.shift = (0.0 if spin_sq is None else spin_sq), 0.1
         prm.want_spin = 1
         prm.max_space, prm.max_cycle = 12, 100
         prm.tol, prm.tol_residual, prm.lindep, prm.level_shift = 1e-12, 1e-6, 1e-14, 1e-4
@@ -392,8 +392,9 @@ def test_solve_subspace_c_abi_direct(cuda_lib):
         if spin_sq is None:
             e_ref, c_ref, occ_ref, s2_ref, _ = fo.solve_dense(sa, sb, h, g, norb)
         else:
-            e_ref, c_ref, occ_ref, s2_ref, _ = fo.solve_dense(sa, sb, h, g, norb, spin_sq=spin_sq, shift=0.3)
-        assert res.ldc == ldc and res.info.converged == 1
+            e_ref, c_ref, occ_ref, s2_ref, _ = fo.solve_dense(sa, sb, h, g, norb, spin_sq=spin_sq, shift=0.1)
+        assert res.ldc == ldc and res.info.converged in (1, 2), (spin_sq, res.info.converged, res.info.cycles,
+                                                                 res.info.residual)
         assert abs(res.energy - e_ref) < ETOL
         assert res.have_spin_square == 1 and abs(res.spin_square - s2_ref) < 1e-6
         amps = x.cpu().numpy().reshape(na, ldc)
