@@ -313,7 +313,10 @@ class _OperatorDev:
 
 
 class _Subspace:
-    """Device state of one product subspace A x B on the current CUDA device / stream."""
+    """One product subspace A x B kept alive on the current CUDA device / stream: tables, operators and
+    vectors through the fine-grained C entry points.  Used by ``SCIState``'s methods (RDMs, <S^2>,
+    occupancies of a stored state) and by the kernel-level tests; a ground-state solve does not go through
+    this class but through the one-call ``sqd_solve_subspace`` (``_solve_on_device``)."""
 
     def __init__(self, strs_a, strs_b, norb: int, hcore, eri, ints: _DeviceIntegrals | None = None,
                  strs_dev=(None, None)):
@@ -435,41 +438,6 @@ class _Subspace:
                                             _lib.stream_ptr(torch)), "sqd_occupancies")
         o = _lib.read_back(torch, occ)
         return o[: self.norb].copy(), o[self.norb:].copy()
-
-    # -- eigensolver -------------------------------------------------------------------------
-    def ground_state(self, op: _OperatorDev, *, tol, tol_residual, max_cycle, max_space, lindep,
-                     level_shift, ci0=None, quad_penalty=None, check_every=4, profile=False,
-                     shard=None):
-        torch, lib = self.torch, self.lib
-        st = _lib.stream_ptr(torch)
-        n = self.na * self.ldc
-        max_space = int(min(max(2, max_space), _lib.MAX_SPACE))
-        x0 = self.new_vector()
-        if ci0 is None:
-            _lib.check(lib.sqd_init_guess(_lib.ptr(op.diag), self.na, self.nb, self.ldc,
-                                          _lib.ptr(x0), _lib.ptr(self._scratch), st),
-                       "sqd_init_guess")
-        else:
-            x0 = self.upload_amplitudes(np.asarray(ci0, dtype=np.float64).reshape(self.na, self.nb))
-        ws_bytes = lib.sqd_davidson_workspace_bytes(self.na, self.ldc, max_space)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-        x = self.new_vector()
-        prm = _lib.DavidsonParams(max_space, int(max_cycle), float(tol), float(tol_residual),
-                                  float(lindep), float(level_shift), int(check_every), None, 0.0, 0.0,
-                                  1 if profile else 0)
-        if quad_penalty is not None:
-            ss_op, shift, ss = quad_penalty
-            prm.ss_op = C.pointer(ss_op.struct)
-            prm.ss_shift = float(shift)
-            prm.ss_value = float(ss)
-        if shard is not None:
-            prm.nccl_comm, prm.row_begin, prm.row_end = shard
-        info = _lib.DavidsonInfo()
-        _lib.check(lib.sqd_davidson(C.byref(op.struct), _lib.ptr(op.diag), _lib.ptr(x0), _lib.ptr(x),
-                                    _lib.ptr(ws), ws_bytes, C.byref(prm), C.byref(info), st),
-                   "sqd_davidson")
-        del ws, n
-        return x, info
 
 
 # ------------------------------------------------------------------------------------------------
