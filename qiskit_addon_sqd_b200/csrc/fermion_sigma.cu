@@ -712,14 +712,14 @@ static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
     const int ldc = op->ldc;
     int threads, cpt;
     // `threads` counts the consumer threads; one more warp (the producer) is added at launch.  One column
-    // per thread up to 992 columns; beyond that CPT columns per thread with at most 480 consumers (the
-    // register budget of the multi-column instances: __launch_bounds__(512))
+    // per thread up to 992 columns; beyond that CPT columns per thread with at most 512 consumers (the
+    // register budget of the multi-column instances: __launch_bounds__(544), 120 registers)
     if (ldc <= 992) {
         threads = ((ldc + 31) / 32) * 32;
         if (threads < 32) threads = 32;
         cpt = 1;
     } else {
-        cpt = (ldc + 479) / 480;
+        cpt = (ldc + 511) / 512;
         cpt = cpt <= 2 ? 2 : cpt <= 4 ? 4 : cpt <= 8 ? 8 : cpt <= 12 ? 12 : 0;
         if (cpt == 0) return false;
         threads = (((ldc + cpt - 1) / cpt + 31) / 32) * 32;
@@ -781,7 +781,9 @@ static int launch_sigma_a_tb(const SigmaArgs& args, const SigmaPlan& pl, cudaStr
         cached_ctas = (per_sm > 0 ? per_sm : 1) * kNumSMs;
         cached_key = key;
     }
-    const int grid = args.op.plan.n_chunks < cached_ctas ? args.op.plan.n_chunks : cached_ctas;
+    static const int knob_persistent = env_int("SQD_SIGMA_PERSISTENT", 1);  // 0: one CTA per chunk
+    const int grid = (!knob_persistent || args.op.plan.n_chunks < cached_ctas) ? args.op.plan.n_chunks
+                                                                                 : cached_ctas;
     kern<<<grid, pl.threads + 32, pl.smem, st>>>(args, pl.stages);
     return check_launch("sigma_a_kernel");
 }
@@ -799,7 +801,7 @@ static int launch_sigma_a(const SigmaArgs& args, const SigmaPlan& pl, cudaStream
             return launch_sigma_a_tb<1, STAGE_PACK, 384, 4>(args, pl, st);
         return launch_sigma_a_tb<1, STAGE_PACK, 1024, 1>(args, pl, st);
     } else {
-        return launch_sigma_a_tb<CPT, STAGE_PACK, 512, 1>(args, pl, st);
+        return launch_sigma_a_tb<CPT, STAGE_PACK, 544, 1>(args, pl, st);
     }
 }
 
