@@ -56,15 +56,42 @@ struct DavState {
     double c1[kMaxS];
     double c2[kMaxS];
     double gcol[kMaxS];         // newest column of V^T H V (reduced once, read by both Rayleigh-Ritz kernels)
+    int ticket[4];              // arrival counters of the "last CTA finishes the step" tails
 };
+
+// The scalar steps of a cycle (Rayleigh-Ritz, convergence test, Gram-Schmidt coefficients) need the sums
+// over all CTAs of the streaming pass before them.  Instead of a separate single-CTA launch, the LAST CTA
+// of the streaming kernel to arrive (ticket counter, after a __threadfence) runs the step in its tail:
+// same fixed summation order as before (the per-CTA partials are reduced in index order), three launches
+// and three launch gaps fewer per cycle.
+__device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nblk, int m, int publish);
+__device__ void ritz_lowest_body(DavState* st, const double* partials, int nblk, int m);
+__device__ void convergence_body(DavState* st, const double* partials, int nblk, int m, int restart,
+                                 double tol, double tol_residual);
+__device__ void norm_body(DavState* st, const double* partials, int nblk, int m, double lindep);
+
+// true on every thread of exactly one CTA of the grid: the last one to get here.  Thread 0 must have
+// issued the CTA's global writes before the call.
+__device__ __forceinline__ bool last_block(int* ticket) {
+    __shared__ int is_last;
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int t = atomicAdd(ticket, 1);
+        is_last = t == (int)gridDim.x - 1;
+        if (is_last) *ticket = 0;  // ready for the next launch
+    }
+    __syncthreads();
+    if (is_last) __threadfence();
+    return is_last != 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // streaming passes
 // ---------------------------------------------------------------------------------------------
 template <int MV>
 __global__ void __launch_bounds__(kRedThreads)
-gram_kernel(const DavState* __restrict__ st, const double* __restrict__ V,
-            const double* __restrict__ w, int64_t n, int m, double* __restrict__ partials) {
+gram_kernel(DavState* st, const double* __restrict__ V, const double* __restrict__ w, int64_t n, int m,
+            double* partials, int ritz_mode) {
     if (st->status != 0) return;
     __shared__ double red[MV * (kRedThreads / 32)];
     double acc[MV];
@@ -83,13 +110,20 @@ gram_kernel(const DavState* __restrict__ st, const double* __restrict__ V,
         for (int i = 0; i < MV; ++i)
             if (i < m) partials[i * gridDim.x + blockIdx.x] = acc[i];
     }
+    // tail: Rayleigh-Ritz on the finished Gram column.  ritz_mode 1: the whole step (decomposition and
+    // lowest pair); 2: lowest pair only, the decomposition follows on the side stream
+    if (last_block(&st->ticket[0])) {
+        if (ritz_mode == 1) rayleigh_ritz_body(st, partials, gridDim.x, m, 1);
+        else ritz_lowest_body(st, partials, gridDim.x, m);
+    }
 }
 
 template <int MV>
 __global__ void __launch_bounds__(kRedThreads)
-residual_kernel(const DavState* __restrict__ st, double* __restrict__ V, double* __restrict__ W,
+residual_kernel(DavState* st, double* __restrict__ V, double* __restrict__ W,
                 const double* __restrict__ hdiag, int64_t n, int m, int restart, double level_shift,
-                double* __restrict__ X, double* __restrict__ T, double* __restrict__ partials) {
+                double* __restrict__ X, double* __restrict__ T, double* partials, double tol,
+                double tol_residual) {
     if (st->status != 0) return;
     __shared__ double red[(MV + 2) * (kRedThreads / 32)];
     __shared__ double ys[MV];
@@ -157,13 +191,15 @@ residual_kernel(const DavState* __restrict__ st, double* __restrict__ V, double*
         partials[kMaxS * gridDim.x + blockIdx.x] = acc[MV];
         partials[(kMaxS + 1) * gridDim.x + blockIdx.x] = acc[MV + 1];
     }
+    // tail: residual norm, convergence flag, first Gram-Schmidt coefficients (and the restart bookkeeping)
+    if (last_block(&st->ticket[1])) convergence_body(st, partials, gridDim.x, m, restart, tol, tol_residual);
 }
 
 // T <- T - sum c1_i V_i ; partial <V_i, T>, |T|^2
 template <int MV>
 __global__ void __launch_bounds__(kRedThreads)
-ortho1_kernel(const DavState* __restrict__ st, const double* __restrict__ V, int64_t n, int m,
-              double* __restrict__ T, double* __restrict__ partials) {
+ortho1_kernel(DavState* st, const double* __restrict__ V, int64_t n, int m, double* __restrict__ T,
+              double* partials, double lindep) {
     if (st->status != 0) return;
     __shared__ double red[(MV + 1) * (kRedThreads / 32)];
     __shared__ double cs[MV];
@@ -197,6 +233,8 @@ ortho1_kernel(const DavState* __restrict__ st, const double* __restrict__ V, int
             if (i < m) partials[i * gridDim.x + blockIdx.x] = acc[i];
         partials[kMaxS * gridDim.x + blockIdx.x] = acc[MV];
     }
+    // tail: second-pass coefficients, norm of the new basis vector, linear-dependency flag
+    if (last_block(&st->ticket[2])) norm_body(st, partials, gridDim.x, m, lindep);
 }
 
 // V_new <- (T - sum c2_i V_i) * inv_norm
@@ -227,7 +265,7 @@ ortho2_kernel(const DavState* __restrict__ st, const double* __restrict__ V, int
 __device__ __forceinline__ double reduce_partials(const double* partials, int row, int nblk) {
     const int lane = threadIdx.x & 31;
     double s = 0.0;
-    for (int b = lane; b < nblk; b += 32) s += partials[row * nblk + b];
+    for (int b = lane; b < nblk; b += 32) s += __ldcg(partials + row * nblk + b);  // written by other CTAs
     return warp_sum(s);
 }
 
@@ -240,9 +278,7 @@ __device__ __forceinline__ double reduce_partials(const double* partials, int ro
 // [z_j / (mu - lam_j); 1].  Directions with z_j = 0 decouple (their eigenpair is (lam_j, e_j)).
 // The full decomposition for the NEXT cycle is rebuilt by rayleigh_ritz_kernel on a side stream, off the
 // critical path.
-__global__ void __launch_bounds__(256)
-ritz_lowest_kernel(DavState* __restrict__ st, const double* __restrict__ partials, int nblk, int m) {
-    if (st->status != 0) return;
+__device__ void ritz_lowest_body(DavState* st, const double* partials, int nblk, int m) {
     __shared__ double g[kMaxS];
     __shared__ double v[kMaxS];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -357,10 +393,7 @@ ritz_lowest_kernel(DavState* __restrict__ st, const double* __restrict__ partial
 //     [    z^T      a ]
 // which parallel-order Jacobi (all disjoint pairs of a round rotated at once by one CTA) diagonalises in
 // 2-4 sweeps because |z| shrinks with the residual.
-__global__ void __launch_bounds__(256)
-rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ partials, int nblk, int m,
-                     int publish) {
-    if (st->status != 0) return;
+__device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nblk, int m, int publish) {
     __shared__ double A[kMaxS][kMaxS + 1];
     __shared__ double J[kMaxS][kMaxS + 1];   // accumulated rotations
     __shared__ double Qo[kMaxS][kMaxS + 1];  // previous eigenvectors, extended by e_new
@@ -515,9 +548,15 @@ rayleigh_ritz_kernel(DavState* __restrict__ st, const double* __restrict__ parti
     }
 }
 
-__global__ void convergence_kernel(DavState* __restrict__ st, const double* __restrict__ partials,
-                                   int nblk, int m, int restart, double tol, double tol_residual) {
+// side-stream launch of the full decomposition (publish == 0)
+__global__ void __launch_bounds__(256)
+rayleigh_ritz_kernel(DavState* st, const double* partials, int nblk, int m, int publish) {
     if (st->status != 0) return;
+    rayleigh_ritz_body(st, partials, nblk, m, publish);
+}
+
+__device__ void convergence_body(DavState* st, const double* partials, int nblk, int m, int restart,
+                                 double tol, double tol_residual) {
     __shared__ double p[kMaxS + 2];
     const int tid = threadIdx.x;
     for (int row = tid >> 5; row < kMaxS + 2; row += blockDim.x >> 5) {
@@ -558,9 +597,7 @@ __global__ void convergence_kernel(DavState* __restrict__ st, const double* __re
     }
 }
 
-__global__ void norm_kernel(DavState* __restrict__ st, const double* __restrict__ partials, int nblk,
-                            int m, double lindep) {
-    if (st->status != 0) return;
+__device__ void norm_body(DavState* st, const double* partials, int nblk, int m, double lindep) {
     __shared__ double p[kMaxS + 1];
     const int tid = threadIdx.x;
     for (int row = tid >> 5; row < kMaxS + 1; row += blockDim.x >> 5) {
@@ -641,6 +678,7 @@ __global__ void init_state_kernel(DavState* st) {
         st->ord[i] = i;
     }
     if (threadIdx.x == 0) st->best = 0;
+    if (threadIdx.x < 4) st->ticket[threadIdx.x] = 0;
 }
 
 // argmin over the (na, nb) block of hdiag (pads excluded): stage 1 per-CTA, stage 2 single thread.
@@ -964,18 +1002,17 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         const int restart = (m == M) ? q_keep : 0;
         int rc = dispatch_mv(m, [&](auto mv) {
             constexpr int MV = decltype(mv)::value;
-            gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n,
-                                                            m, ws.partials);
             static const int knob_side = getenv("SQD_RITZ_SIDE") ? atoi(getenv("SQD_RITZ_SIDE")) : -1;
             const bool one_kernel = knob_side >= 0 ? knob_side == 0 : prm->single_stream_ritz != 0;
-            if (one_kernel) {
-                // many solves share the GPU: their streams hide each other's latency, one launch is cheaper
-                rayleigh_ritz_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m, 1);
-            } else {
-                // lowest Ritz pair on the main stream; the full decomposition (needed by the next cycle,
-                // and by this one only when it restarts) on the side stream
-                if (full_pending) SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));
-                ritz_lowest_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m);
+            // the full decomposition of the previous cycle must be in place before this Rayleigh-Ritz
+            if (full_pending) SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));
+            full_pending = false;
+            gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n, m,
+                                                            ws.partials, one_kernel ? 1 : 2);
+            if (!one_kernel) {
+                // the lowest Ritz pair came out of the tail of gram_kernel (secular equation); the full
+                // decomposition (needed by the next cycle, and by this one only when it restarts) runs on
+                // the side stream beside the residual / orthogonalisation / next sigma build
                 SQD_CUDA_OK(cudaEventRecord(side->ev_fork, st));
                 SQD_CUDA_OK(cudaStreamWaitEvent(side->s, side->ev_fork, 0));
                 rayleigh_ritz_kernel<<<1, 256, 0, side->s>>>(ws.state, ws.partials, blocks, m, 0);
@@ -988,20 +1025,18 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
             }
             residual_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, d_hdiag, n, m,
                                                                 restart, prm->level_shift, ws.X, ws.T,
-                                                                ws.partials);
-            convergence_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, m, restart, prm->tol,
-                                                 prm->tol_residual);
-            return check_launch("davidson cycle (1)", 5);
+                                                                ws.partials, prm->tol, prm->tol_residual);
+            return check_launch("davidson cycle (1)", one_kernel ? 2 : 3);
         });
         if (rc) return -2;
         const int me = restart ? restart : m;
         rc = dispatch_mv(me, [&](auto mv) {
             constexpr int MV = decltype(mv)::value;
-            ortho1_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T, ws.partials);
-            norm_kernel<<<1, 256, 0, st>>>(ws.state, ws.partials, blocks, me, prm->lindep);
+            ortho1_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T, ws.partials,
+                                                              prm->lindep);
             ortho2_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T,
                                                               ws.V + (int64_t)me * n);
-            return check_launch("davidson cycle (2)", 3);
+            return check_launch("davidson cycle (2)", 2);
         });
         if (rc) return -2;
         m = me + 1;
