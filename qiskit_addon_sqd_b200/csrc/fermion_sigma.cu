@@ -725,22 +725,27 @@ static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
         threads = (((ldc + cpt - 1) / cpt + 31) / 32) * 32;
     }
     const int cpt_t = cpt;
-    // beta SELL table staged in shared memory when it costs at most 24 KB
+    // beta SELL table staged in shared memory: up to 24 KB for the one-column instances (their CTAs share
+    // an SM, see the ring budget below); the multi-column instances are alone on their SM (96 registers x
+    // 544 threads), so the table may take whatever two ring stages leave free
     const size_t pack_bytes = ((size_t)op->bd.n_entries * 4 + 15) / 16 * 16;
     const int n2 = op->norb * op->norb;
-    const bool stage_pack = op->bd.n_entries > 0 && pack_bytes <= (size_t)knob_pack && ldc <= 8191 &&
-                            n2 <= 4095 && op->ldg >= n2 + 1;
-    auto smem_of = [&](int nst) {
+    auto smem_with = [&](int nst, bool staged) {
         return (size_t)(ldc + nst * (ldc + op->ldg) + kLongA * 32) * sizeof(double) +
-               (2 * kMaxStages) * sizeof(uint64_t) + kTileC * 12 + (stage_pack ? pack_bytes : 0);
+               (2 * kMaxStages) * sizeof(uint64_t) + kTileC * 12 + (staged ? pack_bytes : 0);
     };
-    if (smem_of(2) > 227 * 1024) return false;
+    const size_t budget = cpt == 1 ? 56 * 1024 : 200 * 1024;
+    const size_t pack_limit = cpt == 1 ? (size_t)knob_pack : (size_t)160 * 1024;
+    const bool stage_pack = op->bd.n_entries > 0 && pack_bytes <= pack_limit && ldc <= 8191 && n2 <= 4095 &&
+                            op->ldg >= n2 + 1 && smem_with(2, true) <= 224 * 1024;
+    auto smem_of = [&](int nst) { return smem_with(nst, stage_pack); };
+    if (smem_of(2) > 224 * 1024) return false;
     // kernel B: kRowsB rows of c + the cross-warp reduction buffer
-    if ((size_t)(kRowsB * ldc + kWarpsB * kRowsB * 32) * sizeof(double) + 16 > 227 * 1024) return false;
-    // ring depth: as deep as fits in ~56 KB (keeps 4 CTAs per SM resident), at least 2, at most 6
+    if ((size_t)(kRowsB * ldc + kWarpsB * kRowsB * 32) * sizeof(double) + 16 > 224 * 1024) return false;
+    // ring depth: as deep as fits in the budget (56 KB keeps 4 one-column CTAs per SM), 2 to 6 stages
     int nst = 2;
-    while (nst < 6 && smem_of(nst + 1) <= 56 * 1024) ++nst;
-    if (knob_stages >= 2 && knob_stages <= kMaxStages && smem_of(knob_stages) <= 227 * 1024)
+    while (nst < 6 && smem_of(nst + 1) <= budget) ++nst;
+    if (knob_stages >= 2 && knob_stages <= kMaxStages && smem_of(knob_stages) <= 224 * 1024)
         nst = knob_stages;
     pl->CPT = cpt_t;
     pl->threads = threads;
