@@ -33,8 +33,8 @@ with open(os.path.join(out, f"{tag}_launch_summary_{wl}.md"), "w") as f:
     f.write(f"# ncu launch list summary ({tag}, workload {wl})\n\n"
             "Command: `ncu --metrics gpu__time_duration.sum --clock-control none python bench.py "
             f"--workload {wl} --steps 1 --warmup 3 --no-cpu-baseline` (the bench command itself; ncu serialises "
-            "the 8 solver threads; `--launch-skip 2800 -c 2900` records one whole step of 8 solves, set-up kernels "
-            "included, after the first warm-up step; every launch runs cold-cache: "
+            "the 8 solver threads; `--launch-skip 2000 -c 2100` records one whole step of 8 solves (about 2000 launches), "
+            "set-up kernels included, after the first warm-up step; every launch runs cold-cache: "
             "compare shares, not absolute times).\n\n"
             "| kernel | launches | total us | avg us | share |\n|---|---:|---:|---:|---:|\n")
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
