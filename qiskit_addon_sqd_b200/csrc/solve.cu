@@ -16,23 +16,38 @@
 
 namespace sqd {
 
+// Scratch of one solve: slabs from the device's stream-ordered pool, carved with a bump pointer.  A solve
+// makes ~50 requests; one cudaMallocAsync each costs ~15 us of host time when eight solver threads
+// contend for the allocator, a slab brings that down to a handful of calls.
 struct Pool {
+    static constexpr size_t kSlab = (size_t)16 << 20;
     cudaStream_t st;
     std::vector<void*> ptrs;
+    char* cur = nullptr;
+    size_t left = 0;
     bool failed = false;
     explicit Pool(cudaStream_t s) : st(s) {}
     template <typename T>
     T* get(size_t n) {
-        void* p = nullptr;
-        const size_t bytes = (n > 0 ? n : 1) * sizeof(T);
-        if (cudaMallocAsync(&p, bytes, st) != cudaSuccess) {
-            set_error("sqd_solve_subspace: cudaMallocAsync of %zu bytes failed: %s", bytes,
-                      cudaGetErrorString(cudaGetLastError()));
-            failed = true;
-            return nullptr;
+        const size_t bytes = (((n > 0 ? n : 1) * sizeof(T)) + 255) & ~(size_t)255;
+        if (bytes > left) {
+            const size_t slab = bytes > kSlab / 4 ? bytes : kSlab;  // large requests get their own block
+            void* p = nullptr;
+            if (cudaMallocAsync(&p, slab, st) != cudaSuccess) {
+                set_error("sqd_solve_subspace: cudaMallocAsync of %zu bytes failed: %s", slab,
+                          cudaGetErrorString(cudaGetLastError()));
+                failed = true;
+                return nullptr;
+            }
+            ptrs.push_back(p);
+            if (slab == bytes && bytes > kSlab / 4) return (T*)p;  // dedicated block: keep the current slab
+            cur = (char*)p;
+            left = slab;
         }
-        ptrs.push_back(p);
-        return (T*)p;
+        T* out = (T*)cur;
+        cur += bytes;
+        left -= bytes;
+        return out;
     }
     ~Pool() {
         for (void* p : ptrs) cudaFreeAsync(p, st);
@@ -226,11 +241,9 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
     const int nsl = (nb + 31) / 32;
     SQD_CUDA_OK(cudaMemcpyAsync(counts + 5, S0.slice_ptr + nsl, sizeof(int), cudaMemcpyDeviceToDevice, st));
     SQD_CUDA_OK(cudaMemcpyAsync(counts + 6, S1.slice_ptr + nsl, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    int hc[8];
-    if (read_back(hc, counts, 7 * sizeof(int), st)) return -2;  // hc[4] unused
-    double* part = P.get<double>((size_t)(hc[1] > 0 ? hc[1] : 1) * ldc);
-    if (P.failed) return -2;
 
+    // ---- operators: integrals, W tables and diagonals do not depend on the plan, so their kernels (and
+    // the start vector) are enqueued BEFORE the host waits for the plan / SELL sizes ----
     sqd_operator base{};
     base.a = ta;
     base.b = tb;
@@ -238,12 +251,6 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
     base.ldc = ldc;
     base.ldg = ldg;
     base.throughput_mode = prm->throughput_mode;
-    base.plan = sqd_sigma_plan{hc[0], hc[1], hc[2], hc[3], chunk[0], chunk[1], chunk[2], chunk[3],
-                               split[0], split[1], split[2], long_idx, long_cols, part};
-    base.bd = sqd_sell{nsl, hc[5], S0.perm, S0.len, S0.slice_ptr, S0.pack, nullptr};
-    base.bb = sqd_sell{nsl, hc[6], S1.perm, S1.len, S1.slice_ptr, S1.pack, S1.val};
-
-    // ---- operators ----
     const int n_alpha = prm->n_alpha, n_beta = prm->n_beta;
     const double sz = 0.5 * (n_alpha > n_beta ? n_alpha - n_beta : n_beta - n_alpha);
     const double szz = 0.5 * (n_alpha - n_beta);
@@ -260,8 +267,6 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
     if (need_s2 && operator_build(P, prm, base, 1, 0.0, szz * (szz + 1.0) + n_beta, false, false, nullptr,
                                   nullptr, &s2op))
         return -2;
-
-    // ---- Davidson ----
     const int M = prm->max_space < 2 ? 2 : (prm->max_space > SQD_MAX_SPACE ? SQD_MAX_SPACE : prm->max_space);
     const int64_t ws_bytes = sqd_davidson_workspace_bytes(na, ldc, M);
     void* ws = P.get<char>((size_t)ws_bytes);
@@ -275,6 +280,22 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
     } else if (sqd_init_guess(ham.diag, na, nb, ldc, x0, scratch, st)) {
         return -2;
     }
+
+    int hc[8];
+    if (read_back(hc, counts, 7 * sizeof(int), st)) return -2;  // hc[4] unused
+    double* part = P.get<double>((size_t)(hc[1] > 0 ? hc[1] : 1) * ldc);
+    if (P.failed) return -2;
+    const sqd_sigma_plan plan{hc[0], hc[1], hc[2], hc[3], chunk[0], chunk[1], chunk[2], chunk[3],
+                              split[0], split[1], split[2], long_idx, long_cols, part};
+    const sqd_sell bd{nsl, hc[5], S0.perm, S0.len, S0.slice_ptr, S0.pack, nullptr};
+    const sqd_sell bb{nsl, hc[6], S1.perm, S1.len, S1.slice_ptr, S1.pack, S1.val};
+    for (sqd_operator* o : {&base, &ham, &s2op}) {
+        o->plan = plan;
+        o->bd = bd;
+        o->bb = bb;
+    }
+
+    // ---- Davidson ----
     sqd_davidson_params dp{};
     dp.max_space = M;
     dp.max_cycle = prm->max_cycle;
