@@ -44,6 +44,7 @@ WORKLOADS = {
     "c2": (16, 5, 5, 100, 100, 102),     # configs[1]: (10e,16o), 1e4 dets per batch
     "c5": (40, 12, 12, 1000, 1000, 105), # configs[4]: (24e,40o), 1e6 dets
     "c1": (6, 3, 3, 20, 20, 101),        # configs[0]: (6e,6o) full space
+    "s7": (30, 15, 15, 3162, 3162, 107), # scale-up point of SURVEY 8(d): 1e7 determinants, vectors >> L2
 }
 METRIC = "subspace_diag_throughput"
 UNIT = "Mdet/s"

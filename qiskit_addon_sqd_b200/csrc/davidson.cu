@@ -97,12 +97,20 @@ gram_kernel(DavState* st, const double* __restrict__ V, const double* __restrict
     double acc[MV];
 #pragma unroll
     for (int i = 0; i < MV; ++i) acc[i] = 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+    // 16-byte loads, all basis vectors of an element pair in flight before the first FMA (n is even and
+    // every vector is 16-byte aligned): at 1e7 determinants these passes stream from HBM
+    const int64_t n2 = n >> 1;
+    const double2* w2 = reinterpret_cast<const double2*>(w);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2;
          j += (int64_t)gridDim.x * blockDim.x) {
-        const double wj = w[j];
+        const double2 wj = w2[j];
+        double2 v[MV];
 #pragma unroll
         for (int i = 0; i < MV; ++i)
-            if (i < m) acc[i] = fma(V[(int64_t)i * n + j], wj, acc[i]);
+            if (i < m) v[i] = reinterpret_cast<const double2*>(V + (int64_t)i * n)[j];
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            if (i < m) acc[i] = fma(v[i].y, wj.y, fma(v[i].x, wj.x, acc[i]));
     }
     block_sum<MV>(acc, red);
     if (threadIdx.x == 0) {
@@ -140,48 +148,65 @@ residual_kernel(DavState* st, double* __restrict__ V, double* __restrict__ W,
     double acc[MV + 2];
 #pragma unroll
     for (int i = 0; i < MV + 2; ++i) acc[i] = 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+    // two elements per thread and iteration, 16-byte loads; the basis values stay in registers for the
+    // projections, the W values are consumed as they arrive (a restart re-reads them: once per sweep)
+    const int64_t n2 = n >> 1;
+    const double2* hd2 = reinterpret_cast<const double2*>(hdiag);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2;
          j += (int64_t)gridDim.x * blockDim.x) {
-        double v[MV], w[MV];
-        double x = 0.0, hx = 0.0;
+        double2 v[MV];
+        double2 x = make_double2(0.0, 0.0), hx = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            v[i] = i < m ? reinterpret_cast<const double2*>(V + (int64_t)i * n)[j] : make_double2(0.0, 0.0);
 #pragma unroll
         for (int i = 0; i < MV; ++i) {
-            v[i] = 0.0;
-            w[i] = 0.0;
             if (i < m) {
-                v[i] = V[(int64_t)i * n + j];
-                w[i] = W[(int64_t)i * n + j];
-                x = fma(ys[i], v[i], x);
-                hx = fma(ys[i], w[i], hx);
+                const double2 wi = reinterpret_cast<const double2*>(W + (int64_t)i * n)[j];
+                x.x = fma(ys[i], v[i].x, x.x);
+                x.y = fma(ys[i], v[i].y, x.y);
+                hx.x = fma(ys[i], wi.x, hx.x);
+                hx.y = fma(ys[i], wi.y, hx.y);
             }
         }
-        const double r = hx - theta * x;
-        double den = hdiag[j] - theta + level_shift;
-        if (fabs(den) < 1e-8) den = den < 0.0 ? -1e-8 : 1e-8;
-        const double t = r / den;
-        X[j] = x;
-        T[j] = t;
+        const double2 hd = hd2[j];
+        const double rx = hx.x - theta * x.x, ry = hx.y - theta * x.y;
+        double dx = hd.x - theta + level_shift, dy = hd.y - theta + level_shift;
+        if (fabs(dx) < 1e-8) dx = dx < 0.0 ? -1e-8 : 1e-8;
+        if (fabs(dy) < 1e-8) dy = dy < 0.0 ? -1e-8 : 1e-8;
+        const double tx = rx / dx, ty = ry / dy;
+        reinterpret_cast<double2*>(X)[j] = x;
+        reinterpret_cast<double2*>(T)[j] = make_double2(tx, ty);
         if (restart) {
             // thick restart: the basis collapses onto the `restart` lowest Ritz vectors (element-wise; this
-            // thread is the only reader and writer of element j of every basis vector)
-            V[j] = x;
-            W[j] = hx;
+            // thread is the only reader and writer of elements 2j, 2j+1 of every basis vector).  All kept
+            // vectors are formed before the first one is stored: they read the slots they overwrite.
+            double2 xk[kKeep], hk[kKeep];
             for (int k = 1; k < restart; ++k) {
-                double xk = 0.0, hk = 0.0;
-#pragma unroll
-                for (int i = 0; i < MV; ++i) {
-                    xk = fma(yk[k][i], v[i], xk);
-                    hk = fma(yk[k][i], w[i], hk);
+                xk[k] = make_double2(0.0, 0.0);
+                hk[k] = make_double2(0.0, 0.0);
+                for (int i = 0; i < m; ++i) {
+                    const double2 wi = reinterpret_cast<const double2*>(W + (int64_t)i * n)[j];
+                    const double2 vi = reinterpret_cast<const double2*>(V + (int64_t)i * n)[j];
+                    const double c = yk[k][i];
+                    xk[k].x = fma(c, vi.x, xk[k].x);
+                    xk[k].y = fma(c, vi.y, xk[k].y);
+                    hk[k].x = fma(c, wi.x, hk[k].x);
+                    hk[k].y = fma(c, wi.y, hk[k].y);
                 }
-                V[(int64_t)k * n + j] = xk;
-                W[(int64_t)k * n + j] = hk;
+            }
+            reinterpret_cast<double2*>(V)[j] = x;
+            reinterpret_cast<double2*>(W)[j] = hx;
+            for (int k = 1; k < restart; ++k) {
+                reinterpret_cast<double2*>(V + (int64_t)k * n)[j] = xk[k];
+                reinterpret_cast<double2*>(W + (int64_t)k * n)[j] = hk[k];
             }
         }
 #pragma unroll
         for (int i = 0; i < MV; ++i)
-            if (i < m) acc[i] = fma(v[i], t, acc[i]);
-        acc[MV] = fma(r, r, acc[MV]);
-        acc[MV + 1] = fma(t, t, acc[MV + 1]);
+            if (i < m) acc[i] = fma(v[i].y, ty, fma(v[i].x, tx, acc[i]));
+        acc[MV] = fma(ry, ry, fma(rx, rx, acc[MV]));
+        acc[MV + 1] = fma(ty, ty, fma(tx, tx, acc[MV + 1]));
     }
     block_sum<MV + 2>(acc, red);
     if (threadIdx.x == 0) {
@@ -208,23 +233,27 @@ ortho1_kernel(DavState* st, const double* __restrict__ V, int64_t n, int m, doub
     double acc[MV + 1];
 #pragma unroll
     for (int i = 0; i < MV + 1; ++i) acc[i] = 0.0;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+    const int64_t n2 = n >> 1;
+    double2* T2 = reinterpret_cast<double2*>(T);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2;
          j += (int64_t)gridDim.x * blockDim.x) {
-        double v[MV];
-        double t = T[j];
-#pragma unroll
-        for (int i = 0; i < MV; ++i) {
-            v[i] = 0.0;
-            if (i < m) {
-                v[i] = V[(int64_t)i * n + j];
-                t = fma(-cs[i], v[i], t);
-            }
-        }
-        T[j] = t;
+        double2 v[MV];
+        double2 t = T2[j];
 #pragma unroll
         for (int i = 0; i < MV; ++i)
-            if (i < m) acc[i] = fma(v[i], t, acc[i]);
-        acc[MV] = fma(t, t, acc[MV]);
+            if (i < m) v[i] = reinterpret_cast<const double2*>(V + (int64_t)i * n)[j];
+#pragma unroll
+        for (int i = 0; i < MV; ++i) {
+            if (i < m) {
+                t.x = fma(-cs[i], v[i].x, t.x);
+                t.y = fma(-cs[i], v[i].y, t.y);
+            }
+        }
+        T2[j] = t;
+#pragma unroll
+        for (int i = 0; i < MV; ++i)
+            if (i < m) acc[i] = fma(v[i].y, t.y, fma(v[i].x, t.x, acc[i]));
+        acc[MV] = fma(t.y, t.y, fma(t.x, t.x, acc[MV]));
     }
     block_sum<MV + 1>(acc, red);
     if (threadIdx.x == 0) {
@@ -247,13 +276,24 @@ ortho2_kernel(const DavState* __restrict__ st, const double* __restrict__ V, int
     if (threadIdx.x < MV) cs[threadIdx.x] = threadIdx.x < m ? st->c2[threadIdx.x] : 0.0;
     __syncthreads();
     const double inv = st->inv_norm;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n;
+    const int64_t n2 = n >> 1;
+    const double2* T2 = reinterpret_cast<const double2*>(T);
+    double2* out2 = reinterpret_cast<double2*>(vnew);
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2;
          j += (int64_t)gridDim.x * blockDim.x) {
-        double t = T[j];
+        double2 t = T2[j];
+        double2 v[MV];
 #pragma unroll
         for (int i = 0; i < MV; ++i)
-            if (i < m) t = fma(-cs[i], V[(int64_t)i * n + j], t);
-        vnew[j] = t * inv;
+            if (i < m) v[i] = reinterpret_cast<const double2*>(V + (int64_t)i * n)[j];
+#pragma unroll
+        for (int i = 0; i < MV; ++i) {
+            if (i < m) {
+                t.x = fma(-cs[i], v[i].x, t.x);
+                t.y = fma(-cs[i], v[i].y, t.y);
+            }
+        }
+        out2[j] = make_double2(t.x * inv, t.y * inv);
     }
 }
 
@@ -963,6 +1003,7 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
     SQD_REQUIRE(M >= 2 && M <= kMaxS, "sqd_davidson: max_space must be in [2, %d] (got %d)", kMaxS, M);
     SQD_REQUIRE(ws_bytes >= workspace_bytes(n, M), "sqd_davidson: workspace too small");
     SQD_REQUIRE(prm->max_cycle >= 1, "sqd_davidson: max_cycle must be >= 1");
+    SQD_REQUIRE(n % 2 == 0, "sqd_davidson: the vector length must be even (16-byte loads); pad the rows");
     Workspace ws;
     carve(d_workspace, n, M, &ws);
     const int blocks = red_blocks(n);
