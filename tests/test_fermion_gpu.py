@@ -430,3 +430,24 @@ def test_fix_sign_and_read_back(cuda_lib):
     _lib.check(cuda_lib.sqd_read_back(out, x.data_ptr(), 32, st))
     assert list(out) == [-0.1, 0.7, -0.7, -0.2]
     assert cuda_lib.sqd_read_back(out, x.data_ptr(), 1 << 20, st) < 0   # larger than the staging buffer
+
+
+def test_solve_sci_batch_over_several_devices(cuda_lib):
+    """One process driving every visible GPU (`devices="all"`): subspace k goes to device k mod G, no
+    collective; results are identical to the single-device run."""
+    import torch
+
+    from qiskit_addon_sqd_b200 import fermion
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    norb = 10
+    h, g = random_integrals(norb, 9)
+    batches = [(hf_centred_strings(norb, 5, 40 + 3 * k, 10 + k), hf_centred_strings(norb, 4, 35 + 2 * k, 20 + k))
+               for k in range(5)]
+    one = fermion.solve_sci_batch(batches, h, g, norb, (5, 4), spin_sq=0.75)
+    many = fermion.solve_sci_batch(batches, h, g, norb, (5, 4), spin_sq=0.75, devices="all")
+    for a, b in zip(one, many):
+        assert a.energy == b.energy
+        assert np.array_equal(a.sci_state.amplitudes, b.sci_state.amplitudes)
+        assert np.array_equal(a.rdm2, b.rdm2)
