@@ -228,7 +228,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 streams[k].wait_stream(main)
                 r = fermion._solve_on_device(batches[k][0], batches[k][1], norb, ints, None, 0.2, opts,
                                              want_spin=False, want_rdm=False, strs_dev=strs_dev[k],
-                                             download=False, profile=profile, throughput=K > 1)
+                                             download=False, profile=profile,
+                                             throughput=fermion._throughput_mode(K, n_det_step))
                 return r
 
         res = list(pool.map(work, range(K)))

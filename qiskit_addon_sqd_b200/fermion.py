@@ -497,6 +497,15 @@ _pool: ThreadPoolExecutor | None = None
 _streams: dict[tuple[int, int], object] = {}
 
 
+def _throughput_mode(n_solves: int, total_dets: int) -> bool:
+    """Launch configuration of concurrent solves on one device.  ``True`` (several solves that together
+    keep the GPU busy, ~3e5 determinants or more): sigma kernels under a register cap with persistent
+    CTAs, one Rayleigh-Ritz kernel on the main stream -- best aggregate throughput.  ``False`` (a lone
+    solve, or a handful of small ones that leave the GPU mostly idle): shortest critical path per solve --
+    lowest Ritz pair from the secular equation, full decomposition on a side stream."""
+    return n_solves > 1 and total_dets >= 300_000
+
+
 def _worker_pool() -> ThreadPoolExecutor:
     """Host threads that drive the concurrent subspaces (created once; ctypes calls release the GIL)."""
     global _pool
@@ -725,7 +734,8 @@ def solve_sci_batch(
                         np.ascontiguousarray(ci0, dtype=np.float64).reshape(j["na"], j["nb"])).to(dev)
                     prm.d_ci0 = j["ci0_d"].data_ptr()
                 prm.cost_per_chunk, prm.long_threshold = int(_SIGMA_COST_PER_CHUNK), int(_SIGMA_LONG_THRESHOLD)
-                prm.throughput_mode = 1 if K > 1 else 0
+                prm.throughput_mode = 1 if _throughput_mode(
+                    len(ks), sum(jobs[q]["na"] * jobs[q]["nb"] for q in ks)) else 0
                 j["prm"], j["res"] = prm, _lib.SolveResult()
                 j["x_ptr"] = x_d.data_ptr() + 8 * x_off[i]
                 j["x_off"] = x_off[i]

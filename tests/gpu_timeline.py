@@ -35,7 +35,9 @@ def step():
             streams[k].wait_stream(main)
             return fermion._solve_on_device(batches[k][0], batches[k][1], norb, ints, None, 0.2, opts,
                                             want_spin=False, want_rdm=False, strs_dev=strs_dev[k],
-                                            download=False, throughput=K > 1)
+                                            download=False,
+                                            throughput=fermion._throughput_mode(
+                                                K, sum(len(a) * len(b) for a, b in batches)))
 
     res = list(pool.map(work, range(K)))
     for s in streams:
