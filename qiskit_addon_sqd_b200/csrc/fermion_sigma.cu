@@ -87,16 +87,40 @@ constexpr int kSingleCost = 16;  // plan cost of one alpha single excitation, in
 //   * columns whose beta single-excitation list is long are taken out of the thread-per-column loops and
 //     reduced cooperatively by one warp each (lane-strided, fixed shuffle tree).
 // ---------------------------------------------------------------------------------------------------
+// cost class 0 .. 63 of a single-chunk row (cost <= cost_per_chunk < 2^24: 32-bit arithmetic; a 64-bit
+// division costs the single planning thread ~150 cycles per row and pass)
+__device__ __forceinline__ int cost_class(int cost, int cost_per_chunk) {
+    return (int)(((unsigned)cost * 64u) / (unsigned)(cost_per_chunk + 1));
+}
+
 __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B, int cost_per_chunk,
                                   int long_threshold, int max_chunks, int* __restrict__ chunk_row,
                                   int* __restrict__ chunk_beg, int* __restrict__ chunk_end,
                                   int* __restrict__ chunk_slot, int* __restrict__ split_row,
                                   int* __restrict__ split_slot_beg, int* __restrict__ split_n,
                                   int* __restrict__ long_idx, int* __restrict__ long_cols,
-                                  int* __restrict__ counts) {
-    // setup-time, O(na + nb) sequential work: a single thread keeps the order trivially deterministic.
+                                  int* __restrict__ counts, int stage_in_smem) {
+    // setup-time, O(na + nb) work.  The ordering logic is sequential (one thread keeps the order trivially
+    // deterministic) but it works from shared-memory copies of the row pointers / list lengths that the
+    // whole CTA loads with coalesced reads first -- the single thread then never waits for global memory.
     // Two passes: rows that need several chunks are emitted first so that the heaviest CTAs start first.
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    extern __shared__ int plan_smem[];
+    if (blockIdx.x != 0) return;
+    const bool staged = stage_in_smem != 0;
+    int* rp_s = plan_smem;                    // [na + 1]
+    int* nsa_s = rp_s + (A.n + 1);            // [na]
+    int* nsb_s = nsa_s + A.n;                 // [nb]
+    if (staged) {
+        for (int i = threadIdx.x; i <= A.n; i += blockDim.x) rp_s[i] = A.row_ptr[i];
+        for (int i = threadIdx.x; i < A.n; i += blockDim.x) nsa_s[i] = A.n_single[i];
+        for (int i = threadIdx.x; i < B.n; i += blockDim.x) nsb_s[i] = B.n_single[i];
+    }
+    for (int b = threadIdx.x; b < B.n; b += blockDim.x) long_idx[b] = -1;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int* a_row_ptr = staged ? rp_s : A.row_ptr;
+    const int* a_n_single = staged ? nsa_s : A.n_single;
+    const int* b_n_single = staged ? nsb_s : B.n_single;
     int nc = 0, nslots = 0, nsplit = 0;
     // Order of the chunk list = order in which the persistent CTAs of kernel A pick their work: rows that
     // need several chunks first (every such chunk is full), then the single-chunk rows by descending cost
@@ -107,14 +131,14 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
     for (int k = 0; k <= kClasses; ++k) class_pos[k] = 0;
     int n_multi_chunks = 0;
     for (int a = 0; a < A.n; ++a) {
-        const int beg = A.row_ptr[a], ns = A.n_single[a], end = A.row_ptr[a + 1];
+        const int beg = a_row_ptr[a], ns = a_n_single[a], end = a_row_ptr[a + 1];
         const int cost = kSingleCost * ns + (end - beg - ns);
         int k = (cost + cost_per_chunk - 1) / cost_per_chunk;
         if (k < 1) k = 1;
         if (k > 1) {
             n_multi_chunks += k;
         } else {
-            int cls = (int)(((long long)cost * kClasses) / (cost_per_chunk + 1));
+            int cls = cost_class(cost, cost_per_chunk);
             cls = kClasses - 1 - (cls < kClasses ? cls : kClasses - 1);  // class 0 = most expensive
             ++class_pos[cls + 1];
         }
@@ -124,7 +148,7 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
     const int single_base = capped ? 0 : n_multi_chunks;
     for (int pass = 0; pass < 2; ++pass) {
         for (int a = 0; a < A.n; ++a) {
-            const int beg = A.row_ptr[a], ns = A.n_single[a], end = A.row_ptr[a + 1];
+            const int beg = a_row_ptr[a], ns = a_n_single[a], end = a_row_ptr[a + 1];
             const int nd = end - beg - ns;
             const int cost = kSingleCost * ns + nd;
             int k = (cost + cost_per_chunk - 1) / cost_per_chunk;
@@ -146,7 +170,7 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
                 const int e1 = p1 < kSingleCost * ns ? p1 / kSingleCost : ns + (p1 - kSingleCost * ns);
                 int at = nc;
                 if (k == 1 && !capped) {
-                    int cls = (int)(((long long)cost * kClasses) / (cost_per_chunk + 1));
+                    int cls = cost_class(cost, cost_per_chunk);
                     cls = kClasses - 1 - (cls < kClasses ? cls : kClasses - 1);
                     at = single_base + class_pos[cls]++;
                 }
@@ -161,16 +185,21 @@ __global__ void sigma_plan_kernel(const sqd_spin_table A, const sqd_spin_table B
     // long columns: the (at most kLongA) beta strings with the longest single-excitation lists above the
     // threshold; their links are spread over all threads of a CTA instead of living in one SELL lane
     int nlong = 0;
-    for (int b = 0; b < B.n; ++b) long_idx[b] = -1;
+    int taken[kLongA];  // long_idx was set to -1 by the whole CTA above
     for (int round = 0; round < kLongA; ++round) {
         int best = -1, best_len = long_threshold;
         for (int b = 0; b < B.n; ++b)
-            if (long_idx[b] < 0 && B.n_single[b] > best_len) {
-                best = b;
-                best_len = B.n_single[b];
+            if (b_n_single[b] > best_len) {
+                bool used = false;
+                for (int r = 0; r < nlong; ++r) used = used || taken[r] == b;
+                if (!used) {
+                    best = b;
+                    best_len = b_n_single[b];
+                }
             }
         if (best < 0) break;
         long_idx[best] = nlong;
+        taken[nlong] = best;
         long_cols[nlong++] = best;
     }
     counts[0] = nc;
@@ -918,9 +947,13 @@ int sqd_sigma_plan_build(const sqd_spin_table* a, const sqd_spin_table* b, int c
     SQD_REQUIRE(cost_per_chunk >= kSingleCost && cost_per_chunk % kSingleCost == 0,
                 "sqd_sigma_plan_build: cost_per_chunk must be a positive multiple of %d", kSingleCost);
     SQD_REQUIRE(max_chunks >= a->n, "sqd_sigma_plan_build: max_chunks must be at least the number of rows");
-    sigma_plan_kernel<<<1, 32, 0, st>>>(*a, *b, cost_per_chunk, long_threshold, max_chunks, d_chunk_row,
-                                        d_chunk_beg, d_chunk_end, d_chunk_slot, d_split_row,
-                                        d_split_slot_beg, d_split_n, d_long_idx, d_long_cols, d_counts);
+    const size_t plan_smem = (size_t)(2 * a->n + 1 + b->n) * sizeof(int);
+    const int stage = plan_smem <= 200 * 1024;
+    static bool cfg_plan[64] = {false};
+    if (stage && opt_in_smem(sigma_plan_kernel, plan_smem, cfg_plan)) return -2;
+    sigma_plan_kernel<<<1, 256, stage ? plan_smem : 0, st>>>(
+        *a, *b, cost_per_chunk, long_threshold, max_chunks, d_chunk_row, d_chunk_beg, d_chunk_end,
+        d_chunk_slot, d_split_row, d_split_slot_beg, d_split_n, d_long_idx, d_long_cols, d_counts, stage);
     if (check_launch("sigma_plan_kernel")) return -2;
     if (h_counts == nullptr) return 0;  // the caller reads d_counts itself
     return read_back(h_counts, d_counts, 4 * sizeof(int), st);
