@@ -147,3 +147,49 @@ def test_loop_on_gpu_matches_reference_loop(ci):
     _check_history(z, ci, history, n_iter, n_batches, 1e-8, 1e-6)
     assert abs(best.energy - float(z[f"c{ci}_best_energy"])) < 1e-8
     assert np.abs(np.array(best.orbital_occupancies) - z[f"c{ci}_best_occ"]).max() < 1e-6
+
+
+def test_subsample_edge_cases_of_the_reference_suite():
+    """reference test/test_subsampling.py: 1-D empty input, mismatching probabilities, batch shapes."""
+    from qiskit_addon_sqd_b200 import subsampling
+
+    out = subsampling.subsample(np.array([]), np.array([]), 1, 1)
+    assert len(out) == 1 and out[0].shape[0] == 0
+    mat = np.array([[0, 1, 0, 1], [1, 0, 1, 0], [1, 1, 0, 0], [0, 0, 1, 1], [0, 1, 1, 0]], dtype=bool)
+    uniform = np.full(5, 0.2)
+    with pytest.raises(ValueError, match="number of elements in the probabilities array must match"):
+        subsampling.subsample(mat, np.array([]), 1, 1)
+    batches = subsampling.subsample(mat, uniform, 2, 10, rand_seed=4)
+    assert len(batches) == 10 and all(b.shape == (2, 4) for b in batches)
+    assert all(len({tuple(r) for r in b}) == 2 for b in batches)          # without replacement
+    whole = subsampling.subsample(mat, uniform, 20, 1)
+    assert len(whole) == 1 and np.array_equal(whole[0], mat)
+    # an int seed and a Generator built from it give the same batches (np.random.default_rng semantics)
+    a = subsampling.subsample(mat, uniform, 3, 4, rand_seed=9)
+    b = subsampling.subsample(mat, uniform, 3, 4, rand_seed=np.random.default_rng(9))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_digest_convergence_and_carryover_rules():
+    """Second half of an iteration (reference fermion.py:563-640) on hand-made results."""
+    from qiskit_addon_sqd_b200.fermion import SCIResult, SCIState, _SQDRun
+
+    def result(e, amps, sa, sb, occ):
+        return SCIResult(e, SCIState(np.asarray(amps, float), np.asarray(sa), np.asarray(sb), 3, (1, 1)),
+                         orbital_occupancies=occ)
+
+    run = _SQDRun(None, None, 3, (1, 1), 2, 1, False, (np.array([], int), np.array([], int)), (None, None),
+                  1e-6, 1e-4, 0.3, np.random.default_rng(0), None)
+    occ = (np.array([1.0, 0.0, 0.0]), np.array([0.0, 1.0, 0.0]))
+    amps = [[0.9, 0.05], [0.31, -0.29]]
+    first = result(-1.0, amps, [1, 4], [2, 4], occ)
+    assert run.digest([first, result(-0.5, amps, [1, 2], [1, 2], occ)]) is False     # nothing to compare with yet
+    assert run.best is first and run.reference is first
+    # |amplitude| > 0.3: (0,0) and (1,0) -> alpha strings {1, 4}, beta string {2}; alpha ranked by row weight
+    assert run.carry_a.tolist() == [1, 4] and run.carry_b.tolist() == [2]
+    # same energy and occupancies within tolerance -> converged, best result kept
+    again = result(-1.0 + 5e-7, amps, [1, 4], [2, 4], (occ[0] + 5e-5, occ[1]))
+    assert run.digest([again]) is True and run.best is first
+    # a lower energy in a later iteration replaces the best result even if not converged
+    lower = result(-1.2, amps, [1, 4], [2, 4], (occ[0] * 0.5, occ[1]))
+    assert run.digest([lower]) is False and run.best is lower
