@@ -305,6 +305,7 @@ class _OperatorDev:
                                     _lib.ptr(self.diag), _lib.ptr(self.gab), _lib.ptr(self.Wa),
                                     _lib.ptr(self.Wb), 1 if same_spin else 0, sub.sigma_plan(),
                                     sub.tb.sell(0, sub._plan_keep[2]), sub.tb.sell(1), 0)
+        self.uses_v2 = False
         if lib.sqd_sigma_smem_bytes(C.byref(self.struct)) < 0:
             raise ValueError(
                 f"subspace shape (na={na}, nb={nb}, norb={norb}) exceeds the shared-memory row "
@@ -319,8 +320,9 @@ class _Subspace:
     this class but through the one-call ``sqd_solve_subspace`` (``_solve_on_device``)."""
 
     def __init__(self, strs_a, strs_b, norb: int, hcore, eri, ints: _DeviceIntegrals | None = None,
-                 strs_dev=(None, None)):
+                 strs_dev=(None, None), sigma_path: str = "auto"):
         self.torch = torch = _lib.require_cuda()
+        self.sigma_path = sigma_path
         self.lib = lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device())
         if norb > 64 or norb < 1:
