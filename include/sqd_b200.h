@@ -141,6 +141,49 @@ typedef struct {
     const double* val;       /* mode 1 only */
 } sqd_sell;
 
+/* ---- sigma build, second generation ("v2", csrc/fermion_sigma2.cu) ---------------------------
+ * Two kernels per build instead of three, chosen when the in-set connectivity is dense enough:
+ *   K1  opposite-spin part, grouped by SOURCE alpha string a': a thread owns one "virtual column" (at
+ *       most `lmax` beta single excitations of one beta string), gathers x_j = sgn_j c[a', b'_j] into
+ *       REGISTERS once per chunk of a' and then, for every alpha single excitation a' -> a (integral row
+ *       g_ab[pq,:] staged by the bulk-copy engine through an mbarrier ring), does one shared-memory gather
+ *       and one FMA per link; the row of results goes to P[item] (item = (a', link) pair).
+ *   K2  64x64 output tiles: same-spin part as dense FP64 tiles  sigma += HaD C + C HbD^T  (K split over
+ *       CTAs, partials summed in a fixed order by the last CTA of a tile), then the epilogue adds
+ *       diag*c, the P rows of the tile's alpha links and the sgn*Wb[pq,b]*c[a',b] terms.
+ * Every element of sigma is still produced in a fixed order (bit-reproducible).
+ * All arrays are device pointers into caller-owned memory (sqd_sigma_v2_plan / sqd_sigma_v2_finish). */
+typedef struct {
+    int enabled;             /* 0: v1 kernels; 1: v2 */
+    int lmax;                /* links per virtual column: 8 or 16 */
+    int n_groups;            /* column groups (K1 grid.y); a beta string's virtual columns share a group */
+    int vc_pad;              /* K1 consumer threads = virtual columns per group, padded to 32 */
+    int n_items;             /* rows of P: na self items + alpha single excitations */
+    int n_chunks;            /* K1 work units (source string, <= items_per_chunk items) */
+    int max_split;           /* capacity of `part` in K splits */
+    int lda, ldb;            /* row strides of HaDT / HbDT */
+    const uint32_t* vc_src;  /* [n_groups][lmax][vc_pad] source column b' | sign << 31 */
+    const uint32_t* vc_off;  /* [n_groups][lmax][vc_pad] byte offset 8*rs into an integral row (pad: zero slot) */
+    const int* vc_len;       /* [n_groups][vc_pad] */
+    const int* grp_ncol;     /* [n_groups] beta strings with links in the group */
+    const int* gcol;         /* [n_groups][vc_pad] beta string of the u-th column of the group (ascending) */
+    const int* gcol_full;    /* [n_groups][vc_pad] first full virtual column of that string */
+    const int* gcol_nfull;   /* [n_groups][vc_pad] number of full virtual columns */
+    const int* gcol_rem;     /* [n_groups][vc_pad] its remainder virtual column or -1 */
+    const int* single_ptr;   /* [na+1] exclusive scan of a.n_single */
+    const int* item_ptr;     /* [na+1] single_ptr[a] + a: P row of a's self item; its k-th single follows at +1+k */
+    const int* chunk_row;    /* [n_chunks] source alpha string, chunks sorted by descending size */
+    const int* chunk_first;  /* [n_chunks] first item of the chunk (0 = self item) */
+    const int* chunk_n;      /* [n_chunks] */
+    const int* rev_slot;     /* [singles_a] P row written for the reverse link of single_ptr[a]+k */
+    int* counter;            /* [128] K1 work counters / exit tickets per group (self-resetting) */
+    int* tile_ticket;        /* [tiles] K2 split-K arrival counters (self-resetting) */
+    const double* HaDT;      /* [lda*lda] dense same-spin alpha block, transposed: HaDT[a'*lda + a] */
+    const double* HbDT;      /* [ldb*ldb] */
+    double* P;               /* [n_items * ldc] */
+    double* part;            /* [max_split * na * ldc] */
+} sqd_sigma_v2;
+
 typedef struct {
     sqd_spin_table a, b;     /* alpha strings index rows, beta strings index columns */
     int norb;
@@ -155,7 +198,31 @@ typedef struct {
     sqd_sell bd;             /* beta single excitations (mode 0; long columns have length 0) */
     sqd_sell bb;             /* every beta entry with its same-spin value (mode 1) */
     int throughput_mode;     /* see sqd_solve_params.throughput_mode */
+    sqd_sigma_v2 v2;         /* v2.enabled != 0: sqd_sigma runs the v2 kernels */
 } sqd_operator;
+
+/* Build the v2 structures of a subspace (operator independent: shared by the Hamiltonian and S^2).
+ * Step 1, sqd_sigma_v2_plan: everything that only needs the tables.  d_plan: sqd_sigma_v2_plan_bytes(...)
+ *   bytes; h_counts: int[16] -- when not NULL the stream is synchronised and the counts are returned
+ *   (a caller that reads d_counts itself passes NULL): [0] n_items, [1] n_chunks, [2] n_groups, [3] vc_pad,
+ *   [4] alpha singles, [5] beta singles, [6] error flag (!= 0: shape unsupported, use v1).
+ * Step 2, sqd_sigma_v2_finish: dense blocks, zeroed P, the struct.  d_scratch: sqd_sigma_v2_scratch_bytes
+ *   bytes.  dense != 0 builds HaDT/HbDT (needed by Hamiltonian-like operators, not by S^2 alone). */
+#define SQD_V2_COUNTS 16
+/* 1 when the v2 kernels are expected to beat v1 for tables of this size: the dense same-spin tiles cost
+ * na*nb*(na+nb) FMAs against nnz_a*nb + nnz_b*na gathered ones, worth it above a few per cent density. */
+int sqd_sigma_v2_recommended(int na, int nb, int64_t nnz_a, int64_t nnz_b);
+int64_t sqd_sigma_v2_plan_bytes(int na, int nb, int64_t nnz_a, int64_t nnz_b, int lmax, int items_per_chunk);
+int sqd_sigma_v2_plan(const sqd_spin_table* a, const sqd_spin_table* b, int norb, int64_t nnz_a,
+                      int64_t nnz_b, int lmax, int items_per_chunk, void* d_plan, int64_t plan_bytes,
+                      int* h_counts, void* stream);
+/* device address of the int[SQD_V2_COUNTS] counts inside d_plan */
+const int* sqd_sigma_v2_counts_ptr(void* d_plan, int na, int nb, int64_t nnz_a, int64_t nnz_b, int lmax,
+                                   int items_per_chunk);
+int64_t sqd_sigma_v2_scratch_bytes(const int* h_counts, int na, int nb, int ldc, int dense, int same_tables);
+int sqd_sigma_v2_finish(const sqd_spin_table* a, const sqd_spin_table* b, int ldc, int64_t nnz_a,
+                        int64_t nnz_b, int lmax, int items_per_chunk, const int* h_counts, void* d_plan,
+                        void* d_scratch, int64_t scratch_bytes, int dense, sqd_sigma_v2* out, void* stream);
 
 /* Build a SELL-32 copy of a table.  mode 0: single excitations only, strings with more than
  * long_threshold of them get length 0 (they are reduced cooperatively, see sqd_sigma_plan_build);
@@ -272,6 +339,9 @@ typedef struct {
     int throughput_mode;         /* != 0: this solve shares the GPU with others (one stream each): the sigma
                                     kernel is launched under a register cap that lets three of its CTAs
                                     share an SM -- slower alone, faster in aggregate */
+    int sigma_path;              /* 0: choose by table density (sqd_sigma_v2_recommended); 1: v1 kernels;
+                                    2: v2 kernels whenever their planner accepts the shape */
+    int v2_lmax, v2_items_per_chunk; /* v2 tuning, 0 = defaults (16, 8) */
 } sqd_solve_params;
 
 typedef struct {
@@ -283,6 +353,7 @@ typedef struct {
     int64_t nnz_a, nnz_b;        /* entries of the two excitation tables */
     int64_t singles_a, singles_b;/* profile != 0: single excitations among them, else -1 */
     int ldc;                     /* row stride of d_x */
+    int sigma_path;              /* 1 / 2: the sigma kernels that ran */
 } sqd_solve_result;
 
 /* d_x: double[na * ldc], ldc = nb rounded up to even, receives the normalised ground state (pad columns

@@ -61,6 +61,26 @@ class Sell(C.Structure):
     ]
 
 
+class SigmaV2(C.Structure):
+    """``sqd_sigma_v2`` of include/sqd_b200.h."""
+
+    _fields_ = [
+        ("enabled", C.c_int), ("lmax", C.c_int), ("n_groups", C.c_int), ("vc_pad", C.c_int),
+        ("n_items", C.c_int), ("n_chunks", C.c_int), ("max_split", C.c_int),
+        ("lda", C.c_int), ("ldb", C.c_int),
+        ("vc_src", C.c_void_p), ("vc_off", C.c_void_p), ("vc_len", C.c_void_p),
+        ("grp_ncol", C.c_void_p), ("gcol", C.c_void_p), ("gcol_full", C.c_void_p),
+        ("gcol_nfull", C.c_void_p), ("gcol_rem", C.c_void_p),
+        ("single_ptr", C.c_void_p), ("item_ptr", C.c_void_p),
+        ("chunk_row", C.c_void_p), ("chunk_first", C.c_void_p), ("chunk_n", C.c_void_p),
+        ("rev_slot", C.c_void_p), ("counter", C.c_void_p), ("tile_ticket", C.c_void_p),
+        ("HaDT", C.c_void_p), ("HbDT", C.c_void_p), ("P", C.c_void_p), ("part", C.c_void_p),
+    ]
+
+
+V2_COUNTS = 16
+
+
 class Operator(C.Structure):
     _fields_ = [
         ("a", SpinTable),
@@ -77,6 +97,7 @@ class Operator(C.Structure):
         ("bd", Sell),
         ("bb", Sell),
         ("throughput_mode", C.c_int),
+        ("v2", SigmaV2),
     ]
 
 
@@ -133,6 +154,7 @@ class SolveParams(C.Structure):
         ("row_begin", C.c_int), ("row_end", C.c_int),
         ("shard_rank", C.c_int), ("shard_world", C.c_int),
         ("throughput_mode", C.c_int),
+        ("sigma_path", C.c_int), ("v2_lmax", C.c_int), ("v2_items_per_chunk", C.c_int),
     ]
 
 
@@ -146,6 +168,7 @@ class SolveResult(C.Structure):
         ("nnz_a", C.c_int64), ("nnz_b", C.c_int64),
         ("singles_a", C.c_int64), ("singles_b", C.c_int64),
         ("ldc", C.c_int),
+        ("sigma_path", C.c_int),
     ]
 
 
@@ -180,6 +203,18 @@ SIGNATURES: dict[str, tuple] = {
         _i,
         [C.POINTER(SpinTable), C.POINTER(SpinTable), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
          _vp, _vp, _vp, _pi, _vp],
+    ),
+    "sqd_sigma_v2_recommended": (_i, [_i, _i, _i64, _i64]),
+    "sqd_sigma_v2_plan_bytes": (_i64, [_i, _i, _i64, _i64, _i, _i]),
+    "sqd_sigma_v2_plan": (
+        _i, [C.POINTER(SpinTable), C.POINTER(SpinTable), _i, _i64, _i64, _i, _i, _vp, _i64, _pi, _vp]
+    ),
+    "sqd_sigma_v2_counts_ptr": (_vp, [_vp, _i, _i, _i64, _i64, _i, _i]),
+    "sqd_sigma_v2_scratch_bytes": (_i64, [_pi, _i, _i, _i, _i, _i]),
+    "sqd_sigma_v2_finish": (
+        _i,
+        [C.POINTER(SpinTable), C.POINTER(SpinTable), _i, _i64, _i64, _i, _i, _pi, _vp, _vp, _i64, _i,
+         C.POINTER(SigmaV2), _vp],
     ),
     "sqd_davidson_workspace_bytes": (_i64, [_i, _i, _i]),
     "sqd_davidson": (

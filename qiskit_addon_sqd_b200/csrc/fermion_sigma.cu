@@ -872,6 +872,10 @@ static thread_local long long* g_prof = nullptr;
 
 int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
                         int row_begin, int row_end, cudaStream_t st);
+// v2 kernels (fermion_sigma2.cu)
+int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
+                         int row_begin, int row_end, cudaStream_t st);
+int64_t sigma2_smem_bytes(const sqd_operator* op);
 
 int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sigma,
                         const int* d_done, cudaStream_t st) {
@@ -880,6 +884,7 @@ int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sig
 
 int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
                         int row_begin, int row_end, cudaStream_t st) {
+    if (op->v2.enabled) return sigma2_dispatch_rows(op, d_c, d_sigma, d_done, row_begin, row_end, st);
     SigmaPlan pl;
     SQD_REQUIRE(op->ldc % 2 == 0 && op->ldg % 2 == 0 && op->ldc >= op->b.n,
                 "sqd_sigma: ldc/ldg must be even and ldc >= nb");
@@ -913,6 +918,7 @@ using namespace sqd;
 extern "C" {
 
 int64_t sqd_sigma_smem_bytes(const sqd_operator* op) {
+    if (op->v2.enabled) return sigma2_smem_bytes(op);
     SigmaPlan pl;
     if (!plan_sigma(op, &pl)) return -1;
     return (int64_t)pl.smem;

@@ -220,27 +220,55 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
         return -2;
     }
 
-    // ---- work plan and SELL copies (one synchronisation: their sizes) ----
-    const int cost = prm->cost_per_chunk > 0 ? prm->cost_per_chunk : 256;
-    const int long_thr = prm->long_threshold > 0 ? prm->long_threshold : 64;
-    const int max_chunks = 2 * na + (int)((16 * (int64_t)(Ta.nnz > 0 ? Ta.nnz : 1)) / cost) + 1;
-    int* chunk[4];
-    for (auto& c : chunk) c = P.get<int>(max_chunks);
-    int* split[3];
-    for (auto& c : split) c = P.get<int>(na);
-    int* long_idx = P.get<int>(nb);
-    int* long_cols = P.get<int>(SQD_MAX_LONG_COLUMNS);
-    int* counts = P.get<int>(8);
-    if (P.failed) return -2;
-    if (sqd_sigma_plan_build(&ta, &tb, cost, long_thr, max_chunks, chunk[0], chunk[1], chunk[2], chunk[3],
-                             split[0], split[1], split[2], long_idx, long_cols, counts, nullptr, st))
-        return -2;
-    SellBufs S0{}, S1{};
-    if (sell_launch(P, tb, Tb.nnz, 0, long_idx, &S0)) return -2;
-    if (sell_launch(P, tb, Tb.nnz, 1, nullptr, &S1)) return -2;
+    // ---- work plan of the sigma build (one synchronisation: its sizes) ----
+    // v2 kernels (fermion_sigma2.cu) when the tables are dense enough, else the v1 plan + SELL copies
+    bool use_v2 = prm->sigma_path == 2 ||
+                  (prm->sigma_path == 0 && sqd_sigma_v2_recommended(na, nb, Ta.nnz, Tb.nnz) != 0);
+    const int v2_lmax = prm->v2_lmax == 8 ? 8 : 16;
+    const int v2_ipc = prm->v2_items_per_chunk > 0 && prm->v2_items_per_chunk <= 32 ? prm->v2_items_per_chunk : 8;
     const int nsl = (nb + 31) / 32;
-    SQD_CUDA_OK(cudaMemcpyAsync(counts + 5, S0.slice_ptr + nsl, sizeof(int), cudaMemcpyDeviceToDevice, st));
-    SQD_CUDA_OK(cudaMemcpyAsync(counts + 6, S1.slice_ptr + nsl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    int* counts = P.get<int>(8 + SQD_V2_COUNTS);
+    if (P.failed) return -2;
+    int* chunk[4] = {};
+    int* split[3] = {};
+    int *long_idx = nullptr, *long_cols = nullptr;
+    SellBufs S0{}, S1{};
+    auto build_v1_plan = [&]() -> int {
+        const int cost = prm->cost_per_chunk > 0 ? prm->cost_per_chunk : 256;
+        const int long_thr = prm->long_threshold > 0 ? prm->long_threshold : 64;
+        const int max_chunks = 2 * na + (int)((16 * (int64_t)(Ta.nnz > 0 ? Ta.nnz : 1)) / cost) + 1;
+        for (auto& c : chunk) c = P.get<int>(max_chunks);
+        for (auto& c : split) c = P.get<int>(na);
+        long_idx = P.get<int>(nb);
+        long_cols = P.get<int>(SQD_MAX_LONG_COLUMNS);
+        if (P.failed) return -2;
+        if (sqd_sigma_plan_build(&ta, &tb, cost, long_thr, max_chunks, chunk[0], chunk[1], chunk[2], chunk[3],
+                                 split[0], split[1], split[2], long_idx, long_cols, counts, nullptr, st))
+            return -2;
+        if (sell_launch(P, tb, Tb.nnz, 0, long_idx, &S0)) return -2;
+        if (sell_launch(P, tb, Tb.nnz, 1, nullptr, &S1)) return -2;
+        SQD_CUDA_OK(cudaMemcpyAsync(counts + 5, S0.slice_ptr + nsl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        SQD_CUDA_OK(cudaMemcpyAsync(counts + 6, S1.slice_ptr + nsl, sizeof(int), cudaMemcpyDeviceToDevice, st));
+        return 0;
+    };
+    void* v2_plan = nullptr;
+    int64_t v2_plan_bytes = 0;
+    if (use_v2) {
+        v2_plan_bytes = sqd_sigma_v2_plan_bytes(na, nb, Ta.nnz, Tb.nnz, v2_lmax, v2_ipc);
+        v2_plan = v2_plan_bytes > 0 ? P.get<char>((size_t)v2_plan_bytes) : nullptr;
+        if (P.failed) return -2;
+        if (v2_plan == nullptr) {
+            use_v2 = false;
+        } else {
+            if (sqd_sigma_v2_plan(&ta, &tb, norb, Ta.nnz, Tb.nnz, v2_lmax, v2_ipc, v2_plan, v2_plan_bytes,
+                                  nullptr, st))
+                return -2;
+            SQD_CUDA_OK(cudaMemcpyAsync(
+                counts + 8, sqd_sigma_v2_counts_ptr(v2_plan, na, nb, Ta.nnz, Tb.nnz, v2_lmax, v2_ipc),
+                SQD_V2_COUNTS * sizeof(int), cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (!use_v2 && build_v1_plan()) return -2;
 
     // ---- operators: integrals, W tables and diagonals do not depend on the plan, so their kernels (and
     // the start vector) are enqueued BEFORE the host waits for the plan / SELL sizes ----
@@ -281,19 +309,40 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
         return -2;
     }
 
-    int hc[8];
-    if (read_back(hc, counts, 7 * sizeof(int), st)) return -2;  // hc[4] unused
-    double* part = P.get<double>((size_t)(hc[1] > 0 ? hc[1] : 1) * ldc);
-    if (P.failed) return -2;
-    const sqd_sigma_plan plan{hc[0], hc[1], hc[2], hc[3], chunk[0], chunk[1], chunk[2], chunk[3],
-                              split[0], split[1], split[2], long_idx, long_cols, part};
-    const sqd_sell bd{nsl, hc[5], S0.perm, S0.len, S0.slice_ptr, S0.pack, nullptr};
-    const sqd_sell bb{nsl, hc[6], S1.perm, S1.len, S1.slice_ptr, S1.pack, S1.val};
-    for (sqd_operator* o : {&base, &ham, &s2op}) {
-        o->plan = plan;
-        o->bd = bd;
-        o->bb = bb;
+    int hc[8 + SQD_V2_COUNTS];
+    if (read_back(hc, counts, sizeof(hc), st)) return -2;  // hc[4], hc[7] unused
+    if (use_v2 && hc[8 + 6] != 0) {
+        // the v2 planner refused the shape (a beta string with thousands of links, or too many strings
+        // for its single-CTA passes): the v1 kernels take over
+        use_v2 = false;
+        if (build_v1_plan()) return -2;
+        if (read_back(hc, counts, 8 * sizeof(int), st)) return -2;
     }
+    if (use_v2) {
+        const int same_tables = same ? 1 : 0;
+        const int64_t sb = sqd_sigma_v2_scratch_bytes(hc + 8, na, nb, ldc, 1, same_tables);
+        SQD_REQUIRE(sb > 0, "sqd_solve_subspace: bad v2 scratch size");
+        void* scratch2 = P.get<char>((size_t)sb);
+        if (P.failed) return -2;
+        sqd_sigma_v2 v2{};
+        if (sqd_sigma_v2_finish(&ta, &tb, ldc, Ta.nnz, Tb.nnz, v2_lmax, v2_ipc, hc + 8, v2_plan, scratch2, sb,
+                                1, &v2, st))
+            return -2;
+        for (sqd_operator* o : {&base, &ham, &s2op}) o->v2 = v2;
+    } else {
+        double* part = P.get<double>((size_t)(hc[1] > 0 ? hc[1] : 1) * ldc);
+        if (P.failed) return -2;
+        const sqd_sigma_plan plan{hc[0], hc[1], hc[2], hc[3], chunk[0], chunk[1], chunk[2], chunk[3],
+                                  split[0], split[1], split[2], long_idx, long_cols, part};
+        const sqd_sell bd{nsl, hc[5], S0.perm, S0.len, S0.slice_ptr, S0.pack, nullptr};
+        const sqd_sell bb{nsl, hc[6], S1.perm, S1.len, S1.slice_ptr, S1.pack, S1.val};
+        for (sqd_operator* o : {&base, &ham, &s2op}) {
+            o->plan = plan;
+            o->bd = bd;
+            o->bb = bb;
+        }
+    }
+    h_res->sigma_path = use_v2 ? 2 : 1;
 
     // ---- Davidson ----
     sqd_davidson_params dp{};

@@ -36,6 +36,9 @@ _DEFAULT_TOL = 1e-12
 # which a beta string's single-excitation list is reduced by a whole warp
 _SIGMA_COST_PER_CHUNK = int(__import__("os").environ.get("SQD_SIGMA_CHUNK_COST", "256"))
 _SIGMA_LONG_THRESHOLD = int(__import__("os").environ.get("SQD_SIGMA_LONG_THRESHOLD", "32"))
+# v2 sigma kernels: links per virtual column (8 or 16) and items (alpha excitations) per work unit
+_SIGMA_V2_LMAX = int(__import__("os").environ.get("SQD_V2_LMAX", "16"))
+_SIGMA_V2_ITEMS_PER_CHUNK = int(__import__("os").environ.get("SQD_V2_ITEMS_PER_CHUNK", "8"))
 _FIX_SPIN_DEFAULT_SHIFT = 0.2  # pyscf.fci.addons.fix_spin_ default, used by solve_sci (fermion.py:715)
 
 
@@ -301,11 +304,12 @@ class _OperatorDev:
             "sqd_opposite_spin_tables")
         if not with_w:
             self.Wb = None
+        v2 = sub.sigma_v2()
         self.struct = _lib.Operator(sub.ta.struct(), sub.tb.struct(), norb, ldc, ldg,
                                     _lib.ptr(self.diag), _lib.ptr(self.gab), _lib.ptr(self.Wa),
                                     _lib.ptr(self.Wb), 1 if same_spin else 0, sub.sigma_plan(),
-                                    sub.tb.sell(0, sub._plan_keep[2]), sub.tb.sell(1), 0)
-        self.uses_v2 = False
+                                    sub.tb.sell(0, sub._plan_keep[2]), sub.tb.sell(1), 0, v2)
+        self.uses_v2 = bool(v2.enabled)
         if lib.sqd_sigma_smem_bytes(C.byref(self.struct)) < 0:
             raise ValueError(
                 f"subspace shape (na={na}, nb={nb}, norb={norb}) exceeds the shared-memory row "
@@ -347,6 +351,7 @@ class _Subspace:
             _SpinTableDev(torch, lib, ub, ints, norb, self.device, strs_dev[1])
         self._ss_op = None
         self._plan = None
+        self._v2 = None
         self._scratch = torch.empty(4096, dtype=torch.float64, device=self.device)
         self._scalar = torch.empty(8, dtype=torch.float64, device=self.device)
 
@@ -378,6 +383,43 @@ class _Subspace:
                                     *[_lib.ptr(t) for t in split], _lib.ptr(long_idx),
                                     _lib.ptr(long_cols), _lib.ptr(part))
         return self._plan
+
+    def sigma_v2(self) -> _lib.SigmaV2:
+        """Tables of the v2 sigma kernels (``csrc/fermion_sigma2.cu``); built once.  ``sigma_path``:
+        ``"v1"`` never, ``"v2"`` whenever the shape is supported, ``"auto"`` by the library's density rule."""
+        if self._v2 is not None:
+            return self._v2
+        torch, lib = self.torch, self.lib
+        na, nb = self.na, self.nb
+        nnz_a, nnz_b = self.ta.nnz, self.tb.nnz
+        want = self.sigma_path == "v2" or (
+            self.sigma_path == "auto" and lib.sqd_sigma_v2_recommended(na, nb, nnz_a, nnz_b))
+        self._v2 = _lib.SigmaV2()
+        if not want:
+            return self._v2
+        lmax, ipc = int(_SIGMA_V2_LMAX), int(_SIGMA_V2_ITEMS_PER_CHUNK)
+        pbytes = int(lib.sqd_sigma_v2_plan_bytes(na, nb, nnz_a, nnz_b, lmax, ipc))
+        if pbytes < 0:
+            return self._v2
+        plan = torch.empty(pbytes, dtype=torch.uint8, device=self.device)
+        counts = (C.c_int * _lib.V2_COUNTS)()
+        ta, tb = self.ta.struct(), self.tb.struct()
+        st = _lib.stream_ptr(torch)
+        _lib.check(lib.sqd_sigma_v2_plan(C.byref(ta), C.byref(tb), self.norb, nnz_a, nnz_b, lmax, ipc,
+                                         _lib.ptr(plan), pbytes, counts, st), "sqd_sigma_v2_plan")
+        same = 1 if self.tb is self.ta else 0
+        sbytes = int(lib.sqd_sigma_v2_scratch_bytes(counts, na, nb, self.ldc, 1, same))
+        if sbytes < 0:   # shape the v2 planner does not support: v1 stays the product path
+            return self._v2
+        scratch = torch.empty(sbytes, dtype=torch.uint8, device=self.device)
+        v2 = _lib.SigmaV2()
+        _lib.check(lib.sqd_sigma_v2_finish(C.byref(ta), C.byref(tb), self.ldc, nnz_a, nnz_b, lmax, ipc,
+                                           counts, _lib.ptr(plan), _lib.ptr(scratch), sbytes, 1,
+                                           C.byref(v2), st), "sqd_sigma_v2_finish")
+        self._v2_keep = (plan, scratch)
+        self.v2_counts = [int(c) for c in counts]
+        self._v2 = v2
+        return v2
 
     def __enter__(self):
         return self
