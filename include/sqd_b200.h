@@ -142,45 +142,45 @@ typedef struct {
 } sqd_sell;
 
 /* ---- sigma build, second generation ("v2", csrc/fermion_sigma2.cu) ---------------------------
- * Two kernels per build instead of three, chosen when the in-set connectivity is dense enough:
+ * Three kernels per build, chosen when the in-set connectivity is dense enough:
  *   K1  opposite-spin part, grouped by SOURCE alpha string a': a thread owns one "virtual column" (at
  *       most `lmax` beta single excitations of one beta string), gathers x_j = sgn_j c[a', b'_j] into
  *       REGISTERS once per chunk of a' and then, for every alpha single excitation a' -> a (integral row
  *       g_ab[pq,:] staged by the bulk-copy engine through an mbarrier ring), does one shared-memory gather
- *       and one FMA per link; the row of results goes to P[item] (item = (a', link) pair).
- *   K2  64x64 output tiles: same-spin part as dense FP64 tiles  sigma += HaD C + C HbD^T  (K split over
- *       CTAs, partials summed in a fixed order by the last CTA of a tile), then the epilogue adds
- *       diag*c, the P rows of the tile's alpha links and the sgn*Wb[pq,b]*c[a',b] terms.
- * Every element of sigma is still produced in a fixed order (bit-reproducible).
+ *       and one FMA per link; the result goes to P[row of (a <- a')][segment of the beta string].  Warps
+ *       never synchronise with each other, only with the ring.
+ *   K2  64x64 output tiles of the same-spin part as dense FP64 products  HaD C + C HbD^T, K split over
+ *       CTAs into partial tiles.
+ *   K3  sigma = partial tiles (fixed order) + diag*c + the P rows of the row's excitations (contiguous:
+ *       P is ordered by TARGET string) + the sgn*Wb[pq,b]*c[a',b] terms.
+ * Every element of sigma is produced in a fixed order (bit-reproducible).
  * All arrays are device pointers into caller-owned memory (sqd_sigma_v2_plan / sqd_sigma_v2_finish). */
 typedef struct {
     int enabled;             /* 0: v1 kernels; 1: v2 */
     int lmax;                /* links per virtual column: 8 or 16 */
-    int n_groups;            /* column groups (K1 grid.y); a beta string's virtual columns share a group */
+    int n_groups;            /* column groups (K1 grid.y) */
     int vc_pad;              /* K1 consumer threads = virtual columns per group, padded to 32 */
     int n_items;             /* rows of P: na self items + alpha single excitations */
     int n_chunks;            /* K1 work units (source string, <= items_per_chunk items) */
     int max_split;           /* capacity of `part` in K splits */
     int lda, ldb;            /* row strides of HaDT / HbDT */
+    int ldp, ldq;            /* row stride of P = ldq (q-part: one column per beta-string segment, padded) +
+                                w-part (one column per beta string: the sgn*Wb[pq,b]*c[a',b] term), padded */
     const uint32_t* vc_src;  /* [n_groups][lmax][vc_pad] source column b' | sign << 31 */
     const uint32_t* vc_off;  /* [n_groups][lmax][vc_pad] byte offset 8*rs into an integral row (pad: zero slot) */
     const int* vc_len;       /* [n_groups][vc_pad] */
-    const int* grp_ncol;     /* [n_groups] beta strings with links in the group */
-    const int* gcol;         /* [n_groups][vc_pad] beta string of the u-th column of the group (ascending) */
-    const int* gcol_full;    /* [n_groups][vc_pad] first full virtual column of that string */
-    const int* gcol_nfull;   /* [n_groups][vc_pad] number of full virtual columns */
-    const int* gcol_rem;     /* [n_groups][vc_pad] its remainder virtual column or -1 */
+    const int* vc_q;         /* [n_groups][vc_pad] column of P the virtual column writes, or -1 */
+    const int* col_seg;      /* [nb+1] first P column of beta string b (its segments are adjacent) */
     const int* single_ptr;   /* [na+1] exclusive scan of a.n_single */
-    const int* item_ptr;     /* [na+1] single_ptr[a] + a: P row of a's self item; its k-th single follows at +1+k */
-    const int* chunk_row;    /* [n_chunks] source alpha string, chunks sorted by descending size */
-    const int* chunk_first;  /* [n_chunks] first item of the chunk (0 = self item) */
-    const int* chunk_n;      /* [n_chunks] */
-    const int* rev_slot;     /* [singles_a] P row written for the reverse link of single_ptr[a]+k */
-    int* counter;            /* [128] K1 work counters / exit tickets per group (self-resetting) */
-    int* tile_ticket;        /* [tiles] K2 split-K arrival counters (self-resetting) */
+    const int* item_ptr;     /* [na+1] single_ptr[a] + a: P row of a's self item; the row fed by its k-th
+                                single excitation (source a.col[k], target a) follows at +1+k */
+    const int* chunk_rec;    /* [n_chunks][4] {source alpha string, first item, items, 0}; sorted by descending size */
+    const int* item_tgt;     /* [n_items] (source order) target alpha string of the item */
+    const uint32_t* item_gsel; /* [n_items] integral row pq of source -> target | sign << 31; bit 30: self item (row of Wa) */
+    const int* item_pslot;   /* [n_items] (source order) P row the item writes */
     const double* HaDT;      /* [lda*lda] dense same-spin alpha block, transposed: HaDT[a'*lda + a] */
     const double* HbDT;      /* [ldb*ldb] */
-    double* P;               /* [n_items * ldc] */
+    double* P;               /* [n_items * ldp] */
     double* part;            /* [max_split * na * ldc] */
 } sqd_sigma_v2;
 
@@ -205,7 +205,8 @@ typedef struct {
  * Step 1, sqd_sigma_v2_plan: everything that only needs the tables.  d_plan: sqd_sigma_v2_plan_bytes(...)
  *   bytes; h_counts: int[16] -- when not NULL the stream is synchronised and the counts are returned
  *   (a caller that reads d_counts itself passes NULL): [0] n_items, [1] n_chunks, [2] n_groups, [3] vc_pad,
- *   [4] alpha singles, [5] beta singles, [6] error flag (!= 0: shape unsupported, use v1).
+ *   [4] alpha singles, [5] beta singles, [6] error flag (!= 0: shape unsupported, use v1), [7] virtual
+ *   columns, [8] P columns.
  * Step 2, sqd_sigma_v2_finish: dense blocks, zeroed P, the struct.  d_scratch: sqd_sigma_v2_scratch_bytes
  *   bytes.  dense != 0 builds HaDT/HbDT (needed by Hamiltonian-like operators, not by S^2 alone). */
 #define SQD_V2_COUNTS 16

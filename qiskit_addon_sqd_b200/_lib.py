@@ -67,13 +67,11 @@ class SigmaV2(C.Structure):
     _fields_ = [
         ("enabled", C.c_int), ("lmax", C.c_int), ("n_groups", C.c_int), ("vc_pad", C.c_int),
         ("n_items", C.c_int), ("n_chunks", C.c_int), ("max_split", C.c_int),
-        ("lda", C.c_int), ("ldb", C.c_int),
-        ("vc_src", C.c_void_p), ("vc_off", C.c_void_p), ("vc_len", C.c_void_p),
-        ("grp_ncol", C.c_void_p), ("gcol", C.c_void_p), ("gcol_full", C.c_void_p),
-        ("gcol_nfull", C.c_void_p), ("gcol_rem", C.c_void_p),
-        ("single_ptr", C.c_void_p), ("item_ptr", C.c_void_p),
-        ("chunk_row", C.c_void_p), ("chunk_first", C.c_void_p), ("chunk_n", C.c_void_p),
-        ("rev_slot", C.c_void_p), ("counter", C.c_void_p), ("tile_ticket", C.c_void_p),
+        ("lda", C.c_int), ("ldb", C.c_int), ("ldp", C.c_int), ("ldq", C.c_int),
+        ("vc_src", C.c_void_p), ("vc_off", C.c_void_p), ("vc_len", C.c_void_p), ("vc_q", C.c_void_p),
+        ("col_seg", C.c_void_p), ("single_ptr", C.c_void_p), ("item_ptr", C.c_void_p),
+        ("chunk_rec", C.c_void_p), ("item_tgt", C.c_void_p), ("item_gsel", C.c_void_p),
+        ("item_pslot", C.c_void_p),
         ("HaDT", C.c_void_p), ("HbDT", C.c_void_p), ("P", C.c_void_p), ("part", C.c_void_p),
     ]
 

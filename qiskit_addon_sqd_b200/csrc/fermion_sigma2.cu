@@ -5,17 +5,18 @@
 //
 //   sigma[a,b] = diag[a,b] c[a,b]
 //              + sum_{a'} Ha[a,a'] c[a',b] + sum_{b'} Hb[b,b'] c[a,b']              dense FP64 tiles   (K2)
-//              + sum_{a' in S_a(a)} sgn_a Wb[pq,b] c[a',b]                           epilogue           (K2)
-//              + P[self(a)][b] + sum_{a' in S_a(a)} P[link(a' -> a)][b]              epilogue           (K2)
+//              + sum_{a' in S_a(a)} sgn_a Wb[pq,b] c[a',b]                           epilogue           (K3)
+//              + sum over the P rows of a (self item + one per a' in S_a(a)), segments of b   epilogue (K3)
 //   P[self(a')][b]     =         sum_{j in S_b(b)} sgn_j Wa[a', rs_j]   c[a', b'_j]                      (K1)
-//   P[link(a'->a)][b]  = sgn_a   sum_{j in S_b(b)} sgn_j g_ab[pq, rs_j] c[a', b'_j]                      (K1)
+//   P[row(a <- a')][b] = sgn_a   sum_{j in S_b(b)} sgn_j g_ab[pq, rs_j] c[a', b'_j]                      (K1)
 //
 // Why: in the v1 kernel every FMA of the opposite-spin part costs three shared-memory reads (link word,
-// c[a',b'_j], g_ab[pq,rs_j]).  Grouping the work by SOURCE string a' makes x_j = sgn_j c[a',b'_j] a constant
-// of the thread for all excitations out of a', so it lives in registers together with the byte offsets of
-// rs_j: one gather and one FMA per link.  The price is that the result rows have to travel through memory
-// (P, L2 resident) because several source strings feed one row of sigma.  The same-spin part of a
-// HF-centred sample set is 15-25 % dense, where dense FP64 tiles beat gathers by a wide margin.
+// c[a',b'_j], g_ab[pq,rs_j]) and all warps of a CTA march in step.  Grouping the work by SOURCE string a'
+// makes x_j = sgn_j c[a',b'_j] a constant of the thread for all excitations out of a', so it lives in
+// registers together with the byte offsets of rs_j: one gather and one FMA per link, and a warp needs
+// nothing from the other warps of its CTA.  The price is that the result rows travel through memory (P, L2
+// resident) because several source strings feed one row of sigma.  The same-spin part of a HF-centred
+// sample set is 15-25 % dense, where dense FP64 tiles beat gathers by a wide margin.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -25,19 +26,19 @@ namespace sqd {
 
 constexpr int kV2MaxGroups = 64;
 constexpr int kV2MaxStages = 8;
-constexpr int kV2GroupTarget = 288;   // virtual columns per group aimed at
-constexpr int kV2GroupMax = 352;      // hard limit (K1 runs vc_pad + 32 threads, launch bound 384)
-enum { C_NITEMS = 0, C_NCHUNKS, C_NGROUPS, C_VCPAD, C_SINGLES_A, C_SINGLES_B, C_ERR, C_NVC, C_NCOLMAX };
+constexpr int kV2GroupTarget = 416;   // virtual columns per group aimed at
+constexpr int kV2GroupMax = 480;      // hard limit (K1 runs vc_pad + 32 <= 512 threads)
+constexpr uint32_t kSelfItem = 0x40000000u;
+enum { C_NITEMS = 0, C_NCHUNKS, C_NGROUPS, C_VCPAD, C_SINGLES_A, C_SINGLES_B, C_ERR, C_NVC, C_NQ };
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // device-memory layout of the plan (byte offsets); every array is sized by upper bounds that are known
 // on the host before the plan kernels run
 struct V2Layout {
-    size_t single_ptr, item_ptr, chunk_row, chunk_first, chunk_n, rev_slot;
-    size_t col_grp, col_u, col_full, col_nfull, col_rem;
-    size_t grp_ncol, vc_src, vc_off, vc_len, gcol, gcol_full, gcol_nfull, gcol_rem;
-    size_t counter, counts, total;
+    size_t single_ptr, item_ptr, chunk_rec, item_tgt, item_gsel, item_pslot;
+    size_t col_grp, col_full, col_nfull, col_rem, col_seg;
+    size_t vc_src, vc_off, vc_len, vc_q, counts, total;
     int maxch, capw;
 };
 
@@ -49,29 +50,25 @@ static V2Layout v2_layout(int na, int nb, int64_t nnz_a, int64_t nnz_b, int lmax
         o += al256(bytes);
         return at;
     };
+    const size_t items = (size_t)na + (size_t)(nnz_a > 0 ? nnz_a : 1);
     L.maxch = (int)(na + (na + nnz_a) / ipc + 1);
     // virtual columns: sum_b ceil(len_b / lmax) <= nb + singles_b / lmax; groups add padding
     L.capw = (int)(2 * ((int64_t)nb + nnz_b / lmax) + kV2MaxGroups * 64 + 64);
     L.single_ptr = take((size_t)(na + 1) * 4);
     L.item_ptr = take((size_t)(na + 1) * 4);
-    L.chunk_row = take((size_t)L.maxch * 4);
-    L.chunk_first = take((size_t)L.maxch * 4);
-    L.chunk_n = take((size_t)L.maxch * 4);
-    L.rev_slot = take((size_t)(nnz_a > 0 ? nnz_a : 1) * 4);
+    L.chunk_rec = take((size_t)L.maxch * 16);
+    L.item_tgt = take(items * 4);
+    L.item_gsel = take(items * 4);
+    L.item_pslot = take(items * 4);
     L.col_grp = take((size_t)nb * 4);
-    L.col_u = take((size_t)nb * 4);
     L.col_full = take((size_t)nb * 4);
     L.col_nfull = take((size_t)nb * 4);
     L.col_rem = take((size_t)nb * 4);
-    L.grp_ncol = take((size_t)kV2MaxGroups * 4);
+    L.col_seg = take((size_t)(nb + 1) * 4);
     L.vc_src = take((size_t)L.capw * lmax * 4);
     L.vc_off = take((size_t)L.capw * lmax * 4);
     L.vc_len = take((size_t)L.capw * 4);
-    L.gcol = take((size_t)L.capw * 4);
-    L.gcol_full = take((size_t)L.capw * 4);
-    L.gcol_nfull = take((size_t)L.capw * 4);
-    L.gcol_rem = take((size_t)L.capw * 4);
-    L.counter = take((size_t)2 * kV2MaxGroups * 4);
+    L.vc_q = take((size_t)L.capw * 4);
     L.counts = take((size_t)SQD_V2_COUNTS * 4);
     L.total = o;
     return L;
@@ -106,12 +103,11 @@ __device__ __forceinline__ int block_excl_scan(int v, int* warp_tot, int* total)
     return (warp == 0 ? 0 : warp_tot[warp - 1]) + s - v;
 }
 
-// alpha side: item numbering and the chunk list, sorted by descending size (heaviest work units first:
-// the CTAs of K1 pull chunks from a counter)
+// alpha side: item numbering and the chunk list, sorted by descending size (the CTAs of K1 take chunks
+// round robin, so every CTA gets one chunk of each size rank)
 __global__ void __launch_bounds__(1024)
 v2_alpha_plan_kernel(const sqd_spin_table A, int ipc, int maxch, int* __restrict__ single_ptr,
-                     int* __restrict__ item_ptr, int* __restrict__ chunk_row,
-                     int* __restrict__ chunk_first, int* __restrict__ chunk_n, int* __restrict__ counts) {
+                     int* __restrict__ item_ptr, int4* __restrict__ chunk_rec, int* __restrict__ counts) {
     __shared__ int warp_tot[32];
     const int na = A.n;
     int carry = 0, tot = 0;
@@ -136,9 +132,10 @@ v2_alpha_plan_kernel(const sqd_spin_table A, int ipc, int maxch, int* __restrict
     for (int cls = ipc; cls >= 1; --cls) {
         for (int base = 0; base < na; base += blockDim.x) {
             const int a = base + threadIdx.x;
-            int cnt = 0, nch = 0, last = 0;
+            int cnt = 0, nch = 0, last = 0, ip = 0;
             if (a < na) {
                 const int T = 1 + A.n_single[a];
+                ip = item_ptr[a];  // written by this very thread above
                 nch = (T + ipc - 1) / ipc;
                 last = T - (nch - 1) * ipc;
                 cnt = (cls == ipc ? nch - 1 : 0) + (last == cls ? 1 : 0);
@@ -147,19 +144,10 @@ v2_alpha_plan_kernel(const sqd_spin_table A, int ipc, int maxch, int* __restrict
             if (a < na && cnt > 0) {
                 int at = pos + ex;
                 if (cls == ipc) {
-                    for (int j = 0; j < nch - 1; ++j, ++at) {
-                        if (at < maxch) {
-                            chunk_row[at] = a;
-                            chunk_first[at] = j * ipc;
-                            chunk_n[at] = ipc;
-                        }
-                    }
+                    for (int j = 0; j < nch - 1; ++j, ++at)
+                        if (at < maxch) chunk_rec[at] = make_int4(a, ip + j * ipc, ipc, 0);
                 }
-                if (last == cls && at < maxch) {
-                    chunk_row[at] = a;
-                    chunk_first[at] = (nch - 1) * ipc;
-                    chunk_n[at] = last;
-                }
+                if (last == cls && at < maxch) chunk_rec[at] = make_int4(a, ip + (nch - 1) * ipc, last, 0);
             }
             pos += tot;
         }
@@ -170,17 +158,26 @@ v2_alpha_plan_kernel(const sqd_spin_table A, int ipc, int maxch, int* __restrict
     }
 }
 
-// P row of the reverse link: entry k of row a points at a'; the link a -> a' (source a, target a') is
-// entry k' of row a' with col == a, so the opposite-spin result of source a' for target a sits in row
+// Per-item arrays in SOURCE order (what K1's producer reads).  Entry k of row a points at partner a'; seen
+// from the source a that is the excitation a -> a' (row `a` stores E_pq a' = a, so a -> a' is E_qp), and its
+// result belongs to the P row of TARGET a' that corresponds to a'-s own entry for partner a:
 // item_ptr[a'] + 1 + k'.  One warp per row, lanes over its single excitations.
-__global__ void v2_rev_slot_kernel(const sqd_spin_table A, const int* __restrict__ single_ptr,
-                                   const int* __restrict__ item_ptr, int* __restrict__ rev_slot) {
+__global__ void v2_item_kernel(const sqd_spin_table A, int norb, const int* __restrict__ item_ptr,
+                               int* __restrict__ item_tgt, uint32_t* __restrict__ item_gsel,
+                               int* __restrict__ item_pslot) {
     const int lane = threadIdx.x & 31;
     const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (a >= A.n) return;
-    const int beg = A.row_ptr[a], ns = A.n_single[a], sp = single_ptr[a];
+    const int beg = A.row_ptr[a], ns = A.n_single[a], ip = item_ptr[a];
+    if (lane == 0) {
+        item_tgt[ip] = a;
+        item_gsel[ip] = kSelfItem;
+        item_pslot[ip] = ip;
+    }
     for (int k = lane; k < ns; k += 32) {
         const int ap = (int)A.col[beg + k];
+        const uint32_t m = A.meta[beg + k];
+        const int pq = (int)(m & 0x7fffffffu), p = pq / norb, q = pq - p * norb;
         const int pb = A.row_ptr[ap];
         int lo = 0, hi = A.n_single[ap] - 1, found = 0;
         while (lo <= hi) {  // singles of a row are sorted by partner index
@@ -192,35 +189,52 @@ __global__ void v2_rev_slot_kernel(const sqd_spin_table A, const int* __restrict
             }
             if (v < a) lo = mid + 1; else hi = mid - 1;
         }
-        rev_slot[sp + k] = item_ptr[ap] + 1 + found;
+        item_tgt[ip + 1 + k] = ap;
+        item_gsel[ip + 1 + k] = (uint32_t)(q * norb + p) | (m & 0x80000000u);
+        item_pslot[ip + 1 + k] = item_ptr[ap] + 1 + found;
     }
 }
 
 // beta side: cut every string's single-excitation list into virtual columns of at most lmax links, deal
 // the strings to groups (round robin over the length-sorted order), and number the virtual columns of a
 // group: full ones first (strings in rank order), then the remainders by descending length, so that the
-// 32 threads of a warp run (almost) the same trip count.  Single CTA; O(nb^2 / 1024) compares per thread.
+// 32 threads of a warp run (almost) the same trip count.  The P column of a virtual column is
+// col_seg[b] + its segment number: segments of a string are adjacent and strings keep their natural order,
+// which is what lets the epilogue read P with (nearly) coalesced loads.
+// Single CTA; O(nb^2 / 1024) compares per thread.
 __global__ void __launch_bounds__(1024)
 v2_beta_plan_kernel(const sqd_spin_table B, int lmax, int capw, int* __restrict__ col_grp,
-                    int* __restrict__ col_u, int* __restrict__ col_full, int* __restrict__ col_nfull,
-                    int* __restrict__ col_rem, int* __restrict__ grp_ncol, int* __restrict__ counts) {
+                    int* __restrict__ col_full, int* __restrict__ col_nfull, int* __restrict__ col_rem,
+                    int* __restrict__ col_seg, int* __restrict__ counts) {
     extern __shared__ int bp_smem[];
     __shared__ int warp_tot[32];
-    __shared__ int g_nfull[kV2MaxGroups], g_nrem[kV2MaxGroups], g_ncol[kV2MaxGroups];
+    __shared__ int g_nfull[kV2MaxGroups], g_nrem[kV2MaxGroups];
     __shared__ int s_G, s_ok;
     const int nb = B.n;
     int* L = bp_smem;          // [nb] list length
     int* rk = L + nb;          // [nb] rank of the string (length descending, index ascending)
     int* by_rank = rk + nb;    // [nb]
-    int nvc = 0, nz = 0, sb = 0;
-    for (int b = threadIdx.x; b < nb; b += blockDim.x) {
-        const int l = B.n_single[b];
-        L[b] = l;
-        nvc += (l + lmax - 1) / lmax;
+    int nvc = 0, nz = 0, sb = 0, carry = 0, tot = 0;
+    for (int base = 0; base < nb; base += blockDim.x) {
+        const int b = base + threadIdx.x;
+        const int l = b < nb ? B.n_single[b] : 0;
+        const int nseg = (l + lmax - 1) / lmax;
+        if (b < nb) L[b] = l;
+        nvc += nseg;
         nz += l > 0;
         sb += l;
+        const int ex = block_excl_scan(nseg, warp_tot, &tot);
+        if (b < nb) col_seg[b] = carry + ex;
+        carry += tot;
     }
-    int tot;
+    if (threadIdx.x == 0) col_seg[nb] = carry;
+    __syncthreads();
+    // the epilogue keeps the P columns of 32 consecutive beta strings in registers: at most 128 of them
+    int wide = 0;
+    for (int b0 = 32 * threadIdx.x; b0 < nb; b0 += 32 * blockDim.x)
+        wide |= col_seg[min(b0 + 32, nb)] - col_seg[b0] > 128;
+    block_excl_scan(wide, warp_tot, &tot);
+    const int too_wide = tot;
     block_excl_scan(nvc, warp_tot, &tot);
     nvc = tot;
     block_excl_scan(nz, warp_tot, &tot);
@@ -242,6 +256,8 @@ v2_beta_plan_kernel(const sqd_spin_table B, int lmax, int capw, int* __restrict_
     // number of groups: smallest G >= nvc / target whose largest group fits the CTA
     if (threadIdx.x == 0) {
         s_G = nvc > 0 ? (nvc + kV2GroupTarget - 1) / kV2GroupTarget : 1;
+        // a group also owns nb / G natural columns for the Wb terms, one per thread
+        if (s_G < (nb + kV2GroupMax - 1) / kV2GroupMax) s_G = (nb + kV2GroupMax - 1) / kV2GroupMax;
         if (s_G > kV2MaxGroups) s_G = kV2MaxGroups;
         s_ok = 0;
     }
@@ -250,16 +266,14 @@ v2_beta_plan_kernel(const sqd_spin_table B, int lmax, int capw, int* __restrict_
         const int G = s_G;
         if (threadIdx.x < G) {
             const int g = threadIdx.x;
-            int nfull = 0, nrem = 0, ncol = 0;
+            int nfull = 0, nrem = 0;
             for (int r = g; r < nz; r += G) {
                 const int l = L[by_rank[r]];
                 nfull += l / lmax;
                 nrem += (l % lmax) != 0;
-                ++ncol;
             }
             g_nfull[g] = nfull;
             g_nrem[g] = nrem;
-            g_ncol[g] = ncol;
         }
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -288,7 +302,6 @@ v2_beta_plan_kernel(const sqd_spin_table B, int lmax, int capw, int* __restrict_
         const int l = L[b], r = rk[b];
         if (l == 0) {
             col_grp[b] = -1;
-            col_u[b] = 0;
             col_full[b] = 0;
             col_nfull[b] = 0;
             col_rem[b] = -1;
@@ -296,40 +309,32 @@ v2_beta_plan_kernel(const sqd_spin_table B, int lmax, int capw, int* __restrict_
         }
         const int g = r % G, rem = l % lmax;
         // remainder rank inside the group: longer remainders first, ties in rank order
-        int rr = 0, u = 0;
+        int rr = 0;
         for (int r2 = g; r2 < nz; r2 += G) {
-            const int b2 = by_rank[r2];
-            const int rem2 = L[b2] % lmax;
+            const int rem2 = L[by_rank[r2]] % lmax;
             rr += (rem2 > rem) || (rem2 == rem && r2 < r);
-            u += b2 < b;
         }
         col_grp[b] = g;
-        col_u[b] = u;
         col_nfull[b] = l / lmax;
         col_rem[b] = rem ? g_nfull[g] + rr : -1;
     }
-    if (threadIdx.x < kV2MaxGroups) grp_ncol[threadIdx.x] = threadIdx.x < G ? g_ncol[threadIdx.x] : 0;
     if (threadIdx.x == 0) {
-        int mx = 0, mc = 0;
-        for (int g = 0; g < G; ++g) {
-            mx = max(mx, g_nfull[g] + g_nrem[g]);
-            mc = max(mc, g_ncol[g]);
-        }
-        const int vc_pad = max(32, (mx + 31) / 32 * 32);
+        int mx = 0;
+        for (int g = 0; g < G; ++g) mx = max(mx, g_nfull[g] + g_nrem[g]);
+        const int wcols = (nb + G - 1) / G;
+        const int vc_pad = max(32, (max(mx, wcols) + 31) / 32 * 32);
         counts[C_NGROUPS] = G;
         counts[C_VCPAD] = vc_pad;
         counts[C_SINGLES_B] = sb;
         counts[C_NVC] = nvc;
-        counts[C_NCOLMAX] = mc;
-        if (s_ok != 1 || (long long)G * vc_pad > capw) counts[C_ERR] = 1;
+        counts[C_NQ] = nvc;  // one P column per virtual column
+        if (s_ok != 1 || (long long)G * vc_pad > capw || too_wide != 0 || vc_pad > kV2GroupMax) counts[C_ERR] = 1;
     }
 }
 
-__global__ void v2_vc_init_kernel(const int* __restrict__ counts, int lmax, int capw, uint32_t zero_off,
-                                  uint32_t* __restrict__ vc_src, uint32_t* __restrict__ vc_off,
-                                  int* __restrict__ vc_len, int* __restrict__ gcol,
-                                  int* __restrict__ gcol_full, int* __restrict__ gcol_nfull,
-                                  int* __restrict__ gcol_rem) {
+__global__ void v2_vc_init_kernel(int lmax, int capw, uint32_t zero_off, uint32_t* __restrict__ vc_src,
+                                  uint32_t* __restrict__ vc_off, int* __restrict__ vc_len,
+                                  int* __restrict__ vc_q) {
     const int64_t n = (int64_t)capw * lmax;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -337,22 +342,18 @@ __global__ void v2_vc_init_kernel(const int* __restrict__ counts, int lmax, int 
         vc_off[i] = zero_off;
         if (i < capw) {
             vc_len[i] = 0;
-            gcol[i] = -1;
-            gcol_full[i] = 0;
-            gcol_nfull[i] = 0;
-            gcol_rem[i] = -1;
+            vc_q[i] = -1;
         }
     }
 }
 
 // one warp per beta string: scatter its links into the virtual-column arrays of its group
 __global__ void v2_vc_fill_kernel(const sqd_spin_table B, const int* __restrict__ counts, int lmax,
-                                  const int* __restrict__ col_grp, const int* __restrict__ col_u,
-                                  const int* __restrict__ col_full, const int* __restrict__ col_nfull,
-                                  const int* __restrict__ col_rem, uint32_t* __restrict__ vc_src,
+                                  const int* __restrict__ col_grp, const int* __restrict__ col_full,
+                                  const int* __restrict__ col_nfull, const int* __restrict__ col_rem,
+                                  const int* __restrict__ col_seg, uint32_t* __restrict__ vc_src,
                                   uint32_t* __restrict__ vc_off, int* __restrict__ vc_len,
-                                  int* __restrict__ gcol, int* __restrict__ gcol_full,
-                                  int* __restrict__ gcol_nfull, int* __restrict__ gcol_rem) {
+                                  int* __restrict__ vc_q) {
     if (counts[C_ERR] != 0) return;
     const int lane = threadIdx.x & 31;
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -361,7 +362,7 @@ __global__ void v2_vc_fill_kernel(const sqd_spin_table B, const int* __restrict_
     if (g < 0) return;
     const int vc_pad = counts[C_VCPAD];
     const int beg = B.row_ptr[b], l = B.n_single[b];
-    const int full0 = col_full[b], nfull = col_nfull[b], rem = col_rem[b];
+    const int full0 = col_full[b], nfull = col_nfull[b], rem = col_rem[b], q0 = col_seg[b];
     for (int k = lane; k < l; k += 32) {
         const uint32_t pk = B.pack[beg + k];
         const int seg = k / lmax, j = k - seg * lmax;
@@ -371,13 +372,14 @@ __global__ void v2_vc_fill_kernel(const sqd_spin_table B, const int* __restrict_
         vc_off[at] = ((pk >> 19) & 0xfffu) * 8u;
     }
     if (lane == 0) {
-        for (int s = 0; s < nfull; ++s) vc_len[g * vc_pad + full0 + s] = lmax;
-        if (rem >= 0) vc_len[g * vc_pad + rem] = l - nfull * lmax;
-        const int u = g * vc_pad + col_u[b];
-        gcol[u] = b;
-        gcol_full[u] = full0;
-        gcol_nfull[u] = nfull;
-        gcol_rem[u] = rem;
+        for (int s = 0; s < nfull; ++s) {
+            vc_len[g * vc_pad + full0 + s] = lmax;
+            vc_q[g * vc_pad + full0 + s] = q0 + s;
+        }
+        if (rem >= 0) {
+            vc_len[g * vc_pad + rem] = l - nfull * lmax;
+            vc_q[g * vc_pad + rem] = q0 + nfull;
+        }
     }
 }
 
@@ -425,24 +427,58 @@ __device__ __forceinline__ void v2_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// stage header: x = type (0 exit, 1 new source string, 2 item), y = P row, z = sign, w = source string
-template <int LMAX>
-__global__ void __launch_bounds__(384, 2)
-sigma2_ab_kernel(const V2Args P, const int NST) {
+// dot product of the first N links: the gathers are issued in batches of BATCH before their FMAs (16 in
+// flight cost 16 more registers than 8 and push the kernel over the budget that lets the dense tile kernel
+// share the SM: the LEAN instance uses 8), four interleaved partial sums keep the FP64 FMA latency off the
+// critical path
+template <int N, int LMAX, int BATCH>
+__device__ __forceinline__ double v2_dot(const double (&x)[LMAX], const uint32_t (&off)[LMAX],
+                                         const char* G) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int j0 = 0; j0 < N; j0 += BATCH) {
+        double gv[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j)
+            if (j0 + j < N) gv[j] = *reinterpret_cast<const double*>(G + off[j0 + j]);
+#pragma unroll
+        for (int j = 0; j < BATCH; j += 4) {
+            if (j0 + j < N) {
+                a0 = fma(x[j0 + j], gv[j], a0);
+                a1 = fma(x[j0 + j + 1], gv[j + 1], a1);
+                a2 = fma(x[j0 + j + 2], gv[j + 2], a2);
+                a3 = fma(x[j0 + j + 3], gv[j + 3], a3);
+            }
+        }
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+
+// stage header: x = type (0 exit, 1 new source string, 2 item, 3 self item), y = P row, z = sign,
+// w = source string.  A type-1 stage carries the row c[a',:] (bulk copy) when `src_smem` is set, so that
+// the gather of x_j = sgn_j c[a', b'_j] hits shared memory and its L2 latency hides behind the ring like
+// the integral rows'.  A type-2 stage carries g_ab[pq,:] and, behind it, Wb[pq,:]: thread t also owns the
+// natural column g*wcols + t of the group and writes sgn*Wb[pq,b]*c[a',b] into the w-part of the P row.
+// LEAN: register cap 96 (launch bound 672) so that one CTA of this kernel and CTAs of the dense tile kernel
+// fit on an SM together (overlapped build of a lone solve); otherwise 128 registers, 16 gathers in flight.
+template <int LMAX, bool LEAN>
+__global__ void __launch_bounds__(LEAN ? 672 : 512, 1)
+sigma2_ab_kernel(const V2Args P, const int NST, const int stage_len, const int src_smem) {
+    constexpr int BATCH = LEAN ? 8 : 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
     const sqd_operator& op = P.op;
     const sqd_sigma_v2& V = op.v2;
     const int g = blockIdx.y;
-    const int vc_pad = V.vc_pad, ldg = op.ldg, ldc = op.ldc;
+    const int vc_pad = V.vc_pad, ldg = op.ldg, ldc = op.ldc, nb = op.b.n;
     const int tid = threadIdx.x, lane = tid & 31;
     const int ncons = blockDim.x - 32, nwarp_c = ncons >> 5;
+    const bool have_wb = op.Wb != nullptr;
 
-    double* stage = reinterpret_cast<double*>(smem_raw);                 // [NST][ldg]
-    double* accv = stage + (size_t)NST * ldg;                             // [2][vc_pad]
-    uint64_t* full = reinterpret_cast<uint64_t*>(accv + 2 * vc_pad);     // [kV2MaxStages]
-    uint64_t* empty = full + kV2MaxStages;                                // [kV2MaxStages]
-    int4* hdr = reinterpret_cast<int4*>(empty + kV2MaxStages);            // [kV2MaxStages]
+    double* stage = reinterpret_cast<double*>(smem_raw);                            // [NST][stage_len]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage + (size_t)NST * stage_len);  // [kV2MaxStages]
+    uint64_t* empty = full + kV2MaxStages;                                           // [kV2MaxStages]
+    int4* hdr = reinterpret_cast<int4*>(empty + kV2MaxStages);                       // [kV2MaxStages]
 
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) {
@@ -454,90 +490,133 @@ sigma2_ab_kernel(const V2Args P, const int NST) {
     __syncthreads();
 
     // =========================== producer warp ===========================
+    // Chunks are dealt round robin over the CTAs of the group (the list is sorted by descending size, so
+    // the loads are balanced to within one chunk); everything a chunk needs from global memory is
+    // fetched one chunk ahead, so the only waits of this warp are the ring's empty barriers.
     if (tid >= ncons) {
         int s = 0, round = 0;
         const bool self_ok = op.Wa != nullptr;
-        const int norb = op.norb;
-        for (;;) {
-            int chunk = 0;
-            if (lane == 0) chunk = atomicAdd(&V.counter[g], 1);
-            chunk = __shfl_sync(0xffffffffu, chunk, 0);
-            if (chunk >= V.n_chunks) break;
-            const int ap = V.chunk_row[chunk], first = V.chunk_first[chunk], n = V.chunk_n[chunk];
-            // lane k describes item first + k of the chunk
-            const int it = first + lane;
-            bool live = false;
-            int slot = 0, sign = 1;
-            const double* grow = nullptr;
-            if (lane < n) {
-                slot = V.item_ptr[ap] + it;
-                if (it == 0) {
-                    live = self_ok && ap >= P.row_begin && ap < P.row_end;
-                    grow = op.Wa + (size_t)ap * ldg;
-                } else {
-                    const int e = op.a.row_ptr[ap] + it - 1;
-                    const int tgt = (int)op.a.col[e];
-                    const uint32_t m = op.a.meta[e];
-                    live = tgt >= P.row_begin && tgt < P.row_end;
-                    // row `ap` stores E_pq tgt = ap; the excitation ap -> tgt is E_qp
-                    const int pq = (int)(m & 0x7fffffffu), p = pq / norb, q = pq - p * norb;
-                    grow = op.gab + (size_t)(q * norb + p) * ldg;
-                    sign = (m >> 31) ? -1 : 1;
-                }
+        const int stride = gridDim.x;
+        const int4* recs = reinterpret_cast<const int4*>(V.chunk_rec);
+        int chunk = blockIdx.x;
+        int4 rec = make_int4(0, 0, 0, 0), rec_next = make_int4(0, 0, 0, 0);
+        int tgt = 0, pslot = 0;
+        uint32_t gs = 0;
+        if (chunk < V.n_chunks) {
+            rec = recs[chunk];
+            if (lane < rec.z) {
+                tgt = V.item_tgt[rec.y + lane];
+                gs = V.item_gsel[rec.y + lane];
+                pslot = V.item_pslot[rec.y + lane];
             }
+        }
+        if (chunk + stride < V.n_chunks) rec_next = recs[chunk + stride];
+        for (; chunk < V.n_chunks; chunk += stride) {
+            const int ap = rec.x, n = rec.z;
+            const bool is_self = (gs & kSelfItem) != 0;
+            const bool live = lane < n && tgt >= P.row_begin && tgt < P.row_end && (!is_self || self_ok);
+            const int my_slot = pslot;
+            const int my_sel = is_self ? -1 : (int)(gs & 0xffffu);
+            const int my_sign = (gs >> 31) ? -1 : 1;
+            // prefetch: lane data of the next chunk, record of the one after
+            const int4 rec_n = rec_next;
+            int tgt_n = 0, pslot_n = 0;
+            uint32_t gs_n = 0;
+            if (chunk + stride < V.n_chunks && lane < rec_n.z) {
+                tgt_n = V.item_tgt[rec_n.y + lane];
+                gs_n = V.item_gsel[rec_n.y + lane];
+                pslot_n = V.item_pslot[rec_n.y + lane];
+            }
+            if (chunk + 2 * stride < V.n_chunks) rec_next = recs[chunk + 2 * stride];
+
             uint32_t rem = __ballot_sync(0xffffffffu, live);
-            if (rem == 0) continue;
-            if (lane == 0) {
-                if (round > 0) v2_wait(&empty[s], (uint32_t)((round - 1) & 1));
-                hdr[s] = make_int4(1, 0, 0, ap);
-                v2_arrive(&full[s]);
-            }
-            if (++s == NST) {
-                s = 0;
-                ++round;
-            }
-            while (rem) {
-                const int k = __ffs(rem) - 1;
-                rem &= rem - 1;
-                const int slot_k = __shfl_sync(0xffffffffu, slot, k);
-                const int sign_k = __shfl_sync(0xffffffffu, sign, k);
-                const unsigned long long gp =
-                    __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)grow, k);
+            if (rem != 0) {
                 if (lane == 0) {
                     if (round > 0) v2_wait(&empty[s], (uint32_t)((round - 1) & 1));
-                    hdr[s] = make_int4(2, slot_k, sign_k, ap);
-                    mbar_expect_tx(&full[s], (uint32_t)(ldg * sizeof(double)));
-                    bulk_g2s(stage + (size_t)s * ldg, reinterpret_cast<const double*>((uintptr_t)gp),
-                             (uint32_t)(ldg * sizeof(double)), &full[s]);
+                    hdr[s] = make_int4(1, 0, 0, ap);
+                    if (src_smem) {
+                        mbar_expect_tx(&full[s], (uint32_t)(ldc * sizeof(double)));
+                        bulk_g2s(stage + (size_t)s * stage_len, P.c + (size_t)ap * ldc,
+                                 (uint32_t)(ldc * sizeof(double)), &full[s]);
+                    } else {
+                        v2_arrive(&full[s]);
+                    }
                 }
                 if (++s == NST) {
                     s = 0;
                     ++round;
                 }
+                while (rem) {
+                    const int k = __ffs(rem) - 1;
+                    rem &= rem - 1;
+                    const int slot_k = __shfl_sync(0xffffffffu, my_slot, k);
+                    const int sign_k = __shfl_sync(0xffffffffu, my_sign, k);
+                    const int sel_k = __shfl_sync(0xffffffffu, my_sel, k);
+                    if (lane == 0) {
+                        if (round > 0) v2_wait(&empty[s], (uint32_t)((round - 1) & 1));
+                        double* dst = stage + (size_t)s * stage_len;
+                        if (sel_k < 0) {
+                            hdr[s] = make_int4(3, slot_k, 1, ap);
+                            mbar_expect_tx(&full[s], (uint32_t)(ldg * sizeof(double)));
+                            bulk_g2s(dst, op.Wa + (size_t)ap * ldg, (uint32_t)(ldg * sizeof(double)), &full[s]);
+                        } else {
+                            hdr[s] = make_int4(2, slot_k, sign_k, ap);
+                            mbar_expect_tx(&full[s], (uint32_t)((ldg + (have_wb ? ldc : 0)) * sizeof(double)));
+                            bulk_g2s(dst, op.gab + (size_t)sel_k * ldg, (uint32_t)(ldg * sizeof(double)),
+                                     &full[s]);
+                            if (have_wb)
+                                bulk_g2s(dst + ldg, op.Wb + (size_t)sel_k * ldc,
+                                         (uint32_t)(ldc * sizeof(double)), &full[s]);
+                        }
+                    }
+                    if (++s == NST) {
+                        s = 0;
+                        ++round;
+                    }
+                }
             }
+            rec = rec_n;
+            tgt = tgt_n;
+            gs = gs_n;
+            pslot = pslot_n;
         }
         if (lane == 0) {
             if (round > 0) v2_wait(&empty[s], (uint32_t)((round - 1) & 1));
             hdr[s] = make_int4(0, 0, 0, 0);
             v2_arrive(&full[s]);
-            // the last CTA of the group to run out of work re-arms the counter for the next build
-            __threadfence();
-            const int t = atomicAdd(&V.counter[kV2MaxGroups + g], 1);
-            if (t == (int)gridDim.x - 1) {
-                V.counter[g] = 0;
-                V.counter[kV2MaxGroups + g] = 0;
-            }
         }
         return;
     }
 
     // =========================== consumer warps ==========================
+    // A warp depends on the ring only: it may run up to NST stages ahead of the slowest warp of its CTA.
     const int t = tid;
     const size_t gbase = (size_t)g * LMAX * vc_pad;
     const int len = V.vc_len[g * vc_pad + t];
+    const int myq = V.vc_q[g * vc_pad + t];
+    // natural column of this thread for the Wb terms
+    const int wcols = (nb + (int)gridDim.y - 1) / (int)gridDim.y;
+    const int wb_col = (t < wcols && g * wcols + t < nb) ? g * wcols + t : -1;
     int wlen = len;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) wlen = max(wlen, __shfl_xor_sync(0xffffffffu, wlen, o));
+    const bool warp_has_w = __any_sync(0xffffffffu, wb_col >= 0) && have_wb;
+    if (wlen == 0 && !warp_has_w) {
+        // a warp of padding lanes still has to release the stages
+        int s = 0, round = 0;
+        for (;;) {
+            v2_wait(&full[s], (uint32_t)(round & 1));
+            const int type = hdr[s].x;
+            if (type == 0) break;
+            __syncwarp();
+            if (lane == 0) v2_arrive(&empty[s]);
+            if (++s == NST) {
+                s = 0;
+                ++round;
+            }
+        }
+        return;
+    }
     uint32_t off[LMAX];
     double x[LMAX];
 #pragma unroll
@@ -545,37 +624,44 @@ sigma2_ab_kernel(const V2Args P, const int NST) {
         off[j] = V.vc_off[gbase + (size_t)j * vc_pad + t];
         x[j] = 0.0;
     }
-    // second role: thread u < ncol adds up the virtual columns of the u-th beta string of the group
-    const int ncol = V.grp_ncol[g];
-    int cb = -1, cfull = 0, cnf = 0, crem = -1;
-    if (t < ncol) {
-        cb = V.gcol[g * vc_pad + t];
-        cfull = V.gcol_full[g * vc_pad + t];
-        cnf = V.gcol_nfull[g * vc_pad + t];
-        crem = V.gcol_rem[g * vc_pad + t];
-    }
-    int s = 0, round = 0, buf = 0;
+    const size_t ldp = (size_t)V.ldp;
+    double* prow = V.P + (myq >= 0 ? myq : 0);
+    double* wrow = V.P + V.ldq + (wb_col >= 0 ? wb_col : 0);
+    double cmine = 0.0;
+    int s = 0, round = 0;
     for (;;) {
         v2_wait(&full[s], (uint32_t)(round & 1));
         const int4 h = hdr[s];
         if (h.x == 0) break;
         if (h.x == 1) {
-            const double* crow = P.c + (size_t)h.w * ldc;
+            // the (source column, sign) words are re-read per source string: 4 bytes per link from L1/L2,
+            // against 16 more registers per thread if they were kept.  Padding entries read column 0.
+            const double* crow = src_smem ? stage + (size_t)s * stage_len : P.c + (size_t)h.w * ldc;
+            if (wlen > 0) {
 #pragma unroll
-            for (int j = 0; j < LMAX; ++j) {
-                if (j < wlen) {
+                for (int j = 0; j < LMAX; ++j) {
                     const uint32_t sv = __ldg(V.vc_src + gbase + (size_t)j * vc_pad + t);
-                    const double v = __ldg(crow + (sv & 0x7fffffffu));
+                    const double v = crow[sv & 0x7fffffffu];
                     x[j] = j < len ? ((sv >> 31) ? -v : v) : 0.0;
                 }
             }
+            cmine = wb_col >= 0 ? crow[wb_col] : 0.0;
         } else {
-            const char* G = reinterpret_cast<const char*>(stage + (size_t)s * ldg);
+            const char* G = reinterpret_cast<const char*>(stage + (size_t)s * stage_len);
+            // all gathers of the item are issued before the first FMA (the trip count is a warp-uniform
+            // multiple of 4), four interleaved partial sums keep the FP64 FMA latency off the critical path
+            double wv = 0.0;
+            if (h.x == 2 && warp_has_w && wb_col >= 0) wv = stage[(size_t)s * stage_len + ldg + wb_col];
             double acc = 0.0;
-#pragma unroll
-            for (int j = 0; j < LMAX; ++j)
-                if (j < wlen) acc = fma(x[j], *reinterpret_cast<const double*>(G + off[j]), acc);
-            accv[buf * vc_pad + t] = h.z < 0 ? -acc : acc;
+            if (wlen > 12 && LMAX >= 16) acc = v2_dot<(LMAX >= 16 ? 16 : LMAX), LMAX, BATCH>(x, off, G);
+            else if (wlen > 8 && LMAX >= 12) acc = v2_dot<(LMAX >= 12 ? 12 : LMAX), LMAX, BATCH>(x, off, G);
+            else if (wlen > 4) acc = v2_dot<8, LMAX, 8>(x, off, G);
+            else if (wlen > 0) acc = v2_dot<4, LMAX, 4>(x, off, G);
+            if (myq >= 0) prow[(size_t)h.y * ldp] = h.z < 0 ? -acc : acc;
+            if (h.x == 2 && warp_has_w && wb_col >= 0) {
+                const double w = wv * cmine;
+                wrow[(size_t)h.y * ldp] = h.z < 0 ? -w : w;
+            }
         }
         __syncwarp();
         if (lane == 0) v2_arrive(&empty[s]);
@@ -583,22 +669,11 @@ sigma2_ab_kernel(const V2Args P, const int NST) {
             s = 0;
             ++round;
         }
-        if (h.x == 2) {
-            asm volatile("bar.sync 1, %0;" ::"r"(ncons) : "memory");
-            if (cb >= 0) {
-                const double* av = accv + buf * vc_pad;
-                double v = 0.0;
-                for (int k = 0; k < cnf; ++k) v += av[cfull + k];
-                if (crem >= 0) v += av[crem];
-                V.P[(size_t)h.y * ldc + cb] = v;
-            }
-            buf ^= 1;
-        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K2: dense same-spin tiles + epilogue
+// K2: dense same-spin partial tiles
 // ---------------------------------------------------------------------------------------------------
 constexpr int kTM = 64, kTN = 64, kKT = 16, kK2Threads = 128, kSdA = 66, kSdB = 64;
 
@@ -606,7 +681,6 @@ __global__ void __launch_bounds__(kK2Threads, 3)
 sigma2_tile_kernel(const V2Args P) {
     __shared__ __align__(16) double As[2][kKT][kSdA];
     __shared__ __align__(16) double Bs[2][kKT][kSdB];
-    __shared__ int is_last_s;
     if (P.done != nullptr && *P.done != 0) return;
     const sqd_operator& op = P.op;
     const sqd_sigma_v2& V = op.v2;
@@ -615,7 +689,6 @@ sigma2_tile_kernel(const V2Args P) {
     const int a_lo = P.row_begin & ~1;
     const int a0 = a_lo + blockIdx.x * kTM, b0 = blockIdx.y * kTN;
     const int split = blockIdx.z, nsplit = gridDim.z;
-    const bool ham = op.use_same_spin != 0;
     const double* __restrict__ c = P.c;
 
     double acc[8][4];
@@ -625,8 +698,9 @@ sigma2_tile_kernel(const V2Args P) {
         for (int q = 0; q < 4; ++q) acc[r][q] = 0.0;
 
     // combined K range: k-tiles [0, nka) run over source alpha strings (HaDT, C), [nka, nka+nkb) over
-    // source beta strings (C^T, HbDT)
-    const int nka = ham ? (na + kKT - 1) / kKT : 0, nkb = ham ? (nb + kKT - 1) / kKT : 0;
+    // source beta strings (C^T, HbDT).  The split boundaries depend on (na, nb, nsplit) only, so a build
+    // restricted to a block of rows adds every element in the same order as the full build.
+    const int nka = (na + kKT - 1) / kKT, nkb = (nb + kKT - 1) / kKT;
     const int ntk = nka + nkb;
     const int t0 = (int)((long long)split * ntk / nsplit), t1 = (int)((long long)(split + 1) * ntk / nsplit);
     double2 ra[4], rb[4];
@@ -710,97 +784,143 @@ sigma2_tile_kernel(const V2Args P) {
         __syncthreads();
     }
 
-    // ---- split-K: partial tiles meet in memory, the last CTA of the tile adds them in split order ----
-    if (nsplit > 1) {
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int a = a0 + ty * 8 + r;
-            if (a >= na) continue;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int b = b0 + 32 * h + 2 * tx;
-                if (b < ldc)
-                    *reinterpret_cast<double2*>(V.part + ((size_t)split * na + a) * ldc + b) =
-                        make_double2(acc[r][2 * h], acc[r][2 * h + 1]);
-            }
-        }
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            int* ticket = V.tile_ticket + blockIdx.y * gridDim.x + blockIdx.x;
-            const int tk = atomicAdd(ticket, 1);
-            is_last_s = tk == nsplit - 1;
-            if (is_last_s) *ticket = 0;
-        }
-        __syncthreads();
-        if (!is_last_s) return;
-        __threadfence();
-#pragma unroll
-        for (int r = 0; r < 8; ++r) {
-            const int a = a0 + ty * 8 + r;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int b = b0 + 32 * h + 2 * tx;
-                double2 v = make_double2(0.0, 0.0);
-                if (a < na && b < ldc) {
-                    for (int sp = 0; sp < nsplit; ++sp) {
-                        const double2 w = __ldcg(
-                            reinterpret_cast<const double2*>(V.part + ((size_t)sp * na + a) * ldc + b));
-                        v.x += w.x;
-                        v.y += w.y;
-                    }
-                }
-                acc[r][2 * h] = v.x;
-                acc[r][2 * h + 1] = v.y;
-            }
-        }
-    }
-
-    // ---- epilogue -------------------------------------------------------------------------------
-    const bool have_self = op.Wa != nullptr;
-    const bool have_wb = op.Wb != nullptr;
+    // ---- partial tile -> memory; the epilogue kernel adds the splits in a fixed order ----
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         const int a = a0 + ty * 8 + r;
-        if (a < P.row_begin || a >= P.row_end) continue;
-        const int rp = op.a.row_ptr[a], ns = op.a.n_single[a], sp = V.single_ptr[a];
-        const int self_row = V.item_ptr[a];
+        if (a >= na) continue;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int b = b0 + 32 * h + 2 * tx;
-            if (b >= ldc) continue;
-            const size_t ab = (size_t)a * ldc + b;
-            const double2 dg = *reinterpret_cast<const double2*>(op.diag + ab);
-            const double2 cc = *reinterpret_cast<const double2*>(c + ab);
-            double vx = acc[r][2 * h], vy = acc[r][2 * h + 1];
-            vx = fma(dg.x, cc.x, vx);
-            vy = fma(dg.y, cc.y, vy);
-            if (have_self) {
-                const double2 ps = *reinterpret_cast<const double2*>(V.P + (size_t)self_row * ldc + b);
-                vx += ps.x;
-                vy += ps.y;
-            }
-            for (int k = 0; k < ns; ++k) {
-                const int slot = V.rev_slot[sp + k];
-                const double2 pv = *reinterpret_cast<const double2*>(V.P + (size_t)slot * ldc + b);
-                vx += pv.x;
-                vy += pv.y;
-                if (have_wb) {
-                    const uint32_t m = op.a.meta[rp + k];
-                    const int ap = (int)op.a.col[rp + k];
-                    const double2 wb =
-                        *reinterpret_cast<const double2*>(op.Wb + (size_t)(m & 0x7fffffffu) * ldc + b);
-                    const double2 cs = *reinterpret_cast<const double2*>(c + (size_t)ap * ldc + b);
-                    const double sg = (m >> 31) ? -1.0 : 1.0;
-                    vx = fma(sg * wb.x, cs.x, vx);
-                    vy = fma(sg * wb.y, cs.y, vy);
-                }
-            }
-            if (b >= nb) vx = 0.0;       // pad column of sigma
-            if (b + 1 >= nb) vy = 0.0;
-            *reinterpret_cast<double2*>(P.sigma + ab) = make_double2(vx, vy);
+            if (b < ldc)
+                *reinterpret_cast<double2*>(V.part + ((size_t)split * na + a) * ldc + b) =
+                    make_double2(acc[r][2 * h], acc[r][2 * h + 1]);
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3: epilogue.  sigma[a,b] = partial tiles (fixed order) + diag*c + column sums of the P rows of a.
+// CTA = one alpha string x 32 beta strings.  The q-part columns of 32 consecutive beta strings are one
+// contiguous range (at most kK3MaxQ wide, enforced by the planner) and their w-part columns are the 32
+// strings themselves, so every lane sums the same few P columns over the row's items with coalesced
+// loads, whatever the lengths of the excitation lists.  The items (self item, then one per single
+// excitation) are cut into contiguous quarters, one per warp; a string with few excitations keeps only
+// warp 0 (the others leave at once), the Hartree-Fock string with its hundreds all four.  The warps meet in
+// shared memory and are added in warp order (fixed summation order).
+// ---------------------------------------------------------------------------------------------------
+constexpr int kK3Cols = 32, kK3Warps = 4, kK3Threads = kK3Cols * kK3Warps, kK3Unroll = 4;
+constexpr int kK3MaxQ = 128;
+
+template <int QC>
+__device__ __forceinline__ void k3_sum_items(const double* pcol, const double* wcol, size_t ldp, int k_beg,
+                                             int k_end, const bool (&qok)[4], bool wok, double (&accq)[4],
+                                             double& accw) {
+    const double* pr = pcol + (size_t)k_beg * ldp;
+    const double* wr = wcol + (size_t)k_beg * ldp;
+    int k = k_beg;
+    for (; k + kK3Unroll <= k_end; k += kK3Unroll) {
+        double pv[kK3Unroll][QC], wv[kK3Unroll];
+#pragma unroll
+        for (int u = 0; u < kK3Unroll; ++u) {
+#pragma unroll
+            for (int i = 0; i < QC; ++i) pv[u][i] = qok[i] ? pr[(size_t)u * ldp + 32 * i] : 0.0;
+            wv[u] = wok ? wr[(size_t)u * ldp] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kK3Unroll; ++u) {
+#pragma unroll
+            for (int i = 0; i < QC; ++i) accq[i] += pv[u][i];
+            accw += wv[u];
+        }
+        pr += (size_t)kK3Unroll * ldp;
+        wr += (size_t)kK3Unroll * ldp;
+    }
+    for (; k < k_end; ++k) {
+#pragma unroll
+        for (int i = 0; i < QC; ++i)
+            if (qok[i]) accq[i] += pr[32 * i];
+        if (wok) accw += wr[0];
+        pr += ldp;
+        wr += ldp;
+    }
+}
+
+__global__ void __launch_bounds__(kK3Threads)
+sigma2_epilogue_kernel(const V2Args P) {
+    __shared__ double Sq[kK3Warps][kK3MaxQ];
+    __shared__ double Sw[kK3Warps][kK3Cols];
+    if (P.done != nullptr && *P.done != 0) return;
+    const sqd_operator& op = P.op;
+    const sqd_sigma_v2& V = op.v2;
+    const int a = P.row_begin + blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ns = op.a.n_single[a];
+    const int nwarps = ns <= 12 ? 1 : kK3Warps;  // warps that have items
+    if (warp >= nwarps) return;
+    const int na = op.a.n, nb = op.b.n, ldc = op.ldc;
+    const int b0 = blockIdx.x * kK3Cols, b = b0 + lane;
+    const bool live = b < nb;
+    const int ip = V.item_ptr[a];
+    const size_t ldp = (size_t)V.ldp;
+    const int qlo = V.col_seg[min(b0, nb)], qhi = V.col_seg[min(b0 + kK3Cols, nb)];
+    const int nqb = qhi - qlo;  // <= kK3MaxQ
+    bool qok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) qok[i] = lane + 32 * i < nqb;
+    const bool wok = live && op.Wb != nullptr;
+    // P rows of the single excitations: ip + 1 + k
+    const double* pcol = V.P + (size_t)(ip + 1) * ldp + qlo + lane;
+    const double* wcol = V.P + (size_t)(ip + 1) * ldp + V.ldq + (live ? b : 0);
+    const int per = (ns + nwarps - 1) / nwarps;
+    const int k_beg = min(ns, warp * per), k_end = min(ns, k_beg + per);
+    double accq[4] = {0.0, 0.0, 0.0, 0.0}, accw = 0.0, base = 0.0;
+    if (warp == 0) {
+        // terms that do not depend on the items: their loads go first
+        if (live) {
+            double pt[4];
+            for (int sp0 = 0; sp0 < P.nsplit; sp0 += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    pt[u] = sp0 + u < P.nsplit ? V.part[((size_t)(sp0 + u) * na + a) * ldc + b] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) base += pt[u];
+            }
+            const size_t ab = (size_t)a * ldc + b;
+            base = fma(op.diag[ab], P.c[ab], base);
+        }
+        if (op.Wa != nullptr) {   // self item: q-part only
+            const double* prow = pcol - ldp;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (qok[i]) accq[i] += prow[32 * i];
+        }
+    }
+    if (nqb <= 32) k3_sum_items<1>(pcol, wcol, ldp, k_beg, k_end, qok, wok, accq, accw);
+    else if (nqb <= 64) k3_sum_items<2>(pcol, wcol, ldp, k_beg, k_end, qok, wok, accq, accw);
+    else k3_sum_items<4>(pcol, wcol, ldp, k_beg, k_end, qok, wok, accq, accw);
+    if (nwarps > 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Sq[warp][lane + 32 * i] = accq[i];
+        Sw[warp][lane] = accw;
+        asm volatile("bar.sync 1, %0;" ::"r"(32 * kK3Warps) : "memory");
+        if (warp != 0) return;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) Sq[0][lane + 32 * i] = accq[i];
+        Sw[0][lane] = accw;
+        __syncwarp();
+    }
+    if (b >= ldc) return;
+    double v = 0.0;
+    if (live) {
+        v = base;
+        for (int w = 0; w < nwarps; ++w) v += Sw[w][lane];
+        const int q0 = V.col_seg[b] - qlo, q1 = V.col_seg[b + 1] - qlo;
+        for (int q = q0; q < q1; ++q)
+            for (int w = 0; w < nwarps; ++w) v += Sq[w][q];
+    }
+    P.sigma[(size_t)a * ldc + b] = v;  // pad column: 0
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -811,23 +931,65 @@ static int v2_env(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+// the row c[a',:] rides the ring (type-1 stages) while it is not much longer than an integral row
+static int v2_src_in_smem(const sqd_operator* op) { return 1; }
+// a stage holds an integral row followed by a Wb row (or, type 1, the source row of c)
+static int v2_stage_len(const sqd_operator* op) { return op->ldg + op->ldc; }
 static size_t v2_k1_smem(const sqd_operator* op, int nst) {
-    return (size_t)nst * op->ldg * sizeof(double) + (size_t)2 * op->v2.vc_pad * sizeof(double) +
-           (size_t)2 * kV2MaxStages * sizeof(uint64_t) + (size_t)kV2MaxStages * sizeof(int4);
+    return (size_t)nst * v2_stage_len(op) * sizeof(double) + (size_t)2 * kV2MaxStages * sizeof(uint64_t) +
+           (size_t)kV2MaxStages * sizeof(int4);
 }
 
 static int v2_pick_stages(const sqd_operator* op) {
     static const int knob = v2_env("SQD_V2_STAGES", 0);
     if (knob >= 2 && knob <= kV2MaxStages) return knob;
-    // deep enough to cover the L2 latency of a row copy behind ~0.2 us items, small enough for 2 CTAs/SM
-    int nst = 4;
-    while (nst > 2 && v2_k1_smem(op, nst) > 100 * 1024) --nst;
+    // deep enough to let the warps of a CTA drift apart and to cover the L2 latency of a row copy, small
+    // enough for three CTAs per SM
+    int nst = 8;
+    while (nst > 2 && v2_k1_smem(op, nst) > 160 * 1024) --nst;
     return nst;
 }
 
 int64_t sigma2_smem_bytes(const sqd_operator* op) {
     const size_t b = v2_k1_smem(op, v2_pick_stages(op));
     return b <= 220 * 1024 ? (int64_t)b : -1;
+}
+
+// K splits of the dense tiles: a function of the operator's shape only (never of the row range of a
+// sharded build), see sigma2_tile_kernel
+static int v2_num_split(int na, int nb, int ldc) {
+    static const int knob_split = v2_env("SQD_V2_SPLIT", 0);
+    const int tiles = ((na + 1 + kTM - 1) / kTM) * ((ldc + kTN - 1) / kTN);
+    const int ntk = (na + kKT - 1) / kKT + (nb + kKT - 1) / kKT;
+    int ns = knob_split > 0 ? knob_split : (2 * kNumSMs) / (tiles > 0 ? tiles : 1);
+    if (ns > ntk / 2) ns = ntk / 2;
+    if (ns > 32) ns = 32;
+    return ns < 1 ? 1 : ns;
+}
+
+// side stream of a host thread (one per device): the dense tile kernel runs there beside K1
+struct V2Side {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int dev = -1;
+};
+static thread_local V2Side g_v2_side;
+static int v2_side(V2Side** out) {
+    int dev = 0;
+    SQD_CUDA_OK(cudaGetDevice(&dev));
+    if (g_v2_side.s == nullptr || g_v2_side.dev != dev) {
+        if (g_v2_side.s != nullptr) {
+            cudaStreamDestroy(g_v2_side.s);
+            cudaEventDestroy(g_v2_side.ev_fork);
+            cudaEventDestroy(g_v2_side.ev_join);
+        }
+        SQD_CUDA_OK(cudaStreamCreateWithFlags(&g_v2_side.s, cudaStreamNonBlocking));
+        SQD_CUDA_OK(cudaEventCreateWithFlags(&g_v2_side.ev_fork, cudaEventDisableTiming));
+        SQD_CUDA_OK(cudaEventCreateWithFlags(&g_v2_side.ev_join, cudaEventDisableTiming));
+        g_v2_side.dev = dev;
+    }
+    *out = &g_v2_side;
+    return 0;
 }
 
 int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
@@ -840,45 +1002,62 @@ int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_si
                 "sqd_sigma: the v2 tables were built without the dense same-spin blocks");
     SQD_REQUIRE(row_begin >= 0 && row_end <= op->a.n && row_begin <= row_end, "sqd_sigma: bad row range");
     if (row_end == row_begin) return 0;
-    V2Args args{*op, d_c, d_sigma, d_done, row_begin, row_end, 1};
+    V2Args args{*op, d_c, d_sigma, d_done, row_begin, row_end, 0};
+    // K2 (FP64-pipe bound) and K1 (shared-memory gather bound) are independent: K2 goes to a side stream
+    // of this host thread and runs beside K1; both join before K3.  SQD_V2_OVERLAP=0 keeps one stream.
+    // Worth it for a lone solve only: when several solves share the GPU their kernels fill each other's gaps.
+    static const int knob_overlap = v2_env("SQD_V2_OVERLAP", -1);
+    V2Side* side = nullptr;
+    const bool want_fork = knob_overlap >= 0 ? knob_overlap != 0 : op->throughput_mode == 0;
+    const bool fork = want_fork && op->use_same_spin != 0 && V.n_chunks > 0;
+    if (fork && v2_side(&side)) return -2;
+    cudaStream_t st2 = fork ? side->s : st;
+    int nsplit = 0;
+    if (op->use_same_spin) {
+        if (fork) {
+            SQD_CUDA_OK(cudaEventRecord(side->ev_fork, st));
+            SQD_CUDA_OK(cudaStreamWaitEvent(st2, side->ev_fork, 0));
+        }
+        const int a_lo = row_begin & ~1;
+        const int tiles_x = (row_end - a_lo + kTM - 1) / kTM, tiles_y = (op->ldc + kTN - 1) / kTN;
+        nsplit = v2_num_split(op->a.n, op->b.n, op->ldc);
+        if (nsplit > V.max_split) nsplit = V.max_split;
+        sigma2_tile_kernel<<<dim3(tiles_x, tiles_y, nsplit), kK2Threads, 0, st2>>>(args);
+        if (check_launch("sigma2_tile_kernel")) return -2;
+        if (fork) SQD_CUDA_OK(cudaEventRecord(side->ev_join, st2));
+    }
     // K1
     const int nst = v2_pick_stages(op);
+    const int src_smem = v2_src_in_smem(op);
+    const int stage_len = v2_stage_len(op);
     const size_t smem = v2_k1_smem(op, nst);
     SQD_REQUIRE(smem <= 220 * 1024, "sqd_sigma: norb=%d does not fit the integral-row ring", op->norb);
-    auto k1 = V.lmax == 8 ? sigma2_ab_kernel<8> : sigma2_ab_kernel<16>;
-    static bool cfg[64][2] = {};
+    auto k1 = V.lmax == 8 ? (fork ? sigma2_ab_kernel<8, true> : sigma2_ab_kernel<8, false>)
+                          : (fork ? sigma2_ab_kernel<16, true> : sigma2_ab_kernel<16, false>);
+    static bool cfg[64][4] = {};
     int dev = 0;
     SQD_CUDA_OK(cudaGetDevice(&dev));
-    const int li = V.lmax == 8 ? 0 : 1;
+    const int li = (V.lmax == 8 ? 0 : 1) + (fork ? 2 : 0);
     if (dev >= 0 && dev < 64 && !cfg[dev][li]) {
         SQD_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         SQD_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          (int)cudaSharedmemCarveoutMaxShared));
         cfg[dev][li] = true;
     }
-    static const int knob_ctas = v2_env("SQD_V2_CTAS_PER_SM", 2);
-    int gx = (knob_ctas * kNumSMs) / V.n_groups;
+    static const int knob_ctas = v2_env("SQD_V2_CTAS_PER_SM", 1);
+    int gx = (knob_ctas * kNumSMs + V.n_groups - 1) / V.n_groups;
     if (gx < 1) gx = 1;
     if (gx > V.n_chunks) gx = V.n_chunks;
     if (V.n_chunks > 0) {
-        k1<<<dim3(gx, V.n_groups), V.vc_pad + 32, smem, st>>>(args, nst);
+        k1<<<dim3(gx, V.n_groups), V.vc_pad + 32, smem, st>>>(args, nst, stage_len, src_smem);
         if (check_launch("sigma2_ab_kernel")) return -2;
     }
-    // K2
-    const int a_lo = row_begin & ~1;
-    const int tiles_x = (row_end - a_lo + kTM - 1) / kTM, tiles_y = (op->ldc + kTN - 1) / kTN;
-    int nsplit = 1;
-    if (op->use_same_spin) {
-        static const int knob_split = v2_env("SQD_V2_SPLIT", 0);
-        const int ntk = (op->a.n + kKT - 1) / kKT + (op->b.n + kKT - 1) / kKT;
-        nsplit = knob_split > 0 ? knob_split : (3 * kNumSMs) / (tiles_x * tiles_y);
-        if (nsplit > ntk / 2) nsplit = ntk / 2;
-        if (nsplit > V.max_split) nsplit = V.max_split;
-        if (nsplit < 1) nsplit = 1;
-    }
+    if (fork) SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));
+    // K3
     args.nsplit = nsplit;
-    sigma2_tile_kernel<<<dim3(tiles_x, tiles_y, nsplit), kK2Threads, 0, st>>>(args);
-    return check_launch("sigma2_tile_kernel");
+    sigma2_epilogue_kernel<<<dim3((op->ldc + kK3Cols - 1) / kK3Cols, row_end - row_begin), kK3Threads, 0, st>>>(
+        args);
+    return check_launch("sigma2_epilogue_kernel");
 }
 
 }  // namespace sqd
@@ -890,7 +1069,7 @@ extern "C" {
 int sqd_sigma_v2_recommended(int na, int nb, int64_t nnz_a, int64_t nnz_b) {
     static const int knob = v2_env("SQD_SIGMA_V2", -1);  // 0 / 1 force, -1 automatic
     if (knob >= 0) return knob != 0;
-    if (na <= 0 || nb <= 0 || nb > 16384 || na > 1 << 19) return 0;
+    if (na <= 0 || nb <= 0 || nb > 8192 || na > 1 << 19) return 0;
     const double dense = (double)na * nb * ((double)na + nb);
     const double sparse = (double)nnz_a * nb + (double)nnz_b * na;
     return dense <= 12.0 * sparse ? 1 : 0;
@@ -922,16 +1101,16 @@ int sqd_sigma_v2_plan(const sqd_spin_table* a, const sqd_spin_table* b, int norb
     auto U = [&](size_t off) { return reinterpret_cast<uint32_t*>(base + off); };
     int* counts = I(L.counts);
     SQD_CUDA_OK(cudaMemsetAsync(counts, 0, SQD_V2_COUNTS * sizeof(int), st));
-    SQD_CUDA_OK(cudaMemsetAsync(I(L.counter), 0, 2 * kV2MaxGroups * sizeof(int), st));
     const size_t bp_smem = (size_t)3 * b->n * sizeof(int);
-    if (bp_smem > 200 * 1024) {
+    if (bp_smem > 200 * 1024 || b->n > 8192) {
         // the single-CTA planner keeps three int arrays of nb entries in shared memory
         int one = 1;
         SQD_CUDA_OK(cudaMemcpyAsync(counts + C_ERR, &one, sizeof(int), cudaMemcpyHostToDevice, st));
     } else {
         v2_alpha_plan_kernel<<<1, 1024, 0, st>>>(*a, ipc, L.maxch, I(L.single_ptr), I(L.item_ptr),
-                                                 I(L.chunk_row), I(L.chunk_first), I(L.chunk_n), counts);
-        v2_rev_slot_kernel<<<(a->n + 7) / 8, 256, 0, st>>>(*a, I(L.single_ptr), I(L.item_ptr), I(L.rev_slot));
+                                                 reinterpret_cast<int4*>(base + L.chunk_rec), counts);
+        v2_item_kernel<<<(a->n + 7) / 8, 256, 0, st>>>(*a, norb, I(L.item_ptr), I(L.item_tgt),
+                                                       U(L.item_gsel), I(L.item_pslot));
         static bool cfg[64] = {};
         int dev = 0;
         SQD_CUDA_OK(cudaGetDevice(&dev));
@@ -940,36 +1119,25 @@ int sqd_sigma_v2_plan(const sqd_spin_table* a, const sqd_spin_table* b, int norb
                                              (int)(200 * 1024)));
             cfg[dev] = true;
         }
-        v2_beta_plan_kernel<<<1, 1024, bp_smem, st>>>(*b, lmax, L.capw, I(L.col_grp), I(L.col_u),
-                                                      I(L.col_full), I(L.col_nfull), I(L.col_rem),
-                                                      I(L.grp_ncol), counts);
+        v2_beta_plan_kernel<<<1, 1024, bp_smem, st>>>(*b, lmax, L.capw, I(L.col_grp), I(L.col_full),
+                                                      I(L.col_nfull), I(L.col_rem), I(L.col_seg), counts);
         const uint32_t zero_off = (uint32_t)(norb * norb * 8);
-        v2_vc_init_kernel<<<kNumSMs, 256, 0, st>>>(counts, lmax, L.capw, zero_off, U(L.vc_src), U(L.vc_off),
-                                                   I(L.vc_len), I(L.gcol), I(L.gcol_full), I(L.gcol_nfull),
-                                                   I(L.gcol_rem));
-        v2_vc_fill_kernel<<<(b->n + 7) / 8, 256, 0, st>>>(*b, counts, lmax, I(L.col_grp), I(L.col_u),
-                                                          I(L.col_full), I(L.col_nfull), I(L.col_rem),
-                                                          U(L.vc_src), U(L.vc_off), I(L.vc_len), I(L.gcol),
-                                                          I(L.gcol_full), I(L.gcol_nfull), I(L.gcol_rem));
+        v2_vc_init_kernel<<<kNumSMs, 256, 0, st>>>(lmax, L.capw, zero_off, U(L.vc_src), U(L.vc_off),
+                                                   I(L.vc_len), I(L.vc_q));
+        v2_vc_fill_kernel<<<(b->n + 7) / 8, 256, 0, st>>>(*b, counts, lmax, I(L.col_grp), I(L.col_full),
+                                                          I(L.col_nfull), I(L.col_rem), I(L.col_seg),
+                                                          U(L.vc_src), U(L.vc_off), I(L.vc_len), I(L.vc_q));
         if (check_launch("sigma v2 plan kernels", 5)) return -2;
     }
     if (h_counts == nullptr) return 0;
     return read_back(h_counts, counts, SQD_V2_COUNTS * sizeof(int), st);
 }
 
-static int v2_max_split(int na, int nb, int ldc) {
-    const int tiles = ((na + 1 + kTM - 1) / kTM) * ((ldc + kTN - 1) / kTN);
-    const int ntk = (na + kKT - 1) / kKT + (nb + kKT - 1) / kKT;
-    int ns = (3 * kNumSMs) / (tiles > 0 ? tiles : 1);
-    if (ns > ntk / 2) ns = ntk / 2;
-    if (ns > 32) ns = 32;
-    return ns < 1 ? 1 : ns;
-}
-
 static int v2_ld_dense(int n) { return (n + 63) / 64 * 64 + 128; }
 
 struct V2Scratch {
-    size_t P, part, ticket, HaDT, HbDT, total;
+    size_t P, part, HaDT, HbDT, total;
+    int ldp, ldq, max_split;
 };
 static V2Scratch v2_scratch(const int* hc, int na, int nb, int ldc, int dense, int same_tables) {
     V2Scratch S{};
@@ -979,10 +1147,12 @@ static V2Scratch v2_scratch(const int* hc, int na, int nb, int ldc, int dense, i
         o += al256(bytes);
         return at;
     };
-    S.P = take((size_t)hc[C_NITEMS] * ldc * sizeof(double));
-    const int ms = dense ? v2_max_split(na, nb, ldc) : 1;
-    S.part = take(ms > 1 ? (size_t)ms * na * ldc * sizeof(double) : 256);
-    S.ticket = take((size_t)(((na + 1 + kTM - 1) / kTM + 1) * ((ldc + kTN - 1) / kTN)) * sizeof(int));
+    S.ldq = (hc[C_NQ] + 31) / 32 * 32;
+    if (S.ldq < 32) S.ldq = 32;
+    S.ldp = S.ldq + (nb + 31) / 32 * 32;
+    S.P = take((size_t)hc[C_NITEMS] * S.ldp * sizeof(double));
+    S.max_split = dense ? v2_num_split(na, nb, ldc) : 1;
+    S.part = take(dense ? (size_t)S.max_split * na * ldc * sizeof(double) : 256);
     if (dense) {
         const size_t lda = v2_ld_dense(na), ldb = v2_ld_dense(nb);
         S.HaDT = take(lda * lda * sizeof(double));
@@ -1016,32 +1186,25 @@ int sqd_sigma_v2_finish(const sqd_spin_table* a, const sqd_spin_table* b, int ld
     V.vc_pad = hc[C_VCPAD];
     V.n_items = hc[C_NITEMS];
     V.n_chunks = hc[C_NCHUNKS];
-    V.max_split = dense ? v2_max_split(na, nb, ldc) : 1;
+    V.max_split = S.max_split;
+    V.ldp = S.ldp;
+    V.ldq = S.ldq;
     V.vc_src = (const uint32_t*)(pb + L.vc_src);
     V.vc_off = (const uint32_t*)(pb + L.vc_off);
     V.vc_len = (const int*)(pb + L.vc_len);
-    V.grp_ncol = (const int*)(pb + L.grp_ncol);
-    V.gcol = (const int*)(pb + L.gcol);
-    V.gcol_full = (const int*)(pb + L.gcol_full);
-    V.gcol_nfull = (const int*)(pb + L.gcol_nfull);
-    V.gcol_rem = (const int*)(pb + L.gcol_rem);
+    V.vc_q = (const int*)(pb + L.vc_q);
+    V.col_seg = (const int*)(pb + L.col_seg);
     V.single_ptr = (const int*)(pb + L.single_ptr);
     V.item_ptr = (const int*)(pb + L.item_ptr);
-    V.chunk_row = (const int*)(pb + L.chunk_row);
-    V.chunk_first = (const int*)(pb + L.chunk_first);
-    V.chunk_n = (const int*)(pb + L.chunk_n);
-    V.rev_slot = (const int*)(pb + L.rev_slot);
-    V.counter = (int*)(pb + L.counter);
-    V.tile_ticket = (int*)(sb + S.ticket);
+    V.chunk_rec = (const int*)(pb + L.chunk_rec);
+    V.item_tgt = (const int*)(pb + L.item_tgt);
+    V.item_gsel = (const uint32_t*)(pb + L.item_gsel);
+    V.item_pslot = (const int*)(pb + L.item_pslot);
     V.P = (double*)(sb + S.P);
     V.part = (double*)(sb + S.part);
     SQD_REQUIRE(V.vc_pad >= 32 && V.vc_pad <= kV2GroupMax && V.n_groups >= 1 && V.n_groups <= kV2MaxGroups,
                 "sqd_sigma_v2_finish: inconsistent plan counts");
-    // P must be zero where K1 never writes (beta strings without single excitations)
-    SQD_CUDA_OK(cudaMemsetAsync(V.P, 0, (size_t)V.n_items * ldc * sizeof(double), st));
-    SQD_CUDA_OK(cudaMemsetAsync(sb + S.ticket, 0,
-                                (size_t)(((na + 1 + kTM - 1) / kTM + 1) * ((ldc + kTN - 1) / kTN)) * sizeof(int),
-                                st));
+    // every P entry the epilogue reads is rewritten by each build; the pad columns are never read
     if (dense) {
         V.lda = v2_ld_dense(na);
         V.ldb = v2_ld_dense(nb);
