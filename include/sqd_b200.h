@@ -386,7 +386,7 @@ int sqd_dot(const double* d_x, const double* d_y, int64_t n, double* d_out, doub
  * d_scratch: at least 4096 doubles. */
 int sqd_fix_sign(double* d_x, int64_t n, void* d_scratch, void* stream);
 
-/* Small (<= 16 KB) device -> host read-back through a per-thread pinned staging buffer followed by a
+/* Small (<= 64 KB) device -> host read-back through a per-thread pinned staging buffer followed by a
  * stream synchronisation; never blocks the launches of other host threads. */
 int sqd_read_back(void* h_dst, const void* d_src, int64_t bytes, void* stream);
 

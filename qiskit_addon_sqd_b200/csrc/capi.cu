@@ -1,5 +1,6 @@
 // Error plumbing and version of the C-ABI (include/sqd_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <atomic>
 
@@ -30,7 +31,30 @@ int check_launch(const char* what, int n_launched) {
 }
 
 static thread_local void* g_pinned = nullptr;
-constexpr size_t kPinnedBytes = 16 * 1024;
+static thread_local cudaEvent_t g_sync_event = nullptr;
+static thread_local int g_sync_event_dev = -1;
+constexpr size_t kPinnedBytes = 64 * 1024;
+
+// Wait for everything enqueued on `st` WITHOUT spinning: the host threads of concurrent solves (8 per
+// process, 8 processes on a 32-core host when all GPUs are in use) would otherwise burn the cores that the
+// launching threads need.
+int stream_wait_blocking(cudaStream_t st) {
+    static const int knob = getenv("SQD_BLOCKING_SYNC") ? atoi(getenv("SQD_BLOCKING_SYNC")) : 0;
+    if (knob == 0) {
+        SQD_CUDA_OK(cudaStreamSynchronize(st));
+        return 0;
+    }
+    int dev = 0;
+    SQD_CUDA_OK(cudaGetDevice(&dev));
+    if (g_sync_event == nullptr || g_sync_event_dev != dev) {
+        if (g_sync_event != nullptr) cudaEventDestroy(g_sync_event);
+        SQD_CUDA_OK(cudaEventCreateWithFlags(&g_sync_event, cudaEventBlockingSync | cudaEventDisableTiming));
+        g_sync_event_dev = dev;
+    }
+    SQD_CUDA_OK(cudaEventRecord(g_sync_event, st));
+    SQD_CUDA_OK(cudaEventSynchronize(g_sync_event));
+    return 0;
+}
 
 int read_back(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
     if (bytes > kPinnedBytes) {
@@ -39,7 +63,7 @@ int read_back(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
     }
     if (g_pinned == nullptr) SQD_CUDA_OK(cudaHostAlloc(&g_pinned, kPinnedBytes, cudaHostAllocPortable));
     SQD_CUDA_OK(cudaMemcpyAsync(g_pinned, d_src, bytes, cudaMemcpyDeviceToHost, st));
-    SQD_CUDA_OK(cudaStreamSynchronize(st));
+    if (stream_wait_blocking(st)) return -2;
     memcpy(h_dst, g_pinned, bytes);
     return 0;
 }

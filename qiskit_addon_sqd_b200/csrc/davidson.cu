@@ -32,6 +32,8 @@ int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sig
                         const int* d_done, cudaStream_t st);
 int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
                         int row_begin, int row_end, cudaStream_t st);
+int sigma_dispatch_ctl(const sqd_operator* op, const double* d_cbase, double* d_sbase, const int* d_done,
+                       const int* d_slot, long long stride, int in_graph, cudaStream_t st);
 int nccl_allreduce_sum_f64(void* comm, double* buf, int64_t n, cudaStream_t st);
 int csr_matvec_flag(const int* d_done, int64_t d, const int32_t* row_ptr, const int32_t* col,
                     const double* val, const double* x, double* y, cudaStream_t st);
@@ -55,17 +57,42 @@ struct DavState {
     double y[kMaxS];
     double c1[kMaxS];
     double c2[kMaxS];
-    double gcol[kMaxS];         // newest column of V^T H V (reduced once, read by both Rayleigh-Ritz kernels)
+    double gcol[kMaxS];         // newest column of V^T H V
+    double G[kMaxS * kMaxS];    // projected matrix V^T H V of the current basis (row stride kMaxS)
     int ticket[4];              // arrival counters of the "last CTA finishes the step" tails
+    // device-driven loop (one CUDA graph whose WHILE node replays the cycle): the cycle's control variables
+    // live here and every kernel of the cycle is launched with the same arguments
+    int m, slot;                // size of the basis, slot of the newest basis vector
+    int M, q_keep, max_cycle;   // max_space, Ritz vectors kept by a thick restart, cycle limit
+    int n_jacobi, n_rqi_iter;   // diagnostics: full decompositions, Rayleigh-quotient iterations
 };
+
+// Control variables of a cycle.  Host-driven loop: passed as kernel arguments (m >= 0).  Device-driven
+// loop: m < 0 and they are read from the state (the advance kernel at the end of the cycle updates them).
+struct Ctl {
+    int m, restart, me, slot;
+};
+__device__ __forceinline__ Ctl read_ctl(const DavState* st, int m_arg, int restart_arg) {
+    Ctl c;
+    if (m_arg >= 0) {
+        c.m = m_arg;
+        c.restart = restart_arg;
+        c.slot = -1;
+    } else {
+        c.m = st->m;
+        c.restart = (c.m == st->M) ? st->q_keep : 0;
+        c.slot = st->slot;
+    }
+    c.me = c.restart ? c.restart : c.m;
+    return c;
+}
 
 // The scalar steps of a cycle (Rayleigh-Ritz, convergence test, Gram-Schmidt coefficients) need the sums
 // over all CTAs of the streaming pass before them.  Instead of a separate single-CTA launch, the LAST CTA
 // of the streaming kernel to arrive (ticket counter, after a __threadfence) runs the step in its tail:
 // same fixed summation order as before (the per-CTA partials are reduced in index order), three launches
 // and three launch gaps fewer per cycle.
-__device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nblk, int m, int publish);
-__device__ void ritz_lowest_body(DavState* st, const double* partials, int nblk, int m);
+__device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nblk, int m, int need_full);
 __device__ void convergence_body(DavState* st, const double* partials, int nblk, int m, int restart,
                                  double tol, double tol_residual);
 __device__ void norm_body(DavState* st, const double* partials, int nblk, int m, double lindep);
@@ -90,9 +117,19 @@ __device__ __forceinline__ bool last_block(int* ticket) {
 // ---------------------------------------------------------------------------------------------
 template <int MV>
 __global__ void __launch_bounds__(kRedThreads)
-gram_kernel(DavState* st, const double* __restrict__ V, const double* __restrict__ w, int64_t n, int m,
+gram_kernel(DavState* st, const double* __restrict__ V, const double* __restrict__ w, int64_t n, int m_arg,
             double* partials, int ritz_mode) {
     if (st->status != 0) return;
+    // device-driven loop: w is the base of W and the newest vector sits in slot st->slot; a restart cycle
+    // needs the full decomposition before the residual pass, so its tail does the whole Rayleigh-Ritz step
+    // ritz_mode: != 0 on a restart cycle of the host-driven loop (the residual pass then needs the full
+    // decomposition); the device-driven loop derives it from the state
+    const Ctl ctl = read_ctl(st, m_arg, 0);
+    const int m = ctl.m;
+    if (m_arg < 0) {
+        w += (int64_t)ctl.slot * n;
+        ritz_mode = ctl.restart != 0;
+    }
     __shared__ double red[MV * (kRedThreads / 32)];
     double acc[MV];
 #pragma unroll
@@ -120,19 +157,18 @@ gram_kernel(DavState* st, const double* __restrict__ V, const double* __restrict
     }
     // tail: Rayleigh-Ritz on the finished Gram column.  ritz_mode 1: the whole step (decomposition and
     // lowest pair); 2: lowest pair only, the decomposition follows on the side stream
-    if (last_block(&st->ticket[0])) {
-        if (ritz_mode == 1) rayleigh_ritz_body(st, partials, gridDim.x, m, 1);
-        else ritz_lowest_body(st, partials, gridDim.x, m);
-    }
+    if (last_block(&st->ticket[0])) rayleigh_ritz_body(st, partials, gridDim.x, m, ritz_mode);
 }
 
 template <int MV>
 __global__ void __launch_bounds__(kRedThreads)
 residual_kernel(DavState* st, double* __restrict__ V, double* __restrict__ W,
-                const double* __restrict__ hdiag, int64_t n, int m, int restart, double level_shift,
+                const double* __restrict__ hdiag, int64_t n, int m_arg, int restart_arg, double level_shift,
                 double* __restrict__ X, double* __restrict__ T, double* partials, double tol,
                 double tol_residual) {
     if (st->status != 0) return;
+    const Ctl ctl = read_ctl(st, m_arg, restart_arg);
+    const int m = ctl.m, restart = ctl.restart;
     __shared__ double red[(MV + 2) * (kRedThreads / 32)];
     __shared__ double ys[MV];
     __shared__ double yk[kKeep][MV];  // thick restart: coefficient columns of the kept Ritz vectors 1..q-1
@@ -223,9 +259,10 @@ residual_kernel(DavState* st, double* __restrict__ V, double* __restrict__ W,
 // T <- T - sum c1_i V_i ; partial <V_i, T>, |T|^2
 template <int MV>
 __global__ void __launch_bounds__(kRedThreads)
-ortho1_kernel(DavState* st, const double* __restrict__ V, int64_t n, int m, double* __restrict__ T,
+ortho1_kernel(DavState* st, const double* __restrict__ V, int64_t n, int m_arg, double* __restrict__ T,
               double* partials, double lindep) {
     if (st->status != 0) return;
+    const int m = m_arg >= 0 ? m_arg : read_ctl(st, -1, 0).me;
     __shared__ double red[(MV + 1) * (kRedThreads / 32)];
     __shared__ double cs[MV];
     if (threadIdx.x < MV) cs[threadIdx.x] = threadIdx.x < m ? st->c1[threadIdx.x] : 0.0;
@@ -269,9 +306,12 @@ ortho1_kernel(DavState* st, const double* __restrict__ V, int64_t n, int m, doub
 // V_new <- (T - sum c2_i V_i) * inv_norm
 template <int MV>
 __global__ void __launch_bounds__(kRedThreads)
-ortho2_kernel(const DavState* __restrict__ st, const double* __restrict__ V, int64_t n, int m,
+ortho2_kernel(const DavState* __restrict__ st, const double* __restrict__ V, int64_t n, int m_arg,
               const double* __restrict__ T, double* __restrict__ vnew) {
     if (st->status != 0) return;
+    // device-driven loop: vnew is the base of V, the new vector goes to slot `me`
+    const int m = m_arg >= 0 ? m_arg : read_ctl(st, -1, 0).me;
+    if (m_arg < 0) vnew += (int64_t)m * n;
     __shared__ double cs[MV];
     if (threadIdx.x < MV) cs[threadIdx.x] = threadIdx.x < m ? st->c2[threadIdx.x] : 0.0;
     __syncthreads();
@@ -309,169 +349,24 @@ __device__ __forceinline__ double reduce_partials(const double* partials, int ro
     return warp_sum(s);
 }
 
-// Lowest Ritz pair only -- the one thing the rest of the cycle waits for.  In the eigenbasis of the
-// previous cycle the projected matrix is the arrowhead [diag(lam) z; z^T a]; its lowest eigenvalue is the
-// root below the smallest pole of the secular function
-//     f(mu) = a - mu - sum_j z_j^2 / (lam_j - mu)          (strictly decreasing there),
-// found with the origin shifted to that pole (tau = mu - p0, so the differences lam_j - mu keep full
-// relative accuracy) by a safeguarded Newton iteration on tau * f(tau), and the eigenvector is
-// [z_j / (mu - lam_j); 1].  Directions with z_j = 0 decouple (their eigenpair is (lam_j, e_j)).
-// The full decomposition for the NEXT cycle is rebuilt by rayleigh_ritz_kernel on a side stream, off the
-// critical path.
-__device__ void ritz_lowest_body(DavState* st, const double* partials, int nblk, int m) {
-    __shared__ double g[kMaxS];
-    __shared__ double v[kMaxS];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = m - 1;
-    for (int row = warp; row < m; row += blockDim.x >> 5) {
-        const double s = reduce_partials(partials, row, nblk);
-        if (lane == 0) {
-            g[row] = s;
-            st->gcol[row] = s;
-        }
-    }
-    __syncthreads();
-    if (warp != 0) return;
-    const double a = g[d];
-    // lane j < d owns pole j (kMaxS <= 32)
-    double pj = 0.0, zj = 0.0;
-    if (lane < d) {
-        pj = st->lam[lane];
-        for (int i = 0; i < d; ++i) zj = fma(st->Q[i * kMaxS + lane], g[i], zj);
-    }
-    double scale = fmax(fabs(a), fmax(fabs(pj), fabs(zj)));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, o));
-    const bool active = lane < d && fabs(zj) > 1e-15 * scale;
-    const double big = 1e300;
-    // smallest active pole (ties: lowest lane), smallest decoupled pole
-    double pa = active ? pj : big, pd = (lane < d && !active) ? pj : big;
-    int ia = active ? lane : 99, id = (lane < d && !active) ? lane : 99;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double pa2 = __shfl_xor_sync(0xffffffffu, pa, o), pd2 = __shfl_xor_sync(0xffffffffu, pd, o);
-        const int ia2 = __shfl_xor_sync(0xffffffffu, ia, o), id2 = __shfl_xor_sync(0xffffffffu, id, o);
-        if (pa2 < pa || (pa2 == pa && ia2 < ia)) { pa = pa2; ia = ia2; }
-        if (pd2 < pd || (pd2 == pd && id2 < id)) { pd = pd2; id = id2; }
-    }
-    double mu, vj = 0.0, vd = 0.0;  // eigenvector in the [Q, e_new] basis: vj on lane j, vd for e_new
-    if (ia == 99) {
-        // nothing couples to the new direction: the matrix is already diagonal
-        mu = fmin(a, pd);
-        if (a <= pd) vd = 1.0; else vj = lane == id ? 1.0 : 0.0;
-    } else {
-        const double p0 = pa, c0 = a - p0;
-        const double dj = pj - p0;               // >= 0 on active lanes, exactly 0 on lane ia
-        const double z2 = active ? zj * zj : 0.0;
-        const bool at0 = active && dj == 0.0;      // poles that coincide with p0 act as one
-        const double z0sq = warp_sum(at0 ? z2 : 0.0);
-        // start: two-term model  c + z0^2/tau - tau = 0  with the other poles frozen at tau = 0
-        double c = (active && !at0) ? z2 / dj : 0.0;
-        c = c0 - warp_sum(c);
-        const double rt = sqrt(c * c + 4.0 * z0sq);
-        double tau = c > 0.0 ? -2.0 * z0sq / (c + rt) : 0.5 * (c - rt);
-        double zn = warp_sum(z2);
-        double lo = -(fabs(c0) + sqrt(zn)) * (1.0 + 1e-12) - 1e-300, hi = 0.0;  // f(lo) > 0 > f(hi^-)
-        if (!(tau > lo && tau < hi)) tau = 0.5 * lo;
-        for (int it = 0; it < 80; ++it) {
-            // f and f' at tau
-            const double den = dj - tau;                      // > 0
-            const double t = active ? z2 / den : 0.0;
-            const double f = c0 - tau - warp_sum(t);
-            const double fp = -1.0 - warp_sum(active ? t / den : 0.0);
-            if (f > 0.0) lo = tau; else hi = tau;
-            if (f == 0.0) break;
-            // Newton on h(tau) = tau f(tau): nearly linear when the origin pole dominates
-            const double h = tau * f, hp = f + tau * fp;
-            double next = tau - h / hp;
-            if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);   // safeguard: bisection
-            const double step = fabs(next - tau);
-            tau = next;
-            if (step <= 4.4e-16 * fabs(tau) || hi - lo <= 4.4e-16 * fabs(lo)) break;
-        }
-        mu = p0 + tau;
-        if (pd < mu) {
-            // a decoupled direction lies even lower
-            mu = pd;
-            vj = lane == id ? 1.0 : 0.0;
-        } else {
-            vj = active ? zj / (tau - dj) : 0.0;   // z_j / (mu - lam_j)
-            vd = 1.0;
-        }
-    }
-    // back to the V basis: y_i = sum_j Q[i][j] v_j (i < d), y_d = vd
-    if (lane < kMaxS) v[lane] = vj;
+// Rayleigh-Ritz step in the tail of gram_kernel (one CTA, the last to arrive).
+//
+// Every cycle needs the LOWEST eigenpair of the projected matrix G (m x m, m <= max_space); only a restart
+// cycle needs more (the q lowest Ritz vectors the basis collapses onto).  So:
+//   * every cycle: Rayleigh-quotient iteration on G by one warp, started from the previous Ritz vector
+//     padded with a zero (its Rayleigh quotient is the previous Ritz value theta_prev).  Two or three
+//     solves of an m x m system (Gaussian elimination with partial pivoting, one row per lane) -- a few
+//     microseconds.  Cauchy interlacing gives the acceptance test for free: lambda_1(G_m) <= theta_prev <=
+//     lambda_2(G_m), so a converged eigenvalue that is not above theta_prev IS the lowest one;
+//   * a restart cycle, or a rejected iteration: the full decomposition by parallel-order Jacobi (all
+//     disjoint pairs of a round rotated at once), the robust slow path -- once per max_space - q cycles.
+// (Round 1 kept a decomposition up to date every cycle -- arrowhead + Jacobi, 40-130 us of one-SM latency on
+// the critical path of every cycle: a third of the summed kernel time of a bench step.)
+__device__ void jacobi_full(DavState* st, double (*A)[kMaxS + 1], double (*J)[kMaxS + 1], int m, int lane,
+                            double* cs_c, double* cs_s, int* pr_p, int* pr_q) {
+    // A: symmetric m x m (destroyed), J: receives the eigenvectors (columns).  One warp.
+    for (int idx = lane; idx < m * m; idx += 32) J[idx / m][idx % m] = (idx / m == idx % m) ? 1.0 : 0.0;
     __syncwarp();
-    double yi = 0.0;
-    if (lane < d) {
-        for (int j = 0; j < d; ++j) yi = fma(st->Q[lane * kMaxS + j], v[j], yi);
-    } else if (lane == d) {
-        yi = vd;
-    }
-    const double nrm2 = warp_sum(yi * yi);
-    // sign: the component of largest magnitude (first such) is positive
-    double mag = lane < m ? fabs(yi) : -1.0;
-    int who = lane;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double m2 = __shfl_xor_sync(0xffffffffu, mag, o);
-        const int w2 = __shfl_xor_sync(0xffffffffu, who, o);
-        if (m2 > mag || (m2 == mag && w2 < who)) { mag = m2; who = w2; }
-    }
-    const double lead = __shfl_sync(0xffffffffu, yi, who);
-    const double f = (lead < 0.0 ? -1.0 : 1.0) / sqrt(nrm2);
-    if (lane < m) st->y[lane] = yi * f;
-    if (lane == 0) {
-        st->theta_prev = st->theta;
-        st->theta = mu;
-    }
-}
-
-// Rayleigh-Ritz.  The eigen-decomposition G = Q diag(lam) Q^T of the previous cycle is kept in the state;
-// appending one basis vector makes the matrix, in the basis [Q, e_new], an ARROWHEAD
-//     [ diag(lam)   z ]        z = Q^T g ,   g = new Gram column
-//     [    z^T      a ]
-// which parallel-order Jacobi (all disjoint pairs of a round rotated at once by one CTA) diagonalises in
-// 2-4 sweeps because |z| shrinks with the residual.
-__device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nblk, int m, int publish) {
-    __shared__ double A[kMaxS][kMaxS + 1];
-    __shared__ double J[kMaxS][kMaxS + 1];   // accumulated rotations
-    __shared__ double Qo[kMaxS][kMaxS + 1];  // previous eigenvectors, extended by e_new
-    __shared__ double g[kMaxS];
-    __shared__ double cs_c[kMaxS / 2], cs_s[kMaxS / 2];
-    __shared__ int pr_p[kMaxS / 2], pr_q[kMaxS / 2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = m - 1;  // dimension of the stored decomposition
-
-    // new Gram column and the previous decomposition.  publish == 0: ritz_lowest_kernel has reduced the
-    // column and published the lowest pair, this kernel runs beside the main stream; publish != 0: this
-    // kernel is the whole Rayleigh-Ritz step (one launch fewer when the GPU is shared by many solves)
-    if (publish) {
-        for (int row = warp; row < m; row += blockDim.x >> 5) {
-            const double v = reduce_partials(partials, row, nblk);
-            if (lane == 0) g[row] = v;
-        }
-    } else {
-        for (int row = tid; row < m; row += blockDim.x) g[row] = st->gcol[row];
-    }
-    for (int idx = tid; idx < m * m; idx += blockDim.x) {
-        const int i = idx / m, j = idx % m;
-        Qo[i][j] = (i < d && j < d) ? st->Q[i * kMaxS + j] : (i == j ? 1.0 : 0.0);
-        J[i][j] = i == j ? 1.0 : 0.0;
-        A[i][j] = (i == j && i < d) ? st->lam[i] : 0.0;
-    }
-    __syncthreads();
-    if (warp != 0) return;
-    // ---- one warp from here on: every phase boundary is a __syncwarp, not a CTA barrier ----
-    for (int j = lane; j < d; j += 32) {
-        double z = 0.0;
-        for (int i = 0; i < d; ++i) z = fma(Qo[i][j], g[i], z);
-        A[j][d] = z;
-        A[d][j] = z;
-    }
-    if (lane == 0) A[d][d] = g[d];
-    __syncwarp();
-
     const int np = (m + 1) / 2;   // pairs per round
     const int nplayers = 2 * np;  // even
     for (int sweep = 0; sweep < 30 && m > 1; ++sweep) {
@@ -548,11 +443,8 @@ __device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nbl
             __syncwarp();
         }
     }
-    // new decomposition: Q <- [Q 0; 0 1] J, lam <- diag(A); lowest eigenpair -> theta, y
-    int best = 0;
-    for (int i = 1; i < m; ++i)
-        if (A[i][i] < A[best][best]) best = i;
-    if (lane == 0) {  // ascending order of the eigenvalues (selection sort, m <= 32)
+    // decomposition -> state: eigenvectors, eigenvalues, ascending order
+    if (lane == 0) {  // selection sort, m <= 32
         unsigned used = 0u;
         for (int r = 0; r < m; ++r) {
             int b = -1;
@@ -560,39 +452,187 @@ __device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nbl
                 if (!((used >> i) & 1u) && (b < 0 || A[i][i] < A[b][b])) b = i;
             used |= 1u << b;
             st->ord[r] = b;
+            if (r == 0) st->best = b;
         }
     }
-    for (int idx = lane; idx < m * m; idx += 32) {
-        const int i = idx / m, j = idx % m;
-        double v = 0.0;
-        for (int k = 0; k < m; ++k) v = fma(Qo[i][k], J[k][j], v);
-        st->Q[i * kMaxS + j] = v;
-        if (j == best) g[i] = v;  // g is free now: park the Ritz column there
-    }
+    for (int idx = lane; idx < m * m; idx += 32) st->Q[(idx / m) * kMaxS + idx % m] = J[idx / m][idx % m];
     for (int i = lane; i < m; i += 32) st->lam[i] = A[i][i];
-    if (lane == 0) st->best = best;
-    if (!publish) return;  // the lowest Ritz pair (theta, y) was published by ritz_lowest_kernel
     __syncwarp();
+}
+
+// publish the Ritz pair (theta, y): unit norm, component of largest magnitude (first such) positive
+__device__ __forceinline__ void publish_pair(DavState* st, double yi, double theta, int m, int lane) {
+    const double nrm2 = warp_sum(lane < m ? yi * yi : 0.0);
+    double mag = lane < m ? fabs(yi) : -1.0;
+    int who = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double m2 = __shfl_xor_sync(0xffffffffu, mag, o);
+        const int w2 = __shfl_xor_sync(0xffffffffu, who, o);
+        if (m2 > mag || (m2 == mag && w2 < who)) { mag = m2; who = w2; }
+    }
+    const double lead = __shfl_sync(0xffffffffu, yi, who);
+    const double f = (lead < 0.0 ? -1.0 : 1.0) / sqrt(nrm2);
+    if (lane < m) st->y[lane] = yi * f;
     if (lane == 0) {
-        double nrm = 0.0;
-        int big = 0;
-        for (int i = 0; i < m; ++i) {
-            nrm += g[i] * g[i];
-            if (fabs(g[i]) > fabs(g[big])) big = i;
-        }
-        const double sg = g[big] < 0.0 ? -1.0 : 1.0;
-        nrm = sg / sqrt(nrm);
-        for (int i = 0; i < m; ++i) st->y[i] = g[i] * nrm;
         st->theta_prev = st->theta;
-        st->theta = A[best][best];
+        st->theta = theta;
     }
 }
 
-// side-stream launch of the full decomposition (publish == 0)
-__global__ void __launch_bounds__(256)
-rayleigh_ritz_kernel(DavState* st, const double* partials, int nblk, int m, int publish) {
-    if (st->status != 0) return;
-    rayleigh_ritz_body(st, partials, nblk, m, publish);
+__device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nblk, int m, int need_full) {
+    __shared__ double A[kMaxS][kMaxS + 1];   // G - mu I (elimination) or the Jacobi work matrix
+    __shared__ double J[kMaxS][kMaxS + 1];   // copy of G (Rayleigh quotients) / accumulated rotations
+    __shared__ double g[kMaxS], bvec[kMaxS], zvec[kMaxS];
+    __shared__ double cs_c[kMaxS / 2], cs_s[kMaxS / 2];
+    __shared__ int pr_p[kMaxS / 2], pr_q[kMaxS / 2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = m - 1;
+    // new Gram column (all warps), then G = [G_old g; g^T a] in the state and in shared memory
+    for (int row = warp; row < m; row += blockDim.x >> 5) {
+        const double v = reduce_partials(partials, row, nblk);
+        if (lane == 0) g[row] = v;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < m * m; idx += blockDim.x) {
+        const int i = idx / m, j = idx % m;
+        double v;
+        if (i == d) v = g[j];
+        else if (j == d) v = g[i];
+        else v = st->G[i * kMaxS + j];
+        J[i][j] = v;
+        if (i == d || j == d) st->G[i * kMaxS + j] = v;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    // ---- one warp from here on ----
+    bool ok = false;
+    double theta = 0.0, yi = 0.0;
+    if (!need_full) {
+        if (m == 1) {
+            ok = true;
+            theta = J[0][0];
+            yi = lane == 0 ? 1.0 : 0.0;
+        } else {
+            // start: previous Ritz vector padded with zero; its Rayleigh quotient is the previous theta
+            const double theta_prev = st->theta;
+            double mu = theta_prev;
+            yi = lane < d ? st->y[lane] : 0.0;
+            double scale = 0.0;
+            for (int idx = lane; idx < m * m; idx += 32) scale = fmax(scale, fabs(J[idx / m][idx % m]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, o));
+            const double tiny = 1e-300 + 1e-18 * scale;
+            for (int it = 0; it < 8; ++it) {
+                // A = G - mu I, rhs = y
+                for (int idx = lane; idx < m * m; idx += 32) {
+                    const int i = idx / m, j = idx % m;
+                    A[i][j] = J[i][j] - (i == j ? mu : 0.0);
+                }
+                if (lane < m) bvec[lane] = yi;
+                __syncwarp();
+                // Gaussian elimination with partial pivoting: lane i owns row i
+                for (int k = 0; k < m; ++k) {
+                    double pv = (lane >= k && lane < m) ? fabs(A[lane][k]) : -1.0;
+                    int pi = lane;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double v2 = __shfl_xor_sync(0xffffffffu, pv, o);
+                        const int i2 = __shfl_xor_sync(0xffffffffu, pi, o);
+                        if (v2 > pv || (v2 == pv && i2 < pi)) { pv = v2; pi = i2; }
+                    }
+                    if (pi != k) {  // swap rows k and pi (lanes over columns)
+                        if (lane < m) {
+                            const double t = A[k][lane];
+                            A[k][lane] = A[pi][lane];
+                            A[pi][lane] = t;
+                        }
+                        if (lane == 0) {
+                            const double t = bvec[k];
+                            bvec[k] = bvec[pi];
+                            bvec[pi] = t;
+                        }
+                    }
+                    __syncwarp();
+                    double piv = A[k][k];
+                    if (fabs(piv) < tiny) piv = piv < 0.0 ? -tiny : tiny;  // mu hit an eigenvalue: that is fine
+                    __syncwarp();
+                    if (lane == 0) A[k][k] = piv;
+                    if (lane > k && lane < m) {
+                        const double f = A[lane][k] / piv;
+                        for (int j = k + 1; j < m; ++j) A[lane][j] = fma(-f, A[k][j], A[lane][j]);
+                        bvec[lane] = fma(-f, bvec[k], bvec[lane]);
+                    }
+                    __syncwarp();
+                }
+                // back substitution
+                for (int k = m - 1; k >= 0; --k) {
+                    double sacc = (lane > k && lane < m) ? A[k][lane] * zvec[lane] : 0.0;
+                    sacc = warp_sum(sacc);
+                    if (lane == 0) zvec[k] = (bvec[k] - sacc) / A[k][k];
+                    __syncwarp();
+                }
+                double zi = lane < m ? zvec[lane] : 0.0;
+                double zmax = fabs(zi);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) zmax = fmax(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
+                if (!(zmax > 0.0) || !isfinite(zmax)) break;  // fall back to Jacobi
+                zi /= zmax;
+                const double nz = sqrt(warp_sum(zi * zi));
+                zi /= nz;
+                if (lane < m) zvec[lane] = zi;
+                __syncwarp();
+                // Rayleigh quotient and residual of the new vector
+                double gz = 0.0;
+                if (lane < m)
+                    for (int j = 0; j < m; ++j) gz = fma(J[lane][j], zvec[j], gz);
+                const double mu_new = warp_sum(lane < m ? zi * gz : 0.0);
+                const double r = lane < m ? gz - mu_new * zi : 0.0;
+                const double rn = sqrt(warp_sum(r * r));
+                yi = zi;
+                const double dmu = fabs(mu_new - mu);
+                mu = mu_new;
+                __syncwarp();
+                if (lane == 0) st->n_rqi_iter += 1;
+                // (mu, z) is an eigenpair of G to working precision (cubic convergence: two or three
+                // iterations; stagnation of mu alone is NOT convergence -- a start vector that mixes +lambda
+                // and -lambda equally keeps its Rayleigh quotient for ever)
+                if (rn <= 2e-14 * scale || (it == 7 && rn <= 1e-11 * scale)) {
+                    // interlacing: lambda_1(G_m) <= theta_prev <= lambda_2(G_m).  An eigenvalue strictly below
+                    // theta_prev is therefore the lowest one; one that equals theta_prev to rounding may be
+                    // the second (a degenerate or decoupled direction) -- the full decomposition decides
+                    ok = mu < theta_prev - 1.5e-14 * (fabs(theta_prev) + scale);
+                    break;
+                }
+            }
+            theta = mu;
+        }
+    }
+    if (!ok) {
+        // full decomposition (restart cycle, or the iteration above was rejected)
+        if (lane == 0) st->n_jacobi += 1;
+        for (int idx = lane; idx < m * m; idx += 32) A[idx / m][idx % m] = J[idx / m][idx % m];
+        __syncwarp();
+        jacobi_full(st, A, J, m, lane, cs_c, cs_s, pr_p, pr_q);
+        const int best = st->ord[0];
+        theta = A[best][best];
+        yi = lane < m ? J[lane][best] : 0.0;
+    }
+    publish_pair(st, yi, theta, m, lane);
+}
+
+// last node of the cycle in the device-driven loop: basis bookkeeping and the WHILE condition
+__global__ void advance_kernel(DavState* st, cudaGraphConditionalHandle handle) {
+    if (threadIdx.x != 0) return;
+    unsigned int go = 0u;
+    if (st->status == 0) {
+        const int m = st->m;
+        const int me = (m == st->M) ? st->q_keep : m;
+        st->m = me + 1;
+        st->slot = me;
+        go = st->cycles < st->max_cycle ? 1u : 0u;
+    }
+    cudaGraphSetConditional(handle, go);
 }
 
 __device__ void convergence_body(DavState* st, const double* partials, int nblk, int m, int restart,
@@ -628,7 +668,10 @@ __device__ void convergence_body(DavState* st, const double* partials, int nblk,
                 st->c1[k] = cj[k];
                 st->lam[k] = lj[k];
                 st->ord[k] = k;
-                for (int i = 0; i < restart; ++i) st->Q[i * kMaxS + k] = i == k ? 1.0 : 0.0;
+                for (int i = 0; i < restart; ++i) {
+                    st->Q[i * kMaxS + k] = i == k ? 1.0 : 0.0;
+                    st->G[i * kMaxS + k] = i == k ? lj[k] : 0.0;  // kept Ritz vectors: G is diagonal
+                }
                 st->y[k] = k == 0 ? 1.0 : 0.0;
             }
         } else {
@@ -702,8 +745,15 @@ __global__ void axpby_kernel(const int* __restrict__ done, double a, const doubl
         z[j] = a * x[j] + b * y[j];
 }
 
-__global__ void init_state_kernel(DavState* st) {
+__global__ void init_state_kernel(DavState* st, int M, int q_keep, int max_cycle) {
     if (threadIdx.x == 0) {
+        st->m = 1;
+        st->slot = 0;
+        st->n_jacobi = 0;
+        st->n_rqi_iter = 0;
+        st->M = M;
+        st->q_keep = q_keep;
+        st->max_cycle = max_cycle;
         st->status = 0;
         st->cycles = 0;
         st->theta = 0.0;
@@ -967,13 +1017,21 @@ static int apply_operator(const sqd_operator* op, const sqd_davidson_params* prm
 }
 
 using ApplyFn = std::function<int(const double*, double*, Workspace&)>;
+// device-driven loop: w[slot] <- O v[slot] with the slot read from device memory (bases passed); may be empty
+using ApplyCtlFn = std::function<int(const double*, double*, const int*, Workspace&, cudaStream_t)>;
+
+static int env_knob(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
 
 // Side stream of a host thread: the full Rayleigh-Ritz decomposition of cycle k runs there, concurrently
 // with the residual / orthogonalisation / next sigma build of the main stream, and is joined before the
 // Rayleigh-Ritz step of cycle k+1 (or before the residual kernel of a restart cycle).
 struct SideStream {
     cudaStream_t s = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t cap = nullptr;  // capture stream used when the caller's stream is a default stream
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_cap = nullptr;
     int dev = -1;
 };
 static thread_local SideStream g_side;
@@ -984,21 +1042,76 @@ static int side_stream(SideStream** out) {
     if (g_side.s == nullptr || g_side.dev != dev) {
         if (g_side.s != nullptr) {
             cudaStreamDestroy(g_side.s);
+            cudaStreamDestroy(g_side.cap);
             cudaEventDestroy(g_side.ev_fork);
             cudaEventDestroy(g_side.ev_join);
+            cudaEventDestroy(g_side.ev_cap);
         }
         SQD_CUDA_OK(cudaStreamCreateWithFlags(&g_side.s, cudaStreamNonBlocking));
+        SQD_CUDA_OK(cudaStreamCreateWithFlags(&g_side.cap, cudaStreamNonBlocking));
         SQD_CUDA_OK(cudaEventCreateWithFlags(&g_side.ev_fork, cudaEventDisableTiming));
         SQD_CUDA_OK(cudaEventCreateWithFlags(&g_side.ev_join, cudaEventDisableTiming));
+        SQD_CUDA_OK(cudaEventCreateWithFlags(&g_side.ev_cap, cudaEventDisableTiming));
         g_side.dev = dev;
     }
     *out = &g_side;
     return 0;
 }
 
+// The whole Davidson loop as ONE graph launch: a WHILE conditional node whose body is one cycle.  Every
+// kernel of the body reads the cycle's control variables (basis size, vector slot, restart) from the
+// device-side state, so the body is captured once and the device replays it until the convergence flag
+// (or the cycle limit) clears the condition -- the host is out of the loop.  Body:
+//   gram (+ lowest Ritz pair; whole Rayleigh-Ritz on a restart cycle)
+//     |- side branch: full decomposition for the next cycle
+//     |- residual -> ortho1 -> ortho2 -> advance (m, slot, condition) -> sigma build on the new vector
+// The first sigma build runs before the graph (eagerly).
+static int davidson_graph_loop(int64_t n, const ApplyCtlFn& apply_ctl, const double* d_hdiag, Workspace& ws,
+                               int M, int blocks, const sqd_davidson_params* prm, SideStream* side,
+                               cudaStream_t st, cudaGraph_t* g_out, cudaGraphExec_t* ex_out) {
+    cudaGraph_t g = nullptr;
+    SQD_CUDA_OK(cudaGraphCreate(&g, 0));
+    *g_out = g;
+    cudaGraphConditionalHandle handle;
+    SQD_CUDA_OK(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+    cp.conditional.handle = handle;
+    cp.conditional.type = cudaGraphCondTypeWhile;
+    cp.conditional.size = 1;
+    cudaGraphNode_t node;
+    SQD_CUDA_OK(cudaGraphAddNode(&node, g, nullptr, 0, &cp));
+    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    SQD_CUDA_OK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+    int rc = dispatch_mv(M, [&](auto mv) {
+        constexpr int MV = decltype(mv)::value;
+        gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, n, -1, ws.partials, 2);
+        residual_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, d_hdiag, n, -1, 0,
+                                                            prm->level_shift, ws.X, ws.T, ws.partials,
+                                                            prm->tol, prm->tol_residual);
+        ortho1_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, -1, ws.T, ws.partials,
+                                                          prm->lindep);
+        ortho2_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, -1, ws.T, ws.V);
+        advance_kernel<<<1, 32, 0, st>>>(ws.state, handle);
+        if (check_launch("davidson cycle (graph)", 5)) return -2;
+        if (apply_ctl(ws.V, ws.W, &ws.state->slot, ws, st)) return -2;
+        return 0;
+    });
+    cudaGraph_t captured = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &captured);
+    if (rc != 0 || e != cudaSuccess) {
+        if (rc == 0) set_error("davidson graph capture failed: %s", cudaGetErrorString(e));
+        cudaGetLastError();
+        return -2;
+    }
+    SQD_CUDA_OK(cudaGraphInstantiate(ex_out, g, 0));
+    SQD_CUDA_OK(cudaGraphLaunch(*ex_out, st));
+    return 0;
+}
+
 static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag, const double* d_x0,
                          double* d_x, void* d_workspace, int64_t ws_bytes,
-                         const sqd_davidson_params* prm, sqd_davidson_info* h_info, cudaStream_t st) {
+                         const sqd_davidson_params* prm, sqd_davidson_info* h_info, cudaStream_t st,
+                         const ApplyCtlFn& apply_ctl = ApplyCtlFn()) {
     const int M = prm->max_space;
     SQD_REQUIRE(M >= 2 && M <= kMaxS, "sqd_davidson: max_space must be in [2, %d] (got %d)", kMaxS, M);
     SQD_REQUIRE(ws_bytes >= workspace_bytes(n, M), "sqd_davidson: workspace too small");
@@ -1008,7 +1121,8 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
     carve(d_workspace, n, M, &ws);
     const int blocks = red_blocks(n);
     const int check_every = prm->check_every > 0 ? prm->check_every : 4;
-    init_state_kernel<<<1, 256, 0, st>>>(ws.state);
+    const int q_keep_all = M / 3 < 1 ? 1 : (M / 3 > kKeep ? kKeep : M / 3);
+    init_state_kernel<<<1, 256, 0, st>>>(ws.state, M, q_keep_all, prm->max_cycle);
     // V_0 = x0 / |x0|
     dot_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_x0, d_x0, n, ws.partials);
     dot_final_kernel<<<1, 32, 0, st>>>(ws.partials, blocks, ws.partials + kRedBlocks);
@@ -1024,9 +1138,37 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
     }
     SideStream* side = nullptr;
     if (side_stream(&side)) return -2;
-    bool full_pending = false;
     int m = 1, slot = 0, status = 0, cycle = 0, sigma_builds = 0;
-    for (; cycle < prm->max_cycle; ++cycle) {
+    static const int knob_graph = env_knob("SQD_DAVIDSON_GRAPH", 0);
+    const bool use_graph = knob_graph != 0 && apply_ctl && !prm->profile && prm->nccl_comm == nullptr &&
+                           prm->ss_op == nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    if (use_graph) {
+        // first sigma build eagerly (it also configures the kernels' attributes outside the capture)
+        if (apply(ws.V, ws.W, ws)) return -2;
+        // a default stream (legacy or per-thread) cannot be captured: the loop then runs on a private
+        // stream of this host thread, ordered after / before the caller's stream with events
+        const bool dflt = st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread;
+        cudaStream_t gst = dflt ? side->cap : st;
+        if (dflt) {
+            SQD_CUDA_OK(cudaEventRecord(side->ev_cap, st));
+            SQD_CUDA_OK(cudaStreamWaitEvent(gst, side->ev_cap, 0));
+        }
+        const int grc = davidson_graph_loop(n, apply_ctl, d_hdiag, ws, M, blocks, prm, side, gst, &graph,
+                                            &graph_exec);
+        if (grc != 0) {
+            if (graph_exec) cudaGraphExecDestroy(graph_exec);
+            if (graph) cudaGraphDestroy(graph);
+            return grc;
+        }
+        if (dflt) {
+            SQD_CUDA_OK(cudaEventRecord(side->ev_cap, gst));
+            SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_cap, 0));
+        }
+        sigma_builds = -1;  // filled in from the device-side cycle count below
+    }
+    for (; !use_graph && cycle < prm->max_cycle; ++cycle) {
         if (prm->profile) {
             cudaEvent_t e0, e1;
             SQD_CUDA_OK(cudaEventCreate(&e0));
@@ -1043,31 +1185,12 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         const int restart = (m == M) ? q_keep : 0;
         int rc = dispatch_mv(m, [&](auto mv) {
             constexpr int MV = decltype(mv)::value;
-            static const int knob_side = getenv("SQD_RITZ_SIDE") ? atoi(getenv("SQD_RITZ_SIDE")) : -1;
-            const bool one_kernel = knob_side >= 0 ? knob_side == 0 : prm->single_stream_ritz != 0;
-            // the full decomposition of the previous cycle must be in place before this Rayleigh-Ritz
-            if (full_pending) SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));
-            full_pending = false;
             gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n, m,
-                                                            ws.partials, one_kernel ? 1 : 2);
-            if (!one_kernel) {
-                // the lowest Ritz pair came out of the tail of gram_kernel (secular equation); the full
-                // decomposition (needed by the next cycle, and by this one only when it restarts) runs on
-                // the side stream beside the residual / orthogonalisation / next sigma build
-                SQD_CUDA_OK(cudaEventRecord(side->ev_fork, st));
-                SQD_CUDA_OK(cudaStreamWaitEvent(side->s, side->ev_fork, 0));
-                rayleigh_ritz_kernel<<<1, 256, 0, side->s>>>(ws.state, ws.partials, blocks, m, 0);
-                SQD_CUDA_OK(cudaEventRecord(side->ev_join, side->s));
-                full_pending = true;
-                if (restart) {
-                    SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));
-                    full_pending = false;
-                }
-            }
+                                                            ws.partials, restart ? 1 : 0);
             residual_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, d_hdiag, n, m,
                                                                 restart, prm->level_shift, ws.X, ws.T,
                                                                 ws.partials, prm->tol, prm->tol_residual);
-            return check_launch("davidson cycle (1)", one_kernel ? 2 : 3);
+            return check_launch("davidson cycle (1)", 2);
         });
         if (rc) return -2;
         const int me = restart ? restart : m;
@@ -1091,10 +1214,16 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         }
     }
     DavState hs;
-    if (full_pending) SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));  // nothing outlives the call
     SQD_CUDA_OK(cudaMemcpyAsync(d_x, ws.X, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     if (prm->profile) SQD_CUDA_OK(cudaEventRecord(ev_end, st));
     if (read_back(&hs, ws.state, sizeof(DavState), st)) return -2;
+    if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (sigma_builds < 0) sigma_builds = hs.cycles + (hs.status == 0 ? 1 : 0);
+    static const int knob_debug = env_knob("SQD_DEBUG_RITZ", 0);
+    if (knob_debug)
+        fprintf(stderr, "[sqd] davidson: cycles %d, full decompositions %d, rqi iterations %d, status %d\n",
+                hs.cycles, hs.n_jacobi, hs.n_rqi_iter, hs.status);
     double sigma_ms = 0.0, total_ms = 0.0;
     if (prm->profile) {
         // only cycles that ran before the device-side stop flag was raised did real work
@@ -1195,7 +1324,11 @@ int sqd_davidson(const sqd_operator* op, const double* d_hdiag, const double* d_
     auto apply = [&](const double* v, double* w, Workspace& ws) {
         return apply_operator(op, prm, v, w, ws, n, st);
     };
-    return davidson_core(n, apply, d_hdiag, d_x0, d_x, d_workspace, ws_bytes, prm, h_info, st);
+    ApplyCtlFn apply_ctl = [&](const double* vbase, double* wbase, const int* slot, Workspace& ws,
+                               cudaStream_t cst) {
+        return sigma_dispatch_ctl(op, vbase, wbase, &ws.state->status, slot, n, 1, cst);
+    };
+    return davidson_core(n, apply, d_hdiag, d_x0, d_x, d_workspace, ws_bytes, prm, h_info, st, apply_ctl);
 }
 
 int64_t sqd_csr_davidson_workspace_bytes(int64_t d, int k, int max_space) {

@@ -39,7 +39,14 @@ struct SigmaArgs {
     const int* done;  // optional device flag: non-zero -> the launch is a no-op (Davidson finished)
     long long* prof;  // optional diagnostics: 8 clock64() stamps per kernel-A CTA (sqd_sigma_profile)
     int row_begin, row_end;  // rows of sigma this launch owns (sharded builds); other rows are untouched
+    // device-driven Davidson loop (CUDA graph replay): c and sigma are BASE pointers and the vector slot is
+    // read from device memory, so that every cycle launches with identical arguments
+    const int* slot_ptr;
+    long long vec_stride;
 };
+__device__ __forceinline__ size_t slot_offset(const int* slot_ptr, long long stride) {
+    return slot_ptr != nullptr ? (size_t)(*slot_ptr) * (size_t)stride : 0;
+}
 
 // try_wait with a suspend-time hint: a warp whose barrier phase is not complete is parked by the hardware
 // (no issue slots consumed) until the phase completes or ~the hint elapses.  Busy-polling here is
@@ -277,6 +284,8 @@ __global__ void __launch_bounds__(kWarpsB * 32)
 sigma_b_kernel(const SigmaArgs P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
+    const double* Pc = P.c + slot_offset(P.slot_ptr, P.vec_stride);
+    double* Psig = P.sigma + slot_offset(P.slot_ptr, P.vec_stride);
     const sqd_operator& op = P.op;
     const sqd_sell& L = op.bb;
     const int na = op.a.n, nb = op.b.n, ldc = op.ldc;
@@ -292,7 +301,7 @@ sigma_b_kernel(const SigmaArgs P) {
     uint64_t* bar = reinterpret_cast<uint64_t*>(red + kWarpsB * kRowsB * 32);
     if (slice >= L.n_slices) {  // only pad positions live here
         if (warp == 0 && pos >= nb && pos < ldc)
-            for (int r = 0; r < nrows; ++r) P.sigma[(size_t)(a0 + r) * ldc + pos] = 0.0;
+            for (int r = 0; r < nrows; ++r) Psig[(size_t)(a0 + r) * ldc + pos] = 0.0;
         return;
     }
     if (tid == 0) {
@@ -303,7 +312,7 @@ sigma_b_kernel(const SigmaArgs P) {
     if (tid == 0) {
         mbar_expect_tx(bar, (uint32_t)(nrows * ldc * sizeof(double)));
         for (int r = 0; r < nrows; ++r)
-            bulk_g2s(Cs + (size_t)r * ldc, P.c + (size_t)(a0 + r) * ldc, (uint32_t)(ldc * sizeof(double)), bar);
+            bulk_g2s(Cs + (size_t)r * ldc, Pc + (size_t)(a0 + r) * ldc, (uint32_t)(ldc * sizeof(double)), bar);
     }
     double acc[kRowsB];
 #pragma unroll
@@ -347,20 +356,22 @@ sigma_b_kernel(const SigmaArgs P) {
                     double t = red[r * 32 + lane];
 #pragma unroll
                     for (int w = 1; w < kWarpsB; ++w) t += red[(w * kRowsB + r) * 32 + lane];
-                    P.sigma[(size_t)(a0 + r) * ldc + b] =
+                    Psig[(size_t)(a0 + r) * ldc + b] =
                         fma(op.diag[(size_t)(a0 + r) * ldc + b], Cs[r * ldc + b], t);
                 }
             }
         } else if (pos < ldc) {
-            for (int r = 0; r < nrows; ++r) P.sigma[(size_t)(a0 + r) * ldc + pos] = 0.0;  // pads
+            for (int r = 0; r < nrows; ++r) Psig[(size_t)(a0 + r) * ldc + pos] = 0.0;  // pads
         }
     }
 }
 
 // sigma[a,:] += sum over the row's chunk partials, in chunk order
 __global__ void sigma_combine_kernel(const int* __restrict__ done, const sqd_sigma_plan pl, int ldc,
-                                     double* __restrict__ sigma, int row_begin, int row_end) {
+                                     double* __restrict__ sigma, int row_begin, int row_end,
+                                     const int* __restrict__ slot_ptr, long long vec_stride) {
     if (done != nullptr && *done != 0) return;
+    sigma += slot_offset(slot_ptr, vec_stride);
     const int j = blockIdx.x;
     const int a = pl.split_row[j], s0 = pl.split_slot_beg[j], k = pl.split_n[j];
     if (a < row_begin || a >= row_end) return;
@@ -417,6 +428,8 @@ __global__ void __launch_bounds__(TB, MINB)
 sigma_a_kernel(const SigmaArgs P, const int NST) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
+    const double* Pc = P.c + slot_offset(P.slot_ptr, P.vec_stride);
+    double* Psig = P.sigma + slot_offset(P.slot_ptr, P.vec_stride);
     const sqd_operator& op = P.op;
     const sqd_sigma_plan& pl = op.plan;
     const sqd_sell& L = op.bd;
@@ -462,11 +475,11 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
                     const double* crow;
                     const double* grow;
                     if (ck.self_item && t == 0) {
-                        crow = P.c + (size_t)ck.a * ldc;
+                        crow = Pc + (size_t)ck.a * ldc;
                         grow = op.Wa + (size_t)ck.a * ldg;
                     } else {
                         const int e = ck.it_beg + t - (ck.self_item ? 1 : 0);
-                        crow = P.c + (size_t)op.a.col[e] * ldc;
+                        crow = Pc + (size_t)op.a.col[e] * ldc;
                         grow = op.gab + (size_t)(op.a.meta[e] & 0x7fffffffu) * ldg;
                     }
                     double* dst = stage + (size_t)s * stage_len;
@@ -568,7 +581,7 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
                         double x[kUnrollC];
 #pragma unroll
                         for (int u = 0; u < kUnrollC; ++u)
-                            x[u] = __ldg(P.c + (size_t)dcol_s[min(e0 + u, tn - 1)] * ldc + b);
+                            x[u] = __ldg(Pc + (size_t)dcol_s[min(e0 + u, tn - 1)] * ldc + b);
 #pragma unroll
                         for (int u = 0; u < kUnrollC; ++u)
                             if (e0 + u < tn) acc_nat[c] = fma(dval_s[e0 + u], x[u], acc_nat[c]);
@@ -698,7 +711,7 @@ sigma_a_kernel(const SigmaArgs P, const int NST) {
             if (li >= 0)
                 for (int w = 0; w < nwarp_c; ++w) v += acc_long[li * 32 + w];
             if (slot < 0)
-                P.sigma[(size_t)a * ldc + b] += v;  // kernel B wrote the element earlier in the stream
+                Psig[(size_t)a * ldc + b] += v;  // kernel B wrote the element earlier in the stream
             else
                 pl.part[(size_t)slot * ldc + b] = v;
         } else if (b < ldc && slot >= 0) {
@@ -862,7 +875,8 @@ static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t
         return -2;
     if (op.plan.n_split > 0) {
         sigma_combine_kernel<<<op.plan.n_split, 256, 0, st>>>(args.done, op.plan, op.ldc, args.sigma,
-                                                              args.row_begin, args.row_end);
+                                                              args.row_begin, args.row_end, args.slot_ptr,
+                                                              args.vec_stride);
         return check_launch("sigma_combine_kernel");
     }
     return 0;
@@ -872,9 +886,12 @@ static thread_local long long* g_prof = nullptr;
 
 int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
                         int row_begin, int row_end, cudaStream_t st);
+int sigma_dispatch_ctl(const sqd_operator* op, const double* d_cbase, double* d_sbase, const int* d_done,
+                       const int* d_slot, long long stride, int in_graph, cudaStream_t st);
 // v2 kernels (fermion_sigma2.cu)
 int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
-                         int row_begin, int row_end, cudaStream_t st);
+                         int row_begin, int row_end, const int* d_slot, long long stride, int in_graph,
+                         cudaStream_t st);
 int64_t sigma2_smem_bytes(const sqd_operator* op);
 
 int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sigma,
@@ -882,9 +899,26 @@ int sigma_dispatch_flag(const sqd_operator* op, const double* d_c, double* d_sig
     return sigma_dispatch_rows(op, d_c, d_sigma, d_done, 0, op->a.n, st);
 }
 
+static int sigma_dispatch_impl(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
+                               int row_begin, int row_end, const int* d_slot, long long stride, int in_graph,
+                               cudaStream_t st);
+
 int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
                         int row_begin, int row_end, cudaStream_t st) {
-    if (op->v2.enabled) return sigma2_dispatch_rows(op, d_c, d_sigma, d_done, row_begin, row_end, st);
+    return sigma_dispatch_impl(op, d_c, d_sigma, d_done, row_begin, row_end, nullptr, 0, 0, st);
+}
+
+// device-driven loop: vector = base + (*d_slot) * stride, for both the input and the output
+int sigma_dispatch_ctl(const sqd_operator* op, const double* d_cbase, double* d_sbase, const int* d_done,
+                       const int* d_slot, long long stride, int in_graph, cudaStream_t st) {
+    return sigma_dispatch_impl(op, d_cbase, d_sbase, d_done, 0, op->a.n, d_slot, stride, in_graph, st);
+}
+
+static int sigma_dispatch_impl(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
+                               int row_begin, int row_end, const int* d_slot, long long stride, int in_graph,
+                               cudaStream_t st) {
+    if (op->v2.enabled)
+        return sigma2_dispatch_rows(op, d_c, d_sigma, d_done, row_begin, row_end, d_slot, stride, in_graph, st);
     SigmaPlan pl;
     SQD_REQUIRE(op->ldc % 2 == 0 && op->ldg % 2 == 0 && op->ldc >= op->b.n,
                 "sqd_sigma: ldc/ldg must be even and ldc >= nb");
@@ -899,7 +933,7 @@ int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sig
                 "(limits: nb <= 5760 and 3*ldc + 2*ldg doubles <= 227 KB)",
                 op->b.n, op->ldc, op->norb);
     SQD_REQUIRE(row_begin >= 0 && row_end <= op->a.n && row_begin <= row_end, "sqd_sigma: bad row range");
-    SigmaArgs args{*op, d_c, d_sigma, d_done, g_prof, row_begin, row_end};
+    SigmaArgs args{*op, d_c, d_sigma, d_done, g_prof, row_begin, row_end, d_slot, stride};
     switch (pl.CPT) {
         case 1: return launch_sigma<1>(args, pl, st);
         case 2: return launch_sigma<2>(args, pl, st);

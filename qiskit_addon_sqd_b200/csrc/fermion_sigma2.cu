@@ -405,7 +405,14 @@ struct V2Args {
     const int* done;
     int row_begin, row_end;
     int nsplit;
+    // device-driven Davidson loop (CUDA graph replay): c and sigma are BASE pointers, the vector slot is
+    // read from device memory
+    const int* slot_ptr;
+    long long vec_stride;
 };
+__device__ __forceinline__ size_t v2_slot_offset(const V2Args& P) {
+    return P.slot_ptr != nullptr ? (size_t)(*P.slot_ptr) * (size_t)P.vec_stride : 0;
+}
 
 __device__ __forceinline__ bool v2_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -467,6 +474,7 @@ sigma2_ab_kernel(const V2Args P, const int NST, const int stage_len, const int s
     constexpr int BATCH = LEAN ? 8 : 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
+    const double* Pc = P.c + v2_slot_offset(P);
     const sqd_operator& op = P.op;
     const sqd_sigma_v2& V = op.v2;
     const int g = blockIdx.y;
@@ -536,7 +544,7 @@ sigma2_ab_kernel(const V2Args P, const int NST, const int stage_len, const int s
                     hdr[s] = make_int4(1, 0, 0, ap);
                     if (src_smem) {
                         mbar_expect_tx(&full[s], (uint32_t)(ldc * sizeof(double)));
-                        bulk_g2s(stage + (size_t)s * stage_len, P.c + (size_t)ap * ldc,
+                        bulk_g2s(stage + (size_t)s * stage_len, Pc + (size_t)ap * ldc,
                                  (uint32_t)(ldc * sizeof(double)), &full[s]);
                     } else {
                         v2_arrive(&full[s]);
@@ -636,7 +644,7 @@ sigma2_ab_kernel(const V2Args P, const int NST, const int stage_len, const int s
         if (h.x == 1) {
             // the (source column, sign) words are re-read per source string: 4 bytes per link from L1/L2,
             // against 16 more registers per thread if they were kept.  Padding entries read column 0.
-            const double* crow = src_smem ? stage + (size_t)s * stage_len : P.c + (size_t)h.w * ldc;
+            const double* crow = src_smem ? stage + (size_t)s * stage_len : Pc + (size_t)h.w * ldc;
             if (wlen > 0) {
 #pragma unroll
                 for (int j = 0; j < LMAX; ++j) {
@@ -689,7 +697,7 @@ sigma2_tile_kernel(const V2Args P) {
     const int a_lo = P.row_begin & ~1;
     const int a0 = a_lo + blockIdx.x * kTM, b0 = blockIdx.y * kTN;
     const int split = blockIdx.z, nsplit = gridDim.z;
-    const double* __restrict__ c = P.c;
+    const double* __restrict__ c = P.c + v2_slot_offset(P);
 
     double acc[8][4];
 #pragma unroll
@@ -887,7 +895,7 @@ sigma2_epilogue_kernel(const V2Args P) {
                 for (int u = 0; u < 4; ++u) base += pt[u];
             }
             const size_t ab = (size_t)a * ldc + b;
-            base = fma(op.diag[ab], P.c[ab], base);
+            base = fma(op.diag[ab], (P.c + v2_slot_offset(P))[ab], base);
         }
         if (op.Wa != nullptr) {   // self item: q-part only
             const double* prow = pcol - ldp;
@@ -920,7 +928,7 @@ sigma2_epilogue_kernel(const V2Args P) {
         for (int q = q0; q < q1; ++q)
             for (int w = 0; w < nwarps; ++w) v += Sq[w][q];
     }
-    P.sigma[(size_t)a * ldc + b] = v;  // pad column: 0
+    (P.sigma + v2_slot_offset(P))[(size_t)a * ldc + b] = v;  // pad column: 0
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -945,8 +953,9 @@ static int v2_pick_stages(const sqd_operator* op) {
     if (knob >= 2 && knob <= kV2MaxStages) return knob;
     // deep enough to let the warps of a CTA drift apart and to cover the L2 latency of a row copy, small
     // enough for three CTAs per SM
+    static const int knob_kb = v2_env("SQD_V2_RING_KB", 100);
     int nst = 8;
-    while (nst > 2 && v2_k1_smem(op, nst) > 160 * 1024) --nst;
+    while (nst > 2 && v2_k1_smem(op, nst) > (size_t)knob_kb * 1024) --nst;
     return nst;
 }
 
@@ -993,7 +1002,8 @@ static int v2_side(V2Side** out) {
 }
 
 int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sigma, const int* d_done,
-                         int row_begin, int row_end, cudaStream_t st) {
+                         int row_begin, int row_end, const int* d_slot, long long stride, int in_graph,
+                         cudaStream_t st) {
     const sqd_sigma_v2& V = op->v2;
     SQD_REQUIRE(V.enabled && V.P != nullptr, "sqd_sigma: the operator has no v2 tables");
     SQD_REQUIRE(op->ldc % 2 == 0 && op->ldg % 2 == 0 && op->ldc >= op->b.n && op->ldg > op->norb * op->norb,
@@ -1002,13 +1012,14 @@ int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_si
                 "sqd_sigma: the v2 tables were built without the dense same-spin blocks");
     SQD_REQUIRE(row_begin >= 0 && row_end <= op->a.n && row_begin <= row_end, "sqd_sigma: bad row range");
     if (row_end == row_begin) return 0;
-    V2Args args{*op, d_c, d_sigma, d_done, row_begin, row_end, 0};
+    V2Args args{*op, d_c, d_sigma, d_done, row_begin, row_end, 0, d_slot, stride};
     // K2 (FP64-pipe bound) and K1 (shared-memory gather bound) are independent: K2 goes to a side stream
     // of this host thread and runs beside K1; both join before K3.  SQD_V2_OVERLAP=0 keeps one stream.
     // Worth it for a lone solve only: when several solves share the GPU their kernels fill each other's gaps.
     static const int knob_overlap = v2_env("SQD_V2_OVERLAP", -1);
     V2Side* side = nullptr;
-    const bool want_fork = knob_overlap >= 0 ? knob_overlap != 0 : op->throughput_mode == 0;
+    // Inside a captured graph the fork costs no host time: always on there.
+    const bool want_fork = knob_overlap >= 0 ? knob_overlap != 0 : (in_graph != 0 || op->throughput_mode == 0);
     const bool fork = want_fork && op->use_same_spin != 0 && V.n_chunks > 0;
     if (fork && v2_side(&side)) return -2;
     cudaStream_t st2 = fork ? side->s : st;
@@ -1032,20 +1043,26 @@ int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_si
     const int stage_len = v2_stage_len(op);
     const size_t smem = v2_k1_smem(op, nst);
     SQD_REQUIRE(smem <= 220 * 1024, "sqd_sigma: norb=%d does not fit the integral-row ring", op->norb);
-    auto k1 = V.lmax == 8 ? (fork ? sigma2_ab_kernel<8, true> : sigma2_ab_kernel<8, false>)
-                          : (fork ? sigma2_ab_kernel<16, true> : sigma2_ab_kernel<16, false>);
+    static const int knob_lean = v2_env("SQD_V2_LEAN", -1);
+    const bool lean = knob_lean >= 0 ? knob_lean != 0 : (fork || op->throughput_mode != 0);
+    auto k1 = V.lmax == 8 ? (lean ? sigma2_ab_kernel<8, true> : sigma2_ab_kernel<8, false>)
+                          : (lean ? sigma2_ab_kernel<16, true> : sigma2_ab_kernel<16, false>);
     static bool cfg[64][4] = {};
     int dev = 0;
     SQD_CUDA_OK(cudaGetDevice(&dev));
-    const int li = (V.lmax == 8 ? 0 : 1) + (fork ? 2 : 0);
+    const int li = (V.lmax == 8 ? 0 : 1) + (lean ? 2 : 0);
     if (dev >= 0 && dev < 64 && !cfg[dev][li]) {
         SQD_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         SQD_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout,
                                          (int)cudaSharedmemCarveoutMaxShared));
         cfg[dev][li] = true;
     }
-    static const int knob_ctas = v2_env("SQD_V2_CTAS_PER_SM", 1);
-    int gx = (knob_ctas * kNumSMs + V.n_groups - 1) / V.n_groups;
+    // lean CTAs (<= 31 K registers, <= 100 KB of ring) share an SM two at a time
+    static const int knob_ctas = v2_env("SQD_V2_CTAS_PER_SM", 0);
+    const int ctas_per_sm = knob_ctas > 0 ? knob_ctas : (lean && !fork ? 2 : 1);
+    int gx = (ctas_per_sm * kNumSMs + V.n_groups - 1) / V.n_groups;
+    static const int knob_grid = v2_env("SQD_V2_K1_GRID", 0);  // experiments: absolute CTA count per group
+    if (knob_grid > 0 && op->throughput_mode != 0) gx = knob_grid;
     if (gx < 1) gx = 1;
     if (gx > V.n_chunks) gx = V.n_chunks;
     if (V.n_chunks > 0) {
