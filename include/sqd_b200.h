@@ -178,6 +178,8 @@ typedef struct {
     const int* item_tgt;     /* [n_items] (source order) target alpha string of the item */
     const uint32_t* item_gsel; /* [n_items] integral row pq of source -> target | sign << 31; bit 30: self item (row of Wa) */
     const int* item_pslot;   /* [n_items] (source order) P row the item writes */
+    const int* heavy_rows;   /* [n_heavy] alpha strings with more than 64 single excitations (own epilogue launch) */
+    int n_heavy;
     const double* HaDT;      /* [lda*lda] dense same-spin alpha block, transposed: HaDT[a'*lda + a] */
     const double* HbDT;      /* [ldb*ldb] */
     double* P;               /* [n_items * ldp] */

@@ -71,7 +71,7 @@ class SigmaV2(C.Structure):
         ("vc_src", C.c_void_p), ("vc_off", C.c_void_p), ("vc_len", C.c_void_p), ("vc_q", C.c_void_p),
         ("col_seg", C.c_void_p), ("single_ptr", C.c_void_p), ("item_ptr", C.c_void_p),
         ("chunk_rec", C.c_void_p), ("item_tgt", C.c_void_p), ("item_gsel", C.c_void_p),
-        ("item_pslot", C.c_void_p),
+        ("item_pslot", C.c_void_p), ("heavy_rows", C.c_void_p), ("n_heavy", C.c_int),
         ("HaDT", C.c_void_p), ("HbDT", C.c_void_p), ("P", C.c_void_p), ("part", C.c_void_p),
     ]
 

@@ -92,6 +92,7 @@ __device__ __forceinline__ Ctl read_ctl(const DavState* st, int m_arg, int resta
 // of the streaming kernel to arrive (ticket counter, after a __threadfence) runs the step in its tail:
 // same fixed summation order as before (the per-CTA partials are reduced in index order), three launches
 // and three launch gaps fewer per cycle.
+template <int MR>
 __device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nblk, int m, int need_full);
 __device__ void convergence_body(DavState* st, const double* partials, int nblk, int m, int restart,
                                  double tol, double tol_residual);
@@ -157,7 +158,7 @@ gram_kernel(DavState* st, const double* __restrict__ V, const double* __restrict
     }
     // tail: Rayleigh-Ritz on the finished Gram column.  ritz_mode 1: the whole step (decomposition and
     // lowest pair); 2: lowest pair only, the decomposition follows on the side stream
-    if (last_block(&st->ticket[0])) rayleigh_ritz_body(st, partials, gridDim.x, m, ritz_mode);
+    if (last_block(&st->ticket[0])) rayleigh_ritz_body<(MV <= 16 ? MV : 16)>(st, partials, gridDim.x, m, ritz_mode);
 }
 
 template <int MV>
@@ -364,30 +365,38 @@ __device__ __forceinline__ double reduce_partials(const double* partials, int ro
 // the critical path of every cycle: a third of the summed kernel time of a bench step.)
 __device__ void jacobi_full(DavState* st, double (*A)[kMaxS + 1], double (*J)[kMaxS + 1], int m, int lane,
                             double* cs_c, double* cs_s, int* pr_p, int* pr_q) {
-    // A: symmetric m x m (destroyed), J: receives the eigenvectors (columns).  One warp.
-    for (int idx = lane; idx < m * m; idx += 32) J[idx / m][idx % m] = (idx / m == idx % m) ? 1.0 : 0.0;
-    __syncwarp();
+    // A: symmetric m x m (destroyed), J: receives the eigenvectors (columns).  One warp.  The index maps use
+    // shifts only: an integer division by a run-time value costs more than the rotation it addresses.
     const int np = (m + 1) / 2;   // pairs per round
     const int nplayers = 2 * np;  // even
+    // lane -> (pair k, row chunk c): kw pairs per "row of lanes" (8 for m <= 16, else 16)
+    const int kw_log = np <= 8 ? 3 : 4, kw = 1 << kw_log, nchunk = 32 >> kw_log;
+    const int k_of = lane & (kw - 1), c_of = lane >> kw_log;
+    for (int i = c_of; i < m; i += nchunk)
+        for (int j = k_of; j < m; j += kw) J[i][j] = i == j ? 1.0 : 0.0;
+    __syncwarp();
     for (int sweep = 0; sweep < 30 && m > 1; ++sweep) {
         double off = 0.0, dia = 0.0;
-        for (int idx = lane; idx < m * m; idx += 32) {
-            const int i = idx / m, j = idx % m;
-            const double v = A[i][j] * A[i][j];
-            if (i == j) dia += v; else off += v;
-        }
+        for (int i = c_of; i < m; i += nchunk)
+            for (int j = k_of; j < m; j += kw) {
+                const double v = A[i][j] * A[i][j];
+                if (i == j) dia += v; else off += v;
+            }
         off = warp_sum(off);
         dia = warp_sum(dia);
         if (off <= 1e-26 * dia) break;  // identical on all lanes
         for (int step = 0; step < nplayers - 1; ++step) {
-            for (int k = lane; k < np; k += 32) {
+            if (lane < np) {
+                const int k = lane;
                 int p, q;
                 if (k == 0) {
                     p = nplayers - 1;
                     q = step;
                 } else {
-                    p = (step + k) % (nplayers - 1);
-                    q = (step - k + (nplayers - 1)) % (nplayers - 1);
+                    p = step + k;
+                    if (p >= nplayers - 1) p -= nplayers - 1;
+                    q = step - k;
+                    if (q < 0) q += nplayers - 1;
                 }
                 if (p > q) {
                     const int t = p;
@@ -414,27 +423,24 @@ __device__ void jacobi_full(DavState* st, double (*A)[kMaxS + 1], double (*J)[kM
                 cs_s[k] = sn;
             }
             __syncwarp();
-            // column update: A <- A R, J <- J R
-            for (int idx = lane; idx < 2 * m * np; idx += 32) {
-                const int which = idx / (m * np);
-                const int rem = idx % (m * np);
-                const int i = rem / np, k = rem % np;
-                const int p = pr_p[k], q = pr_q[k];
-                if (p != q) {
-                    const double c = cs_c[k], sn = cs_s[k];
-                    double(*M)[kMaxS + 1] = which ? J : A;
-                    const double xp = M[i][p], xq = M[i][q];
-                    M[i][p] = c * xp - sn * xq;
-                    M[i][q] = sn * xp + c * xq;
+            const bool have = k_of < np;
+            const int p = have ? pr_p[k_of] : 0, q = have ? pr_q[k_of] : 0;
+            const double c = have ? cs_c[k_of] : 1.0, sn = have ? cs_s[k_of] : 0.0;
+            // column update: A <- A R, J <- J R  (pairs are disjoint: no two lanes touch the same column)
+            if (p != q) {
+                for (int i = c_of; i < m; i += nchunk) {
+                    const double xp = A[i][p], xq = A[i][q];
+                    A[i][p] = c * xp - sn * xq;
+                    A[i][q] = sn * xp + c * xq;
+                    const double yp = J[i][p], yq = J[i][q];
+                    J[i][p] = c * yp - sn * yq;
+                    J[i][q] = sn * yp + c * yq;
                 }
             }
             __syncwarp();
             // row update: A <- R^T A
-            for (int idx = lane; idx < m * np; idx += 32) {
-                const int j = idx / np, k = idx % np;
-                const int p = pr_p[k], q = pr_q[k];
-                if (p != q) {
-                    const double c = cs_c[k], sn = cs_s[k];
+            if (p != q) {
+                for (int j = c_of; j < m; j += nchunk) {
                     const double xp = A[p][j], xq = A[q][j];
                     A[p][j] = c * xp - sn * xq;
                     A[q][j] = sn * xp + c * xq;
@@ -455,7 +461,8 @@ __device__ void jacobi_full(DavState* st, double (*A)[kMaxS + 1], double (*J)[kM
             if (r == 0) st->best = b;
         }
     }
-    for (int idx = lane; idx < m * m; idx += 32) st->Q[(idx / m) * kMaxS + idx % m] = J[idx / m][idx % m];
+    for (int i = c_of; i < m; i += nchunk)
+        for (int j = k_of; j < m; j += kw) st->Q[i * kMaxS + j] = J[i][j];
     for (int i = lane; i < m; i += 32) st->lam[i] = A[i][i];
     __syncwarp();
 }
@@ -480,6 +487,125 @@ __device__ __forceinline__ void publish_pair(DavState* st, double yi, double the
     }
 }
 
+// Rayleigh-quotient iteration with the whole problem in registers: lane i owns row i of G (MR >= m doubles;
+// rows and columns beyond m are an identity block).  Gaussian elimination with partial pivoting WITHOUT row
+// swaps (the pivot lane of every step is remembered instead), the pivot row is broadcast by shuffles, the
+// solution vector is replicated on all lanes during back substitution.  A 12 x 12 solve is ~1.5 k cycles of
+// one warp -- the shared-memory version it replaces took ten times that.
+// Returns true when (mu, y) is an eigenpair of G to working precision AND certified lowest (interlacing).
+template <int MR>
+__device__ __forceinline__ bool rqi_lowest(const double (*Gs)[kMaxS + 1], int m, int lane, double theta_prev,
+                                           const double* y_prev, double scale, double* mu_out, double* yi_out,
+                                           int* iters) {
+    const int d = m - 1;
+    double grow[MR];
+#pragma unroll
+    for (int j = 0; j < MR; ++j) grow[j] = (lane < m && j < m) ? Gs[lane][j] : 0.0;
+    double z[MR];  // current vector, replicated on all lanes
+#pragma unroll
+    for (int j = 0; j < MR; ++j) z[j] = j < d ? y_prev[j] : 0.0;
+    double mu = theta_prev;
+    const double tiny = 1e-300 + 1e-18 * scale;
+    bool ok = false;
+    for (int it = 0; it < 8; ++it) {
+        double a[MR], b = 0.0;
+#pragma unroll
+        for (int j = 0; j < MR; ++j) {
+            a[j] = grow[j] - (j == lane ? mu : 0.0);
+            if (lane >= m) a[j] = j == lane ? 1.0 : 0.0;
+            if (j == lane) b = z[j];
+        }
+        if (lane >= m) b = 0.0;
+        bool used = lane >= m;  // lanes that have served as a pivot row (identity rows never take part)
+        int piv[MR];
+#pragma unroll
+        for (int k = 0; k < MR; ++k) {
+            piv[k] = k;  // identity block
+            if (k < m) {
+                double pv = used ? -1.0 : fabs(a[k]);
+                int pi = lane;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double v2 = __shfl_xor_sync(0xffffffffu, pv, o);
+                    const int i2 = __shfl_xor_sync(0xffffffffu, pi, o);
+                    if (v2 > pv || (v2 == pv && i2 < pi)) { pv = v2; pi = i2; }
+                }
+                piv[k] = pi;
+                double pk = __shfl_sync(0xffffffffu, a[k], pi);
+                if (fabs(pk) < tiny) pk = pk < 0.0 ? -tiny : tiny;  // mu hit an eigenvalue: that is fine
+                if (lane == pi) {
+                    a[k] = pk;
+                    used = true;
+                }
+                const double pb = __shfl_sync(0xffffffffu, b, pi);
+                const double f = used ? 0.0 : a[k] / pk;
+#pragma unroll
+                for (int j = k + 1; j < MR; ++j) {
+                    const double pj = __shfl_sync(0xffffffffu, a[j], pi);
+                    if (j < m) a[j] = fma(-f, pj, a[j]);
+                }
+                b = fma(-f, pb, b);
+            }
+        }
+        // back substitution: the row with pivot k lives on lane piv[k]
+#pragma unroll
+        for (int k = MR - 1; k >= 0; --k) {
+            if (k < m) {
+                double acc = b;
+#pragma unroll
+                for (int j = k + 1; j < MR; ++j)
+                    if (j < m) acc = fma(-a[j], z[j], acc);
+                z[k] = __shfl_sync(0xffffffffu, acc / a[k], piv[k]);
+            } else {
+                z[k] = 0.0;
+            }
+        }
+        double zmax = 0.0, n2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < MR; ++j) zmax = fmax(zmax, fabs(z[j]));
+        if (!(zmax > 0.0) || !isfinite(zmax)) break;
+        const double inv = 1.0 / zmax;
+#pragma unroll
+        for (int j = 0; j < MR; ++j) {
+            z[j] *= inv;
+            n2 = fma(z[j], z[j], n2);
+        }
+        const double invn = rsqrt(n2);
+#pragma unroll
+        for (int j = 0; j < MR; ++j) z[j] *= invn;
+        // Rayleigh quotient and residual
+        double gz = 0.0, zi = 0.0;
+#pragma unroll
+        for (int j = 0; j < MR; ++j) {
+            gz = fma(grow[j], z[j], gz);
+            if (j == lane) zi = z[j];
+        }
+        const double mu_new = warp_sum(lane < m ? zi * gz : 0.0);
+        const double r = lane < m ? gz - mu_new * zi : 0.0;
+        const double rn = sqrt(warp_sum(r * r));
+        mu = mu_new;
+        *iters += 1;
+        // (mu, z) is an eigenpair of G to working precision (cubic convergence: two or three iterations;
+        // stagnation of mu alone is NOT convergence -- a start vector that mixes +lambda and -lambda equally
+        // keeps its Rayleigh quotient for ever)
+        if (rn <= 2e-14 * scale || (it == 7 && rn <= 1e-11 * scale)) {
+            // interlacing: lambda_1(G_m) <= theta_prev <= lambda_2(G_m).  An eigenvalue strictly below
+            // theta_prev is therefore the lowest one; one that equals theta_prev to rounding may be the
+            // second (a degenerate or decoupled direction) -- the full decomposition decides
+            ok = mu < theta_prev - 1.5e-14 * (fabs(theta_prev) + scale);
+            break;
+        }
+    }
+    double yi = 0.0;
+#pragma unroll
+    for (int j = 0; j < MR; ++j)
+        if (j == lane) yi = z[j];
+    *mu_out = mu;
+    *yi_out = yi;
+    return ok;
+}
+
+template <int MR>
 __device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nblk, int m, int need_full) {
     __shared__ double A[kMaxS][kMaxS + 1];   // G - mu I (elimination) or the Jacobi work matrix
     __shared__ double J[kMaxS][kMaxS + 1];   // copy of G (Rayleigh quotients) / accumulated rotations
@@ -494,8 +620,9 @@ __device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nbl
         if (lane == 0) g[row] = v;
     }
     __syncthreads();
-    for (int idx = tid; idx < m * m; idx += blockDim.x) {
-        const int i = idx / m, j = idx % m;
+    for (int idx = tid; idx < kMaxS * m; idx += blockDim.x) {
+        const int i = idx / kMaxS, j = idx % kMaxS;  // compile-time divisor
+        if (j >= m) continue;
         double v;
         if (i == d) v = g[j];
         else if (j == d) v = g[i];
@@ -516,102 +643,25 @@ __device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nbl
         } else {
             // start: previous Ritz vector padded with zero; its Rayleigh quotient is the previous theta
             const double theta_prev = st->theta;
-            double mu = theta_prev;
-            yi = lane < d ? st->y[lane] : 0.0;
+            if (lane < d) bvec[lane] = st->y[lane];
             double scale = 0.0;
-            for (int idx = lane; idx < m * m; idx += 32) scale = fmax(scale, fabs(J[idx / m][idx % m]));
+            for (int i = 0; i < m; ++i)
+                if (lane < m) scale = fmax(scale, fabs(J[i][lane]));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(0xffffffffu, scale, o));
-            const double tiny = 1e-300 + 1e-18 * scale;
-            for (int it = 0; it < 8; ++it) {
-                // A = G - mu I, rhs = y
-                for (int idx = lane; idx < m * m; idx += 32) {
-                    const int i = idx / m, j = idx % m;
-                    A[i][j] = J[i][j] - (i == j ? mu : 0.0);
-                }
-                if (lane < m) bvec[lane] = yi;
-                __syncwarp();
-                // Gaussian elimination with partial pivoting: lane i owns row i
-                for (int k = 0; k < m; ++k) {
-                    double pv = (lane >= k && lane < m) ? fabs(A[lane][k]) : -1.0;
-                    int pi = lane;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const double v2 = __shfl_xor_sync(0xffffffffu, pv, o);
-                        const int i2 = __shfl_xor_sync(0xffffffffu, pi, o);
-                        if (v2 > pv || (v2 == pv && i2 < pi)) { pv = v2; pi = i2; }
-                    }
-                    if (pi != k) {  // swap rows k and pi (lanes over columns)
-                        if (lane < m) {
-                            const double t = A[k][lane];
-                            A[k][lane] = A[pi][lane];
-                            A[pi][lane] = t;
-                        }
-                        if (lane == 0) {
-                            const double t = bvec[k];
-                            bvec[k] = bvec[pi];
-                            bvec[pi] = t;
-                        }
-                    }
-                    __syncwarp();
-                    double piv = A[k][k];
-                    if (fabs(piv) < tiny) piv = piv < 0.0 ? -tiny : tiny;  // mu hit an eigenvalue: that is fine
-                    __syncwarp();
-                    if (lane == 0) A[k][k] = piv;
-                    if (lane > k && lane < m) {
-                        const double f = A[lane][k] / piv;
-                        for (int j = k + 1; j < m; ++j) A[lane][j] = fma(-f, A[k][j], A[lane][j]);
-                        bvec[lane] = fma(-f, bvec[k], bvec[lane]);
-                    }
-                    __syncwarp();
-                }
-                // back substitution
-                for (int k = m - 1; k >= 0; --k) {
-                    double sacc = (lane > k && lane < m) ? A[k][lane] * zvec[lane] : 0.0;
-                    sacc = warp_sum(sacc);
-                    if (lane == 0) zvec[k] = (bvec[k] - sacc) / A[k][k];
-                    __syncwarp();
-                }
-                double zi = lane < m ? zvec[lane] : 0.0;
-                double zmax = fabs(zi);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) zmax = fmax(zmax, __shfl_xor_sync(0xffffffffu, zmax, o));
-                if (!(zmax > 0.0) || !isfinite(zmax)) break;  // fall back to Jacobi
-                zi /= zmax;
-                const double nz = sqrt(warp_sum(zi * zi));
-                zi /= nz;
-                if (lane < m) zvec[lane] = zi;
-                __syncwarp();
-                // Rayleigh quotient and residual of the new vector
-                double gz = 0.0;
-                if (lane < m)
-                    for (int j = 0; j < m; ++j) gz = fma(J[lane][j], zvec[j], gz);
-                const double mu_new = warp_sum(lane < m ? zi * gz : 0.0);
-                const double r = lane < m ? gz - mu_new * zi : 0.0;
-                const double rn = sqrt(warp_sum(r * r));
-                yi = zi;
-                const double dmu = fabs(mu_new - mu);
-                mu = mu_new;
-                __syncwarp();
-                if (lane == 0) st->n_rqi_iter += 1;
-                // (mu, z) is an eigenpair of G to working precision (cubic convergence: two or three
-                // iterations; stagnation of mu alone is NOT convergence -- a start vector that mixes +lambda
-                // and -lambda equally keeps its Rayleigh quotient for ever)
-                if (rn <= 2e-14 * scale || (it == 7 && rn <= 1e-11 * scale)) {
-                    // interlacing: lambda_1(G_m) <= theta_prev <= lambda_2(G_m).  An eigenvalue strictly below
-                    // theta_prev is therefore the lowest one; one that equals theta_prev to rounding may be
-                    // the second (a degenerate or decoupled direction) -- the full decomposition decides
-                    ok = mu < theta_prev - 1.5e-14 * (fabs(theta_prev) + scale);
-                    break;
-                }
-            }
+            __syncwarp();
+            double mu = theta_prev;
+            int iters = 0;
+            if (m <= MR) ok = rqi_lowest<MR>(J, m, lane, theta_prev, bvec, scale, &mu, &yi, &iters);
+            if (lane == 0) st->n_rqi_iter += iters;
             theta = mu;
         }
     }
     if (!ok) {
         // full decomposition (restart cycle, or the iteration above was rejected)
         if (lane == 0) st->n_jacobi += 1;
-        for (int idx = lane; idx < m * m; idx += 32) A[idx / m][idx % m] = J[idx / m][idx % m];
+        for (int i = 0; i < m; ++i)
+            if (lane < m) A[i][lane] = J[i][lane];
         __syncwarp();
         jacobi_full(st, A, J, m, lane, cs_c, cs_s, pr_p, pr_q);
         const int best = st->ord[0];
@@ -1183,11 +1233,12 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         // thick restart: keep the lowest min(kKeep, M/3) Ritz vectors when the space is full
         const int q_keep = M / 3 < 1 ? 1 : (M / 3 > kKeep ? kKeep : M / 3);
         const int restart = (m == M) ? q_keep : 0;
+        static const int knob_skip = env_knob("SQD_DAV_SKIP", 0);  // timing experiments: bit 0 residual, 1 ortho
         int rc = dispatch_mv(m, [&](auto mv) {
             constexpr int MV = decltype(mv)::value;
             gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n, m,
                                                             ws.partials, restart ? 1 : 0);
-            residual_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, d_hdiag, n, m,
+            if (!(knob_skip & 1)) residual_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, d_hdiag, n, m,
                                                                 restart, prm->level_shift, ws.X, ws.T,
                                                                 ws.partials, prm->tol, prm->tol_residual);
             return check_launch("davidson cycle (1)", 2);
@@ -1196,10 +1247,12 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         const int me = restart ? restart : m;
         rc = dispatch_mv(me, [&](auto mv) {
             constexpr int MV = decltype(mv)::value;
-            ortho1_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T, ws.partials,
-                                                              prm->lindep);
-            ortho2_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T,
-                                                              ws.V + (int64_t)me * n);
+            if (!(knob_skip & 2)) {
+                ortho1_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T, ws.partials,
+                                                                  prm->lindep);
+                ortho2_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, me, ws.T,
+                                                                  ws.V + (int64_t)me * n);
+            }
             return check_launch("davidson cycle (2)", 2);
         });
         if (rc) return -2;

@@ -29,7 +29,8 @@ constexpr int kV2MaxStages = 8;
 constexpr int kV2GroupTarget = 416;   // virtual columns per group aimed at
 constexpr int kV2GroupMax = 480;      // hard limit (K1 runs vc_pad + 32 <= 512 threads)
 constexpr uint32_t kSelfItem = 0x40000000u;
-enum { C_NITEMS = 0, C_NCHUNKS, C_NGROUPS, C_VCPAD, C_SINGLES_A, C_SINGLES_B, C_ERR, C_NVC, C_NQ };
+enum { C_NITEMS = 0, C_NCHUNKS, C_NGROUPS, C_VCPAD, C_SINGLES_A, C_SINGLES_B, C_ERR, C_NVC, C_NQ, C_NHEAVY };
+constexpr int kV2HeavyRow = 64;  // alpha strings with more single excitations get a CTA per column block in the epilogue
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -38,7 +39,7 @@ static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct V2Layout {
     size_t single_ptr, item_ptr, chunk_rec, item_tgt, item_gsel, item_pslot;
     size_t col_grp, col_full, col_nfull, col_rem, col_seg;
-    size_t vc_src, vc_off, vc_len, vc_q, counts, total;
+    size_t vc_src, vc_off, vc_len, vc_q, heavy_rows, counts, total;
     int maxch, capw;
 };
 
@@ -69,6 +70,7 @@ static V2Layout v2_layout(int na, int nb, int64_t nnz_a, int64_t nnz_b, int lmax
     L.vc_off = take((size_t)L.capw * lmax * 4);
     L.vc_len = take((size_t)L.capw * 4);
     L.vc_q = take((size_t)L.capw * 4);
+    L.heavy_rows = take((size_t)na * 4);
     L.counts = take((size_t)SQD_V2_COUNTS * 4);
     L.total = o;
     return L;
@@ -164,7 +166,8 @@ v2_alpha_plan_kernel(const sqd_spin_table A, int ipc, int maxch, int* __restrict
 // item_ptr[a'] + 1 + k'.  One warp per row, lanes over its single excitations.
 __global__ void v2_item_kernel(const sqd_spin_table A, int norb, const int* __restrict__ item_ptr,
                                int* __restrict__ item_tgt, uint32_t* __restrict__ item_gsel,
-                               int* __restrict__ item_pslot) {
+                               int* __restrict__ item_pslot, int* __restrict__ heavy_rows,
+                               int* __restrict__ counts) {
     const int lane = threadIdx.x & 31;
     const int a = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (a >= A.n) return;
@@ -173,6 +176,8 @@ __global__ void v2_item_kernel(const sqd_spin_table A, int norb, const int* __re
         item_tgt[ip] = a;
         item_gsel[ip] = kSelfItem;
         item_pslot[ip] = ip;
+        // list of strings with many excitations (any order: every string is summed on its own)
+        if (ns > kV2HeavyRow) heavy_rows[atomicAdd(&counts[C_NHEAVY], 1)] = a;
     }
     for (int k = lane; k < ns; k += 32) {
         const int ap = (int)A.col[beg + k];
@@ -383,6 +388,48 @@ __global__ void v2_vc_fill_kernel(const sqd_spin_table B, const int* __restrict_
     }
 }
 
+// Bank-aware order of the links inside a virtual column.  In K1 the 16 lanes of a half warp gather one
+// 8-byte word each from the staged integral row at step j; words whose index is equal mod 16 share a bank
+// pair and serialise (ncu: half of K1's shared-memory wavefronts were conflicts with the links in table
+// order).  The order of a thread's links is free, so lane l aims at bank (l + 3 j) mod 16 at step j -- the 16
+// lanes of a half warp then aim at 16 different banks -- and takes, among its unused links, the one whose
+// bank is closest to the target.  One thread per virtual column, no communication; O(len^2), set-up time.
+__global__ void v2_vc_order_kernel(const int* __restrict__ counts, int lmax, uint32_t* __restrict__ vc_src,
+                                   uint32_t* __restrict__ vc_off, const int* __restrict__ vc_len) {
+    if (counts[C_ERR] != 0) return;
+    const int vc_pad = counts[C_VCPAD], G = counts[C_NGROUPS];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= G * vc_pad) return;
+    const int g = idx / vc_pad, t = idx - g * vc_pad;
+    const int len = vc_len[idx];
+    if (len <= 1) return;
+    uint32_t off[16], src[16];
+    const size_t base = (size_t)g * lmax * vc_pad + t;
+    for (int j = 0; j < len; ++j) {
+        off[j] = vc_off[base + (size_t)j * vc_pad];
+        src[j] = vc_src[base + (size_t)j * vc_pad];
+    }
+    unsigned used = 0u;
+    const int l16 = t & 15;
+    for (int j = 0; j < len; ++j) {
+        const int target = (l16 + 3 * j) & 15;
+        int best = -1, best_d = 99;
+        for (int k = 0; k < len; ++k) {
+            if ((used >> k) & 1u) continue;
+            const int bank = (int)(off[k] >> 3) & 15;
+            int d = (bank - target) & 15;
+            if (d > 8) d = 16 - d;
+            if (d < best_d) {
+                best_d = d;
+                best = k;
+            }
+        }
+        used |= 1u << best;
+        vc_off[base + (size_t)j * vc_pad] = off[best];
+        vc_src[base + (size_t)j * vc_pad] = src[best];
+    }
+}
+
 // HDT[col*ld + row] = val(row, col): transposed so that the tile loader of K2 reads, for a fixed source
 // string k, the elements <a|H|k> of consecutive target strings a with coalesced 16-byte loads -- and uses
 // exactly the table values of row a (the v1 kernels and the oracle use those; <a|H|k> and <k|H|a> may
@@ -439,15 +486,21 @@ __device__ __forceinline__ void v2_arrive(uint64_t* bar) {
 // share the SM: the LEAN instance uses 8), four interleaved partial sums keep the FP64 FMA latency off the
 // critical path
 template <int N, int LMAX, int BATCH>
-__device__ __forceinline__ double v2_dot(const double (&x)[LMAX], const uint32_t (&off)[LMAX],
+__device__ __forceinline__ double v2_dot(const double (&x)[LMAX], const uint32_t (&off2)[LMAX / 2],
                                          const char* G) {
+    // off2[j/2] holds the byte offsets of links j (low half) and j+1 (high half): 8 registers instead of 16
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
     for (int j0 = 0; j0 < N; j0 += BATCH) {
         double gv[BATCH];
 #pragma unroll
-        for (int j = 0; j < BATCH; ++j)
-            if (j0 + j < N) gv[j] = *reinterpret_cast<const double*>(G + off[j0 + j]);
+        for (int j = 0; j < BATCH; ++j) {
+            if (j0 + j < N) {
+                const uint32_t w = off2[(j0 + j) >> 1];
+                const uint32_t o = ((j0 + j) & 1) ? (w >> 16) : (w & 0xffffu);
+                gv[j] = *reinterpret_cast<const double*>(G + o);
+            }
+        }
 #pragma unroll
         for (int j = 0; j < BATCH; j += 4) {
             if (j0 + j < N) {
@@ -466,12 +519,12 @@ __device__ __forceinline__ double v2_dot(const double (&x)[LMAX], const uint32_t
 // the gather of x_j = sgn_j c[a', b'_j] hits shared memory and its L2 latency hides behind the ring like
 // the integral rows'.  A type-2 stage carries g_ab[pq,:] and, behind it, Wb[pq,:]: thread t also owns the
 // natural column g*wcols + t of the group and writes sgn*Wb[pq,b]*c[a',b] into the w-part of the P row.
-// LEAN: register cap 96 (launch bound 672) so that one CTA of this kernel and CTAs of the dense tile kernel
-// fit on an SM together (overlapped build of a lone solve); otherwise 128 registers, 16 gathers in flight.
+// LEAN: register cap 96 (launch bound 640) so that one CTA of this kernel and a CTA of the dense tile kernel
+// fit on an SM together (overlapped build of a lone solve); otherwise 128 registers.
 template <int LMAX, bool LEAN>
-__global__ void __launch_bounds__(LEAN ? 672 : 512, 1)
+__global__ void __launch_bounds__(LEAN ? 640 : 512, 1)
 sigma2_ab_kernel(const V2Args P, const int NST, const int stage_len, const int src_smem) {
-    constexpr int BATCH = LEAN ? 8 : 16;
+    constexpr int BATCH = 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
     const double* Pc = P.c + v2_slot_offset(P);
@@ -625,12 +678,13 @@ sigma2_ab_kernel(const V2Args P, const int NST, const int stage_len, const int s
         }
         return;
     }
-    uint32_t off[LMAX];
+    uint32_t off[LMAX / 2];  // two 16-bit byte offsets per register (8 * norb^2 <= 32768)
     double x[LMAX];
 #pragma unroll
-    for (int j = 0; j < LMAX; ++j) {
-        off[j] = V.vc_off[gbase + (size_t)j * vc_pad + t];
+    for (int j = 0; j < LMAX; j += 2) {
+        off[j >> 1] = V.vc_off[gbase + (size_t)j * vc_pad + t] | (V.vc_off[gbase + (size_t)(j + 1) * vc_pad + t] << 16);
         x[j] = 0.0;
+        x[j + 1] = 0.0;
     }
     const size_t ldp = (size_t)V.ldp;
     double* prow = V.P + (myq >= 0 ? myq : 0);
@@ -809,42 +863,40 @@ sigma2_tile_kernel(const V2Args P) {
 
 // ---------------------------------------------------------------------------------------------------
 // K3: epilogue.  sigma[a,b] = partial tiles (fixed order) + diag*c + column sums of the P rows of a.
-// CTA = one alpha string x 32 beta strings.  The q-part columns of 32 consecutive beta strings are one
-// contiguous range (at most kK3MaxQ wide, enforced by the planner) and their w-part columns are the 32
-// strings themselves, so every lane sums the same few P columns over the row's items with coalesced
-// loads, whatever the lengths of the excitation lists.  The items (self item, then one per single
-// excitation) are cut into contiguous quarters, one per warp; a string with few excitations keeps only
-// warp 0 (the others leave at once), the Hartree-Fock string with its hundreds all four.  The warps meet in
-// shared memory and are added in warp order (fixed summation order).
+// One WARP per (alpha string, 32 beta strings); a CTA of four warps walks kK3Rows consecutive strings
+// (few, fat CTAs: with one CTA per string most of the kernel's cost was CTA launches).  The q-part columns
+// of 32 consecutive beta strings are one contiguous range (at most kK3MaxQ wide, enforced by the planner)
+// and their w-part columns are the 32 strings themselves, so every lane sums the same few P columns over the
+// string's items with coalesced loads, kK3Unroll items in flight, whatever the lengths of the excitation
+// lists.  No shared-memory traffic except the final q-column -> beta-string fold inside the warp.
 // ---------------------------------------------------------------------------------------------------
-constexpr int kK3Cols = 32, kK3Warps = 4, kK3Threads = kK3Cols * kK3Warps, kK3Unroll = 4;
+constexpr int kK3Cols = 32, kK3Warps = 4, kK3Threads = kK3Cols * kK3Warps;
 constexpr int kK3MaxQ = 128;
 
-template <int QC>
-__device__ __forceinline__ void k3_sum_items(const double* pcol, const double* wcol, size_t ldp, int k_beg,
-                                             int k_end, const bool (&qok)[4], bool wok, double (&accq)[4],
-                                             double& accw) {
-    const double* pr = pcol + (size_t)k_beg * ldp;
-    const double* wr = wcol + (size_t)k_beg * ldp;
-    int k = k_beg;
-    for (; k + kK3Unroll <= k_end; k += kK3Unroll) {
-        double pv[kK3Unroll][QC], wv[kK3Unroll];
+template <int QC, int UN>
+__device__ __forceinline__ void k3_sum_items(const double* pcol, const double* wcol, size_t ldp, int n_items,
+                                             const bool (&qok)[4], bool wok, double (&accq)[4], double& accw) {
+    const double* pr = pcol;
+    const double* wr = wcol;
+    int k = 0;
+    for (; k + UN <= n_items; k += UN) {
+        double pv[UN][QC], wv[UN];
 #pragma unroll
-        for (int u = 0; u < kK3Unroll; ++u) {
+        for (int u = 0; u < UN; ++u) {
 #pragma unroll
             for (int i = 0; i < QC; ++i) pv[u][i] = qok[i] ? pr[(size_t)u * ldp + 32 * i] : 0.0;
             wv[u] = wok ? wr[(size_t)u * ldp] : 0.0;
         }
 #pragma unroll
-        for (int u = 0; u < kK3Unroll; ++u) {
+        for (int u = 0; u < UN; ++u) {
 #pragma unroll
             for (int i = 0; i < QC; ++i) accq[i] += pv[u][i];
             accw += wv[u];
         }
-        pr += (size_t)kK3Unroll * ldp;
-        wr += (size_t)kK3Unroll * ldp;
+        pr += (size_t)UN * ldp;
+        wr += (size_t)UN * ldp;
     }
-    for (; k < k_end; ++k) {
+    for (; k < n_items; ++k) {
 #pragma unroll
         for (int i = 0; i < QC; ++i)
             if (qok[i]) accq[i] += pr[32 * i];
@@ -854,81 +906,134 @@ __device__ __forceinline__ void k3_sum_items(const double* pcol, const double* w
     }
 }
 
+// Shared body: column sums of the items [k_beg, k_end) of string a for the column block starting at b0.
+struct K3Ctx {
+    int lane, b, nqb, q0, q1, qlo;
+    bool live, wok;
+    bool qok[4];
+};
+__device__ __forceinline__ K3Ctx k3_ctx(const V2Args& P, int b0, int lane) {
+    const sqd_sigma_v2& V = P.op.v2;
+    const int nb = P.op.b.n;
+    K3Ctx c;
+    c.lane = lane;
+    c.b = b0 + lane;
+    c.live = c.b < nb;
+    c.qlo = V.col_seg[min(b0, nb)];
+    c.nqb = V.col_seg[min(b0 + kK3Cols, nb)] - c.qlo;  // <= kK3MaxQ
+    c.q0 = c.live ? V.col_seg[c.b] - c.qlo : 0;
+    c.q1 = c.live ? V.col_seg[c.b + 1] - c.qlo : 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c.qok[i] = lane + 32 * i < c.nqb;
+    c.wok = c.live && P.op.Wb != nullptr;
+    return c;
+}
+__device__ __forceinline__ double k3_base(const V2Args& P, const K3Ctx& c, int a) {
+    const sqd_sigma_v2& V = P.op.v2;
+    const int na = P.op.a.n, ldc = P.op.ldc;
+    double base = 0.0;
+    if (c.live) {
+        double pt[4];
+        for (int sp0 = 0; sp0 < P.nsplit; sp0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                pt[u] = sp0 + u < P.nsplit ? V.part[((size_t)(sp0 + u) * na + a) * ldc + c.b] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) base += pt[u];
+        }
+        const size_t ab = (size_t)a * ldc + c.b;
+        base = fma(P.op.diag[ab], (P.c + v2_slot_offset(P))[ab], base);
+    }
+    return base;
+}
+__device__ __forceinline__ void k3_items(const V2Args& P, const K3Ctx& c, int ip, int k_beg, int k_end,
+                                         bool with_self, double (&accq)[4], double& accw) {
+    const sqd_sigma_v2& V = P.op.v2;
+    const size_t ldp = (size_t)V.ldp;
+    // P rows of the string: ip = self item (q-part only, present when the operator has Wa), then one row
+    // per single excitation
+    if (with_self && P.op.Wa != nullptr) {
+        const double* prow = V.P + (size_t)ip * ldp + c.qlo + c.lane;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (c.qok[i]) accq[i] += prow[32 * i];
+    }
+    const double* pcol = V.P + (size_t)(ip + 1 + k_beg) * ldp + c.qlo + c.lane;
+    const double* wcol = V.P + (size_t)(ip + 1 + k_beg) * ldp + V.ldq + (c.live ? c.b : 0);
+    const int n = k_end - k_beg;
+    if (c.nqb <= 32) k3_sum_items<1, 4>(pcol, wcol, ldp, n, c.qok, c.wok, accq, accw);
+    else if (c.nqb <= 64) k3_sum_items<2, 4>(pcol, wcol, ldp, n, c.qok, c.wok, accq, accw);
+    else k3_sum_items<4, 4>(pcol, wcol, ldp, n, c.qok, c.wok, accq, accw);
+}
+
+// K3.  Light CTAs (strings with at most kV2HeavyRow excitations): one WARP per (alpha string, 32 beta strings),
+// the four warps of a CTA take four neighbouring column blocks of the same string, no synchronisation between
+// warps.  Heavy CTAs (the few strings with many excitations -- the Hartree-Fock string has hundreds): one CTA
+// per (string, 32 beta strings), its four warps split the items into contiguous parts and meet in shared
+// memory in warp order.  The heavy CTAs come first in the grid (blockIdx.y < heavy_ctas_y) so that the
+// longest chains start first.
 __global__ void __launch_bounds__(kK3Threads)
-sigma2_epilogue_kernel(const V2Args P) {
+sigma2_epilogue_kernel(const V2Args P, const int heavy_ctas_y, const int ncb) {
     __shared__ double Sq[kK3Warps][kK3MaxQ];
     __shared__ double Sw[kK3Warps][kK3Cols];
     if (P.done != nullptr && *P.done != 0) return;
     const sqd_operator& op = P.op;
     const sqd_sigma_v2& V = op.v2;
-    const int a = P.row_begin + blockIdx.y;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int ns = op.a.n_single[a];
-    const int nwarps = ns <= 12 ? 1 : kK3Warps;  // warps that have items
-    if (warp >= nwarps) return;
-    const int na = op.a.n, nb = op.b.n, ldc = op.ldc;
-    const int b0 = blockIdx.x * kK3Cols, b = b0 + lane;
-    const bool live = b < nb;
-    const int ip = V.item_ptr[a];
-    const size_t ldp = (size_t)V.ldp;
-    const int qlo = V.col_seg[min(b0, nb)], qhi = V.col_seg[min(b0 + kK3Cols, nb)];
-    const int nqb = qhi - qlo;  // <= kK3MaxQ
-    bool qok[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) qok[i] = lane + 32 * i < nqb;
-    const bool wok = live && op.Wb != nullptr;
-    // P rows of the single excitations: ip + 1 + k
-    const double* pcol = V.P + (size_t)(ip + 1) * ldp + qlo + lane;
-    const double* wcol = V.P + (size_t)(ip + 1) * ldp + V.ldq + (live ? b : 0);
-    const int per = (ns + nwarps - 1) / nwarps;
-    const int k_beg = min(ns, warp * per), k_end = min(ns, k_beg + per);
-    double accq[4] = {0.0, 0.0, 0.0, 0.0}, accw = 0.0, base = 0.0;
-    if (warp == 0) {
-        // terms that do not depend on the items: their loads go first
-        if (live) {
-            double pt[4];
-            for (int sp0 = 0; sp0 < P.nsplit; sp0 += 4) {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    pt[u] = sp0 + u < P.nsplit ? V.part[((size_t)(sp0 + u) * na + a) * ldc + b] : 0.0;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) base += pt[u];
-            }
-            const size_t ab = (size_t)a * ldc + b;
-            base = fma(op.diag[ab], (P.c + v2_slot_offset(P))[ab], base);
-        }
-        if (op.Wa != nullptr) {   // self item: q-part only
-            const double* prow = pcol - ldp;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (qok[i]) accq[i] += prow[32 * i];
-        }
-    }
-    if (nqb <= 32) k3_sum_items<1>(pcol, wcol, ldp, k_beg, k_end, qok, wok, accq, accw);
-    else if (nqb <= 64) k3_sum_items<2>(pcol, wcol, ldp, k_beg, k_end, qok, wok, accq, accw);
-    else k3_sum_items<4>(pcol, wcol, ldp, k_beg, k_end, qok, wok, accq, accw);
-    if (nwarps > 1) {
+    const int ldc = op.ldc;
+    if ((int)blockIdx.y < heavy_ctas_y) {
+        // ---- heavy role ----
+        const int h = blockIdx.y * gridDim.x + blockIdx.x;  // (heavy string, column block) pair
+        const int hi = h / ncb, cb = h - hi * ncb;
+        if (hi >= V.n_heavy) return;
+        const int a = V.heavy_rows[hi];
+        if (a < P.row_begin || a >= P.row_end) return;
+        const int ns = op.a.n_single[a];
+        const K3Ctx c = k3_ctx(P, cb * kK3Cols, lane);
+        const double base = warp == 0 ? k3_base(P, c, a) : 0.0;
+        const int per = (ns + kK3Warps - 1) / kK3Warps;
+        const int k_beg = min(ns, warp * per), k_end = min(ns, k_beg + per);
+        double accq[4] = {0.0, 0.0, 0.0, 0.0}, accw = 0.0;
+        k3_items(P, c, V.item_ptr[a], k_beg, k_end, warp == 0, accq, accw);
 #pragma unroll
         for (int i = 0; i < 4; ++i) Sq[warp][lane + 32 * i] = accq[i];
         Sw[warp][lane] = accw;
-        asm volatile("bar.sync 1, %0;" ::"r"(32 * kK3Warps) : "memory");
-        if (warp != 0) return;
-    } else {
+        __syncthreads();
+        if (warp != 0 || c.b >= ldc) return;
+        double v = 0.0;
+        if (c.live) {
+            v = base;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) Sq[0][lane + 32 * i] = accq[i];
-        Sw[0][lane] = accw;
-        __syncwarp();
+            for (int w = 0; w < kK3Warps; ++w) v += Sw[w][lane];
+            for (int q = c.q0; q < c.q1; ++q)
+#pragma unroll
+                for (int w = 0; w < kK3Warps; ++w) v += Sq[w][q];
+        }
+        (P.sigma + v2_slot_offset(P))[(size_t)a * ldc + c.b] = v;  // pad column: 0
+        return;
     }
-    if (b >= ldc) return;
-    double v = 0.0;
-    if (live) {
-        v = base;
-        for (int w = 0; w < nwarps; ++w) v += Sw[w][lane];
-        const int q0 = V.col_seg[b] - qlo, q1 = V.col_seg[b + 1] - qlo;
-        for (int q = q0; q < q1; ++q)
-            for (int w = 0; w < nwarps; ++w) v += Sq[w][q];
+    // ---- light role ----
+    const int b0 = (blockIdx.x * kK3Warps + warp) * kK3Cols;
+    if (b0 >= ldc) return;
+    const int a = P.row_begin + (int)blockIdx.y - heavy_ctas_y;
+    const int ns = op.a.n_single[a];
+    if (ns > kV2HeavyRow) return;  // a heavy CTA owns this string
+    const K3Ctx c = k3_ctx(P, b0, lane);
+    const double base = k3_base(P, c, a);
+    double accq[4] = {0.0, 0.0, 0.0, 0.0}, accw = 0.0;
+    k3_items(P, c, V.item_ptr[a], 0, ns, true, accq, accw);
+    // fold the q columns onto the beta strings (segments of a string are adjacent)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) Sq[warp][lane + 32 * i] = accq[i];
+    __syncwarp();
+    if (c.b < ldc) {
+        double v = 0.0;
+        if (c.live) {
+            v = base + accw;
+            for (int q = c.q0; q < c.q1; ++q) v += Sq[warp][q];
+        }
+        (P.sigma + v2_slot_offset(P))[(size_t)a * ldc + c.b] = v;  // pad column: 0
     }
-    (P.sigma + v2_slot_offset(P))[(size_t)a * ldc + b] = v;  // pad column: 0
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1013,13 +1118,15 @@ int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_si
     SQD_REQUIRE(row_begin >= 0 && row_end <= op->a.n && row_begin <= row_end, "sqd_sigma: bad row range");
     if (row_end == row_begin) return 0;
     V2Args args{*op, d_c, d_sigma, d_done, row_begin, row_end, 0, d_slot, stride};
-    // K2 (FP64-pipe bound) and K1 (shared-memory gather bound) are independent: K2 goes to a side stream
-    // of this host thread and runs beside K1; both join before K3.  SQD_V2_OVERLAP=0 keeps one stream.
-    // Worth it for a lone solve only: when several solves share the GPU their kernels fill each other's gaps.
+    static const int knob_skip = v2_env("SQD_V2_SKIP", 0);  // timing experiments only: bit 0 K1, 1 K2, 2 K3
+    // K2 (FP64-pipe bound) and K1 (shared-memory gather bound) are independent: K2 can go to a side stream
+    // of this host thread and run beside K1, both joining before K3.  Measured on a lone (30e,30o) 316 x 316
+    // build: 43.0 us forked against 43.4 us in one stream -- the two event dependencies cost what the
+    // overlap saves -- so the fork is used only inside a captured graph (no host cost there) or on request
+    // (SQD_V2_OVERLAP=1).
     static const int knob_overlap = v2_env("SQD_V2_OVERLAP", -1);
+    const bool want_fork = knob_overlap >= 0 ? knob_overlap != 0 : in_graph != 0;
     V2Side* side = nullptr;
-    // Inside a captured graph the fork costs no host time: always on there.
-    const bool want_fork = knob_overlap >= 0 ? knob_overlap != 0 : (in_graph != 0 || op->throughput_mode == 0);
     const bool fork = want_fork && op->use_same_spin != 0 && V.n_chunks > 0;
     if (fork && v2_side(&side)) return -2;
     cudaStream_t st2 = fork ? side->s : st;
@@ -1033,7 +1140,7 @@ int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_si
         const int tiles_x = (row_end - a_lo + kTM - 1) / kTM, tiles_y = (op->ldc + kTN - 1) / kTN;
         nsplit = v2_num_split(op->a.n, op->b.n, op->ldc);
         if (nsplit > V.max_split) nsplit = V.max_split;
-        sigma2_tile_kernel<<<dim3(tiles_x, tiles_y, nsplit), kK2Threads, 0, st2>>>(args);
+        if (!(knob_skip & 2)) sigma2_tile_kernel<<<dim3(tiles_x, tiles_y, nsplit), kK2Threads, 0, st2>>>(args);
         if (check_launch("sigma2_tile_kernel")) return -2;
         if (fork) SQD_CUDA_OK(cudaEventRecord(side->ev_join, st2));
     }
@@ -1044,7 +1151,7 @@ int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_si
     const size_t smem = v2_k1_smem(op, nst);
     SQD_REQUIRE(smem <= 220 * 1024, "sqd_sigma: norb=%d does not fit the integral-row ring", op->norb);
     static const int knob_lean = v2_env("SQD_V2_LEAN", -1);
-    const bool lean = knob_lean >= 0 ? knob_lean != 0 : (fork || op->throughput_mode != 0);
+    const bool lean = knob_lean >= 0 ? knob_lean != 0 : fork;
     auto k1 = V.lmax == 8 ? (lean ? sigma2_ab_kernel<8, true> : sigma2_ab_kernel<8, false>)
                           : (lean ? sigma2_ab_kernel<16, true> : sigma2_ab_kernel<16, false>);
     static bool cfg[64][4] = {};
@@ -1065,15 +1172,20 @@ int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_si
     if (knob_grid > 0 && op->throughput_mode != 0) gx = knob_grid;
     if (gx < 1) gx = 1;
     if (gx > V.n_chunks) gx = V.n_chunks;
-    if (V.n_chunks > 0) {
+    if (V.n_chunks > 0 && !(knob_skip & 1)) {
         k1<<<dim3(gx, V.n_groups), V.vc_pad + 32, smem, st>>>(args, nst, stage_len, src_smem);
         if (check_launch("sigma2_ab_kernel")) return -2;
     }
     if (fork) SQD_CUDA_OK(cudaStreamWaitEvent(st, side->ev_join, 0));
     // K3
     args.nsplit = nsplit;
-    sigma2_epilogue_kernel<<<dim3((op->ldc + kK3Cols - 1) / kK3Cols, row_end - row_begin), kK3Threads, 0, st>>>(
-        args);
+    if (!(knob_skip & 4)) {
+        const int ncb = (op->ldc + kK3Cols - 1) / kK3Cols;
+        const int gx3 = (ncb + kK3Warps - 1) / kK3Warps;
+        const int heavy_y = (V.n_heavy * ncb + gx3 - 1) / gx3;
+        sigma2_epilogue_kernel<<<dim3(gx3, heavy_y + row_end - row_begin), kK3Threads, 0, st>>>(args, heavy_y,
+                                                                                                ncb);
+    }
     return check_launch("sigma2_epilogue_kernel");
 }
 
@@ -1127,7 +1239,7 @@ int sqd_sigma_v2_plan(const sqd_spin_table* a, const sqd_spin_table* b, int norb
         v2_alpha_plan_kernel<<<1, 1024, 0, st>>>(*a, ipc, L.maxch, I(L.single_ptr), I(L.item_ptr),
                                                  reinterpret_cast<int4*>(base + L.chunk_rec), counts);
         v2_item_kernel<<<(a->n + 7) / 8, 256, 0, st>>>(*a, norb, I(L.item_ptr), I(L.item_tgt),
-                                                       U(L.item_gsel), I(L.item_pslot));
+                                                       U(L.item_gsel), I(L.item_pslot), I(L.heavy_rows), counts);
         static bool cfg[64] = {};
         int dev = 0;
         SQD_CUDA_OK(cudaGetDevice(&dev));
@@ -1144,7 +1256,11 @@ int sqd_sigma_v2_plan(const sqd_spin_table* a, const sqd_spin_table* b, int norb
         v2_vc_fill_kernel<<<(b->n + 7) / 8, 256, 0, st>>>(*b, counts, lmax, I(L.col_grp), I(L.col_full),
                                                           I(L.col_nfull), I(L.col_rem), I(L.col_seg),
                                                           U(L.vc_src), U(L.vc_off), I(L.vc_len), I(L.vc_q));
-        if (check_launch("sigma v2 plan kernels", 5)) return -2;
+        static const int knob_order = v2_env("SQD_V2_BANK_ORDER", 1);
+        if (knob_order)
+            v2_vc_order_kernel<<<(L.capw + 127) / 128, 128, 0, st>>>(counts, lmax, U(L.vc_src), U(L.vc_off),
+                                                                   I(L.vc_len));
+        if (check_launch("sigma v2 plan kernels", 6)) return -2;
     }
     if (h_counts == nullptr) return 0;
     return read_back(h_counts, counts, SQD_V2_COUNTS * sizeof(int), st);
@@ -1217,6 +1333,8 @@ int sqd_sigma_v2_finish(const sqd_spin_table* a, const sqd_spin_table* b, int ld
     V.item_tgt = (const int*)(pb + L.item_tgt);
     V.item_gsel = (const uint32_t*)(pb + L.item_gsel);
     V.item_pslot = (const int*)(pb + L.item_pslot);
+    V.heavy_rows = (const int*)(pb + L.heavy_rows);
+    V.n_heavy = hc[C_NHEAVY];
     V.P = (double*)(sb + S.P);
     V.part = (double*)(sb + S.part);
     SQD_REQUIRE(V.vc_pad >= 32 && V.vc_pad <= kV2GroupMax && V.n_groups >= 1 && V.n_groups <= kV2MaxGroups,

@@ -12,13 +12,16 @@ from qiskit_addon_sqd_b200 import fermion  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "c4"
 K = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+extra = {}
+if len(sys.argv) > 4:   # fixed number of cycles (timing experiments): max_cycle, never converge
+    extra = dict(max_cycle=int(sys.argv[4]), tol=1e-30)
 norb, nelec, h, g, batches = bench.make_batches(wl, 0, K)
 for _ in range(3):
-    res = fermion.solve_sci_batch(batches, h, g, norb, nelec, compute_rdms=False)
+    res = fermion.solve_sci_batch(batches, h, g, norb, nelec, compute_rdms=False, **extra)
 torch.cuda.synchronize()
 t0 = time.perf_counter()
 for _ in range(reps):
-    res = fermion.solve_sci_batch(batches, h, g, norb, nelec, compute_rdms=False)
+    res = fermion.solve_sci_batch(batches, h, g, norb, nelec, compute_rdms=False, **extra)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / reps
 st = fermion.last_solve_stats()
