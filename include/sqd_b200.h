@@ -388,6 +388,12 @@ int sqd_dot(const double* d_x, const double* d_y, int64_t n, double* d_out, doub
  * d_scratch: at least 4096 doubles. */
 int sqd_fix_sign(double* d_x, int64_t n, void* d_scratch, void* stream);
 
+/* Wait until everything enqueued on `stream` has finished.  Unlike cudaStreamSynchronize the wait can be
+ * told not to spin (environment SQD_WAIT_MODE: 0 spin, 1 blocking-sync event, 2 poll + yield/sleep; default 2
+ * when the process is one of more than two ranks, WORLD_SIZE > 2, else 0): with 8 ranks x 8 solver threads on
+ * a 32-core host spinning waits starve the launching threads. */
+int sqd_stream_wait(void* stream);
+
 /* Small (<= 64 KB) device -> host read-back through a per-thread pinned staging buffer followed by a
  * stream synchronisation; never blocks the launches of other host threads. */
 int sqd_read_back(void* h_dst, const void* d_src, int64_t bytes, void* stream);

@@ -178,6 +178,7 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_version": (_i, []),
     "sqd_last_error": (C.c_char_p, []),
     "sqd_launch_count": (C.c_longlong, [_i]),
+    "sqd_stream_wait": (_i, [_vp]),
     "sqd_pack_bitstrings": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
     "sqd_check_hamming": (_i, [_vp, _i64, _vp, _pi, _pi, _pi, _vp]),
     "sqd_excitation_count": (_i, [_vp, _i, _vp, _vp, _vp]),
@@ -339,6 +340,7 @@ def download(torch, t):
         buf = cache[t.dtype] = torch.empty(max(n, 1 << 16), dtype=t.dtype, pin_memory=True)
     view = buf[:n]
     view.copy_(t.reshape(-1), non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    # the library's wait does not spin when many ranks share the host (sqd_stream_wait)
+    check(load().sqd_stream_wait(stream_ptr(torch)), "sqd_stream_wait")
     return np.array(view.numpy(), copy=True).reshape(tuple(t.shape))
 

@@ -1,6 +1,10 @@
 // Error plumbing and version of the C-ABI (include/sqd_b200.h).
+#include <sched.h>
 #include <stdarg.h>
 #include <stdlib.h>
+#include <unistd.h>
+
+#include <chrono>
 
 #include <atomic>
 
@@ -35,11 +39,19 @@ static thread_local cudaEvent_t g_sync_event = nullptr;
 static thread_local int g_sync_event_dev = -1;
 constexpr size_t kPinnedBytes = 64 * 1024;
 
-// Wait for everything enqueued on `st` WITHOUT spinning: the host threads of concurrent solves (8 per
-// process, 8 processes on a 32-core host when all GPUs are in use) would otherwise burn the cores that the
-// launching threads need.
+// Wait for everything enqueued on `st`.  cudaStreamSynchronize spins: fine for one process, but the host
+// threads of concurrent solves (8 per process, 8 processes on a 32-core host when all GPUs are in use) then
+// burn the cores that the launching threads need (round 1: 0.58 weak-scaling efficiency at 8 GPUs with no
+// collective on the data path).  Modes (SQD_WAIT_MODE): 0 = cudaStreamSynchronize; 1 = blocking-sync event
+// (the thread sleeps in the driver: no CPU, but ~100 us wake-up latency); 2 = hybrid (default when the
+// process is one of several ranks): poll the event, yielding for the first 40 us, then sleeping 20 us a time.
 int stream_wait_blocking(cudaStream_t st) {
-    static const int knob = getenv("SQD_BLOCKING_SYNC") ? atoi(getenv("SQD_BLOCKING_SYNC")) : 0;
+    static const int knob = [] {
+        const char* v = getenv("SQD_WAIT_MODE");
+        if (v) return atoi(v);
+        const char* w = getenv("WORLD_SIZE");
+        return (w && atoi(w) > 2) ? 2 : 0;
+    }();
     if (knob == 0) {
         SQD_CUDA_OK(cudaStreamSynchronize(st));
         return 0;
@@ -48,12 +60,28 @@ int stream_wait_blocking(cudaStream_t st) {
     SQD_CUDA_OK(cudaGetDevice(&dev));
     if (g_sync_event == nullptr || g_sync_event_dev != dev) {
         if (g_sync_event != nullptr) cudaEventDestroy(g_sync_event);
-        SQD_CUDA_OK(cudaEventCreateWithFlags(&g_sync_event, cudaEventBlockingSync | cudaEventDisableTiming));
+        SQD_CUDA_OK(cudaEventCreateWithFlags(
+            &g_sync_event, (knob == 1 ? cudaEventBlockingSync : cudaEventDefault) | cudaEventDisableTiming));
         g_sync_event_dev = dev;
     }
     SQD_CUDA_OK(cudaEventRecord(g_sync_event, st));
-    SQD_CUDA_OK(cudaEventSynchronize(g_sync_event));
-    return 0;
+    if (knob == 1) {
+        SQD_CUDA_OK(cudaEventSynchronize(g_sync_event));
+        return 0;
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const cudaError_t e = cudaEventQuery(g_sync_event);
+        if (e == cudaSuccess) return 0;
+        if (e != cudaErrorNotReady) {
+            set_error("cudaEventQuery failed: %s", cudaGetErrorString(e));
+            return -2;
+        }
+        const auto us = std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0)
+                            .count();
+        if (us < 40) sched_yield();
+        else usleep(20);
+    }
 }
 
 int read_back(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
@@ -75,6 +103,8 @@ extern "C" {
 int sqd_version(void) { return SQD_B200_VERSION; }
 
 const char* sqd_last_error(void) { return sqd::g_err; }
+
+int sqd_stream_wait(void* stream) { return sqd::stream_wait_blocking((cudaStream_t)stream); }
 
 long long sqd_launch_count(int reset) {
     return reset ? sqd::g_launches.exchange(0) : sqd::g_launches.load();

@@ -1128,7 +1128,9 @@ int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_si
     const bool want_fork = knob_overlap >= 0 ? knob_overlap != 0 : in_graph != 0;
     V2Side* side = nullptr;
     const bool fork = want_fork && op->use_same_spin != 0 && V.n_chunks > 0;
-    if (fork && v2_side(&side)) return -2;
+    // created on first use by this host thread -- also when this build does not fork, so that a later
+    // build inside a stream capture never has to create a stream
+    if (op->use_same_spin != 0 && v2_side(&side)) return -2;
     cudaStream_t st2 = fork ? side->s : st;
     int nsplit = 0;
     if (op->use_same_spin) {
