@@ -120,10 +120,12 @@ def recover_configurations(
                         _lib.ptr(status), _lib.ptr(ws), ws_bytes, st),
         "sqd_recover")
     status_h = status.cpu().numpy()
+    if words is not None:
+        # also when numpy would have raised: the generator has consumed the draws of the rows before the
+        # failing ``choice`` call (configuration_recovery.py:247-249 raises before drawing for that call)
+        _set_pcg64_words(rng, state_dev.cpu().numpy().view(np.uint64))
     if status_h[0] != 0:
         raise ValueError("Fewer non-zero entries in p than size")
-    if words is not None:
-        _set_pcg64_words(rng, state_dev.cpu().numpy().view(np.uint64))
     lo = left_out.cpu().numpy().view(np.uint64)
     ro = right_out.cpu().numpy().view(np.uint64)
 

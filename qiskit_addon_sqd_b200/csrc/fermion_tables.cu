@@ -81,8 +81,10 @@ __global__ void excitation_count_kernel(const uint64_t* __restrict__ strs, int n
 // exclusive scan (single CTA, n up to a few million: this is setup, not the hot loop)
 // --------------------------------------------------------------------------------------------
 __global__ void exclusive_scan_kernel(const int* __restrict__ in, int* __restrict__ out, int n) {
+    // the running total is kept in 64 bits: a total beyond INT_MAX is reported as out[n] = -1 (the callers
+    // size 32-bit indexed tables from it and must refuse) instead of wrapping around silently
     __shared__ int warp_tot[32];
-    __shared__ int carry_s;
+    __shared__ long long carry_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     if (threadIdx.x == 0) carry_s = 0;
     __syncthreads();
@@ -104,17 +106,17 @@ __global__ void exclusive_scan_kernel(const int* __restrict__ in, int* __restric
                 const int t = __shfl_up_sync(0xffffffffu, w, o);
                 if (lane >= o) w += t;
             }
-            warp_tot[lane] = w;  // inclusive over warps
+            warp_tot[lane] = w;  // inclusive over warps (one tile of <= 1024 rows of < 2^20 entries: no overflow)
         }
         __syncthreads();
-        const int carry = carry_s;
+        const long long carry = carry_s;
         const int woff = warp == 0 ? 0 : warp_tot[warp - 1];
-        if (idx < n) out[idx] = carry + woff + s - v;
+        if (idx < n) out[idx] = (int)(carry + woff + s - v);
         __syncthreads();
         if (threadIdx.x == 0) carry_s = carry + warp_tot[nwarp - 1];
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[n] = carry_s;
+    if (threadIdx.x == 0) out[n] = carry_s > 2147483647ll ? -1 : (int)carry_s;
 }
 
 // --------------------------------------------------------------------------------------------

@@ -211,6 +211,12 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
     if (read_back(h_pair, pair, sizeof(h_pair), st)) return -2;
     Ta.nnz = h_pair[0];
     Tb.nnz = h_pair[1];
+    // the tables are indexed with 32-bit integers (the scan reports a total beyond INT_MAX as -1), and the
+    // SELL copies of the v1 kernels need nnz + 36 n + 256 entries
+    SQD_REQUIRE(Ta.nnz >= 0 && Tb.nnz >= 0 && (int64_t)Ta.nnz + 36ll * na + 256 < 2147483647ll &&
+                    (int64_t)Tb.nnz + 36ll * nb + 256 < 2147483647ll,
+                "sqd_solve_subspace: the excitation tables of this subspace have more than 2^31 entries "
+                "(na=%d, nb=%d): beyond the 32-bit table index of this library", na, nb);
     sqd_spin_table ta{}, tb{};
     if (table_fill(P, prm->d_strs_a, na, norb, prm->d_h, prm->d_g, &Ta, &ta)) return -2;
     if (same) {

@@ -128,6 +128,19 @@ def _as_uint64(strs) -> np.ndarray:
     return np.ascontiguousarray(arr).astype(np.uint64, copy=False)
 
 
+def _validate_strings(u: np.ndarray, which: str) -> None:
+    """The C-ABI builds its excitation tables from string lists that are sorted ascending, unique and of one
+    Hamming weight (``include/sqd_b200.h``; the SQD loop delivers them that way, ``fermion.py:556-557``).
+    Anything else would silently produce a wrong Hamiltonian, so it is rejected here -- O(n) on the host."""
+    if u.size > 1 and not bool(np.all(u[1:] > u[:-1])):
+        raise ValueError(f"The {which} CI string list must be sorted in ascending order without duplicates.")
+    pc = np.bitwise_count(u)
+    if pc.size and not bool(np.all(pc == pc[0])):
+        raise ValueError(
+            f"Ci string in {which} list does not match hamming weight of the first string in that list."
+        )
+
+
 def _popcounts(strs_u64: np.ndarray) -> np.ndarray:
     return np.bitwise_count(strs_u64).astype(np.int64)
 
@@ -232,6 +245,9 @@ class _SpinTableDev:
         _lib.check(lib.sqd_exclusive_scan(_lib.ptr(n_total), _lib.ptr(self.row_ptr), n,
                                           C.byref(total), st), "sqd_exclusive_scan")
         self.nnz = int(total.value)
+        if self.nnz < 0 or self.nnz + 36 * n + 256 >= 2**31:
+            raise ValueError(f"The excitation table of {n} strings has more than 2^31 entries: beyond the "
+                             "32-bit table index of qiskit_addon_sqd_b200.")
         m = max(self.nnz, 1)
         self.col = torch.empty(m, dtype=torch.int32, device=device)
         self.val = torch.empty(m, dtype=torch.float64, device=device)
@@ -722,6 +738,9 @@ def solve_sci_batch(
         ub = ua if same else _as_uint64(strs_b)
         if ua.size == 0 or ub.size == 0:
             raise ValueError("The subspace must contain at least one alpha and one beta string.")
+        _validate_strings(ua, "first")
+        if not same:
+            _validate_strings(ub, "second")
         same = same or (ua.shape == ub.shape and np.array_equal(ua, ub))
         d = dev_list[k % len(dev_list)]
         per_device[d].append(k)

@@ -192,6 +192,11 @@ def _lowest_eigenpair_device(torch, lib, csr: "_DeviceCSR", kw: dict, max_rounds
     lower bounds ``A_ii - sum_j |A_ij|`` to find unvisited rows whose block could still hold a lower
     eigenvalue, and solve from the lowest-diagonal one of those; stop when no candidate is left.  Exact
     up to the Davidson tolerance; ARPACK's random start vector plays the same role in the reference.
+
+    The start vector is the basis state plus a small deterministic perturbation on every row that has not
+    been visited yet (pyscf perturbs its unit start vector for the same reason, ARPACK starts from a random
+    vector): a ground state with a node on the start row, or one that lives in a block the start row does
+    not belong to, still has a component in the start vector.
     """
     d = csr.d
     dev = csr.row_ptr.device
@@ -213,12 +218,16 @@ def _lowest_eigenpair_device(torch, lib, csr: "_DeviceCSR", kw: dict, max_rounds
     v0 = kw.get("v0")
     row = int(torch.argmin(diag).item())
     inf = torch.tensor(float("inf"), dtype=torch.float64, device=dev)
+    # deterministic perturbation in [-1, 1): golden-ratio sequence, generated once on the host
+    noise = torch.from_numpy(2.0 * ((np.arange(1, d + 1) * 0.6180339887498949) % 1.0) - 1.0).to(dev)
     for rnd in range(max_rounds):
         start.zero_()
-        if rnd == 0 and v0 is not None:
+        from_v0 = rnd == 0 and v0 is not None
+        if from_v0:
             start.copy_(torch.from_numpy(np.ascontiguousarray(v0, dtype=np.complex128).reshape(-1)
                                          .view(np.float64)))
         else:
+            start.view(d, 2)[:, 0] = torch.where(visited, torch.zeros_like(noise), 1e-3 * noise)
             start[2 * row] = 1.0
         evals = (C.c_double * 1)()
         cycles, resid = C.c_int(0), C.c_double(0.0)
@@ -228,7 +237,8 @@ def _lowest_eigenpair_device(torch, lib, csr: "_DeviceCSR", kw: dict, max_rounds
                    "sqd_csr_davidson")
         amp2 = evec.view(d, 2).pow(2).sum(dim=1)
         visited |= amp2 > 1e-20 * amp2.max()
-        visited[row] = True
+        if not from_v0:
+            visited[row] = True   # with a caller-supplied v0 the run did not start from this row
         if best_e is None or evals[0] < best_e:
             best_e, best_vec = float(evals[0]), evec.clone()
         # unvisited rows whose block might still beat the best eigenvalue found so far

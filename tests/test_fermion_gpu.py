@@ -451,3 +451,52 @@ def test_solve_sci_batch_over_several_devices(cuda_lib):
         assert a.energy == b.energy
         assert np.array_equal(a.sci_state.amplitudes, b.sci_state.amplitudes)
         assert np.array_equal(a.rdm2, b.rdm2)
+
+
+# ---- external pin: hydrogen chains with textbook STO-3G integrals (oracle/sto3g.py) -------------------
+def test_h2_sto3g_matches_szabo_ostlund(cuda_lib):
+    """``solve_fermion`` on the full (1 alpha, 1 beta) space of minimal-basis H2 at R = 1.4 a0 reproduces the
+    full-CI energy printed in Szabo & Ostlund (-1.1373 Ha with 1/R), and on the Hartree-Fock determinant
+    alone the RHF energy (-1.1167 Ha).  Replaces the reference's pyscf pin (``test/test_fermion.py:54-125``)."""
+    from oracle import sto3g
+    from qiskit_addon_sqd_b200 import fermion
+
+    h, g, en = sto3g.hydrogen_chain(2, sto3g.H2_R)
+    bits = np.array([[0, 1, 0, 1], [1, 0, 1, 0], [0, 1, 1, 0], [1, 0, 0, 1]], dtype=bool)
+    for spin_sq in (None, 0.0):
+        e, state, occ, s2 = fermion.solve_fermion(bits, h, g, spin_sq=spin_sq)
+        assert abs(e + en - sto3g.H2_E_FCI) < 5e-5
+        assert state.amplitudes.shape == (2, 2) and abs(s2) < 1e-8
+        assert abs(occ[0].sum() - 1.0) < 1e-9 and abs(occ[1].sum() - 1.0) < 1e-9
+    S, hao, gao, _ = sto3g.hydrogen_chain_ao(2, sto3g.H2_R)
+    C = np.stack([np.array([1.0, 1.0]) / np.sqrt(2 + 2 * S[0, 1]), np.array([1.0, -1.0]) / np.sqrt(2 - 2 * S[0, 1])],
+                 axis=1)
+    h_mo = C.T @ hao @ C
+    g_mo = np.einsum("ap,bq,cr,ds,abcd->pqrs", C, C, C, C, gao)
+    e_hf, *_ = fermion.solve_fermion((np.array([1]), np.array([1])), h_mo, g_mo)
+    assert abs(e_hf + en - sto3g.H2_E_HF) < 5e-5
+
+
+@pytest.mark.parametrize("n_atoms", [4, 6])
+def test_hydrogen_chain_full_and_sampled_subspaces(cuda_lib, n_atoms):
+    """H4 / H6 chains: full space == the recorded full-CI energy (cross-checked against Jordan-Wigner in
+    tests/test_oracle_cpu.py); sampled subspaces == dense oracle within 1e-8 Ha, with and without the spin
+    penalty; the variational bound E_sub >= E_FCI holds."""
+    from oracle import sto3g
+    from qiskit_addon_sqd_b200 import fermion
+
+    h, g, en = sto3g.hydrogen_chain(n_atoms, 1.4)
+    ne = n_atoms // 2
+    full = _all_strings(n_atoms, ne)
+    e_fci, state, occ, s2 = fermion.solve_fermion((full, full), h, g)
+    expected = {4: -2.139442706994545, 6: -3.1435083836572515}[n_atoms]
+    assert abs(e_fci + en - expected) < ETOL and abs(s2) < 1e-7
+    rng = np.random.default_rng(n_atoms)
+    for trial in range(3):
+        sa = np.sort(rng.choice(full, size=max(2, len(full) * 2 // 3), replace=False))
+        sb = np.sort(rng.choice(full, size=max(2, len(full) // 2), replace=False))
+        for spin_sq in (None, 0.0):
+            e, st, oc, ss = fermion.solve_fermion((sa, sb), h, g, spin_sq=spin_sq, shift=0.1)
+            e_ref, *_ = fo.solve_dense(sa, sb, h, g, n_atoms, spin_sq=spin_sq, shift=0.1)
+            assert abs(e - e_ref) < ETOL
+            assert e >= e_fci - 1e-9
