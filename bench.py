@@ -305,6 +305,18 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if dist is not None:
         dist.barrier()
 
+    # ---- secondary measurements (bench_extras.py) ----
+    extra = {}
+    if args.extras != "none":
+        import bench_extras as bx
+
+        me = sys.modules[__name__]
+        if world > 1:
+            # all ranks take part: configs[4] sharded over the ranks, and the literal configs[3]
+            extra["c5_sharded"] = bx.sharded_extras(me, torch, dist, fermion, rank, world, dev)
+            extra["c4_strong"] = bx.strong_extras(me, torch, dist, fermion, rank, world, dev)
+            dist.barrier()
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -316,8 +328,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         peaks = json.load(open(pk_file))
     peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    if args.extras != "none" and world == 1:
+        with torch.cuda.stream(streams[0]):
+            wls = ("c4", "t", "c5") if args.extras == "all" else ("c4", "t")
+            extra["fermion"] = bx.fermion_extras(me, torch, fermion, dev, peak_gbs, wls)
+            extra["t"] = extra["fermion"]["t"]
+            if args.extras == "all":
+                cpu = not args.no_cpu_baseline
+                extra["qubit_c3"] = bx.qubit_extras(torch, dev, peak_gbs, cpu)
+                extra["pauli_z40"] = bx.pauli_z40_extras(torch, dev, args.z40_rows)
+                extra["recovery"] = bx.recovery_extras(torch, dev, cpu)
     sig_ms = np.mean([s.sigma_ms / max(s.cycles, 1) for s in stats_prof])
     sig_bytes = np.mean([sigma_algorithmic_bytes(s) for s in stats_prof])
+    v2 = all(s.sigma_path == 2 for s in stats_prof)
     achieved = sig_bytes / (sig_ms * 1e-3) / 1e9
     # applied matrix elements per sigma build: opposite-spin (links+diagonal of both spins), same-spin doubles
     # and singles of each spin against every string of the other, operator diagonal
@@ -351,12 +374,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {
-            "kernel": "sigma_kernel (CI sigma-vector build inside the Davidson loop)",
+            "kernel": ("sigma2_ab_kernel + sigma2_tile_kernel + sigma2_epilogue_kernel (one CI sigma-vector "
+                       "build = these three launches, timed together inside the Davidson loop)"
+                       if v2 else "sigma_b_kernel + sigma_a_kernel + sigma_combine_kernel (one sigma build)"),
             "bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-            "frac": achieved / peak_gbs, "peak_source": peak_src, "traffic": ncu_traffic(),
+            "frac": achieved / peak_gbs, "peak_source": peak_src, "traffic": ncu_traffic(v2),
             "bytes_per_launch": sig_bytes, "ms_per_launch": sig_ms,
             "gflops": 2.0 * applied / (sig_ms * 1e-3) / 1e9, "matrix_elements_per_launch": applied,
-            "dram_gbs_from_ncu_traffic": (ncu_traffic() or 0.0) / (sig_ms * 1e-3) / 1e9,
+            "dram_gbs_from_ncu_traffic": (ncu_traffic(v2) or 0.0) / (sig_ms * 1e-3) / 1e9,
             "share_of_davidson_loop": sig_share, "davidson_loop_ms": dav_ms,
             "note": "algorithmic bytes = 16 n_det + 8 norb^4 + 12 nnz + 8 links (SURVEY 8d); the working "
                     "set is L2-resident, the kernel is bound by shared-memory gathers and FP64 FMA "
@@ -366,6 +391,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                             "mean": float(np.mean(cycles))},
         "energies": [float(r["energy"]) for r in res_dev][:4],
     }
+    if extra:
+        line["extra"] = extra
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, batches, h, g, res_dev)
     print(json.dumps(line), flush=True)
@@ -373,12 +400,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
-def ncu_traffic():
-    """DRAM bytes per sigma build (kernel A + kernel B) from the committed `ncu --set full` captures
-    (profiles/r1_sigma_{a,b}_ncu_raw_c4.txt); null when the summaries are not there."""
+def ncu_traffic(v2: bool = True):
+    """DRAM bytes per sigma build (all kernels of one build) from the committed `ncu --set full` captures
+    (profiles/r2_sigma2_{ab,tile,epilogue}_ncu_raw_c4.txt, or round 1's sigma_a/sigma_b for the v1 path);
+    null when the summaries are not there."""
+    names = [f"r2_sigma2_{k}_ncu_raw_c4.txt" for k in ("ab", "tile", "epilogue")] if v2 else \
+            [f"r1_sigma_{k}_ncu_raw_c4.txt" for k in ("a", "b")]
     tot, found = 0.0, False
-    for k in ("a", "b"):
-        path = os.path.join(ROOT, "profiles", f"r1_sigma_{k}_ncu_raw_c4.txt")
+    for name in names:
+        path = os.path.join(ROOT, "profiles", name)
         if not os.path.exists(path):
             continue
         found = True
@@ -430,6 +460,9 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=2, help="subspaces per step on the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-pyscf-style", action="store_true")
+    ap.add_argument("--extras", default="all", choices=["all", "fermion", "none"],
+                    help="secondary measurements under the 'extra' key (bench_extras.py)")
+    ap.add_argument("--z40-rows", type=int, default=50_000_000, help="rows of the Z^(x)40 projection extra")
     ap.add_argument("--no-clock-sampler", action="store_true", help="diagnostics: do not poll nvidia-smi")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -278,6 +278,11 @@ typedef struct {
      * builds rows [row_begin, row_end) of every sigma vector and the blocks are all-reduced (sum) */
     void* nccl_comm;
     int row_begin, row_end;
+    /* sharded build, optional: row bounds of ALL ranks (shard_world + 1 ints, host memory, valid during the
+     * call; bounds[r] = first row of rank r).  When given, the ranks exchange their disjoint row blocks
+     * (grouped broadcasts, (W-1)/W of the vector per rank) instead of all-reducing zero-padded vectors. */
+    const int* shard_bounds;
+    int shard_world;
     /* 0: the lowest Ritz pair comes from the secular equation on the main stream and the full
      * Rayleigh-Ritz decomposition runs on a side stream (shortest critical path of ONE solve);
      * != 0: one Rayleigh-Ritz kernel on the main stream (fewer launches when many solves share the GPU) */
@@ -457,6 +462,31 @@ int sqd_csr_matvec_c128(int64_t d, const int32_t* d_row_ptr, const int32_t* d_co
  * lies below the minimum of d_lower over that component). */
 int sqd_csr_gershgorin(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, const double* d_val,
                        double* d_diag, double* d_lower, void* stream);
+
+/* Connected components of a Hermitian CSR matrix (the block structure of the projected operator: sets of
+ * configurations no Pauli term connects).  d_label[i] = smallest row index of the component of row i.
+ * Single-row components are exact eigenpairs (A_ii, e_i) and are reduced on the device:
+ * h_head[0] = number of multi-row components (their records, in no particular order, in d_rec[0..min(.,cap)) ),
+ * h_head[1] = number of single-row components, h_head[2] = row of the lowest one (-1 if none) and
+ * *h_best_single = its diagonal.  d_diag / d_lower come from sqd_csr_gershgorin. */
+typedef struct sqd_component {
+    int32_t root;          /* label of the component */
+    int32_t size;          /* rows in it (>= 2) */
+    int32_t row_min_diag;  /* first row with the smallest diagonal: the Davidson start row */
+    int32_t pad;
+    double lower;          /* min over the rows of A_ii - sum_j |A_ij|: no eigenvalue of the block is below it */
+    double diag;           /* smallest diagonal: the block's lowest eigenvalue is <= it */
+} sqd_component;
+int64_t sqd_csr_components_workspace_bytes(int64_t d);
+int sqd_csr_components(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, const double* d_diag,
+                       const double* d_lower, int32_t* d_label, sqd_component* d_rec, int64_t rec_cap,
+                       int32_t* h_head /* [3] */, double* h_best_single, void* d_workspace,
+                       int64_t ws_bytes, void* stream);
+/* complex128[d] start vector confined to one component: e_row + scale * deterministic noise in [-1, 1) on the
+ * rows with d_label == root (pyscf perturbs its unit start vector for the same reason: a ground state with a
+ * node on the start row must still have a component in the start vector). */
+int sqd_csr_component_start(int64_t d, const int32_t* d_label, int32_t root, int32_t row, double scale,
+                            double* d_start, void* stream);
 
 /* Lowest eigenpair (k must be 1) of the Hermitian matrix A -- the matrix the reference hands to eigsh
  * (qubit.py:73) -- by the device-resident Davidson on the (re, im) embedding, replacing ARPACK.

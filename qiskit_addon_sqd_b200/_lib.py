@@ -115,6 +115,8 @@ class DavidsonParams(C.Structure):
         ("nccl_comm", C.c_void_p),
         ("row_begin", C.c_int),
         ("row_end", C.c_int),
+        ("shard_bounds", C.c_void_p),
+        ("shard_world", C.c_int),
         ("single_stream_ritz", C.c_int),
     ]
 
@@ -242,6 +244,9 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_csr_matvec_c128": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_csr_davidson_workspace_bytes": (_i64, [_i64, _i, _i]),
     "sqd_csr_gershgorin": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sqd_csr_components_workspace_bytes": (_i64, [_i64]),
+    "sqd_csr_components": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
+    "sqd_csr_component_start": (_i, [_i64, _vp, _i, _i, _d, _vp, _vp]),
     "sqd_csr_davidson": (
         _i, [_i64, _vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _pi, _vp, _vp, _i64, _vp]
     ),

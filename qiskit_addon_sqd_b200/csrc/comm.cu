@@ -22,6 +22,9 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
     ncclResult_t (*CommDestroy)(ncclComm_t);
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
+    ncclResult_t (*GroupStart)();
+    ncclResult_t (*GroupEnd)();
     const char* (*GetErrorString)(ncclResult_t);
     bool ok;
 };
@@ -37,7 +40,11 @@ static NcclApi& nccl() {
             a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
             a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
             a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
-            a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.GetErrorString;
+            a.Broadcast = (decltype(a.Broadcast))dlsym(h, "ncclBroadcast");
+            a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
+            a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
+            a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllReduce && a.GetErrorString &&
+                   a.Broadcast && a.GroupStart && a.GroupEnd;
         }
         return a;
     }();
@@ -49,6 +56,27 @@ int nccl_allreduce_sum_f64(void* comm, double* buf, int64_t n, cudaStream_t st) 
     SQD_REQUIRE(a.ok, "NCCL is not available in this process");
     const ncclResult_t r = a.AllReduce(buf, buf, (size_t)n, kNcclDouble, kNcclSum, (ncclComm_t)comm, st);
     SQD_REQUIRE(r == 0, "ncclAllReduce failed: %s", a.GetErrorString(r));
+    return 0;
+}
+
+// Exchange of DISJOINT blocks: rank r has written elements [offs[r], offs[r+1]) of buf; afterwards every rank
+// holds all of buf.  One grouped call of `world` broadcasts (the blocks have unequal sizes, which rules out
+// ncclAllGather): each rank receives (world-1)/world of the vector -- half of what the all-reduce of
+// zero-padded full vectors moved (round 1) -- and nothing is added, so the result is the unsharded sigma
+// bit for bit by construction.
+int nccl_allgather_blocks(void* comm, double* buf, const long long* offs, int world, cudaStream_t st) {
+    NcclApi& a = nccl();
+    SQD_REQUIRE(a.ok, "NCCL is not available in this process");
+    ncclResult_t r = a.GroupStart();
+    SQD_REQUIRE(r == 0, "ncclGroupStart failed: %s", a.GetErrorString(r));
+    for (int root = 0; root < world; ++root) {
+        const long long cnt = offs[root + 1] - offs[root];
+        if (cnt <= 0) continue;
+        r = a.Broadcast(buf + offs[root], buf + offs[root], (size_t)cnt, kNcclDouble, root, (ncclComm_t)comm, st);
+        SQD_REQUIRE(r == 0, "ncclBroadcast failed: %s", a.GetErrorString(r));
+    }
+    r = a.GroupEnd();
+    SQD_REQUIRE(r == 0, "ncclGroupEnd failed: %s", a.GetErrorString(r));
     return 0;
 }
 

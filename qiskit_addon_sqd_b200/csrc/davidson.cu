@@ -35,6 +35,7 @@ int sigma_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_sig
 int sigma_dispatch_ctl(const sqd_operator* op, const double* d_cbase, double* d_sbase, const int* d_done,
                        const int* d_slot, long long stride, int in_graph, cudaStream_t st);
 int nccl_allreduce_sum_f64(void* comm, double* buf, int64_t n, cudaStream_t st);
+int nccl_allgather_blocks(void* comm, double* buf, const long long* offs, int world, cudaStream_t st);
 int csr_matvec_flag(const int* d_done, int64_t d, const int32_t* row_ptr, const int32_t* col,
                     const double* val, const double* x, double* y, cudaStream_t st);
 int csr_diag_embed(int64_t d, const int32_t* row_ptr, const int32_t* col, const double* val,
@@ -1046,9 +1047,17 @@ static int apply_operator(const sqd_operator* op, const sqd_davidson_params* prm
     if (prm->nccl_comm != nullptr) {
         // sharded build: this rank owns rows [row_begin, row_end) of sigma; the other rows are zero and
         // the blocks meet in an all-reduce over NVLink.  Every rank runs the identical enqueue sequence.
-        SQD_CUDA_OK(cudaMemsetAsync(w, 0, (size_t)n * sizeof(double), st));
-        if (sigma_dispatch_rows(op, v, w, done, prm->row_begin, prm->row_end, st)) return -2;
-        if (nccl_allreduce_sum_f64(prm->nccl_comm, w, n, st)) return -2;
+        if (prm->shard_bounds != nullptr && prm->shard_world > 0 && prm->shard_world <= 64) {
+            // disjoint row blocks: every rank writes its rows in place, then the blocks travel
+            if (sigma_dispatch_rows(op, v, w, done, prm->row_begin, prm->row_end, st)) return -2;
+            long long offs[65];
+            for (int r = 0; r <= prm->shard_world; ++r) offs[r] = (long long)prm->shard_bounds[r] * op->ldc;
+            if (nccl_allgather_blocks(prm->nccl_comm, w, offs, prm->shard_world, st)) return -2;
+        } else {
+            SQD_CUDA_OK(cudaMemsetAsync(w, 0, (size_t)n * sizeof(double), st));
+            if (sigma_dispatch_rows(op, v, w, done, prm->row_begin, prm->row_end, st)) return -2;
+            if (nccl_allreduce_sum_f64(prm->nccl_comm, w, n, st)) return -2;
+        }
     } else if (sigma_dispatch_flag(op, v, w, done, st)) {
         return -2;
     }

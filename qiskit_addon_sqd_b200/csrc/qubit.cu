@@ -8,6 +8,8 @@
 // groups: binary search of key^xmask in the key list, then the group's terms are accumulated in their
 // original order (same floating-point sum order as the reference's term-by-term `operator += ...`).
 // Hits are ballot-compacted into the row's CSR segment and rank-sorted by column.
+#include <string.h>
+
 #include "common.cuh"
 #include "../../include/sqd_b200.h"
 
@@ -184,6 +186,127 @@ __global__ void csr_gershgorin_kernel(int64_t d, const int32_t* __restrict__ row
     }
 }
 
+// ---- connected components of the projected operator (block structure of the subspace) -------------------
+// label[i] = smallest row index of the component of row i.  Min-label hooking over the stored entries
+// (the matrix is Hermitian, so the structure is symmetric) alternated with full pointer jumping; the host
+// loop stops after the first hooking pass that changes nothing.
+__global__ void cc_init_kernel(int64_t d, int32_t* __restrict__ label) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d) label[i] = (int32_t)i;
+}
+
+__global__ void cc_hook_kernel(int64_t d, const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                               int32_t* label, int32_t* __restrict__ changed) {
+    const int lane = threadIdx.x & 31;
+    const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= d) return;
+    const int32_t li = label[i];
+    int32_t m = li;
+    for (int e = row_ptr[i] + lane; e < row_ptr[i + 1]; e += 32) m = min(m, label[col[e]]);
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m < li) {
+        atomicMin(label + li, m);   // hook the old representative too: whole trees move at once
+        atomicMin(label + i, m);
+        *changed = 1;
+    }
+}
+
+__global__ void cc_jump_kernel(int64_t d, int32_t* label) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    int32_t l = label[i];
+    int32_t ll = label[l];
+    while (ll != l) {   // label[x] <= x: the chain is strictly decreasing and ends at a fixed point
+        l = ll;
+        ll = label[l];
+    }
+    label[i] = l;
+}
+
+// order-preserving map double -> uint64 (for atomicMin)
+__device__ __forceinline__ unsigned long long enc_f64(double x) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dec_f64(unsigned long long e) {
+    const unsigned long long u = (e >> 63) ? (e & 0x7fffffffffffffffull) : ~e;
+    return __longlong_as_double((long long)u);
+}
+
+// per component (stored at its representative row): size, min Gershgorin bound, min diagonal
+__global__ void cc_stats_kernel(int64_t d, const int32_t* __restrict__ label, const double* __restrict__ diag,
+                                const double* __restrict__ lower, int32_t* __restrict__ size,
+                                unsigned long long* __restrict__ min_lower,
+                                unsigned long long* __restrict__ min_diag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    const int32_t r = label[i];
+    atomicAdd(size + r, 1);
+    atomicMin(min_lower + r, enc_f64(lower[i]));
+    atomicMin(min_diag + r, enc_f64(diag[i]));
+}
+
+// first row (smallest index) attaining the component's minimum diagonal
+__global__ void cc_argmin_kernel(int64_t d, const int32_t* __restrict__ label, const double* __restrict__ diag,
+                                 const unsigned long long* __restrict__ min_diag, int32_t* __restrict__ arg_row) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    const int32_t r = label[i];
+    if (enc_f64(diag[i]) == min_diag[r]) atomicMin(arg_row + r, (int32_t)i);
+}
+
+// head[0] = number of multi-row components, head[1] = number of single-row components,
+// head[2] = row of the lowest single-row component (or -1); best[0] = its (encoded) diagonal.
+// Multi-row components are appended to `rec` (order not deterministic: the host sorts them).
+__global__ void cc_summary_kernel(int64_t d, const int32_t* __restrict__ label, const int32_t* __restrict__ size,
+                                  const unsigned long long* __restrict__ min_lower,
+                                  const unsigned long long* __restrict__ min_diag,
+                                  const int32_t* __restrict__ arg_row, int32_t* __restrict__ head,
+                                  unsigned long long* __restrict__ best, sqd_component* __restrict__ rec,
+                                  int64_t cap) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d || label[i] != (int32_t)i) return;
+    if (size[i] == 1) {
+        atomicAdd(head + 1, 1);
+        atomicMin(best, min_diag[i]);
+    } else {
+        const int32_t slot = atomicAdd(head + 0, 1);
+        if (slot < cap) {
+            sqd_component c;
+            c.root = (int32_t)i;
+            c.size = size[i];
+            c.row_min_diag = arg_row[i];
+            c.pad = 0;
+            c.lower = dec_f64(min_lower[i]);
+            c.diag = dec_f64(min_diag[i]);
+            rec[slot] = c;
+        }
+    }
+}
+
+__global__ void cc_best_single_kernel(int64_t d, const int32_t* __restrict__ label, const int32_t* __restrict__ size,
+                                      const unsigned long long* __restrict__ min_diag,
+                                      const unsigned long long* __restrict__ best, int32_t* __restrict__ head) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d || label[i] != (int32_t)i || size[i] != 1) return;
+    if (min_diag[i] == *best) atomicMin(head + 2, (int32_t)i);
+}
+
+// start vector of a Davidson run confined to one component: e_row + scale * noise on the component's rows,
+// noise_i = 2 frac((i + 1) / golden ratio) - 1 (deterministic, no generator state)
+__global__ void cc_start_kernel(int64_t d, const int32_t* __restrict__ label, int32_t root, int32_t row,
+                                double scale, double2* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    double v = 0.0;
+    if (label[i] == root) {
+        const double t = (double)(i + 1) * 0.6180339887498949;
+        v = scale * (2.0 * (t - floor(t)) - 1.0);
+    }
+    if (i == row) v = 1.0;
+    out[i] = make_double2(v, 0.0);
+}
+
 int csr_matvec_flag(const int* d_done, int64_t d, const int32_t* row_ptr, const int32_t* col,
                     const double* val, const double* x, double* y, cudaStream_t st) {
     const int wpb = 8;
@@ -257,6 +380,73 @@ int sqd_csr_gershgorin(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col
     csr_gershgorin_kernel<<<(unsigned)((d + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
         d, d_row_ptr, d_col, (const double2*)d_val, d_diag, d_lower);
     return check_launch("csr_gershgorin_kernel");
+}
+
+int64_t sqd_csr_components_workspace_bytes(int64_t d) {
+    if (d <= 0) return -1;
+    // size (i32) + arg_row (i32) + min_lower (u64) + min_diag (u64) per row, + changed flag, head[4], best
+    return (int64_t)(d * (4 + 4 + 8 + 8) + 256);
+}
+
+int sqd_csr_components(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col, const double* d_diag,
+                       const double* d_lower, int32_t* d_label, sqd_component* d_rec, int64_t rec_cap,
+                       int32_t* h_head, double* h_best_single, void* d_workspace, int64_t ws_bytes,
+                       void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SQD_REQUIRE(d > 0 && d < 2147483647LL, "sqd_csr_components: d=%lld out of range", (long long)d);
+    SQD_REQUIRE(ws_bytes >= sqd_csr_components_workspace_bytes(d), "sqd_csr_components: workspace too small");
+    char* p = (char*)d_workspace;
+    unsigned long long* min_lower = (unsigned long long*)p;  p += 8 * d;
+    unsigned long long* min_diag = (unsigned long long*)p;   p += 8 * d;
+    unsigned long long* best = (unsigned long long*)p;       p += 64;
+    int32_t* size = (int32_t*)p;                             p += 4 * d;
+    int32_t* arg_row = (int32_t*)p;                          p += 4 * d;
+    int32_t* head = (int32_t*)p;                             p += 64;
+    int32_t* changed = (int32_t*)p;
+    const unsigned tb = 256, nb1 = (unsigned)((d + tb - 1) / tb), nbw = (unsigned)((d + 7) / 8);
+    cc_init_kernel<<<nb1, tb, 0, st>>>(d, d_label);
+    if (check_launch("cc_init_kernel")) return -2;
+    for (int it = 0;; ++it) {
+        SQD_REQUIRE(it < 100000, "sqd_csr_components: label propagation did not settle");
+        SQD_CUDA_OK(cudaMemsetAsync(changed, 0, sizeof(int32_t), st));
+        cc_hook_kernel<<<nbw, 256, 0, st>>>(d, d_row_ptr, d_col, d_label, changed);
+        cc_jump_kernel<<<nb1, tb, 0, st>>>(d, d_label);
+        if (check_launch("cc_hook/jump kernels", 2)) return -2;
+        int32_t h_changed = 0;
+        if (read_back(&h_changed, changed, sizeof(int32_t), st)) return -2;
+        if (!h_changed) break;
+    }
+    SQD_CUDA_OK(cudaMemsetAsync(min_lower, 0xff, 16 * (size_t)d + 64, st));      // min_lower, min_diag, best
+    SQD_CUDA_OK(cudaMemsetAsync(size, 0, 4 * (size_t)d, st));
+    SQD_CUDA_OK(cudaMemsetAsync(arg_row, 0x7f, 4 * (size_t)d, st));
+    SQD_CUDA_OK(cudaMemsetAsync(head, 0, 64, st));
+    SQD_CUDA_OK(cudaMemsetAsync(head + 2, 0x7f, 4, st));
+    cc_stats_kernel<<<nb1, tb, 0, st>>>(d, d_label, d_diag, d_lower, size, min_lower, min_diag);
+    cc_argmin_kernel<<<nb1, tb, 0, st>>>(d, d_label, d_diag, min_diag, arg_row);
+    cc_summary_kernel<<<nb1, tb, 0, st>>>(d, d_label, size, min_lower, min_diag, arg_row, head, best, d_rec,
+                                         rec_cap);
+    cc_best_single_kernel<<<nb1, tb, 0, st>>>(d, d_label, size, min_diag, best, head);
+    if (check_launch("cc summary kernels", 4)) return -2;
+    struct { int32_t head[16]; } hh;
+    unsigned long long h_best = 0;
+    if (read_back(&hh, head, 64, st)) return -2;
+    if (read_back(&h_best, best, 8, st)) return -2;
+    h_head[0] = hh.head[0];
+    h_head[1] = hh.head[1];
+    h_head[2] = hh.head[1] > 0 ? hh.head[2] : -1;
+    const unsigned long long u = (h_best >> 63) ? (h_best & 0x7fffffffffffffffull) : ~h_best;
+    double bd;
+    memcpy(&bd, &u, 8);
+    *h_best_single = hh.head[1] > 0 ? bd : 0.0;
+    return 0;
+}
+
+int sqd_csr_component_start(int64_t d, const int32_t* d_label, int32_t root, int32_t row, double scale,
+                            double* d_start, void* stream) {
+    SQD_REQUIRE(d > 0 && row >= 0 && row < d, "sqd_csr_component_start: bad row");
+    cc_start_kernel<<<(unsigned)((d + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, d_label, root, row, scale,
+                                                                                 (double2*)d_start);
+    return check_launch("cc_start_kernel");
 }
 
 int sqd_csr_matvec_c128(int64_t d, const int32_t* d_row_ptr, const int32_t* d_col,

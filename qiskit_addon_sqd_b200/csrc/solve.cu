@@ -9,6 +9,8 @@
 // every stream idle most of the time; here the host thread stays inside C from the first kernel to the
 // last read-back.  Scratch memory comes from the device's stream-ordered pool (cudaMallocAsync) and is
 // returned before the call ends; results are written to caller-owned buffers.
+#include <stdlib.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -369,7 +371,7 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
     dp.nccl_comm = prm->nccl_comm;
     dp.row_begin = prm->row_begin;
     dp.row_end = prm->row_end;
-    std::vector<int> h_ns, h_ptr;
+    std::vector<int> h_ns, h_ptr, shard_bounds;
     if (prm->profile || (prm->nccl_comm != nullptr && prm->row_begin < 0)) {
         h_ns.resize(na);
         h_ptr.resize(na + 1);
@@ -397,6 +399,14 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
         };
         dp.row_begin = bound(prm->shard_rank);
         dp.row_end = bound(prm->shard_rank + 1);
+        // every rank derives the same bounds from the same tables: the blocks can be exchanged as they are
+        static const int knob_gather = getenv("SQD_SHARD_GATHER") ? atoi(getenv("SQD_SHARD_GATHER")) : 1;
+        if (knob_gather && prm->shard_world <= 64) {
+            shard_bounds.resize(prm->shard_world + 1);
+            for (int r = 0; r <= prm->shard_world; ++r) shard_bounds[r] = bound(r);
+            dp.shard_bounds = shard_bounds.data();
+            dp.shard_world = prm->shard_world;
+        }
     }
     sqd_davidson_info info{};
     if (sqd_davidson(&ham, ham.diag, x0, d_x, ws, ws_bytes, &dp, &info, st)) return -2;

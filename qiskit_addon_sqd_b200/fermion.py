@@ -549,6 +549,7 @@ class SolveStats:
     nb: int = 0
     norb: int = 0
     host_ms: tuple = ()     # host wall time of (preparation, library call, downloads)
+    sigma_path: int = 0     # 1: fermion_sigma.cu, 2: fermion_sigma2.cu (what the solve actually ran)
 
 
 _tls = threading.local()
@@ -657,7 +658,8 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
     stats = SolveStats(info.cycles, info.sigma_builds, info.converged, info.residual, info.theta,
                        na * nb, int(res.nnz_a), int(res.nnz_b), max(int(res.singles_a), 0),
                        max(int(res.singles_b), 0), info.sigma_ms, info.total_ms, na, nb, norb,
-                       (1e3 * (t_host1 - t_host0), 1e3 * (t_host2 - t_host1), 1e3 * (t_host3 - t_host2)))
+                       (1e3 * (t_host1 - t_host0), 1e3 * (t_host2 - t_host1), 1e3 * (t_host3 - t_host2)),
+                       int(res.sigma_path))
     if not hasattr(_tls, "stats"):
         _tls.stats = []
     _tls.stats.append(stats)

@@ -183,20 +183,29 @@ def project_operator_to_subspace(
     return _project_device(torch, lib, keys, hamiltonian).to_scipy()
 
 
+#: numpy view of ``sqd_component`` records (include/sqd_b200.h)
+_COMPONENT_DTYPE = np.dtype([("root", np.int32), ("size", np.int32), ("row", np.int32), ("pad", np.int32),
+                             ("lower", np.float64), ("diag", np.float64)])
+_START_NOISE = 1e-3
+
+
 def _lowest_eigenpair_device(torch, lib, csr: "_DeviceCSR", kw: dict, max_rounds: int = 64):
     """Lowest eigenpair of the projected operator with the device-resident Davidson.
 
-    The projected matrix is usually block diagonal (sets of configurations no Pauli term connects), and a
-    Davidson run started from a basis state never leaves that state's block.  So: solve from the
-    lowest-diagonal state, mark the block as visited (support of the eigenvector), then use the Gershgorin
-    lower bounds ``A_ii - sum_j |A_ij|`` to find unvisited rows whose block could still hold a lower
-    eigenvalue, and solve from the lowest-diagonal one of those; stop when no candidate is left.  Exact
-    up to the Davidson tolerance; ARPACK's random start vector plays the same role in the reference.
+    The projected matrix is usually block diagonal (sets of configurations no Pauli term connects), so the
+    blocks are found first (``sqd_csr_components``: label propagation over the CSR structure):
 
-    The start vector is the basis state plus a small deterministic perturbation on every row that has not
-    been visited yet (pyscf perturbs its unit start vector for the same reason, ARPACK starts from a random
-    vector): a ground state with a node on the start row, or one that lives in a block the start row does
-    not belong to, still has a component in the start vector.
+    * a single-row block is an exact eigenpair ``(A_ii, e_i)``; the lowest one is reduced on the device;
+    * multi-row blocks are visited in order of their Gershgorin lower bound ``min_i (A_ii - sum_j |A_ij|)``
+      and only while that bound is below the best eigenvalue found so far.  Each is solved by a Davidson run
+      started from the block's lowest-diagonal basis state plus a small deterministic perturbation on the rows
+      OF THAT BLOCK (pyscf perturbs its unit start vector for the same reason, ARPACK starts from a random
+      vector: a ground state with a node on the start row still has a component in the start vector).  The
+      perturbation never leaves the block: rows of other blocks stay exactly zero, so the run is the
+      diagonalisation of that block alone.
+
+    Exact up to the Davidson tolerance.  Returns ``(None, None)`` when a run does not converge or more than
+    ``max_rounds`` blocks would have to be solved; the caller then lets ARPACK drive the GPU matvec.
     """
     d = csr.d
     dev = csr.row_ptr.device
@@ -209,45 +218,67 @@ def _lowest_eigenpair_device(torch, lib, csr: "_DeviceCSR", kw: dict, max_rounds
     lower = torch.empty(d, dtype=torch.float64, device=dev)
     _lib.check(lib.sqd_csr_gershgorin(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col), _lib.ptr(csr.val),
                                       _lib.ptr(diag), _lib.ptr(lower), st), "sqd_csr_gershgorin")
+    label = torch.empty(d, dtype=torch.int32, device=dev)
+    rec_cap = d // 2 + 1
+    rec = torch.empty(rec_cap * _COMPONENT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+    cws_bytes = lib.sqd_csr_components_workspace_bytes(d)
+    cws = torch.empty(cws_bytes, dtype=torch.uint8, device=dev)
+    head = (C.c_int32 * 3)()
+    best_single = C.c_double(0.0)
+    _lib.check(lib.sqd_csr_components(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col), _lib.ptr(diag),
+                                      _lib.ptr(lower), _lib.ptr(label), _lib.ptr(rec), rec_cap, head,
+                                      C.byref(best_single), _lib.ptr(cws), cws_bytes, st), "sqd_csr_components")
+    n_multi, n_single, single_row = int(head[0]), int(head[1]), int(head[2])
+    comps = np.zeros(0, dtype=_COMPONENT_DTYPE)
+    if n_multi:
+        comps = rec[: n_multi * _COMPONENT_DTYPE.itemsize].cpu().numpy().view(_COMPONENT_DTYPE)
+        comps = comps[np.lexsort((comps["root"], comps["lower"]))]   # the device appends in no fixed order
+
     ws_bytes = lib.sqd_csr_davidson_workspace_bytes(d, 1, max_space)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    visited = torch.zeros(d, dtype=torch.bool, device=dev)
-    start = torch.zeros(2 * d, dtype=torch.float64, device=dev)
+    start = torch.empty(2 * d, dtype=torch.float64, device=dev)
     evec = torch.empty(2 * d, dtype=torch.float64, device=dev)
-    best_e, best_vec = None, None
-    v0 = kw.get("v0")
-    row = int(torch.argmin(diag).item())
-    inf = torch.tensor(float("inf"), dtype=torch.float64, device=dev)
-    # deterministic perturbation in [-1, 1): golden-ratio sequence, generated once on the host
-    noise = torch.from_numpy(2.0 * ((np.arange(1, d + 1) * 0.6180339887498949) % 1.0) - 1.0).to(dev)
-    for rnd in range(max_rounds):
-        start.zero_()
-        from_v0 = rnd == 0 and v0 is not None
-        if from_v0:
-            start.copy_(torch.from_numpy(np.ascontiguousarray(v0, dtype=np.complex128).reshape(-1)
-                                         .view(np.float64)))
-        else:
-            start.view(d, 2)[:, 0] = torch.where(visited, torch.zeros_like(noise), 1e-3 * noise)
-            start[2 * row] = 1.0
+    best_e, best_vec, best_row = None, None, -1
+
+    def run():
         evals = (C.c_double * 1)()
         cycles, resid = C.c_int(0), C.c_double(0.0)
         _lib.check(lib.sqd_csr_davidson(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col), _lib.ptr(csr.val), 1,
                                         max_space, max_cycle, tol, _lib.ptr(start), _lib.ptr(evec), evals,
                                         C.byref(cycles), C.byref(resid), _lib.ptr(ws), ws_bytes, st),
                    "sqd_csr_davidson")
-        amp2 = evec.view(d, 2).pow(2).sum(dim=1)
-        visited |= amp2 > 1e-20 * amp2.max()
-        if not from_v0:
-            visited[row] = True   # with a caller-supplied v0 the run did not start from this row
-        if best_e is None or evals[0] < best_e:
-            best_e, best_vec = float(evals[0]), evec.clone()
-        # unvisited rows whose block might still beat the best eigenvalue found so far
-        cand = torch.where(visited | (lower >= best_e), inf, diag)
-        row = int(torch.argmin(cand).item())
-        if not bool(torch.isfinite(cand[row]).item()):
-            vec = best_vec.cpu().numpy().view(np.complex128)
-            return best_e, vec
-    return None, None
+        converged = cycles.value < max_cycle or resid.value <= 10.0 * np.sqrt(tol) * max(1.0, abs(evals[0]))
+        return float(evals[0]), converged
+
+    v0 = kw.get("v0")
+    if v0 is not None:
+        # the caller's start vector, over whatever blocks it touches; the block search below still runs
+        start.copy_(torch.from_numpy(np.ascontiguousarray(v0, dtype=np.complex128).reshape(-1).view(np.float64)))
+        e, ok = run()
+        if not ok:
+            return None, None
+        best_e, best_vec = e, evec.clone()
+    if n_single and (best_e is None or best_single.value < best_e):
+        best_e, best_vec, best_row = float(best_single.value), None, single_row
+    rounds = 0
+    for c in comps:
+        if best_e is not None and c["lower"] >= best_e:
+            break   # sorted by lower bound: no later block can hold a lower eigenvalue either
+        rounds += 1
+        if rounds > max_rounds:
+            return None, None
+        _lib.check(lib.sqd_csr_component_start(d, _lib.ptr(label), int(c["root"]), int(c["row"]), _START_NOISE,
+                                               _lib.ptr(start), st), "sqd_csr_component_start")
+        e, ok = run()
+        if not ok:
+            return None, None
+        if best_e is None or e < best_e:
+            best_e, best_vec, best_row = e, evec.clone(), -1
+    if best_vec is None:
+        vec = np.zeros(d, dtype=np.complex128)
+        vec[best_row] = 1.0
+        return best_e, vec
+    return best_e, best_vec.cpu().numpy().view(np.complex128)
 
 
 def _native_ok(kw: dict) -> bool:

@@ -124,3 +124,100 @@ def test_medium_random_operator_against_oracle(cuda_lib):
     e, v = qubit.solve_qubit(rows, op, k=1, which="SA")
     e_ref, _ = eigsh(ref, k=1, which="SA")
     assert abs(e[0] - e_ref[0]) < 1e-8
+
+
+def _device_csr(torch, A):
+    from qiskit_addon_sqd_b200 import qubit
+
+    A = A.tocsr().astype(np.complex128)
+    A.sort_indices()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return qubit._DeviceCSR(A.shape[0], torch.from_numpy(A.indptr.astype(np.int32)).to(dev),
+                            torch.from_numpy(A.indices.astype(np.int32)).to(dev),
+                            torch.from_numpy(np.ascontiguousarray(A.data).view(np.float64)).to(dev))
+
+
+def test_components_match_scipy(cuda_lib):
+    """Block structure found on the device == scipy.sparse.csgraph.connected_components."""
+    import ctypes as C
+
+    import torch
+    from scipy.sparse import random as sprandom
+    from scipy.sparse.csgraph import connected_components
+
+    from qiskit_addon_sqd_b200 import _lib, qubit
+
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    for d, density in ((1, 1.0), (50, 0.02), (3000, 0.0004), (20000, 0.00004)):
+        M = sprandom(d, d, density=density, random_state=rng.integers(1 << 30), format="csr")
+        A = (M + M.T + coo_matrix((rng.standard_normal(d), (np.arange(d), np.arange(d))), shape=(d, d))).tocsr()
+        # a long chain inside: worst case for label propagation
+        if d >= 3000:
+            idx = np.arange(1000, 1999)
+            A = (A + coo_matrix((np.ones(999), (idx, idx + 1)), shape=(d, d))
+                 + coo_matrix((np.ones(999), (idx + 1, idx)), shape=(d, d))).tocsr()
+        csr = _device_csr(torch, A)
+        dev = csr.row_ptr.device
+        st = _lib.stream_ptr(torch)
+        diag = torch.empty(d, dtype=torch.float64, device=dev)
+        lower = torch.empty(d, dtype=torch.float64, device=dev)
+        _lib.check(lib.sqd_csr_gershgorin(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col), _lib.ptr(csr.val),
+                                          _lib.ptr(diag), _lib.ptr(lower), st), "gershgorin")
+        label = torch.empty(d, dtype=torch.int32, device=dev)
+        cap = d // 2 + 1
+        rec = torch.empty(cap * qubit._COMPONENT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        wsb = lib.sqd_csr_components_workspace_bytes(d)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        head = (C.c_int32 * 3)()
+        best = C.c_double(0.0)
+        _lib.check(lib.sqd_csr_components(d, _lib.ptr(csr.row_ptr), _lib.ptr(csr.col), _lib.ptr(diag), _lib.ptr(lower),
+                                          _lib.ptr(label), _lib.ptr(rec), cap, head, C.byref(best), _lib.ptr(ws),
+                                          wsb, st), "components")
+        lab = label.cpu().numpy()
+        nc, ref = connected_components(A, directed=False)
+        # same partition, and every label is the smallest member of its block
+        first = np.full(nc, d, dtype=np.int64)
+        np.minimum.at(first, ref, np.arange(d))
+        assert np.array_equal(lab, first[ref])
+        sizes = np.bincount(ref)
+        assert head[0] == np.count_nonzero(sizes > 1) and head[1] == np.count_nonzero(sizes == 1)
+        dg = A.diagonal().real
+        if head[1]:
+            single = np.flatnonzero(sizes[ref] == 1)
+            assert best.value == dg[single].min() and head[2] == single[np.argmin(dg[single])]
+        recs = rec[: head[0] * qubit._COMPONENT_DTYPE.itemsize].cpu().numpy().view(qubit._COMPONENT_DTYPE)
+        off = np.asarray(abs(A).sum(axis=1)).reshape(-1) - np.abs(dg)
+        for r in recs:
+            members = np.flatnonzero(lab == r["root"])
+            assert r["size"] == len(members) and r["diag"] == dg[members].min()
+            assert r["row"] == members[np.argmin(dg[members])]
+            assert abs(r["lower"] - (dg[members] - off[members]).min()) < 1e-12
+
+
+def test_ground_state_with_node_on_start_row(cuda_lib):
+    """The block's lowest state has zero amplitude on the block's lowest-diagonal row: a unit start
+    vector never reaches it; the perturbed start does.  Plus single-row blocks around it."""
+    import torch
+
+    from qiskit_addon_sqd_b200 import _lib, qubit
+
+    d = 40
+    A = np.diag(np.linspace(1.0, 2.0, d)).astype(np.complex128)
+    a, b, c = 7, 8, 9
+    A[a, a] = A[c, c] = 0.1
+    A[b, b] = 0.0
+    A[a, b] = A[b, a] = A[b, c] = A[c, b] = 0.1
+    A[a, c] = A[c, a] = 5.0                      # (a - c)/sqrt(2): energy 0.1 - 5, node on b
+    A[20, 21] = A[21, 20] = 0.3j * 1j            # another small block, not the lowest
+    from scipy.sparse import csr_matrix
+
+    csr = _device_csr(torch, csr_matrix(A))
+    e, vec = qubit._lowest_eigenpair_device(torch, _lib.load(), csr, {"k": 1, "which": "SA"})
+    w = np.linalg.eigvalsh(A)
+    assert abs(e - w[0]) < 1e-10 and abs(e + 4.9) < 1e-10
+    assert abs(abs(vec[a]) - 2 ** -0.5) < 1e-7 and abs(vec[b]) < 1e-7
+    # all blocks single rows: the answer is the lowest diagonal entry, no Davidson run at all
+    D = np.diag(np.array([3.0, -2.5, 0.5, -2.5]))
+    e, vec = qubit._lowest_eigenpair_device(torch, _lib.load(), _device_csr(torch, csr_matrix(D)), {})
+    assert e == -2.5 and np.array_equal(vec, np.array([0, 1, 0, 0], dtype=np.complex128))
