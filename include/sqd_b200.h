@@ -432,22 +432,38 @@ int sqd_rdm2s(const sqd_operator* op, const double* d_c, int64_t nnz_a, int64_t 
 /* big-endian bool rows -> int64 keys (qubit.py:280-300); nbits <= 63 */
 int sqd_bits_to_keys(const uint8_t* d_bits, int64_t n, int nbits, int64_t* d_keys, void* stream);
 
+/* key -> row hash table over the (unique) keys of the subspace: open addressing, linear probing, capacity a
+ * power of two >= 4 d (>= 2 d above 2^24 rows), 12 bytes per slot.  The projection kernels below take it as
+ * an optional argument (NULL: binary search of the sorted key list, as in round 1): "is key ^ xmask in the
+ * subspace" is almost always answered no, which a probe of a sparse table settles in ~1.4 L2 accesses instead
+ * of log2(d) dependent ones.  (Reference: np.isin + searchsorted per term, qubit.py:225-237.) */
+int64_t sqd_key_table_capacity(int64_t d);
+int64_t sqd_key_table_bytes(int64_t d);
+int sqd_key_table_build(const int64_t* d_keys, int64_t d, void* d_table, int64_t table_bytes, void* stream);
+
 /* One Pauli term (qubit.py:167-240): for every row i whose image key_i ^ xmask is in the sorted key
- * list, amplitude (-1)^popc(key_i & zmask) * i^ny, row i, col index of the image.
- * d_hit[d]: 0/1 flag; d_col[d]; amplitude is derived on the host from the parity bit d_par[d]. */
-int sqd_pauli_connect(const int64_t* d_keys, int64_t d, uint64_t xmask, uint64_t zmask, int32_t* d_col,
-                      uint8_t* d_par, void* stream);
+ * list, amplitude (-1)^popc(key_i & zmask) * i^ny, row i, col index of the image (-1: not in the subspace).
+ * sqd_pauli_connect returns the parity bit; sqd_pauli_elements returns the outputs in the reference's own
+ * types (complex128 amplitude, int64 column; d_col may be NULL when xmask == 0, where col[i] = i) and the
+ * number of rows without an image in *d_n_missing. */
+int sqd_pauli_connect(const int64_t* d_keys, int64_t d, const void* d_table /* or NULL */, uint64_t xmask,
+                      uint64_t zmask, int32_t* d_col, uint8_t* d_par, void* stream);
+int sqd_pauli_elements(const int64_t* d_keys, int64_t d, const void* d_table /* or NULL */, uint64_t xmask,
+                       uint64_t zmask, int ny, int64_t* d_col, double* d_amp /* re,im pairs */,
+                       int32_t* d_n_missing, void* stream);
 
 /* Projection of a whole operator (qubit.py:78-144).  Terms are pre-grouped by X mask on the host:
  * group k owns terms [grp_ptr[k], grp_ptr[k+1]) (original order kept inside a group), each with a
  * zmask, a number of Y's and a complex coefficient.  Pass 1 counts, pass 2 fills a CSR matrix whose
  * row i holds A[i, col] for every group that connects row i (transpose convention of the reference:
  * A[source, image]), columns ascending, exact zeros dropped (scipy canonical format). */
-int sqd_pauli_project_count(const int64_t* d_keys, int64_t d, const uint64_t* d_grp_xmask,
+int sqd_pauli_project_count(const int64_t* d_keys, int64_t d, const void* d_table /* or NULL */,
+                            const uint64_t* d_grp_xmask,
                             const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
                             const int32_t* d_ny, const double* d_coeff /* re,im pairs */,
                             int32_t* d_row_nnz, void* stream);
-int sqd_pauli_project_fill(const int64_t* d_keys, int64_t d, const uint64_t* d_grp_xmask,
+int sqd_pauli_project_fill(const int64_t* d_keys, int64_t d, const void* d_table /* or NULL */,
+                           const uint64_t* d_grp_xmask,
                            const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
                            const int32_t* d_ny, const double* d_coeff, const int32_t* d_row_ptr,
                            int32_t* d_col_tmp, double* d_val_tmp /* scratch, nnz entries each */,

@@ -236,10 +236,14 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_rdm2s_workspace_bytes": (_i64, [C.POINTER(Operator), _i64, _i64]),
     "sqd_rdm2s": (_i, [C.POINTER(Operator), _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "sqd_bits_to_keys": (_i, [_vp, _i64, _i, _vp, _vp]),
-    "sqd_pauli_connect": (_i, [_vp, _i64, _u64, _u64, _vp, _vp, _vp]),
-    "sqd_pauli_project_count": (_i, [_vp, _i64, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "sqd_key_table_capacity": (_i64, [_i64]),
+    "sqd_key_table_bytes": (_i64, [_i64]),
+    "sqd_key_table_build": (_i, [_vp, _i64, _vp, _i64, _vp]),
+    "sqd_pauli_connect": (_i, [_vp, _i64, _vp, _u64, _u64, _vp, _vp, _vp]),
+    "sqd_pauli_elements": (_i, [_vp, _i64, _vp, _u64, _u64, _i, _vp, _vp, _vp, _vp]),
+    "sqd_pauli_project_count": (_i, [_vp, _i64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "sqd_pauli_project_fill": (
-        _i, [_vp, _i64, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        _i, [_vp, _i64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     ),
     "sqd_csr_matvec_c128": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_csr_davidson_workspace_bytes": (_i64, [_i64, _i, _i]),

@@ -102,11 +102,21 @@ class PauliTerm:
         return "".join(tab[(bool(a), bool(b))] for a, b in zip(self.x[::-1], self.z[::-1]))
 
 
+class PauliTable(list):
+    """Duck-type of ``qiskit.quantum_info.PauliList``: a sequence of terms that also exposes the whole
+    ``(T, nq)`` boolean ``x`` and ``z`` tables."""
+
+    def __init__(self, x_bits, z_bits):
+        self.x = np.atleast_2d(np.asarray(x_bits, dtype=bool))
+        self.z = np.atleast_2d(np.asarray(z_bits, dtype=bool))
+        super().__init__(PauliTerm(x, z) for x, z in zip(self.x, self.z))
+
+
 class PauliSum:
     """Minimal duck-type of ``qiskit.quantum_info.SparsePauliOp``: ``.paulis``, ``.coeffs``, ``.size``."""
 
     def __init__(self, x_bits, z_bits, coeffs):
-        self.paulis = [PauliTerm(x, z) for x, z in zip(x_bits, z_bits)]
+        self.paulis = PauliTable(x_bits, z_bits)
         self.coeffs = np.asarray(coeffs, dtype=np.complex128)
 
     @classmethod

@@ -47,6 +47,26 @@ constexpr int kRedThreads = 256;
 constexpr int kPartialRows = kMaxS + 4;
 constexpr int kKeep = 4;  // Ritz vectors kept by a thick restart
 
+// Restart policy when the basis is full (m == max_space):
+//   mode 1 (default): collapse onto TWO vectors -- the current Ritz vector and the previous cycle's Ritz vector
+//     orthogonalised against it ("GD+1" / locally optimal restart: the pair spans the conjugate-gradient-like
+//     recurrence, so convergence barely notices the restart).  Needs only the lowest Ritz pair, which the
+//     Rayleigh-quotient iteration delivers in a few microseconds;
+//   mode 0: thick restart on the min(kKeep, M/3) lowest Ritz vectors, which needs the full decomposition of the
+//     projected matrix (parallel Jacobi by one warp: ~150 us at m = 12, as long as a whole cycle).
+static int env_knob(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+inline int restart_mode_knob() {
+    static const int mode = env_knob("SQD_RESTART_MODE", 1);
+    return mode;
+}
+inline int restart_keep(int M) {
+    if (restart_mode_knob() == 1) return M >= 3 ? 2 : 1;
+    return M / 3 < 1 ? 1 : (M / 3 > kKeep ? kKeep : M / 3);
+}
+
 struct DavState {
     int status;  // 0 running, 1 converged, 2 linear dependency, 3 (host) max_cycle
     int cycles;
@@ -66,6 +86,7 @@ struct DavState {
     int m, slot;                // size of the basis, slot of the newest basis vector
     int M, q_keep, max_cycle;   // max_space, Ritz vectors kept by a thick restart, cycle limit
     int n_jacobi, n_rqi_iter;   // diagnostics: full decompositions, Rayleigh-quotient iterations
+    int restart_mode;           // 1: keep {Ritz vector, previous Ritz vector} (no decomposition), 0: thick restart
 };
 
 // Control variables of a cycle.  Host-driven loop: passed as kernel arguments (m >= 0).  Device-driven
@@ -488,105 +509,106 @@ __device__ __forceinline__ void publish_pair(DavState* st, double yi, double the
     }
 }
 
-// Rayleigh-quotient iteration with the whole problem in registers: lane i owns row i of G (MR >= m doubles;
-// rows and columns beyond m are an identity block).  Gaussian elimination with partial pivoting WITHOUT row
-// swaps (the pivot lane of every step is remembered instead), the pivot row is broadcast by shuffles, the
-// solution vector is replicated on all lanes during back substitution.  A 12 x 12 solve is ~1.5 k cycles of
-// one warp -- the shared-memory version it replaces took ten times that.
-// Returns true when (mu, y) is an eigenpair of G to working precision AND certified lowest (interlacing).
+// Rayleigh-quotient iteration with the whole problem in registers: lane i owns row i of G (MR >= m doubles) and
+// component i of the iterate.
+//   * start: the exact lowest Ritz pair of the 2-D space spanned by the previous Ritz vector (padded with a
+//     zero) and the new basis vector -- a closed form, and already below theta_prev;
+//   * each iteration solves (G - mu I) z' = z by elimination WITHOUT pivot search, from the last row upwards:
+//     the rows of the newer basis vectors (Rayleigh quotients well above mu) are the pivots, the row of the
+//     vector that carries the Ritz vector is eliminated last and takes the near-singular pivot -- exactly where
+//     inverse iteration wants it.  All indices are compile-time constants (no local memory), a step is one
+//     reciprocal, k shuffles and k FMAs: ~1.5 us per iteration at m = 12 where the pivoting version took ~20.
+// Nothing here has to be trusted: the pair is accepted only if its residual against the ORIGINAL G is at
+// rounding level and Cauchy interlacing certifies it as the lowest; otherwise the caller falls back to the
+// full Jacobi decomposition.
 template <int MR>
 __device__ __forceinline__ bool rqi_lowest(const double (*Gs)[kMaxS + 1], int m, int lane, double theta_prev,
                                            const double* y_prev, double scale, double* mu_out, double* yi_out,
                                            int* iters) {
     const int d = m - 1;
+    const unsigned full = 0xffffffffu;
     double grow[MR];
 #pragma unroll
     for (int j = 0; j < MR; ++j) grow[j] = (lane < m && j < m) ? Gs[lane][j] : 0.0;
-    double z[MR];  // current vector, replicated on all lanes
-#pragma unroll
-    for (int j = 0; j < MR; ++j) z[j] = j < d ? y_prev[j] : 0.0;
+    // 2 x 2 start: [theta_prev b; b a] in the basis {(y_prev, 0), e_d}
+    double zi = lane < d ? y_prev[lane] : 0.0;
+    const double bcoup = warp_sum(lane < d ? Gs[d][lane] * zi : 0.0);
+    const double a_new = Gs[d][d];
     double mu = theta_prev;
+    if (bcoup != 0.0) {
+        const double half = 0.5 * (a_new - theta_prev);
+        const double root = sqrt(half * half + bcoup * bcoup);
+        // lower root of the 2 x 2 problem, written without cancellation
+        const double shift = half >= 0.0 ? -bcoup * bcoup / (half + root) : half - root;
+        mu = theta_prev + shift;
+        const double t = shift / bcoup;   // eigenvector (1, t)
+        const double inv = rsqrt(1.0 + t * t);
+        zi = lane < d ? zi * inv : (lane == d ? t * inv : 0.0);
+    }
     const double tiny = 1e-300 + 1e-18 * scale;
     bool ok = false;
     for (int it = 0; it < 8; ++it) {
-        double a[MR], b = 0.0;
+        double a[MR];
 #pragma unroll
-        for (int j = 0; j < MR; ++j) {
-            a[j] = grow[j] - (j == lane ? mu : 0.0);
-            if (lane >= m) a[j] = j == lane ? 1.0 : 0.0;
-            if (j == lane) b = z[j];
+        for (int j = 0; j < MR; ++j) a[j] = grow[j] - (j == lane ? mu : 0.0);
+        double b = lane < m ? zi : 0.0;
+        double rinv[MR];
+        // elimination, pivots k = m-1 ... 1 (row 0 is last and takes the near-singular pivot)
+#pragma unroll
+        for (int k = MR - 1; k >= 1; --k) {
+            rinv[k] = 1.0;
+            if (k < m) {
+                double pk = __shfl_sync(full, a[k], k);
+                if (fabs(pk) < tiny) pk = pk < 0.0 ? -tiny : tiny;
+                const double r = 1.0 / pk;
+                rinv[k] = r;
+                const double f = lane < k ? a[k] * r : 0.0;
+                const double pb = __shfl_sync(full, b, k);
+                b = fma(-f, pb, b);
+#pragma unroll
+                for (int j = 0; j < k; ++j) {
+                    const double pj = __shfl_sync(full, a[j], k);
+                    a[j] = fma(-f, pj, a[j]);
+                }
+            }
         }
-        if (lane >= m) b = 0.0;
-        bool used = lane >= m;  // lanes that have served as a pivot row (identity rows never take part)
-        int piv[MR];
+        {
+            double p0 = __shfl_sync(full, a[0], 0);
+            if (fabs(p0) < tiny) p0 = p0 < 0.0 ? -tiny : tiny;   // mu hit the eigenvalue: that is fine
+            rinv[0] = 1.0 / p0;
+        }
+        // forward substitution on the lower-triangular remainder, column oriented: z_k known -> every later
+        // row removes its column-k term
+        double znew = 0.0;
 #pragma unroll
         for (int k = 0; k < MR; ++k) {
-            piv[k] = k;  // identity block
             if (k < m) {
-                double pv = used ? -1.0 : fabs(a[k]);
-                int pi = lane;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double v2 = __shfl_xor_sync(0xffffffffu, pv, o);
-                    const int i2 = __shfl_xor_sync(0xffffffffu, pi, o);
-                    if (v2 > pv || (v2 == pv && i2 < pi)) { pv = v2; pi = i2; }
-                }
-                piv[k] = pi;
-                double pk = __shfl_sync(0xffffffffu, a[k], pi);
-                if (fabs(pk) < tiny) pk = pk < 0.0 ? -tiny : tiny;  // mu hit an eigenvalue: that is fine
-                if (lane == pi) {
-                    a[k] = pk;
-                    used = true;
-                }
-                const double pb = __shfl_sync(0xffffffffu, b, pi);
-                const double f = used ? 0.0 : a[k] / pk;
-#pragma unroll
-                for (int j = k + 1; j < MR; ++j) {
-                    const double pj = __shfl_sync(0xffffffffu, a[j], pi);
-                    if (j < m) a[j] = fma(-f, pj, a[j]);
-                }
-                b = fma(-f, pb, b);
+                const double zk = __shfl_sync(full, b, k) * rinv[k];
+                if (lane == k) znew = zk;
+                if (lane > k) b = fma(-a[k], zk, b);
             }
         }
-        // back substitution: the row with pivot k lives on lane piv[k]
+        // normalise (scale first: the solution is huge when mu is converged)
+        double zmax = lane < m ? fabs(znew) : 0.0;
 #pragma unroll
-        for (int k = MR - 1; k >= 0; --k) {
-            if (k < m) {
-                double acc = b;
-#pragma unroll
-                for (int j = k + 1; j < MR; ++j)
-                    if (j < m) acc = fma(-a[j], z[j], acc);
-                z[k] = __shfl_sync(0xffffffffu, acc / a[k], piv[k]);
-            } else {
-                z[k] = 0.0;
-            }
-        }
-        double zmax = 0.0, n2 = 0.0;
-#pragma unroll
-        for (int j = 0; j < MR; ++j) zmax = fmax(zmax, fabs(z[j]));
+        for (int o = 16; o > 0; o >>= 1) zmax = fmax(zmax, __shfl_xor_sync(full, zmax, o));
         if (!(zmax > 0.0) || !isfinite(zmax)) break;
-        const double inv = 1.0 / zmax;
+        znew *= 1.0 / zmax;
+        const double n2 = warp_sum(lane < m ? znew * znew : 0.0);
+        zi = znew * rsqrt(n2);
+        // Rayleigh quotient and residual against the original G: gz_i = sum_j G[i][j] z_j
+        double gz = 0.0;
 #pragma unroll
         for (int j = 0; j < MR; ++j) {
-            z[j] *= inv;
-            n2 = fma(z[j], z[j], n2);
-        }
-        const double invn = rsqrt(n2);
-#pragma unroll
-        for (int j = 0; j < MR; ++j) z[j] *= invn;
-        // Rayleigh quotient and residual
-        double gz = 0.0, zi = 0.0;
-#pragma unroll
-        for (int j = 0; j < MR; ++j) {
-            gz = fma(grow[j], z[j], gz);
-            if (j == lane) zi = z[j];
+            const double zj = __shfl_sync(full, zi, j);
+            gz = fma(grow[j], zj, gz);
         }
         const double mu_new = warp_sum(lane < m ? zi * gz : 0.0);
         const double r = lane < m ? gz - mu_new * zi : 0.0;
         const double rn = sqrt(warp_sum(r * r));
         mu = mu_new;
         *iters += 1;
-        // (mu, z) is an eigenpair of G to working precision (cubic convergence: two or three iterations;
+        // (mu, z) is an eigenpair of G to working precision (cubic convergence: one to three iterations;
         // stagnation of mu alone is NOT convergence -- a start vector that mixes +lambda and -lambda equally
         // keeps its Rayleigh quotient for ever)
         if (rn <= 2e-14 * scale || (it == 7 && rn <= 1e-11 * scale)) {
@@ -597,12 +619,8 @@ __device__ __forceinline__ bool rqi_lowest(const double (*Gs)[kMaxS + 1], int m,
             break;
         }
     }
-    double yi = 0.0;
-#pragma unroll
-    for (int j = 0; j < MR; ++j)
-        if (j == lane) yi = z[j];
     *mu_out = mu;
-    *yi_out = yi;
+    *yi_out = lane < m ? zi : 0.0;
     return ok;
 }
 
@@ -636,7 +654,8 @@ __device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nbl
     // ---- one warp from here on ----
     bool ok = false;
     double theta = 0.0, yi = 0.0;
-    if (!need_full) {
+    const bool pair_restart = need_full && st->restart_mode == 1 && m >= 2 && m <= MR;
+    if (!need_full || pair_restart) {
         if (m == 1) {
             ok = true;
             theta = J[0][0];
@@ -668,6 +687,41 @@ __device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nbl
         const int best = st->ord[0];
         theta = A[best][best];
         yi = lane < m ? J[lane][best] : 0.0;
+    } else if (pair_restart) {
+        // second vector of the collapsed basis: the previous Ritz vector (padded with a zero) orthogonalised
+        // against the new one.  G y = theta y, so ANY unit u orthogonal to y gives a diagonal collapsed matrix
+        // diag(theta, u^T G u): no decomposition needed.
+        const unsigned full = 0xffffffffu;
+        double u = lane < d ? bvec[lane] : 0.0;
+        u -= warp_sum(u * yi) * yi;
+        double nu2 = warp_sum(u * u);
+        if (!(nu2 > 1e-12)) {
+            // the Ritz vector did not move (converged, or the first cycles): use the newest basis vector
+            const double yd = __shfl_sync(full, yi, d);
+            u = (lane == d ? 1.0 : 0.0) - yd * yi;
+            if (lane >= m) u = 0.0;
+            nu2 = warp_sum(u * u);
+        }
+        u *= rsqrt(nu2);
+        u -= warp_sum(u * yi) * yi;   // second pass: orthogonal to rounding after the normalisation
+        u *= rsqrt(warp_sum(u * u));
+        double gu = 0.0;
+        for (int j = 0; j < m; ++j) {
+            const double uj = __shfl_sync(full, u, j);
+            if (lane < m) gu = fma(J[lane][j], uj, gu);
+        }
+        const double rho = warp_sum(lane < m ? u * gu : 0.0);
+        if (lane < m) {
+            st->Q[lane * kMaxS + 0] = yi;
+            st->Q[lane * kMaxS + 1] = u;
+        }
+        if (lane == 0) {
+            st->ord[0] = 0;
+            st->ord[1] = 1;
+            st->best = 0;
+            st->lam[0] = theta;
+            st->lam[1] = rho;
+        }
     }
     publish_pair(st, yi, theta, m, lane);
 }
@@ -796,8 +850,9 @@ __global__ void axpby_kernel(const int* __restrict__ done, double a, const doubl
         z[j] = a * x[j] + b * y[j];
 }
 
-__global__ void init_state_kernel(DavState* st, int M, int q_keep, int max_cycle) {
+__global__ void init_state_kernel(DavState* st, int M, int q_keep, int max_cycle, int restart_mode) {
     if (threadIdx.x == 0) {
+        st->restart_mode = restart_mode;
         st->m = 1;
         st->slot = 0;
         st->n_jacobi = 0;
@@ -1079,11 +1134,6 @@ using ApplyFn = std::function<int(const double*, double*, Workspace&)>;
 // device-driven loop: w[slot] <- O v[slot] with the slot read from device memory (bases passed); may be empty
 using ApplyCtlFn = std::function<int(const double*, double*, const int*, Workspace&, cudaStream_t)>;
 
-static int env_knob(const char* name, int dflt) {
-    const char* v = getenv(name);
-    return v ? atoi(v) : dflt;
-}
-
 // Side stream of a host thread: the full Rayleigh-Ritz decomposition of cycle k runs there, concurrently
 // with the residual / orthogonalisation / next sigma build of the main stream, and is joined before the
 // Rayleigh-Ritz step of cycle k+1 (or before the residual kernel of a restart cycle).
@@ -1180,8 +1230,8 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
     carve(d_workspace, n, M, &ws);
     const int blocks = red_blocks(n);
     const int check_every = prm->check_every > 0 ? prm->check_every : 4;
-    const int q_keep_all = M / 3 < 1 ? 1 : (M / 3 > kKeep ? kKeep : M / 3);
-    init_state_kernel<<<1, 256, 0, st>>>(ws.state, M, q_keep_all, prm->max_cycle);
+    const int q_keep_all = restart_keep(M);
+    init_state_kernel<<<1, 256, 0, st>>>(ws.state, M, q_keep_all, prm->max_cycle, restart_mode_knob());
     // V_0 = x0 / |x0|
     dot_partial_kernel<<<blocks, kRedThreads, 0, st>>>(d_x0, d_x0, n, ws.partials);
     dot_final_kernel<<<1, 32, 0, st>>>(ws.partials, blocks, ws.partials + kRedBlocks);
@@ -1239,8 +1289,8 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         if (apply(ws.V + (int64_t)slot * n, ws.W + (int64_t)slot * n, ws)) return -2;
         if (prm->profile) SQD_CUDA_OK(cudaEventRecord(ev.back(), st));
         ++sigma_builds;
-        // thick restart: keep the lowest min(kKeep, M/3) Ritz vectors when the space is full
-        const int q_keep = M / 3 < 1 ? 1 : (M / 3 > kKeep ? kKeep : M / 3);
+        // restart when the space is full (see restart_keep)
+        const int q_keep = restart_keep(M);
         const int restart = (m == M) ? q_keep : 0;
         static const int knob_skip = env_knob("SQD_DAV_SKIP", 0);  // timing experiments: bit 0 residual, 1 ortho
         int rc = dispatch_mv(m, [&](auto mv) {

@@ -47,14 +47,97 @@ __device__ __forceinline__ int64_t find_key(const int64_t* __restrict__ keys, in
     return (lo < d && __ldg(keys + lo) == target) ? lo : -1;
 }
 
-__global__ void pauli_connect_kernel(const int64_t* __restrict__ keys, int64_t d, uint64_t xmask,
-                                     uint64_t zmask, int32_t* __restrict__ col,
+// ---- key -> row hash table (open addressing, linear probing, load <= 1/2) ------------------------------
+// The projection asks "is key ^ xmask in the subspace?" n_groups times per row and the answer is almost
+// always no; a probe of a half-empty table settles that in ~1.5 L2 accesses where the binary search over the
+// sorted keys needs log2(d) dependent ones.
+constexpr int64_t kEmptyKey = (int64_t)0x8000000000000000ull;   // keys are < 2^63
+
+__device__ __forceinline__ uint64_t hash_key(uint64_t h) {
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 33;
+    return h;
+}
+
+struct KeyTable {
+    const int64_t* slot_key;
+    const int32_t* slot_row;
+    uint64_t mask;   // capacity - 1 (capacity is a power of two)
+};
+
+__global__ void key_table_clear_kernel(int64_t* __restrict__ slot_key, int64_t cap) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cap) slot_key[i] = kEmptyKey;
+}
+
+__global__ void key_table_build_kernel(const int64_t* __restrict__ keys, int64_t d, int64_t* slot_key,
+                                       int32_t* __restrict__ slot_row, uint64_t mask) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    const int64_t k = keys[i];
+    uint64_t s = hash_key((uint64_t)k) & mask;
+    for (;;) {
+        const unsigned long long old = atomicCAS((unsigned long long*)(slot_key + s), (unsigned long long)kEmptyKey,
+                                                 (unsigned long long)k);
+        if (old == (unsigned long long)kEmptyKey || old == (unsigned long long)k) {
+            // duplicates (the caller promises there are none) keep the smallest row
+            atomicMin(slot_row + s, (int32_t)i);
+            return;
+        }
+        s = (s + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ int64_t table_find(const KeyTable& t, int64_t target) {
+    uint64_t s = hash_key((uint64_t)target) & t.mask;
+    for (;;) {
+        const int64_t k = __ldg(t.slot_key + s);
+        if (k == target) return __ldg(t.slot_row + s);
+        if (k == kEmptyKey) return -1;
+        s = (s + 1) & t.mask;
+    }
+}
+
+__global__ void pauli_connect_kernel(const int64_t* __restrict__ keys, int64_t d, KeyTable table, int use_table,
+                                     uint64_t xmask, uint64_t zmask, int32_t* __restrict__ col,
                                      uint8_t* __restrict__ par) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= d) return;
     const int64_t key = keys[i];
-    col[i] = (int32_t)find_key(keys, d, key ^ (int64_t)xmask);
+    // a diagonal Pauli (no X or Y) connects every configuration to itself: no search
+    col[i] = xmask == 0 ? (int32_t)i
+                        : (int32_t)(use_table ? table_find(table, key ^ (int64_t)xmask)
+                                              : find_key(keys, d, key ^ (int64_t)xmask));
     par[i] = (uint8_t)(popc64((uint64_t)key & zmask) & 1);
+}
+
+// same, with the outputs in the reference's own types: complex128 amplitude i^ny (-1)^popc(key & zmask) and
+// int64 column (-1: the image is not in the subspace); *n_missing counts those rows
+__global__ void pauli_elements_kernel(const int64_t* __restrict__ keys, int64_t d, KeyTable table, int use_table,
+                                      uint64_t xmask, uint64_t zmask, int ny, int64_t* __restrict__ col,
+                                      double2* __restrict__ amp, int32_t* __restrict__ n_missing) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t j = 0;
+    if (i < d) {
+        const int64_t key = keys[i];
+        j = xmask == 0 ? i
+                       : (use_table ? table_find(table, key ^ (int64_t)xmask) : find_key(keys, d, key ^ (int64_t)xmask));
+        const double sgn = (popc64((uint64_t)key & zmask) & 1) ? -1.0 : 1.0;
+        double2 a;
+        switch (ny & 3) {
+            case 0: a = make_double2(sgn, 0.0); break;
+            case 1: a = make_double2(0.0, sgn); break;
+            case 2: a = make_double2(-sgn, 0.0); break;
+            default: a = make_double2(0.0, -sgn); break;
+        }
+        if (col) col[i] = j;
+        amp[i] = a;
+    }
+    const unsigned miss = __ballot_sync(0xffffffffu, j < 0);
+    if ((threadIdx.x & 31) == 0 && miss) atomicAdd(n_missing, __popc(miss));
 }
 
 // coefficient * i^ny * (+-1)
@@ -75,41 +158,68 @@ __device__ __forceinline__ void accumulate_term(double& re, double& im, double c
     im += ti;
 }
 
-template <bool FILL>
-__global__ void pauli_project_kernel(const int64_t* __restrict__ keys, int64_t d,
+// USE_TABLE: hash probes (4 independent probes per lane in flight); otherwise binary search of the key list
+template <bool FILL, bool USE_TABLE>
+__global__ void pauli_project_kernel(const int64_t* __restrict__ keys, int64_t d, KeyTable table,
                                      const uint64_t* __restrict__ grp_xmask,
                                      const int32_t* __restrict__ grp_ptr, int32_t n_groups,
                                      const uint64_t* __restrict__ zmask, const int32_t* __restrict__ ny,
                                      const double* __restrict__ coeff,
                                      const int32_t* __restrict__ row_ptr, int32_t* __restrict__ row_nnz,
                                      int32_t* __restrict__ col, double* __restrict__ val) {
+    constexpr int U = USE_TABLE ? 4 : 1;
     const int lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= d) return;
     const int64_t key = keys[i];
     int count = 0;
-    int base = FILL ? row_ptr[i] : 0;
-    for (int32_t k0 = 0; k0 < n_groups; k0 += 32) {
-        const int32_t k = k0 + lane;
-        int64_t j = -1;
-        double re = 0.0, im = 0.0;
-        if (k < n_groups) {
-            j = find_key(keys, d, key ^ (int64_t)grp_xmask[k]);
-            if (j >= 0) {
+    const int base = FILL ? row_ptr[i] : 0;
+    for (int32_t k0 = 0; k0 < n_groups; k0 += 32 * U) {
+        int64_t j[U];
+        if (USE_TABLE) {
+            // first probe of every group issued before any is examined
+            uint64_t slot[U];
+            int64_t tgt[U], got[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int32_t k = k0 + u * 32 + lane;
+                tgt[u] = key ^ (int64_t)(k < n_groups ? grp_xmask[k] : 0ull);
+                slot[u] = hash_key((uint64_t)tgt[u]) & table.mask;
+                got[u] = k < n_groups ? __ldg(table.slot_key + slot[u]) : kEmptyKey;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                int64_t g = got[u];
+                uint64_t sl = slot[u];
+                while (g != tgt[u] && g != kEmptyKey) {
+                    sl = (sl + 1) & table.mask;
+                    g = __ldg(table.slot_key + sl);
+                }
+                j[u] = (g == tgt[u] && k0 + u * 32 + lane < n_groups) ? __ldg(table.slot_row + sl) : -1;
+            }
+        } else {
+            const int32_t k = k0 + lane;
+            j[0] = k < n_groups ? find_key(keys, d, key ^ (int64_t)grp_xmask[k]) : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int32_t k = k0 + u * 32 + lane;
+            double re = 0.0, im = 0.0;
+            if (j[u] >= 0) {
                 for (int32_t t = grp_ptr[k]; t < grp_ptr[k + 1]; ++t)
                     accumulate_term(re, im, coeff[2 * t], coeff[2 * t + 1], ny[t],
                                     popc64((uint64_t)key & zmask[t]) & 1);
-                if (re == 0.0 && im == 0.0) j = -1;  // scipy drops exact zeros when summing
+                if (re == 0.0 && im == 0.0) j[u] = -1;  // scipy drops exact zeros when summing
             }
+            const uint32_t m = __ballot_sync(0xffffffffu, j[u] >= 0);
+            if (FILL && j[u] >= 0) {
+                const int o = base + count + __popc(m & ((1u << lane) - 1u));
+                col[o] = (int32_t)j[u];
+                val[2 * o] = re;
+                val[2 * o + 1] = im;
+            }
+            count += __popc(m);
         }
-        const uint32_t m = __ballot_sync(0xffffffffu, j >= 0);
-        if (FILL && j >= 0) {
-            const int o = base + count + __popc(m & ((1u << lane) - 1u));
-            col[o] = (int32_t)j;
-            val[2 * o] = re;
-            val[2 * o + 1] = im;
-        }
-        count += __popc(m);
     }
     if (!FILL && lane == 0) row_nnz[i] = count;
 }
@@ -337,40 +447,101 @@ int sqd_bits_to_keys(const uint8_t* d_bits, int64_t n, int nbits, int64_t* d_key
     return check_launch("bits_to_keys_kernel");
 }
 
-int sqd_pauli_connect(const int64_t* d_keys, int64_t d, uint64_t xmask, uint64_t zmask,
+int64_t sqd_key_table_capacity(int64_t d) {
+    if (d < 0) return -1;
+    int64_t cap = 1024;
+    const int64_t want = d <= (1LL << 24) ? 4 * d : 2 * d;   // load <= 1/4 (<= 1/2 for very large subspaces)
+    while (cap < want) cap <<= 1;
+    return cap;
+}
+
+int64_t sqd_key_table_bytes(int64_t d) {
+    const int64_t cap = sqd_key_table_capacity(d);
+    return cap < 0 ? -1 : cap * 12;
+}
+
+int sqd_key_table_build(const int64_t* d_keys, int64_t d, void* d_table, int64_t table_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t cap = sqd_key_table_capacity(d);
+    SQD_REQUIRE(d >= 0 && d < 2147483647LL, "sqd_key_table_build: d=%lld out of range", (long long)d);
+    SQD_REQUIRE(table_bytes >= cap * 12, "sqd_key_table_build: table too small");
+    int64_t* slot_key = (int64_t*)d_table;
+    int32_t* slot_row = (int32_t*)(slot_key + cap);
+    SQD_CUDA_OK(cudaMemsetAsync(slot_row, 0x7f, (size_t)cap * 4, st));
+    key_table_clear_kernel<<<(unsigned)((cap + 255) / 256), 256, 0, st>>>(slot_key, cap);
+    if (d > 0)
+        key_table_build_kernel<<<(unsigned)((d + 255) / 256), 256, 0, st>>>(d_keys, d, slot_key, slot_row,
+                                                                            (uint64_t)cap - 1);
+    return check_launch("key_table kernels", d > 0 ? 2 : 1);
+}
+
+static KeyTable make_table(const void* d_table, int64_t d) {
+    KeyTable t;
+    const int64_t cap = sqd_key_table_capacity(d);
+    t.slot_key = (const int64_t*)d_table;
+    t.slot_row = (const int32_t*)(t.slot_key + cap);
+    t.mask = (uint64_t)cap - 1;
+    return t;
+}
+
+int sqd_pauli_connect(const int64_t* d_keys, int64_t d, const void* d_table, uint64_t xmask, uint64_t zmask,
                       int32_t* d_col, uint8_t* d_par, void* stream) {
     if (d == 0) return 0;
     pauli_connect_kernel<<<(unsigned)((d + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        d_keys, d, xmask, zmask, d_col, d_par);
+        d_keys, d, d_table ? make_table(d_table, d) : KeyTable{nullptr, nullptr, 0}, d_table != nullptr, xmask,
+        zmask, d_col, d_par);
     return check_launch("pauli_connect_kernel");
 }
 
-int sqd_pauli_project_count(const int64_t* d_keys, int64_t d, const uint64_t* d_grp_xmask,
+int sqd_pauli_elements(const int64_t* d_keys, int64_t d, const void* d_table, uint64_t xmask, uint64_t zmask,
+                       int ny, int64_t* d_col, double* d_amp, int32_t* d_n_missing, void* stream) {
+    if (d == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    SQD_CUDA_OK(cudaMemsetAsync(d_n_missing, 0, sizeof(int32_t), st));
+    pauli_elements_kernel<<<(unsigned)((d + 255) / 256), 256, 0, st>>>(
+        d_keys, d, d_table ? make_table(d_table, d) : KeyTable{nullptr, nullptr, 0}, d_table != nullptr, xmask,
+        zmask, ny, d_col, (double2*)d_amp, d_n_missing);
+    return check_launch("pauli_elements_kernel");
+}
+
+int sqd_pauli_project_count(const int64_t* d_keys, int64_t d, const void* d_table, const uint64_t* d_grp_xmask,
                             const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
                             const int32_t* d_ny, const double* d_coeff, int32_t* d_row_nnz,
                             void* stream) {
     if (d == 0) return 0;
     const int wpb = 8;
-    pauli_project_kernel<false><<<(unsigned)((d + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
-        d_keys, d, d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff, nullptr, d_row_nnz,
-        nullptr, nullptr);
+    const unsigned nb = (unsigned)((d + wpb - 1) / wpb);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d_table)
+        pauli_project_kernel<false, true><<<nb, wpb * 32, 0, st>>>(
+            d_keys, d, make_table(d_table, d), d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff, nullptr,
+            d_row_nnz, nullptr, nullptr);
+    else
+        pauli_project_kernel<false, false><<<nb, wpb * 32, 0, st>>>(
+            d_keys, d, KeyTable{nullptr, nullptr, 0}, d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff,
+            nullptr, d_row_nnz, nullptr, nullptr);
     return check_launch("pauli_project_kernel<count>");
 }
 
-int sqd_pauli_project_fill(const int64_t* d_keys, int64_t d, const uint64_t* d_grp_xmask,
+int sqd_pauli_project_fill(const int64_t* d_keys, int64_t d, const void* d_table, const uint64_t* d_grp_xmask,
                            const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
                            const int32_t* d_ny, const double* d_coeff, const int32_t* d_row_ptr,
                            int32_t* d_col_tmp, double* d_val_tmp, int32_t* d_col, double* d_val,
                            void* stream) {
     if (d == 0) return 0;
     const int wpb = 8;
+    const unsigned nb = (unsigned)((d + wpb - 1) / wpb);
     cudaStream_t st = (cudaStream_t)stream;
-    pauli_project_kernel<true><<<(unsigned)((d + wpb - 1) / wpb), wpb * 32, 0, st>>>(
-        d_keys, d, d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff, d_row_ptr, nullptr,
-        d_col_tmp, d_val_tmp);
+    if (d_table)
+        pauli_project_kernel<true, true><<<nb, wpb * 32, 0, st>>>(
+            d_keys, d, make_table(d_table, d), d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff, d_row_ptr,
+            nullptr, d_col_tmp, d_val_tmp);
+    else
+        pauli_project_kernel<true, false><<<nb, wpb * 32, 0, st>>>(
+            d_keys, d, KeyTable{nullptr, nullptr, 0}, d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff,
+            d_row_ptr, nullptr, d_col_tmp, d_val_tmp);
     if (check_launch("pauli_project_kernel<fill>")) return -2;
-    csr_row_sort_kernel<<<(unsigned)((d + wpb - 1) / wpb), wpb * 32, 0, st>>>(d, d_row_ptr, d_col_tmp,
-                                                                            d_val_tmp, d_col, d_val);
+    csr_row_sort_kernel<<<nb, wpb * 32, 0, st>>>(d, d_row_ptr, d_col_tmp, d_val_tmp, d_col, d_val);
     return check_launch("csr_row_sort_kernel");
 }
 

@@ -30,11 +30,25 @@ _LEN_ERR = "Bitstrings (rows) in bitstring_matrix must have length < 64."
 def _keys_device(torch, lib, bitstring_matrix: np.ndarray):
     n, nq = bitstring_matrix.shape
     dev = torch.device("cuda", torch.cuda.current_device())
-    bits = torch.from_numpy(np.ascontiguousarray(bitstring_matrix, dtype=np.uint8)).to(dev)
+    if bitstring_matrix.dtype in (np.bool_, np.uint8, np.int8) and bitstring_matrix.flags.c_contiguous:
+        host = bitstring_matrix.view(np.uint8)      # no host-side copy of a (possibly multi-GB) bool matrix
+    else:
+        host = np.ascontiguousarray(bitstring_matrix != 0).view(np.uint8)
+    bits = torch.from_numpy(host).to(dev)
     keys = torch.empty(n, dtype=torch.int64, device=dev)
     _lib.check(lib.sqd_bits_to_keys(_lib.ptr(bits), n, nq, _lib.ptr(keys), _lib.stream_ptr(torch)),
                "sqd_bits_to_keys")
     return keys
+
+
+def _key_table(torch, lib, keys):
+    """Hash table key -> row over the unique keys of the subspace (``sqd_key_table_build``)."""
+    d = int(keys.numel())
+    nbytes = lib.sqd_key_table_bytes(d)
+    table = torch.empty(nbytes, dtype=torch.uint8, device=keys.device)
+    _lib.check(lib.sqd_key_table_build(_lib.ptr(keys), d, _lib.ptr(table), nbytes, _lib.stream_ptr(torch)),
+               "sqd_key_table_build")
+    return table
 
 
 def _masks(x: np.ndarray, z: np.ndarray) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
@@ -76,15 +90,25 @@ def matrix_elements_from_pauli(bitstring_matrix: np.ndarray, pauli):
         return np.zeros(0, dtype=np.complex128), np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.int64)
     keys = _keys_device(torch, lib, bitstring_matrix)
     xm, zm, ny = _masks(pauli.x, pauli.z)
-    col = torch.empty(d, dtype=torch.int32, device=keys.device)
-    par = torch.empty(d, dtype=torch.uint8, device=keys.device)
-    _lib.check(lib.sqd_pauli_connect(_lib.ptr(keys), d, int(xm[0]), int(zm[0]), _lib.ptr(col),
-                                     _lib.ptr(par), _lib.stream_ptr(torch)), "sqd_pauli_connect")
-    col_h = col.cpu().numpy().astype(np.int64)
-    par_h = par.cpu().numpy()
+    diagonal = int(xm[0]) == 0
+    dev = keys.device
+    table = None if diagonal else _key_table(torch, lib, keys)
+    col = None if diagonal else torch.empty(d, dtype=torch.int64, device=dev)
+    amp = torch.empty(2 * d, dtype=torch.float64, device=dev)
+    n_missing = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(lib.sqd_pauli_elements(_lib.ptr(keys), d, _lib.ptr(table), int(xm[0]), int(zm[0]), int(ny[0]),
+                                      _lib.ptr(col), _lib.ptr(amp), _lib.ptr(n_missing), _lib.stream_ptr(torch)),
+               "sqd_pauli_elements")
+    del keys
+    amp_h = amp.cpu().numpy().view(np.complex128)
+    rows = np.arange(d)
+    if diagonal:
+        return amp_h, rows, rows.copy()       # a Pauli without X or Y connects every configuration to itself
+    col_h = col.cpu().numpy()
+    if int(n_missing.item()) == 0:
+        return amp_h, rows, col_h
     mask = col_h >= 0
-    amp = (1.0 - 2.0 * par_h.astype(np.float64)) * (1j ** int(ny[0] % 4))
-    return amp[mask].astype(np.complex128), np.arange(d)[mask], col_h[mask]
+    return amp_h[mask], rows[mask], col_h[mask]
 
 
 class _DeviceCSR:
@@ -101,18 +125,24 @@ class _DeviceCSR:
                           shape=(self.d, self.d))
 
 
-def _project_device(torch, lib, keys, hamiltonian) -> _DeviceCSR:
+def _project_device(torch, lib, keys, hamiltonian, timings: dict | None = None) -> _DeviceCSR:
     d = int(keys.numel())
     dev = keys.device
     st = _lib.stream_ptr(torch)
-    paulis = list(hamiltonian.paulis)
-    T = len(paulis)
+    paulis = hamiltonian.paulis
+    # qiskit's PauliList exposes the whole (T, nq) x and z tables; anything else is read term by term
+    px, pz = getattr(paulis, "x", None), getattr(paulis, "z", None)
+    if px is None or pz is None or np.ndim(px) != 2:
+        plist = list(paulis)
+        px = np.array([p.x for p in plist], dtype=bool).reshape(len(plist), -1)
+        pz = np.array([p.z for p in plist], dtype=bool).reshape(len(plist), -1)
+    T = int(np.shape(px)[0])
     coeffs = np.asarray(hamiltonian.coeffs, dtype=np.complex128).reshape(-1)
     if T == 0 or d == 0:
         z = torch.zeros(d + 1, dtype=torch.int32, device=dev)
         return _DeviceCSR(d, z, torch.zeros(0, dtype=torch.int32, device=dev),
                           torch.zeros(0, dtype=torch.float64, device=dev))
-    xm, zm, ny = _masks(np.array([p.x for p in paulis]), np.array([p.z for p in paulis]))
+    xm, zm, ny = _masks(px, pz)
     # group terms by X mask; groups in order of first appearance, original order inside a group
     uniq, first, inv = np.unique(xm, return_index=True, return_inverse=True)
     g_order = np.argsort(first, kind="stable")
@@ -135,9 +165,15 @@ def _project_device(torch, lib, keys, hamiltonian) -> _DeviceCSR:
     d_ny = up(ny[perm].astype(np.int32), np.int32)
     d_cf = torch.from_numpy(np.ascontiguousarray(coeffs[perm]).view(np.float64)).to(dev)
     row_nnz = torch.empty(d, dtype=torch.int32, device=dev)
-    _lib.check(lib.sqd_pauli_project_count(_lib.ptr(keys), d, _lib.ptr(d_gx), _lib.ptr(d_gp),
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timings is not None else None
+    if ev:
+        ev[0].record()
+    table = _key_table(torch, lib, keys)
+    _lib.check(lib.sqd_pauli_project_count(_lib.ptr(keys), d, _lib.ptr(table), _lib.ptr(d_gx), _lib.ptr(d_gp),
                                            len(uniq), _lib.ptr(d_z), _lib.ptr(d_ny), _lib.ptr(d_cf),
                                            _lib.ptr(row_nnz), st), "sqd_pauli_project_count")
+    if ev:
+        ev[1].record()
     row_ptr = torch.empty(d + 1, dtype=torch.int32, device=dev)
     total = C.c_int(0)
     _lib.check(lib.sqd_exclusive_scan(_lib.ptr(row_nnz), _lib.ptr(row_ptr), d, C.byref(total), st),
@@ -147,12 +183,19 @@ def _project_device(torch, lib, keys, hamiltonian) -> _DeviceCSR:
     val = torch.empty(2 * nnz, dtype=torch.float64, device=dev)
     col_tmp = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)
     val_tmp = torch.empty(max(2 * nnz, 1), dtype=torch.float64, device=dev)
+    if ev:
+        ev[2].record()
     if nnz:
-        _lib.check(lib.sqd_pauli_project_fill(_lib.ptr(keys), d, _lib.ptr(d_gx), _lib.ptr(d_gp),
+        _lib.check(lib.sqd_pauli_project_fill(_lib.ptr(keys), d, _lib.ptr(table), _lib.ptr(d_gx), _lib.ptr(d_gp),
                                               len(uniq), _lib.ptr(d_z), _lib.ptr(d_ny),
                                               _lib.ptr(d_cf), _lib.ptr(row_ptr), _lib.ptr(col_tmp),
                                               _lib.ptr(val_tmp), _lib.ptr(col), _lib.ptr(val), st),
                    "sqd_pauli_project_fill")
+    if ev:
+        ev[3].record()
+        torch.cuda.synchronize()
+        timings["table_and_count_ms"] = ev[0].elapsed_time(ev[1])
+        timings["fill_and_sort_ms"] = ev[2].elapsed_time(ev[3])
     return _DeviceCSR(d, row_ptr, col, val)
 
 
