@@ -38,10 +38,12 @@ def _set_pcg64_words(rng: np.random.Generator, words: np.ndarray) -> None:
 
 
 def _unpack_halves(left: np.ndarray, right: np.ndarray, norb: int) -> np.ndarray:
-    shifts = np.arange(norb - 1, -1, -1, dtype=np.uint64)
-    lb = ((left[:, None] >> shifts[None, :]) & np.uint64(1)).astype(bool)
-    rb = ((right[:, None] >> shifts[None, :]) & np.uint64(1)).astype(bool)
-    return np.concatenate([lb, rb], axis=1)
+    """Packed halves -> bool rows ``[left_{N-1}..left_0, right_{N-1}..right_0]`` (big-endian bytes + unpackbits)."""
+    def half(words):
+        b = np.ascontiguousarray(words, dtype=np.uint64).astype(">u8").view(np.uint8).reshape(-1, 8)
+        return np.unpackbits(b, axis=1)[:, 64 - norb:]
+
+    return np.concatenate([half(left), half(right)], axis=1).astype(bool)
 
 
 def recover_configurations(
@@ -140,8 +142,10 @@ def recover_configurations(
     order = np.argsort(first, kind="stable")          # unique groups in first-seen order
     rank = np.empty_like(order)
     rank[order] = np.arange(len(order))
-    sums = np.zeros(len(first), dtype=np.float64)
-    np.add.at(sums, rank[inverse], np.asarray(probabilities, dtype=np.float64))
+    # np.bincount accumulates the weights of a bin in input order, one after the other: the same
+    # floating-point sums as the reference's row-by-row ``freqs[idx] += p`` (and as np.add.at, 10x slower)
+    sums = np.bincount(rank[inverse], weights=np.asarray(probabilities, dtype=np.float64),
+                       minlength=len(first)).astype(np.float64)
     sel = first[order]
     bs_mat_out = _unpack_halves(lo[sel], ro[sel], norb)
     freqs_out = np.abs(sums) / np.sum(np.abs(sums))

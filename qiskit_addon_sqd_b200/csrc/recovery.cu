@@ -11,12 +11,21 @@
 //                     (draw size-n_uniq uniforms, searchsorted(cdf, x, 'right'), keep first
 //                     occurrences, zero p[found], retry).  One warp evaluates searchsorted for a draw
 //                     with two ballots (lane c holds cdf[c] and cdf[c+32]).
-//       mode 0 (exact stream): ONE warp walks the rows in order and consumes the caller's PCG64
-//               stream exactly as numpy would -- the stream offset of row i depends on the collisions
-//               of every earlier row, a true sequential chain -- with the next row's cdf prefetched.
-//               Output and final generator state are bit-identical to the seeded reference.
+//       mode 0 (exact stream): the caller's PCG64 stream is consumed exactly as numpy would.  The
+//               stream offset of half-row i depends on the collisions of every earlier half-row -- a
+//               true sequential chain -- but the chain only has to carry ONE small integer (how many
+//               draws beyond the collision-free count have been consumed so far).  So, per window of
+//               kWinRecs half-rows (see "speculative exact stream" below): a parallel kernel tabulates,
+//               for every half-row and for each of kHyp hypotheses about that integer, how many draws
+//               the half-row would consume (PCG64 jump-ahead gives every thread its uniforms); one warp
+//               then walks the window with one shared-memory lookup per half-row; a last parallel pass
+//               redoes the sampling of every half-row at its now known offset.  Output and final
+//               generator state are bit-identical to the seeded reference.  (The round-1 kernel, one
+//               warp sampling the rows one after the other, is kept behind SQD_RECOVER_CHAIN=1.)
 //       mode 1 (substreams): one warp per row, each with its own PCG64 stream derived from
 //               (seed, row) -- same distribution, embarrassingly parallel, not stream-identical.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "../../include/sqd_b200.h"
 
@@ -313,6 +322,356 @@ __global__ void recover_select_parallel_kernel(const uint64_t* __restrict__ left
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// speculative exact stream
+// ---------------------------------------------------------------------------------------------
+constexpr int kHyp = 256;        // hypotheses per half-row (threads of a table CTA)
+constexpr int kWinRecs = 2048;   // half-rows per window
+constexpr int kMaxDraws = 96;    // draws a tabulated hypothesis may consume (more: the walk samples it itself)
+constexpr int kUBuf = kHyp + kMaxDraws;
+constexpr uint8_t kTabOverflow = 255;   // hypothesis not tabulated: the walk samples the half-row itself
+constexpr uint8_t kTabFail = 254;       // numpy raises at this half-row
+constexpr int kWalkStages = 4;          // chunks of 32 table rows in flight (cp.async ring)
+
+__device__ __forceinline__ u128 pcg_mult() {
+    return ((u128)0x2360ED051FC65DA4ull << 64) | (u128)0x4385DF649FCCF645ull;
+}
+__device__ __forceinline__ uint64_t pcg_output(u128 state) {
+    const uint64_t hi = (uint64_t)(state >> 64), lo = (uint64_t)state;
+    const uint64_t x = hi ^ lo;
+    const unsigned rot = (unsigned)(state >> 122);
+    return (x >> rot) | (x << ((64u - rot) & 63u));
+}
+// LCG skip-ahead: (mult, plus) with state_after_delta_steps = mult * state + plus
+__device__ __forceinline__ void pcg_skip(u128 inc, uint64_t delta, u128* m_out, u128* p_out) {
+    u128 acc_m = 1, acc_p = 0, cur_m = pcg_mult(), cur_p = inc;
+    while (delta) {
+        if (delta & 1ull) {
+            acc_m *= cur_m;
+            acc_p = acc_p * cur_m + cur_p;
+        }
+        cur_p = (cur_m + 1) * cur_p;
+        cur_m *= cur_m;
+        delta >>= 1;
+    }
+    *m_out = acc_m;
+    *p_out = acc_p;
+}
+__device__ __forceinline__ u128 pcg_advance(u128 state, u128 inc, uint64_t delta) {
+    u128 m, p;
+    pcg_skip(inc, delta, &m, &p);
+    return m * state + p;
+}
+
+// numpy's Generator.choice(replace=False, p=...) on one thread.  draw() returns the next uniform double of
+// the stream; cdf0 is the normalised first-round cdf, prow the probabilities.  Returns the number of draws
+// consumed (-1: more than max_draws would be needed) and the set of chosen candidate ordinals.
+template <class Draw>
+__device__ __forceinline__ int thread_choice(Draw& draw, const double* prow, const double* cdf0, int n_cand, int k,
+                                             int max_draws, uint64_t* found_out) {
+    uint64_t found = 0ull;
+    int n_uniq = 0, used = 0;
+    bool first = true;
+    while (n_uniq < k) {
+        const int need = k - n_uniq;
+        if (used + need > max_draws) return -1;
+        if (first) {
+            for (int dr = 0; dr < need; ++dr) {
+                const double x = draw();
+                int lo = 0, hi = n_cand;   // searchsorted(cdf, x, 'right') = number of entries <= x
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cdf0[mid] <= x) lo = mid + 1; else hi = mid;
+                }
+                if (lo >= n_cand) lo = n_cand - 1;
+                found |= 1ull << lo;
+            }
+        } else {
+            // p[found] = 0; cdf = cumsum(p); cdf /= cdf[-1]  (sequential order)
+            double last = 0.0;
+            for (int c = 0; c < n_cand; ++c) {
+                const double pv = ((found >> c) & 1ull) ? 0.0 : prow[c];
+                last = c == 0 ? pv : __dadd_rn(last, pv);
+            }
+            uint64_t round_found = 0ull;
+            for (int dr = 0; dr < need; ++dr) {
+                const double x = draw();
+                double acc = 0.0;
+                int idx = 0;
+                for (int c = 0; c < n_cand; ++c) {
+                    const double pv = ((found >> c) & 1ull) ? 0.0 : prow[c];
+                    acc = c == 0 ? pv : __dadd_rn(acc, pv);
+                    idx += (__ddiv_rn(acc, last) <= x) ? 1 : 0;
+                }
+                if (idx >= n_cand) idx = n_cand - 1;
+                round_found |= 1ull << idx;
+            }
+            found |= round_found;
+        }
+        used += need;
+        n_uniq = popc64(found);
+        first = false;
+    }
+    *found_out = found;
+    return used;
+}
+
+// Walk state of the exact stream (device memory; the host only reads `done`)
+struct RecoverCtl {
+    uint64_t state_hi, state_lo;   // generator state at the start of the current window
+    int64_t cursor;                // first half-row of the current window
+    int64_t offset;                // draws consumed before `cursor`
+    int64_t extras_total;          // draws beyond the collision-free count so far (drift estimate)
+    uint32_t rho;                  // expected extra draws per half-row, 16.16 fixed point
+    int32_t done;                  // 1: all half-rows walked (or numpy's error met)
+    int32_t failed;
+    int32_t pad;
+};
+
+__device__ __forceinline__ int drift_of(uint32_t rho, int j) { return (int)(((uint64_t)rho * (uint64_t)j) >> 16); }
+
+// draws of a half-row when nothing collides (0: nothing to sample; 255: numpy raises)
+__global__ void recover_counts_kernel(const HalfHeader* __restrict__ hdr, int64_t recs, uint8_t* __restrict__ kq,
+                                      int32_t* __restrict__ kcount) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= recs) return;
+    const HalfHeader h = hdr[r];
+    int k = 0;
+    uint8_t q = 0;
+    if (h.n_cand < 0) q = 255;
+    else if (h.n_cand > 0) { k = h.n_diff > 0 ? h.n_diff : -h.n_diff; q = (uint8_t)k; }
+    kq[r] = q;
+    kcount[r] = k;
+}
+
+// skip tables: state after t+1 steps = M[t] * base + P[t]
+__global__ void recover_skip_table_kernel(const uint64_t* __restrict__ rng_state, u128* __restrict__ skipM,
+                                          u128* __restrict__ skipP, RecoverCtl* ctl,
+                                          uint64_t* __restrict__ init_state) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const u128 inc = ((u128)rng_state[2] << 64) | (u128)rng_state[3];
+    if (t < kUBuf) pcg_skip(inc, (uint64_t)t + 1, skipM + t, skipP + t);
+    if (t == 0) {
+        init_state[0] = rng_state[0];
+        init_state[1] = rng_state[1];
+        ctl->state_hi = rng_state[0];
+        ctl->state_lo = rng_state[1];
+        ctl->cursor = 0;
+        ctl->offset = 0;
+        ctl->extras_total = 0;
+        ctl->rho = 0;
+        ctl->done = 0;
+        ctl->failed = 0;
+    }
+}
+
+// One CTA per half-row of the window, one thread per hypothesis e: "the walk arrives here having consumed
+// kprefix + drift_j + (e - kHyp/2) draws since the window start".  table[j][e] = extra draws (beyond k) the
+// half-row then consumes, or kTabOverflow / kTabFail.
+__global__ void __launch_bounds__(kHyp)
+recover_table_kernel(const RecoverCtl* __restrict__ ctl, int64_t recs, int norb, const HalfHeader* __restrict__ hdr,
+                     const double* __restrict__ pc, const double* __restrict__ cdf,
+                     const int32_t* __restrict__ kprefix, const uint64_t* __restrict__ rng_state,
+                     const u128* __restrict__ skipM, const u128* __restrict__ skipP, uint8_t* __restrict__ table) {
+    if (ctl->done) return;
+    const int j = blockIdx.x;
+    const int64_t r0 = ctl->cursor;
+    const int64_t rec = r0 + j;
+    if (rec >= recs) return;
+    const HalfHeader h = hdr[rec];
+    const int e = threadIdx.x;
+    const int cj = drift_of(ctl->rho, j);
+    uint8_t* trow = table + (int64_t)j * kHyp;
+    if (h.n_cand <= 0) {   // nothing to sample (or numpy's error): no draws
+        trow[e] = h.n_cand < 0 ? kTabFail : (uint8_t)0;
+        return;
+    }
+    __shared__ double s_cdf[64], s_p[64], s_u[kUBuf];
+    __shared__ u128 s_base;
+    const int e_lo = cj >= kHyp / 2 ? 0 : kHyp / 2 - cj;
+    if (e < h.n_cand) {
+        s_cdf[e] = cdf[rec * norb + e];
+        s_p[e] = pc[rec * norb + e];
+    }
+    if (e == 0) {
+        const u128 inc = ((u128)rng_state[2] << 64) | (u128)rng_state[3];
+        const u128 st = ((u128)ctl->state_hi << 64) | (u128)ctl->state_lo;
+        const uint64_t delta = (uint64_t)((int64_t)(kprefix[rec] - kprefix[r0]) + cj + e_lo - kHyp / 2);
+        s_base = pcg_advance(st, inc, delta);
+    }
+    __syncthreads();
+    const u128 base = s_base;
+    for (int t = e; t < kUBuf; t += kHyp)
+        s_u[t] = (double)(pcg_output(skipM[t] * base + skipP[t]) >> 11) * (1.0 / 9007199254740992.0);
+    __syncthreads();
+    uint8_t out = kTabOverflow;
+    if (e >= e_lo) {
+        const int k = h.n_diff > 0 ? h.n_diff : -h.n_diff;
+        const double* up = s_u + (e - e_lo);
+        int pos = 0;
+        auto draw = [&]() { return up[pos++]; };
+        uint64_t found;
+        const int used = thread_choice(draw, s_p, s_cdf, h.n_cand, k, kMaxDraws, &found);
+        if (used >= 0 && used - k < kTabFail) out = (uint8_t)(used - k);
+    }
+    trow[e] = out;
+}
+
+// The sequential part: one warp, ONE shared-memory lookup per half-row on the critical path
+// (e += table[j][e] - drift increment).  The table rows stream through a ring of kWalkStages chunks of 32 rows
+// filled by cp.async, so the L2 latency of a chunk is hidden behind the walk of the chunks before it.  Records
+// the absolute stream offset of every half-row it passes, ends the window when the hypothesis index leaves
+// [0, kHyp) and re-bases.
+__global__ void __launch_bounds__(32)
+recover_walk_kernel(RecoverCtl* ctl, int64_t recs, int norb, const HalfHeader* __restrict__ hdr,
+                    const double* __restrict__ pc, const double* __restrict__ cdf,
+                    const int32_t* __restrict__ kprefix, const uint8_t* __restrict__ table,
+                    uint64_t* __restrict__ rng_state, int64_t* __restrict__ off_abs, int32_t* __restrict__ status) {
+    if (ctl->done) return;
+    __shared__ __align__(16) uint8_t s_tab[kWalkStages][32 * kHyp];
+    __shared__ int s_dc[kWalkStages][32];
+    __shared__ double s_cdf[64];
+    const int lane = threadIdx.x & 31;
+    const int64_t r0 = ctl->cursor;
+    const uint32_t rho = ctl->rho;
+    const u128 inc = ((u128)rng_state[2] << 64) | (u128)rng_state[3];
+    const u128 win_state = ((u128)ctl->state_hi << 64) | (u128)ctl->state_lo;
+    const int64_t off0 = ctl->offset;
+    const int nwin = (int)((recs - r0) < kWinRecs ? (recs - r0) : kWinRecs);
+    const int nchunks = (nwin + 31) / 32;
+    auto stage = [&](int chunk) {   // 32 table rows = 8 KB, 16 asynchronous 16-byte copies per lane
+        if (chunk < nchunks) {
+            const int buf = chunk % kWalkStages;
+            const int rows = nwin - chunk * 32 < 32 ? nwin - chunk * 32 : 32;
+            const uint8_t* src = table + (int64_t)chunk * 32 * kHyp;
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tab[buf]);
+            for (int i = lane; i < rows * (kHyp / 16); i += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * i));
+            const int jg = chunk * 32 + lane;
+            s_dc[buf][lane] = drift_of(rho, jg + 1) - drift_of(rho, jg);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group keeps the count uniform)
+    };
+    int e = kHyp / 2;        // hypothesis index of the current half-row
+    int j = 0;               // half-rows walked
+    bool failed = false, out_of_band = false;
+    for (int c = 0; c < kWalkStages - 1; ++c) stage(c);
+    for (int chunk = 0; chunk < nchunks && !out_of_band && !failed; ++chunk) {
+        const int buf = chunk % kWalkStages;
+        stage(chunk + kWalkStages - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(kWalkStages - 1) : "memory");   // chunk `chunk` has landed
+        __syncwarp();
+        const int rows = nwin - chunk * 32 < 32 ? nwin - chunk * 32 : 32;
+        int e_mine = 0;      // lane jj remembers the index the walk held at row jj of the chunk
+        int done_rows = 0;
+        for (int jj = 0; jj < rows; ++jj) {
+            if (lane == jj) e_mine = e;
+            done_rows = jj + 1;
+            int extra = s_tab[buf][jj * kHyp + e];
+            if (extra >= kTabFail) {
+                const int64_t rec = r0 + chunk * 32 + jj;
+                if (extra == kTabFail) {   // numpy raises here: the generator has consumed everything before it
+                    failed = true;
+                    if (lane == 0) {
+                        status[0] = 1;
+                        status[1] = (int32_t)(rec >> 1);
+                    }
+                    break;
+                }
+                // not tabulated (many retries): sample this half-row here, as the round-1 kernel did
+                const int jg = chunk * 32 + jj;
+                const HalfHeader h = hdr[rec];
+                const int k = h.n_diff > 0 ? h.n_diff : -h.n_diff;
+                const int64_t off_rel = (int64_t)(kprefix[rec] - kprefix[r0]) + drift_of(rho, jg) + e - kHyp / 2;
+                Pcg64 rng;
+                rng.inc = inc;
+                rng.state = pcg_advance(win_state, inc, (uint64_t)off_rel);
+                const double* crow = cdf + rec * norb;
+                const double c_lo = lane < h.n_cand ? crow[lane] : INFINITY;
+                const double c_hi = lane + 32 < h.n_cand ? crow[lane + 32] : INFINITY;
+                const u128 before = rng.state;
+                warp_choice(rng, pc + rec * norb, c_lo, c_hi, h.n_cand, k, s_cdf);
+                Pcg64 probe;   // draws used = steps between the two states (rare path: count them)
+                probe.inc = inc;
+                probe.state = before;
+                int used = 0;
+                while (probe.state != rng.state) {
+                    probe.next();
+                    ++used;
+                }
+                extra = used - k;
+            }
+            e += extra - s_dc[buf][jj];
+            ++j;
+            if ((unsigned)e >= (unsigned)kHyp) {
+                out_of_band = true;
+                break;
+            }
+        }
+        // stream offsets of the rows of this chunk, in parallel
+        if (lane < done_rows) {
+            const int jg = chunk * 32 + lane;
+            const int64_t rec = r0 + jg;
+            off_abs[rec] = off0 + (int64_t)(kprefix[rec] - kprefix[r0]) + drift_of(rho, jg) + e_mine - kHyp / 2;
+        }
+        __syncwarp();
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    // j half-rows walked (a failing one not counted); e is the hypothesis index AT half-row r0 + j in every
+    // exit path, i.e. draws consumed beyond the collision-free count = drift_j + e - kHyp/2
+    const int64_t next = r0 + j;
+    const int64_t extras_win = (int64_t)drift_of(rho, j) + e - kHyp / 2;
+    const int64_t off_next = off0 + (int64_t)(kprefix[next] - kprefix[r0]) + extras_win;
+    if (lane == 0) {
+        const u128 st = pcg_advance(win_state, inc, (uint64_t)(off_next - off0));
+        ctl->state_hi = (uint64_t)(st >> 64);
+        ctl->state_lo = (uint64_t)st;
+        ctl->cursor = next;
+        ctl->offset = off_next;
+        ctl->extras_total += extras_win;
+        if (next > 0) {
+            const double r = (double)ctl->extras_total / (double)next;
+            ctl->rho = (uint32_t)(r * 65536.0 + 0.5);
+        }
+        if (failed || next >= recs) {
+            ctl->done = 1;
+            ctl->failed = failed ? 1 : 0;
+            rng_state[0] = (uint64_t)(st >> 64);   // the caller's generator continues from here
+            rng_state[1] = (uint64_t)st;
+        }
+    }
+}
+
+// Every half-row again, now at its known stream offset: the flips themselves.  One thread per half-row.
+__global__ void recover_apply_kernel(const RecoverCtl* __restrict__ ctl, const uint64_t* __restrict__ left,
+                                     const uint64_t* __restrict__ right, int64_t recs, int norb,
+                                     const HalfHeader* __restrict__ hdr, const uint8_t* __restrict__ cand,
+                                     const double* __restrict__ pc, const double* __restrict__ cdf,
+                                     const int64_t* __restrict__ off_abs, const uint64_t* __restrict__ init_state,
+                                     const uint64_t* __restrict__ rng_state, uint64_t* __restrict__ left_out,
+                                     uint64_t* __restrict__ right_out) {
+    const int64_t rec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (rec >= recs) return;
+    uint64_t word = (rec & 1) ? right[rec >> 1] : left[rec >> 1];
+    const HalfHeader h = hdr[rec];
+    const bool live = !(ctl->failed && rec >= ctl->cursor);   // nothing after numpy's error counts
+    if (live && h.n_cand > 0) {
+        const int k = h.n_diff > 0 ? h.n_diff : -h.n_diff;
+        Pcg64 rng;
+        rng.inc = ((u128)rng_state[2] << 64) | (u128)rng_state[3];
+        rng.state = pcg_advance(((u128)init_state[0] << 64) | (u128)init_state[1], rng.inc,
+                                (uint64_t)off_abs[rec]);
+        auto draw = [&]() { return rng.next_double(); };
+        uint64_t found = 0ull;
+        thread_choice(draw, pc + rec * norb, cdf + rec * norb, h.n_cand, k, 1 << 30, &found);
+        const uint8_t* krow = cand + rec * norb;
+        for (int c = 0; c < h.n_cand; ++c)
+            if ((found >> c) & 1ull) word ^= 1ull << (norb - 1 - krow[c]);
+    }
+    if (rec & 1) right_out[rec >> 1] = word; else left_out[rec >> 1] = word;
+}
+
 }  // namespace sqd
 
 using namespace sqd;
@@ -327,6 +686,11 @@ int64_t sqd_recover_workspace_bytes(int64_t n, int norb) {
     b += ((recs * norb + 255) / 256) * 256;                             // cand (u8)
     b += ((recs * norb * (int64_t)sizeof(double) + 255) / 256) * 256;  // p
     b += ((recs * norb * (int64_t)sizeof(double) + 255) / 256) * 256;  // cdf
+    // speculative exact stream: kq, kcount, kprefix, off_abs, window table, skip tables, walk state
+    b += ((recs + 255) / 256) * 256;
+    b += 2 * (((recs + 1) * 4 + 255) / 256) * 256;
+    b += ((recs * 8 + 255) / 256) * 256;
+    b += (int64_t)kWinRecs * kHyp + 2 * (int64_t)kUBuf * 16 + 512;
     return b + 256;
 }
 
@@ -357,11 +721,60 @@ int sqd_recover(const uint64_t* d_left, const uint64_t* d_right, int64_t n, int 
         d_left, d_right, n, norb, d_occ_left, d_occ_right, hamming_left, hamming_right, hdr, cand, pc,
         cdf);
     if (check_launch("recover_prepare_kernel")) return -2;
+    p += ((recs * norb * (int64_t)sizeof(double) + 255) / 256) * 256;
     if (mode == 0) {
         SQD_REQUIRE(d_rng_state != nullptr, "sqd_recover: mode 0 needs the PCG64 state");
-        recover_select_chain_kernel<<<1, 32, 0, st>>>(d_left, d_right, n, norb, hdr, cand, pc, cdf,
-                                                      d_rng_state, d_left_out, d_right_out, d_status);
-        return check_launch("recover_select_chain_kernel");
+        static const int knob_chain = getenv("SQD_RECOVER_CHAIN") ? atoi(getenv("SQD_RECOVER_CHAIN")) : 0;
+        const bool speculative = !knob_chain && recs * 64 < 2147483647LL;
+        if (!speculative) {
+            recover_select_chain_kernel<<<1, 32, 0, st>>>(d_left, d_right, n, norb, hdr, cand, pc, cdf,
+                                                          d_rng_state, d_left_out, d_right_out, d_status);
+            return check_launch("recover_select_chain_kernel");
+        }
+        uint8_t* kq = (uint8_t*)p;
+        p += ((recs + 255) / 256) * 256;
+        int32_t* kcount = (int32_t*)p;
+        p += (((recs + 1) * 4 + 255) / 256) * 256;
+        int32_t* kprefix = (int32_t*)p;
+        p += (((recs + 1) * 4 + 255) / 256) * 256;
+        int64_t* off_abs = (int64_t*)p;
+        p += ((recs * 8 + 255) / 256) * 256;
+        uint8_t* table = (uint8_t*)p;
+        p += (int64_t)kWinRecs * kHyp;
+        u128* skipM = (u128*)p;
+        p += (int64_t)kUBuf * 16;
+        u128* skipP = (u128*)p;
+        p += (int64_t)kUBuf * 16;
+        RecoverCtl* ctl = (RecoverCtl*)p;
+        uint64_t* init_state = (uint64_t*)(p + 256);
+        recover_counts_kernel<<<(unsigned)((recs + 255) / 256), 256, 0, st>>>(hdr, recs, kq, kcount);
+        if (check_launch("recover_counts_kernel")) return -2;
+        if (sqd_exclusive_scan(kcount, kprefix, (int)recs, nullptr, stream)) return -2;
+        recover_skip_table_kernel<<<(kUBuf + 127) / 128, 128, 0, st>>>(d_rng_state, skipM, skipP, ctl, init_state);
+        if (check_launch("recover_skip_table_kernel")) return -2;
+        // a window ends early when the walk drifts out of its band of hypotheses: launch the minimum number of
+        // windows, then look at the done flag every few windows
+        const int64_t min_windows = (recs + kWinRecs - 1) / kWinRecs;
+        int64_t launched = 0;
+        for (;;) {
+            const int64_t batch = launched == 0 ? min_windows : 8;
+            for (int64_t w = 0; w < batch; ++w) {
+                recover_table_kernel<<<kWinRecs, kHyp, 0, st>>>(ctl, recs, norb, hdr, pc, cdf, kprefix, d_rng_state,
+                                                               skipM, skipP, table);
+                recover_walk_kernel<<<1, 32, 0, st>>>(ctl, recs, norb, hdr, pc, cdf, kprefix, table, d_rng_state,
+                                                      off_abs, d_status);
+            }
+            if (check_launch("recover table/walk kernels", (int)(2 * batch))) return -2;
+            launched += batch;
+            RecoverCtl h_ctl;
+            if (read_back(&h_ctl, ctl, sizeof(RecoverCtl), st)) return -2;
+            if (h_ctl.done) break;
+            SQD_REQUIRE(launched < 64 * min_windows + 1024, "sqd_recover: the exact-stream walk does not advance");
+        }
+        recover_apply_kernel<<<(unsigned)((recs + 127) / 128), 128, 0, st>>>(
+            ctl, d_left, d_right, recs, norb, hdr, cand, pc, cdf, off_abs, init_state, d_rng_state, d_left_out,
+            d_right_out);
+        return check_launch("recover_apply_kernel");
     }
     recover_select_parallel_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(
         d_left, d_right, n, norb, hdr, cand, pc, cdf, seed, d_left_out, d_right_out, d_status);

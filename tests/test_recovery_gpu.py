@@ -115,3 +115,76 @@ def test_too_few_candidates_raises_like_numpy(cuda_lib):
         ro.recover_configurations(bs, np.array([1.0]), (occ_a, occ_b), 0, 1, 1)
     with pytest.raises(ValueError, match="Fewer non-zero entries in p than size"):
         recover_configurations(bs, np.array([1.0]), (occ_a, occ_b), 0, 1, 1)
+
+
+@pytest.mark.parametrize("chain", ["0", "1"])
+def test_error_in_the_middle_leaves_the_generator_where_numpy_does(cuda_lib, chain, monkeypatch):
+    """Thousands of rows consume draws, then a row makes numpy raise: same exception, and the caller's
+    generator has advanced exactly as far as numpy's (speculative walk and the one-warp chain)."""
+    import subprocess
+    import sys
+
+    code = r'''
+import numpy as np
+from oracle import recovery_oracle as ro
+from qiskit_addon_sqd_b200.configuration_recovery import recover_configurations
+norb, n = 4, 6000
+rng = np.random.default_rng(3)
+bs = rng.integers(2, size=(n, 2 * norb), dtype=np.int64).astype(bool)
+occ_b = np.array([1.0, 1.0, 1.0, 0.0]); occ_a = np.array([0.3, 0.6, 0.2, 0.9])
+bad = 4321
+bs[bad] = [True, True, True, True, False, True, False, False]   # beta half: 3 too many, one candidate
+probs = np.full(n, 1.0 / n)
+out = []
+for fn in (ro.recover_configurations, recover_configurations):
+    g = np.random.default_rng(11)
+    try:
+        fn(bs, probs, (occ_a, occ_b), 1, 1, g)
+        out.append(("no error", None))
+    except ValueError as e:
+        out.append((str(e), g.bit_generator.state["state"]["state"]))
+assert out[0][0] == out[1][0] == "Fewer non-zero entries in p than size", out
+assert out[0][1] == out[1][1], out
+print("ok")
+'''
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SQD_RECOVER_CHAIN=chain, PYTHONPATH=root)
+    p = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "ok" in p.stdout, p.stdout + p.stderr
+
+
+def test_exact_stream_speculative_walk_equals_chain(cuda_lib):
+    """1e5 half-rows with heavy collisions (few candidates, many draws): the windowed speculative walk, the
+    round-1 one-warp chain and the oracle on a prefix agree bit for bit, generator state included."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import numpy as np, sys
+from qiskit_addon_sqd_b200.configuration_recovery import recover_configurations
+norb, n = 10, 50000
+rng = np.random.default_rng(5)
+bs = rng.integers(2, size=(n, 2 * norb), dtype=np.int64).astype(bool)
+occ = (rng.random(norb) ** 3, rng.random(norb) ** 3)      # skewed weights: many collisions
+g = np.random.default_rng(2024)
+mat, freqs = recover_configurations(bs, np.full(n, 1.0 / n), occ, 3, 7, g)
+np.save(sys.argv[1], mat); np.save(sys.argv[2], freqs)
+print(g.bit_generator.state["state"]["state"])
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as td:
+        for chain in ("0", "1"):
+            env = dict(os.environ, SQD_RECOVER_CHAIN=chain, PYTHONPATH=root)
+            a, b = os.path.join(td, f"m{chain}.npy"), os.path.join(td, f"f{chain}.npy")
+            p = subprocess.run([sys.executable, "-c", code, a, b], cwd=root, env=env, capture_output=True,
+                               text=True, timeout=600)
+            assert p.returncode == 0, p.stderr
+            outs.append((np.load(a), np.load(b), p.stdout.strip()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][2] == outs[1][2]
