@@ -457,15 +457,22 @@ int sqd_pauli_elements(const int64_t* d_keys, int64_t d, const void* d_table /* 
  * zmask, a number of Y's and a complex coefficient.  Pass 1 counts, pass 2 fills a CSR matrix whose
  * row i holds A[i, col] for every group that connects row i (transpose convention of the reference:
  * A[source, image]), columns ascending, exact zeros dropped (scipy canonical format). */
+/* Optional pre-pass for the diagonal group (X mask 0, terms [t0, t1) ): d_out[2i], d_out[2i+1] = the sum of
+ * the group's terms for row i, in term order.  Hand the group's index and d_out to count/fill (diag_group,
+ * d_diag_val; -1 / NULL: none) and they read the sums instead of re-evaluating thousands of Z strings per row. */
+int sqd_pauli_diag_group(const int64_t* d_keys, int64_t d, const uint64_t* d_zmask, const int32_t* d_ny,
+                         const double* d_coeff, int32_t t0, int32_t t1, double* d_out, void* stream);
 int sqd_pauli_project_count(const int64_t* d_keys, int64_t d, const void* d_table /* or NULL */,
                             const uint64_t* d_grp_xmask,
                             const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
                             const int32_t* d_ny, const double* d_coeff /* re,im pairs */,
+                            int32_t diag_group, const double* d_diag_val,
                             int32_t* d_row_nnz, void* stream);
 int sqd_pauli_project_fill(const int64_t* d_keys, int64_t d, const void* d_table /* or NULL */,
                            const uint64_t* d_grp_xmask,
                            const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
-                           const int32_t* d_ny, const double* d_coeff, const int32_t* d_row_ptr,
+                           const int32_t* d_ny, const double* d_coeff, int32_t diag_group,
+                           const double* d_diag_val, const int32_t* d_row_ptr,
                            int32_t* d_col_tmp, double* d_val_tmp /* scratch, nnz entries each */,
                            int32_t* d_col, double* d_val /* re,im pairs */, void* stream);
 

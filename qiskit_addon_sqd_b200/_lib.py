@@ -241,9 +241,12 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_key_table_build": (_i, [_vp, _i64, _vp, _i64, _vp]),
     "sqd_pauli_connect": (_i, [_vp, _i64, _vp, _u64, _u64, _vp, _vp, _vp]),
     "sqd_pauli_elements": (_i, [_vp, _i64, _vp, _u64, _u64, _i, _vp, _vp, _vp, _vp]),
-    "sqd_pauli_project_count": (_i, [_vp, _i64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "sqd_pauli_diag_group": (_i, [_vp, _i64, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp, _vp]),
+    "sqd_pauli_project_count": (
+        _i, [_vp, _i64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp]
+    ),
     "sqd_pauli_project_fill": (
-        _i, [_vp, _i64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+        _i, [_vp, _i64, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     ),
     "sqd_csr_matvec_c128": (_i, [_i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sqd_csr_davidson_workspace_bytes": (_i64, [_i64, _i, _i]),

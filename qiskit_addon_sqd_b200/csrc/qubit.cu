@@ -8,6 +8,7 @@
 // groups: binary search of key^xmask in the key list, then the group's terms are accumulated in their
 // original order (same floating-point sum order as the reference's term-by-term `operator += ...`).
 // Hits are ballot-compacted into the row's CSR segment and rank-sorted by column.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -158,7 +159,23 @@ __device__ __forceinline__ void accumulate_term(double& re, double& im, double c
     im += ti;
 }
 
-// USE_TABLE: hash probes (4 independent probes per lane in flight); otherwise binary search of the key list
+// signed value of one term for a source key: coefficient * i^ny * (+-1)
+__device__ __forceinline__ void term_value(double cr, double ci, int ny, bool neg, double& tr, double& ti) {
+    switch (ny & 3) {
+        case 0: tr = cr; ti = ci; break;
+        case 1: tr = -ci; ti = cr; break;   // * i
+        case 2: tr = -cr; ti = -ci; break;  // * -1
+        default: tr = ci; ti = -cr; break;  // * -i
+    }
+    if (neg) {
+        tr = -tr;
+        ti = -ti;
+    }
+}
+
+// USE_TABLE: hash probes (4 independent probes per lane in flight); otherwise binary search of the key list.
+// (A shared-memory membership filter in front of the table was tried and measured slower: the probes are not
+// what the kernel spends its time on once the large term groups are evaluated cooperatively.)
 template <bool FILL, bool USE_TABLE>
 __global__ void pauli_project_kernel(const int64_t* __restrict__ keys, int64_t d, KeyTable table,
                                      const uint64_t* __restrict__ grp_xmask,
@@ -166,7 +183,8 @@ __global__ void pauli_project_kernel(const int64_t* __restrict__ keys, int64_t d
                                      const uint64_t* __restrict__ zmask, const int32_t* __restrict__ ny,
                                      const double* __restrict__ coeff,
                                      const int32_t* __restrict__ row_ptr, int32_t* __restrict__ row_nnz,
-                                     int32_t* __restrict__ col, double* __restrict__ val) {
+                                     int32_t* __restrict__ col, double* __restrict__ val, int32_t diag_group,
+                                     const double* __restrict__ diag_val) {
     constexpr int U = USE_TABLE ? 4 : 1;
     const int lane = threadIdx.x & 31;
     const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -205,12 +223,49 @@ __global__ void pauli_project_kernel(const int64_t* __restrict__ keys, int64_t d
         for (int u = 0; u < U; ++u) {
             const int32_t k = k0 + u * 32 + lane;
             double re = 0.0, im = 0.0;
+            int32_t g0 = 0, g1 = 0;
             if (j[u] >= 0) {
-                for (int32_t t = grp_ptr[k]; t < grp_ptr[k + 1]; ++t)
+                g0 = grp_ptr[k];
+                g1 = grp_ptr[k + 1];
+            }
+            // A group with many terms (the diagonal group of a Hamiltonian easily holds thousands of Z strings)
+            // is evaluated by the whole warp: 32 terms at a time, every lane the signed value of one term, then
+            // the values are added IN TERM ORDER (shuffles) -- the same floating-point sums as the owning
+            // lane's own loop, at a tenth of the instructions.
+            const bool pre = j[u] >= 0 && k == diag_group;   // summed beforehand by pauli_diag_group_kernel
+            if (pre) {
+                re = diag_val[2 * i];
+                im = diag_val[2 * i + 1];
+            }
+            const bool big = !pre && g1 - g0 >= 8;
+            if (j[u] >= 0 && !big && !pre) {
+                for (int32_t t = g0; t < g1; ++t)
                     accumulate_term(re, im, coeff[2 * t], coeff[2 * t + 1], ny[t],
                                     popc64((uint64_t)key & zmask[t]) & 1);
-                if (re == 0.0 && im == 0.0) j[u] = -1;  // scipy drops exact zeros when summing
             }
+            uint32_t mb = __ballot_sync(0xffffffffu, big);
+            while (mb) {
+                const int owner = __ffs(mb) - 1;
+                mb &= mb - 1;
+                const int32_t b0 = __shfl_sync(0xffffffffu, g0, owner), b1 = __shfl_sync(0xffffffffu, g1, owner);
+                double sre = 0.0, sim = 0.0;
+                for (int32_t t0 = b0; t0 < b1; t0 += 32) {
+                    const int32_t t = t0 + lane;
+                    double tr = 0.0, ti = 0.0;
+                    if (t < b1)
+                        term_value(coeff[2 * t], coeff[2 * t + 1], ny[t], popc64((uint64_t)key & zmask[t]) & 1, tr, ti);
+                    const int cnt = b1 - t0 < 32 ? b1 - t0 : 32;
+                    for (int l = 0; l < cnt; ++l) {
+                        sre += __shfl_sync(0xffffffffu, tr, l);
+                        sim += __shfl_sync(0xffffffffu, ti, l);
+                    }
+                }
+                if (lane == owner) {
+                    re = sre;
+                    im = sim;
+                }
+            }
+            if (j[u] >= 0 && re == 0.0 && im == 0.0) j[u] = -1;  // scipy drops exact zeros when summing
             const uint32_t m = __ballot_sync(0xffffffffu, j[u] >= 0);
             if (FILL && j[u] >= 0) {
                 const int o = base + count + __popc(m & ((1u << lane) - 1u));
@@ -222,6 +277,25 @@ __global__ void pauli_project_kernel(const int64_t* __restrict__ keys, int64_t d
         }
     }
     if (!FILL && lane == 0) row_nnz[i] = count;
+}
+
+// The diagonal group (X mask 0: every row is its own image) of a Hamiltonian easily holds thousands of Z strings
+// and EVERY row needs its sum.  One thread per row, the terms in order: all threads of a warp read the same
+// term (uniform loads) and add its signed value to their own row's running sum -- the sequential summation
+// order of the reference, ~8 instructions per (32 rows, term).
+__global__ void pauli_diag_group_kernel(const int64_t* __restrict__ keys, int64_t d,
+                                        const uint64_t* __restrict__ zmask, const int32_t* __restrict__ ny,
+                                        const double* __restrict__ coeff, int32_t t0, int32_t t1,
+                                        double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= d) return;
+    const uint64_t key = (uint64_t)keys[i];
+    double re = 0.0, im = 0.0;
+    for (int32_t t = t0; t < t1; ++t)
+        accumulate_term(re, im, __ldg(coeff + 2 * t), __ldg(coeff + 2 * t + 1), __ldg(ny + t),
+                        popc64(key & __ldg(zmask + t)) & 1);
+    out[2 * i] = re;
+    out[2 * i + 1] = im;
 }
 
 // rank sort of each CSR row by column (columns are unique inside a row)
@@ -504,42 +578,54 @@ int sqd_pauli_elements(const int64_t* d_keys, int64_t d, const void* d_table, ui
     return check_launch("pauli_elements_kernel");
 }
 
+int sqd_pauli_diag_group(const int64_t* d_keys, int64_t d, const uint64_t* d_zmask, const int32_t* d_ny,
+                         const double* d_coeff, int32_t t0, int32_t t1, double* d_out, void* stream) {
+    if (d == 0) return 0;
+    SQD_REQUIRE(t0 >= 0 && t1 >= t0, "sqd_pauli_diag_group: bad term range");
+    pauli_diag_group_kernel<<<(unsigned)((d + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_keys, d, d_zmask, d_ny,
+                                                                                         d_coeff, t0, t1, d_out);
+    return check_launch("pauli_diag_group_kernel");
+}
+
 int sqd_pauli_project_count(const int64_t* d_keys, int64_t d, const void* d_table, const uint64_t* d_grp_xmask,
                             const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
-                            const int32_t* d_ny, const double* d_coeff, int32_t* d_row_nnz,
-                            void* stream) {
+                            const int32_t* d_ny, const double* d_coeff, int32_t diag_group,
+                            const double* d_diag_val, int32_t* d_row_nnz, void* stream) {
     if (d == 0) return 0;
     const int wpb = 8;
     const unsigned nb = (unsigned)((d + wpb - 1) / wpb);
     cudaStream_t st = (cudaStream_t)stream;
+    const int32_t dg = d_diag_val ? diag_group : -1;
     if (d_table)
         pauli_project_kernel<false, true><<<nb, wpb * 32, 0, st>>>(
             d_keys, d, make_table(d_table, d), d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff, nullptr,
-            d_row_nnz, nullptr, nullptr);
+            d_row_nnz, nullptr, nullptr, dg, d_diag_val);
     else
         pauli_project_kernel<false, false><<<nb, wpb * 32, 0, st>>>(
             d_keys, d, KeyTable{nullptr, nullptr, 0}, d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff,
-            nullptr, d_row_nnz, nullptr, nullptr);
+            nullptr, d_row_nnz, nullptr, nullptr, dg, d_diag_val);
     return check_launch("pauli_project_kernel<count>");
 }
 
 int sqd_pauli_project_fill(const int64_t* d_keys, int64_t d, const void* d_table, const uint64_t* d_grp_xmask,
                            const int32_t* d_grp_ptr, int32_t n_groups, const uint64_t* d_zmask,
-                           const int32_t* d_ny, const double* d_coeff, const int32_t* d_row_ptr,
+                           const int32_t* d_ny, const double* d_coeff, int32_t diag_group,
+                           const double* d_diag_val, const int32_t* d_row_ptr,
                            int32_t* d_col_tmp, double* d_val_tmp, int32_t* d_col, double* d_val,
                            void* stream) {
     if (d == 0) return 0;
     const int wpb = 8;
     const unsigned nb = (unsigned)((d + wpb - 1) / wpb);
     cudaStream_t st = (cudaStream_t)stream;
+    const int32_t dg = d_diag_val ? diag_group : -1;
     if (d_table)
         pauli_project_kernel<true, true><<<nb, wpb * 32, 0, st>>>(
             d_keys, d, make_table(d_table, d), d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff, d_row_ptr,
-            nullptr, d_col_tmp, d_val_tmp);
+            nullptr, d_col_tmp, d_val_tmp, dg, d_diag_val);
     else
         pauli_project_kernel<true, false><<<nb, wpb * 32, 0, st>>>(
             d_keys, d, KeyTable{nullptr, nullptr, 0}, d_grp_xmask, d_grp_ptr, n_groups, d_zmask, d_ny, d_coeff,
-            d_row_ptr, nullptr, d_col_tmp, d_val_tmp);
+            d_row_ptr, nullptr, d_col_tmp, d_val_tmp, dg, d_diag_val);
     if (check_launch("pauli_project_kernel<fill>")) return -2;
     csr_row_sort_kernel<<<nb, wpb * 32, 0, st>>>(d, d_row_ptr, d_col_tmp, d_val_tmp, d_col, d_val);
     return check_launch("csr_row_sort_kernel");

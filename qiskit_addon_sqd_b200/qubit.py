@@ -169,8 +169,18 @@ def _project_device(torch, lib, keys, hamiltonian, timings: dict | None = None) 
     if ev:
         ev[0].record()
     table = _key_table(torch, lib, keys)
+    # the diagonal group (X mask 0: every row is its own image): summed once per row by a thread-per-row pre-pass
+    diag_group, diag_val = -1, None
+    zero = np.flatnonzero(grp_x == 0)
+    if zero.size and counts[zero[0]] >= 32:
+        diag_group = int(zero[0])
+        diag_val = torch.empty(2 * d, dtype=torch.float64, device=dev)
+        _lib.check(lib.sqd_pauli_diag_group(_lib.ptr(keys), d, _lib.ptr(d_z), _lib.ptr(d_ny), _lib.ptr(d_cf),
+                                            int(grp_ptr[diag_group]), int(grp_ptr[diag_group + 1]),
+                                            _lib.ptr(diag_val), st), "sqd_pauli_diag_group")
     _lib.check(lib.sqd_pauli_project_count(_lib.ptr(keys), d, _lib.ptr(table), _lib.ptr(d_gx), _lib.ptr(d_gp),
                                            len(uniq), _lib.ptr(d_z), _lib.ptr(d_ny), _lib.ptr(d_cf),
+                                           diag_group, _lib.ptr(diag_val),
                                            _lib.ptr(row_nnz), st), "sqd_pauli_project_count")
     if ev:
         ev[1].record()
@@ -188,7 +198,8 @@ def _project_device(torch, lib, keys, hamiltonian, timings: dict | None = None) 
     if nnz:
         _lib.check(lib.sqd_pauli_project_fill(_lib.ptr(keys), d, _lib.ptr(table), _lib.ptr(d_gx), _lib.ptr(d_gp),
                                               len(uniq), _lib.ptr(d_z), _lib.ptr(d_ny),
-                                              _lib.ptr(d_cf), _lib.ptr(row_ptr), _lib.ptr(col_tmp),
+                                              _lib.ptr(d_cf), diag_group, _lib.ptr(diag_val),
+                                              _lib.ptr(row_ptr), _lib.ptr(col_tmp),
                                               _lib.ptr(val_tmp), _lib.ptr(col), _lib.ptr(val), st),
                    "sqd_pauli_project_fill")
     if ev:
@@ -255,7 +266,9 @@ def _lowest_eigenpair_device(torch, lib, csr: "_DeviceCSR", kw: dict, max_rounds
     st = _lib.stream_ptr(torch)
     tol = float(kw.get("tol", 0) or 0)
     tol = tol * tol if tol > 0 else 1e-14  # eigsh's tol bounds the relative accuracy of the Ritz value
-    max_space = int(min(kw.get("ncv") or 20, _lib.MAX_SPACE))
+    # basis of at most 16 vectors: up to there the Rayleigh-Ritz step of a cycle is the register-resident
+    # Rayleigh-quotient iteration (a few microseconds); beyond, every cycle pays a full Jacobi decomposition
+    max_space = int(min(kw.get("ncv") or 16, 16, _lib.MAX_SPACE))
     max_cycle = int(kw.get("maxiter") or 500)
     diag = torch.empty(d, dtype=torch.float64, device=dev)
     lower = torch.empty(d, dtype=torch.float64, device=dev)
