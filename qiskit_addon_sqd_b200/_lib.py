@@ -339,7 +339,9 @@ _pinned_cache = threading.local()
 
 def download(torch, t):
     """Large device tensor -> fresh numpy array, staged through a per-thread pinned buffer that is
-    reused between calls (asynchronous copy + stream synchronisation, then one host memcpy)."""
+    reused between calls (asynchronous copy + stream synchronisation, then one host memcpy).
+    (Copying straight into a pinned block that the returned array keeps was measured slower: results outlive
+    the call, so torch's caching host allocator has to pin fresh memory on almost every call.)"""
     import numpy as np
 
     t = t.contiguous()
@@ -355,4 +357,3 @@ def download(torch, t):
     # the library's wait does not spin when many ranks share the host (sqd_stream_wait)
     check(load().sqd_stream_wait(stream_ptr(torch)), "sqd_stream_wait")
     return np.array(view.numpy(), copy=True).reshape(tuple(t.shape))
-

@@ -15,6 +15,8 @@ tensors, torch is plumbing only.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 import threading
 import time
 import warnings
@@ -1068,8 +1070,17 @@ class ShardGroup:
         box = [buf.raw if self.rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         self._comm = C.c_void_p()
-        _lib.check(lib.sqd_nccl_init(box[0], self.rank, self.world, C.byref(self._comm)),
-                   "sqd_nccl_init")
+        # NCCL announces its version on stdout when a communicator is created; a caller that prints
+        # machine-readable output there (bench.py's JSON line) must not see it: route fd 1 to stderr meanwhile
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            rc = lib.sqd_nccl_init(box[0], self.rank, self.world, C.byref(self._comm))
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        _lib.check(rc, "sqd_nccl_init")
 
     def close(self):
         if self._comm:
