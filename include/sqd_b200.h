@@ -38,7 +38,8 @@ long long sqd_launch_count(int reset);
 /* ------------------------------------------------------------------------------------------ *
  * Determinant strings and excitation tables
  * replaces: pyscf selected_ci._all_linkstr_index (cre_des_linkstr / des_des_linkstr) reached from
- *           fermion.py:721,810; string checks fermion.py:1075-1097; packing counts.py:186-201
+ *           fermion.py:721,810; packing counts.py:186-201 (the string checks of fermion.py:1075-1097 are host
+ *           code: a popcount per string on arrays the caller already holds on the host)
  * ------------------------------------------------------------------------------------------ */
 
 /* Pack a bool bitstring matrix (n rows, nbits columns, 1 byte per bit, column 0 = most significant)
@@ -46,11 +47,6 @@ long long sqd_launch_count(int reset);
  * (alpha).  nbits/2 <= 64.  (counts.py:186-201, fermion.py:1026-1030) */
 int sqd_pack_bitstrings(const uint8_t* d_bits, int64_t n, int nbits, uint64_t* d_left,
                         uint64_t* d_right, void* stream);
-
-/* popcount of every string; h_bad_index receives the first index whose popcount differs from string
- * 0, or -1.  Synchronises the stream.  (fermion.py:1075-1097) */
-int sqd_check_hamming(const uint64_t* d_strs, int64_t n, int* d_scratch2, int* h_bad_index,
-                      int* h_weight0, int* h_weight_bad, void* stream);
 
 /* Pass 1: for each string i count the in-set single (xor-popcount 2) and single+double (2 or 4)
  * excitation partners.  d_n_single, d_n_total: int[n]. */

@@ -182,7 +182,6 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_launch_count": (C.c_longlong, [_i]),
     "sqd_stream_wait": (_i, [_vp]),
     "sqd_pack_bitstrings": (_i, [_vp, _i64, _i, _vp, _vp, _vp]),
-    "sqd_check_hamming": (_i, [_vp, _i64, _vp, _pi, _pi, _pi, _vp]),
     "sqd_excitation_count": (_i, [_vp, _i, _vp, _vp, _vp]),
     "sqd_exclusive_scan": (_i, [_vp, _vp, _i, _pi, _vp]),
     "sqd_excitation_fill": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -39,19 +39,6 @@ __global__ void pack_bitstrings_kernel(const uint8_t* __restrict__ bits, int64_t
 }
 
 // --------------------------------------------------------------------------------------------
-// hamming check
-// --------------------------------------------------------------------------------------------
-__global__ void check_hamming_kernel(const uint64_t* __restrict__ strs, int64_t n, int* out2) {
-    // out2[0] = min index whose popcount differs from string 0 (INT_MAX if none)
-    const int w0 = popc64(strs[0]);
-    int bad = 0x7fffffff;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x)
-        if (popc64(strs[i]) != w0) bad = min(bad, (int)i);
-    if (bad != 0x7fffffff) atomicMin(out2, bad);
-}
-
-// --------------------------------------------------------------------------------------------
 // pass 1: count partners.  One warp per string; lanes stride the partner index.
 // --------------------------------------------------------------------------------------------
 __global__ void excitation_count_kernel(const uint64_t* __restrict__ strs, int n,
@@ -323,31 +310,6 @@ int sqd_pack_bitstrings(const uint8_t* d_bits, int64_t n, int nbits, uint64_t* d
     pack_bitstrings_kernel<<<(unsigned)((n + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
         d_bits, n, nbits, d_left, d_right);
     return check_launch("pack_bitstrings_kernel");
-}
-
-int sqd_check_hamming(const uint64_t* d_strs, int64_t n, int* d_scratch2, int* h_bad_index,
-                      int* h_weight0, int* h_weight_bad, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    SQD_REQUIRE(n > 0, "sqd_check_hamming: empty string list");
-    const int init = 0x7fffffff;
-    SQD_CUDA_OK(cudaMemcpyAsync(d_scratch2, &init, sizeof(int), cudaMemcpyHostToDevice, st));
-    const int blocks = (int)min((int64_t)kNumSMs * 4, (n + 255) / 256);
-    check_hamming_kernel<<<blocks, 256, 0, st>>>(d_strs, n, d_scratch2);
-    if (check_launch("check_hamming_kernel")) return -2;
-    int bad = 0;
-    if (read_back(&bad, d_scratch2, sizeof(int), st)) return -2;
-    uint64_t s0 = 0, sb = 0;
-    if (read_back(&s0, d_strs, sizeof(uint64_t), st)) return -2;
-    *h_weight0 = __builtin_popcountll(s0);
-    if (bad == 0x7fffffff) {
-        *h_bad_index = -1;
-        *h_weight_bad = *h_weight0;
-    } else {
-        if (read_back(&sb, d_strs + bad, sizeof(uint64_t), st)) return -2;
-        *h_bad_index = bad;
-        *h_weight_bad = __builtin_popcountll(sb);
-    }
-    return 0;
 }
 
 int sqd_excitation_count(const uint64_t* d_strs, int n, int* d_n_single, int* d_n_total,

@@ -10,6 +10,17 @@ tensors, torch is plumbing only.  There is no CPU fallback.
 
 ``solve_sci_batch`` is a drop-in ``sci_solver`` for ``diagonalize_fermionic_hamiltonian``
 (``fermion.py:216-220, 432``): ``functools.partial(solve_sci_batch, spin_sq=0.0)``.
+
+Limits of the solvers (``solve_fermion``, ``solve_sci``, ``solve_sci_batch``, ``solve_sci_sharded``); a
+violation raises ``ValueError`` / ``RuntimeError`` naming the limit, nothing falls back silently:
+
+* ``norb <= 64`` spatial orbitals (one 64-bit word per determinant string);
+* at most 2^19 = 524 288 strings per spin, and fewer than 2^31 stored same-spin table entries per spin;
+* beta strings per subspace: ``nb <= 8192`` when the subspace is dense enough for the v2 sigma kernels
+  (every BASELINE.json shape is), otherwise ``nb <= 5760`` (the v1 kernels stage whole rows of the CI matrix in
+  shared memory: ``3*ldc + 2*norb^2`` doubles must fit 227 KB); the alpha side has no such bound, so for
+  ``nb`` beyond the limit swap the roles of the two spins where the problem allows it;
+* ``nroots > 1`` is not supported (``kernel_fixed_space`` default 1 is what the reference uses).
 """
 
 from __future__ import annotations
