@@ -26,8 +26,12 @@ namespace sqd {
 
 constexpr int kV2MaxGroups = 64;
 constexpr int kV2MaxStages = 8;
-constexpr int kV2GroupTarget = 416;   // virtual columns per group aimed at
-constexpr int kV2GroupMax = 480;      // hard limit (K1 runs vc_pad + 32 <= 512 threads)
+// virtual columns per K1 group aimed at / hard limit (K1 runs vc_pad + 32 threads).  With 8 links per column
+// the kernel fits 80 registers and two CTAs of <= 416 threads share an SM (the K1 kernels of two concurrent
+// solves then overlap instead of taking turns on the whole GPU); 16 links per column: one CTA of <= 512.
+__host__ __device__ constexpr int v2_group_target(int lmax) { return lmax == 8 ? 352 : 416; }
+__host__ __device__ constexpr int v2_group_max(int lmax) { return lmax == 8 ? 384 : 480; }
+constexpr int kV2GroupMax = 480;
 constexpr uint32_t kSelfItem = 0x40000000u;
 enum { C_NITEMS = 0, C_NCHUNKS, C_NGROUPS, C_VCPAD, C_SINGLES_A, C_SINGLES_B, C_ERR, C_NVC, C_NQ, C_NHEAVY };
 constexpr int kV2HeavyRow = 64;  // alpha strings with more single excitations get a CTA per column block in the epilogue
@@ -260,9 +264,9 @@ v2_beta_plan_kernel(const sqd_spin_table B, int lmax, int capw, int* __restrict_
     __syncthreads();
     // number of groups: smallest G >= nvc / target whose largest group fits the CTA
     if (threadIdx.x == 0) {
-        s_G = nvc > 0 ? (nvc + kV2GroupTarget - 1) / kV2GroupTarget : 1;
+        s_G = nvc > 0 ? (nvc + v2_group_target(lmax) - 1) / v2_group_target(lmax) : 1;
         // a group also owns nb / G natural columns for the Wb terms, one per thread
-        if (s_G < (nb + kV2GroupMax - 1) / kV2GroupMax) s_G = (nb + kV2GroupMax - 1) / kV2GroupMax;
+        if (s_G < (nb + v2_group_max(lmax) - 1) / v2_group_max(lmax)) s_G = (nb + v2_group_max(lmax) - 1) / v2_group_max(lmax);
         if (s_G > kV2MaxGroups) s_G = kV2MaxGroups;
         s_ok = 0;
     }
@@ -284,7 +288,7 @@ v2_beta_plan_kernel(const sqd_spin_table B, int lmax, int capw, int* __restrict_
         if (threadIdx.x == 0) {
             int mx = 0;
             for (int g = 0; g < G; ++g) mx = max(mx, g_nfull[g] + g_nrem[g]);
-            if (mx <= kV2GroupMax) s_ok = 1;
+            if (mx <= v2_group_max(lmax)) s_ok = 1;
             else if (G < kV2MaxGroups) s_G = G + 1;
             else s_ok = -1;
         }
@@ -333,7 +337,7 @@ v2_beta_plan_kernel(const sqd_spin_table B, int lmax, int capw, int* __restrict_
         counts[C_SINGLES_B] = sb;
         counts[C_NVC] = nvc;
         counts[C_NQ] = nvc;  // one P column per virtual column
-        if (s_ok != 1 || (long long)G * vc_pad > capw || too_wide != 0 || vc_pad > kV2GroupMax) counts[C_ERR] = 1;
+        if (s_ok != 1 || (long long)G * vc_pad > capw || too_wide != 0 || vc_pad > v2_group_max(lmax)) counts[C_ERR] = 1;
     }
 }
 
@@ -522,7 +526,7 @@ __device__ __forceinline__ double v2_dot(const double (&x)[LMAX], const uint32_t
 // LEAN: register cap 96 (launch bound 640) so that one CTA of this kernel and a CTA of the dense tile kernel
 // fit on an SM together (overlapped build of a lone solve); otherwise 128 registers.
 template <int LMAX, bool LEAN>
-__global__ void __launch_bounds__(LEAN ? 640 : 512, 1)
+__global__ void __launch_bounds__(LMAX == 8 ? 416 : (LEAN ? 640 : 512), LMAX == 8 ? 2 : 1)
 sigma2_ab_kernel(const V2Args P, const int NST, const int stage_len, const int src_smem) {
     constexpr int BATCH = 16;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1339,7 +1343,7 @@ int sqd_sigma_v2_finish(const sqd_spin_table* a, const sqd_spin_table* b, int ld
     V.n_heavy = hc[C_NHEAVY];
     V.P = (double*)(sb + S.P);
     V.part = (double*)(sb + S.part);
-    SQD_REQUIRE(V.vc_pad >= 32 && V.vc_pad <= kV2GroupMax && V.n_groups >= 1 && V.n_groups <= kV2MaxGroups,
+    SQD_REQUIRE(V.vc_pad >= 32 && V.vc_pad <= v2_group_max(V.lmax) && V.n_groups >= 1 && V.n_groups <= kV2MaxGroups,
                 "sqd_sigma_v2_finish: inconsistent plan counts");
     // every P entry the epilogue reads is rewritten by each build; the pad columns are never read
     if (dense) {

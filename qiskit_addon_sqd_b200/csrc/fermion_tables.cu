@@ -170,21 +170,20 @@ __device__ __forceinline__ double diagonal_element(uint64_t s, int norb, const d
 }
 
 // --------------------------------------------------------------------------------------------
-// pass 2: fill.  One warp per row (target t = strs[i]); two sweeps over the partner index keep
-// the "singles first, ascending" then "doubles, ascending" order with ballot/popcount compaction.
+// pass 2: fill.  Structure first -- one warp per row (target t = strs[i]), ballot/popcount compaction keeps
+// the "singles first, ascending" then "doubles, ascending" order -- then the values: one THREAD per table entry
+// (and per diagonal element).  The Slater-Condon evaluation of an entry is a dependent chain of ~2 n_elec
+// integral loads; with one warp per row (round 1) only ~300 warps shared that latency and the kernel took
+// 110 us at 316 strings; per entry, 24 000 threads do.
 // --------------------------------------------------------------------------------------------
 __global__ void excitation_fill_kernel(const uint64_t* __restrict__ strs, int n, int norb,
-                                       const double* __restrict__ h, const double* __restrict__ g,
                                        const int* __restrict__ row_ptr,
                                        const int* __restrict__ n_single, uint32_t* __restrict__ col,
-                                       double* __restrict__ val, uint32_t* __restrict__ meta,
-                                       uint32_t* __restrict__ pack, double* __restrict__ diag) {
+                                       uint32_t* __restrict__ meta, uint32_t* __restrict__ pack) {
     const int lane = threadIdx.x & 31;
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (i >= n) return;
     const uint64_t t = strs[i];
-    const bool have_ints = (h != nullptr) && (g != nullptr);  // structure-only tables when NULL
-    if (lane == 0) diag[i] = have_ints ? diagonal_element(t, norb, h, g) : 0.0;
     int pos1 = row_ptr[i];
     int pos2 = pos1 + n_single[i];
     for (int j0 = 0; j0 < n; j0 += 32) {
@@ -197,22 +196,53 @@ __global__ void excitation_fill_kernel(const uint64_t* __restrict__ strs, int n,
         if (pc == 2) {
             const int q = lowbit64((s ^ t) & s);  // annihilated in the source
             const int p = lowbit64((s ^ t) & t);  // created in the target
-            int sign = (popc64(s & between_mask(p, q)) & 1) ? -1 : 1;
-            const double v = have_ints ? single_element(s, p, q, norb, h, g, &sign) : 0.0;
+            const int sign = (popc64(s & between_mask(p, q)) & 1) ? -1 : 1;
             const int o = pos1 + __popc(m1 & lt);
             col[o] = (uint32_t)j;
-            val[o] = v;
             meta[o] = (uint32_t)(p * norb + q) | (sign < 0 ? 0x80000000u : 0u);
             pack[o] = (uint32_t)j | ((uint32_t)(p * norb + q) << 19) | (sign < 0 ? 0x80000000u : 0u);
         } else if (pc == 4) {
             const int o = pos2 + __popc(m2 & lt);
             col[o] = (uint32_t)j;
-            val[o] = have_ints ? double_element(s, t, norb, g) : 0.0;
             meta[o] = 0u;
             pack[o] = (uint32_t)j;
         }
         pos1 += __popc(m1);
         pos2 += __popc(m2);
+    }
+}
+
+__global__ void excitation_values_kernel(const uint64_t* __restrict__ strs, int n, int norb,
+                                         const double* __restrict__ h, const double* __restrict__ g,
+                                         const int* __restrict__ row_ptr, const int* __restrict__ n_single,
+                                         const uint32_t* __restrict__ col, const uint32_t* __restrict__ meta,
+                                         double* __restrict__ val, double* __restrict__ diag) {
+    const bool have_ints = (h != nullptr) && (g != nullptr);  // structure-only tables when NULL
+    const int nnz = row_ptr[n];
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz + n; e += gridDim.x * blockDim.x) {
+        if (e >= nnz) {
+            const int i = e - nnz;
+            diag[i] = have_ints ? diagonal_element(strs[i], norb, h, g) : 0.0;
+            continue;
+        }
+        if (!have_ints) {
+            val[e] = 0.0;
+            continue;
+        }
+        int lo = 0, hi = n;   // row of entry e: the last i with row_ptr[i] <= e
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (row_ptr[mid] <= e) lo = mid; else hi = mid;
+        }
+        const int i = lo;
+        const uint64_t t = strs[i], s = strs[col[e]];
+        if (e < row_ptr[i] + n_single[i]) {
+            const int pq = (int)(meta[e] & 0x7fffffffu);
+            int sign;
+            val[e] = single_element(s, pq / norb, pq % norb, norb, h, g, &sign);
+        } else {
+            val[e] = double_element(s, t, norb, g);
+        }
     }
 }
 
@@ -340,9 +370,15 @@ int sqd_excitation_fill(const uint64_t* d_strs, int n, int norb, const double* d
                 norb);
     SQD_REQUIRE(n <= (1 << 19), "sqd_excitation_fill: at most 2^19 strings per spin (got %d)", n);
     const int wpb = 8;
-    excitation_fill_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(
-        d_strs, n, norb, d_h, d_g, d_row_ptr, d_n_single, d_col, d_val, d_meta, d_pack, d_diag);
-    return check_launch("excitation_fill_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    excitation_fill_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, st>>>(d_strs, n, norb, d_row_ptr, d_n_single, d_col,
+                                                                   d_meta, d_pack);
+    // ~75-150 entries per string at the BASELINE shapes: a grid that covers them in one or two strides
+    const int64_t guess = (int64_t)n * 128;
+    const int blocks = (int)min((int64_t)kNumSMs * 8, (guess + 255) / 256);
+    excitation_values_kernel<<<blocks, 256, 0, st>>>(d_strs, n, norb, d_h, d_g, d_row_ptr, d_n_single, d_col, d_meta,
+                                                    d_val, d_diag);
+    return check_launch("excitation fill/values kernels", 2);
 }
 
 int sqd_make_gab(const double* d_g, int norb, double shift, int mode, double* d_gab, int ldg,
