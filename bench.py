@@ -384,8 +384,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "dram_gbs_from_ncu_traffic": (ncu_traffic(v2) or 0.0) / (sig_ms * 1e-3) / 1e9,
             "share_of_davidson_loop": sig_share, "davidson_loop_ms": dav_ms,
             "note": "algorithmic bytes = 16 n_det + 8 norb^4 + 12 nnz + 8 links (SURVEY 8d); the working "
-                    "set is L2-resident, the kernel is bound by shared-memory gathers and FP64 FMA "
-                    "issue, not by HBM (DESIGN.md)",
+                    "set is L2-resident, the kernels are bound by shared-memory gathers, FP64 FMA issue and "
+                    "latency, not by HBM (DESIGN.md 4); `traffic` is the COLD-cache DRAM traffic of the three "
+                    "kernels (ncu flushes L2 before every kernel): 26 MB of it is the epilogue re-reading the "
+                    "partial-product array the first kernel wrote, which stays in L2 in operation",
         },
         "davidson_cycles": {"min": int(min(cycles)), "max": int(max(cycles)),
                             "mean": float(np.mean(cycles))},

@@ -394,6 +394,10 @@ int sqd_fix_sign(double* d_x, int64_t n, void* d_scratch, void* stream);
  * when the process is one of more than two ranks, WORLD_SIZE > 2, else 0): with 8 ranks x 8 solver threads on
  * a 32-core host spinning waits starve the launching threads. */
 int sqd_stream_wait(void* stream);
+/* Device -> host copy into the caller's (pageable or pinned) array, stream-ordered, returns when the data
+ * has arrived.  For bindings whose host language holds a global lock while it copies (Python): the copy
+ * runs inside the call, outside that lock. */
+int sqd_download(void* h_dst, const void* d_src, long long bytes, void* stream);
 
 /* Small (<= 64 KB) device -> host read-back through a per-thread pinned staging buffer followed by a
  * stream synchronisation; never blocks the launches of other host threads. */

@@ -106,6 +106,39 @@ const char* sqd_last_error(void) { return sqd::g_err; }
 
 int sqd_stream_wait(void* stream) { return sqd::stream_wait_blocking((cudaStream_t)stream); }
 
+int sqd_download(void* h_dst, const void* d_src, long long bytes, void* stream) {
+    // device -> caller's host array through a per-thread pinned staging buffer, the final memcpy included: the
+    // calling Python thread has released the interpreter lock for the duration of the call, so the K solver
+    // threads of a batch copy their results concurrently (a numpy-side copy out of the staging buffer holds
+    // the lock: 58 MB per bench step, serialised; a D2H straight into pageable memory was measured slower)
+    if (bytes < 0) {
+        sqd::set_error("sqd_download: negative size");
+        return -1;
+    }
+    if (bytes == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local char* stage = nullptr;
+    static thread_local size_t stage_bytes = 0;
+    const size_t chunk_max = (size_t)32 << 20;
+    const size_t want = (size_t)bytes < chunk_max ? (size_t)bytes : chunk_max;
+    if (stage_bytes < want) {
+        if (stage) cudaFreeHost(stage);
+        stage = nullptr;
+        stage_bytes = 0;
+        size_t cap = (size_t)1 << 20;
+        while (cap < want) cap <<= 1;
+        SQD_CUDA_OK(cudaHostAlloc((void**)&stage, cap, cudaHostAllocPortable));
+        stage_bytes = cap;
+    }
+    for (size_t off = 0; off < (size_t)bytes; off += stage_bytes) {
+        const size_t n = (size_t)bytes - off < stage_bytes ? (size_t)bytes - off : stage_bytes;
+        SQD_CUDA_OK(cudaMemcpyAsync(stage, (const char*)d_src + off, n, cudaMemcpyDeviceToHost, st));
+        if (sqd::stream_wait_blocking(st)) return -2;
+        memcpy((char*)h_dst + off, stage, n);
+    }
+    return 0;
+}
+
 long long sqd_launch_count(int reset) {
     return reset ? sqd::g_launches.exchange(0) : sqd::g_launches.load();
 }

@@ -1165,9 +1165,12 @@ int sigma2_dispatch_rows(const sqd_operator* op, const double* d_c, double* d_si
     SQD_CUDA_OK(cudaGetDevice(&dev));
     const int li = (V.lmax == 8 ? 0 : 1) + (lean ? 2 : 0);
     if (dev >= 0 && dev < 64 && !cfg[dev][li]) {
+        static const int knob_carve = v2_env("SQD_V2_CARVEOUT", 100);     // experiments: -1 leaves the default
+        static const int knob_cache = v2_env("SQD_CACHE_CONFIG", -1);     // experiments: cudaFuncCache value
         SQD_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        SQD_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                         (int)cudaSharedmemCarveoutMaxShared));
+        if (knob_carve >= 0)
+            SQD_CUDA_OK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, knob_carve));
+        if (knob_cache >= 0) SQD_CUDA_OK(cudaDeviceSetCacheConfig((cudaFuncCache)knob_cache));
         cfg[dev][li] = true;
     }
     // lean CTAs (<= 31 K registers, <= 100 KB of ring) share an SM two at a time
