@@ -1292,10 +1292,10 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
         // restart when the space is full (see restart_keep)
         const int q_keep = restart_keep(M);
         const int restart = (m == M) ? q_keep : 0;
-        static const int knob_skip = env_knob("SQD_DAV_SKIP", 0);  // timing experiments: bit 0 residual, 1 ortho
+        static const int knob_skip = env_knob("SQD_DAV_SKIP", 0);  // timing experiments: skip bit 0 residual, 1 ortho, 2 gram
         int rc = dispatch_mv(m, [&](auto mv) {
             constexpr int MV = decltype(mv)::value;
-            gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n, m,
+            if (!(knob_skip & 4)) gram_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W + (int64_t)slot * n, n, m,
                                                             ws.partials, restart ? 1 : 0);
             if (!(knob_skip & 1)) residual_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, ws.W, d_hdiag, n, m,
                                                                 restart, prm->level_shift, ws.X, ws.T,

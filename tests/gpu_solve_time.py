@@ -15,6 +15,8 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
 extra = {}
 if len(sys.argv) > 4:   # fixed number of cycles (timing experiments): max_cycle, never converge
     extra = dict(max_cycle=int(sys.argv[4]), tol=1e-30)
+if os.environ.get("MAX_SPACE"):
+    extra["max_space"] = int(os.environ["MAX_SPACE"])
 norb, nelec, h, g, batches = bench.make_batches(wl, 0, K)
 for _ in range(3):
     res = fermion.solve_sci_batch(batches, h, g, norb, nelec, compute_rdms=False, **extra)
