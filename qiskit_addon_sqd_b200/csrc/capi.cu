@@ -23,9 +23,17 @@ void set_error(const char* fmt, ...) {
 }
 
 static std::atomic<long long> g_launches{0};
+static thread_local long long t_launches = 0;   // launches issued (or captured) by this host thread
+
+long long thread_launches() { return t_launches; }
+void add_launches(long long n) {
+    g_launches.fetch_add(n, std::memory_order_relaxed);
+    t_launches += n;
+}
 
 int check_launch(const char* what, int n_launched) {
     g_launches.fetch_add(n_launched, std::memory_order_relaxed);
+    t_launches += n_launched;
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("launch of %s failed: %s", what, cudaGetErrorString(e));

@@ -10,6 +10,8 @@ namespace sqd {
 // ---- error plumbing (C-ABI: 0 = ok, <0 = error, message via sqd_last_error) ------------------
 void set_error(const char* fmt, ...);
 int check_launch(const char* what, int n_launched = 1);  // also counts kernel launches
+long long thread_launches();        // kernels launched or captured by this host thread so far
+void add_launches(long long n);     // replays of a captured graph: count the kernels they stand for
 // Small device -> host read-back through a per-thread PINNED staging buffer, then a stream sync.  A copy
 // into pageable memory makes the runtime hold a context-wide lock until the stream has drained, which
 // stalls the launches of every other host thread (one thread per concurrent subspace solve).

@@ -116,6 +116,15 @@ __device__ __forceinline__ Ctl read_ctl(const DavState* st, int m_arg, int resta
 // and three launch gaps fewer per cycle.
 template <int MR>
 __device__ void rayleigh_ritz_body(DavState* st, const double* partials, int nblk, int m, int need_full);
+// the same bookkeeping for a cycle graph that the HOST replays (no conditional node)
+__global__ void advance_plain_kernel(DavState* st) {
+    if (threadIdx.x != 0 || st->status != 0) return;
+    const int m = st->m;
+    const int me = (m == st->M) ? st->q_keep : m;
+    st->m = me + 1;
+    st->slot = me;
+}
+
 __device__ void convergence_body(DavState* st, const double* partials, int nblk, int m, int restart,
                                  double tol, double tol_residual);
 __device__ void norm_body(DavState* st, const double* partials, int nblk, int m, double lindep);
@@ -1175,21 +1184,27 @@ static int side_stream(SideStream** out) {
 //     |- side branch: full decomposition for the next cycle
 //     |- residual -> ortho1 -> ortho2 -> advance (m, slot, condition) -> sigma build on the new vector
 // The first sigma build runs before the graph (eagerly).
+// while_node = false: the graph is ONE cycle and the host replays it (a graph launch instead of seven kernel
+// launches per cycle: the host cost of a cycle drops from ~45 us to ~10 us, which is what limits the ranks of
+// a box that share few host cores); kernels after convergence return at once (status flag).
 static int davidson_graph_loop(int64_t n, const ApplyCtlFn& apply_ctl, const double* d_hdiag, Workspace& ws,
                                int M, int blocks, const sqd_davidson_params* prm, SideStream* side,
-                               cudaStream_t st, cudaGraph_t* g_out, cudaGraphExec_t* ex_out) {
+                               cudaStream_t st, cudaGraph_t* g_out, cudaGraphExec_t* ex_out, bool while_node) {
     cudaGraph_t g = nullptr;
     SQD_CUDA_OK(cudaGraphCreate(&g, 0));
     *g_out = g;
-    cudaGraphConditionalHandle handle;
-    SQD_CUDA_OK(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
-    cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
-    cp.conditional.handle = handle;
-    cp.conditional.type = cudaGraphCondTypeWhile;
-    cp.conditional.size = 1;
-    cudaGraphNode_t node;
-    SQD_CUDA_OK(cudaGraphAddNode(&node, g, nullptr, 0, &cp));
-    cudaGraph_t body = cp.conditional.phGraph_out[0];
+    cudaGraphConditionalHandle handle = 0;
+    cudaGraph_t body = g;
+    if (while_node) {
+        SQD_CUDA_OK(cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault));
+        cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
+        cp.conditional.handle = handle;
+        cp.conditional.type = cudaGraphCondTypeWhile;
+        cp.conditional.size = 1;
+        cudaGraphNode_t node;
+        SQD_CUDA_OK(cudaGraphAddNode(&node, g, nullptr, 0, &cp));
+        body = cp.conditional.phGraph_out[0];
+    }
     SQD_CUDA_OK(cudaStreamBeginCaptureToGraph(st, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
     int rc = dispatch_mv(M, [&](auto mv) {
         constexpr int MV = decltype(mv)::value;
@@ -1200,7 +1215,8 @@ static int davidson_graph_loop(int64_t n, const ApplyCtlFn& apply_ctl, const dou
         ortho1_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, -1, ws.T, ws.partials,
                                                           prm->lindep);
         ortho2_kernel<MV><<<blocks, kRedThreads, 0, st>>>(ws.state, ws.V, n, -1, ws.T, ws.V);
-        advance_kernel<<<1, 32, 0, st>>>(ws.state, handle);
+        if (while_node) advance_kernel<<<1, 32, 0, st>>>(ws.state, handle);
+        else advance_plain_kernel<<<1, 32, 0, st>>>(ws.state);
         if (check_launch("davidson cycle (graph)", 5)) return -2;
         if (apply_ctl(ws.V, ws.W, &ws.state->slot, ws, st)) return -2;
         return 0;
@@ -1213,7 +1229,7 @@ static int davidson_graph_loop(int64_t n, const ApplyCtlFn& apply_ctl, const dou
         return -2;
     }
     SQD_CUDA_OK(cudaGraphInstantiate(ex_out, g, 0));
-    SQD_CUDA_OK(cudaGraphLaunch(*ex_out, st));
+    if (while_node) SQD_CUDA_OK(cudaGraphLaunch(*ex_out, st));
     return 0;
 }
 
@@ -1264,8 +1280,30 @@ static int davidson_core(int64_t n, const ApplyFn& apply, const double* d_hdiag,
             SQD_CUDA_OK(cudaEventRecord(side->ev_cap, st));
             SQD_CUDA_OK(cudaStreamWaitEvent(gst, side->ev_cap, 0));
         }
-        const int grc = davidson_graph_loop(n, apply_ctl, d_hdiag, ws, M, blocks, prm, side, gst, &graph,
-                                            &graph_exec);
+        const bool while_node = knob_graph == 1;
+        const long long launches_before = thread_launches();
+        int grc = davidson_graph_loop(n, apply_ctl, d_hdiag, ws, M, blocks, prm, side, gst, &graph, &graph_exec,
+                                      while_node);
+        if (grc == 0 && !while_node) {
+            // host-replayed cycle graph: the launches are counted like the kernels they stand for
+            const long long per_cycle = thread_launches() - launches_before;   // kernels captured in the graph
+            add_launches(-per_cycle);                                           // (the capture launched nothing)
+            for (cycle = 0; cycle < prm->max_cycle; ++cycle) {
+                add_launches(per_cycle);
+                if (cudaGraphLaunch(graph_exec, gst) != cudaSuccess) {
+                    set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    grc = -2;
+                    break;
+                }
+                if ((cycle + 1) % check_every == 0 || cycle + 1 == prm->max_cycle) {
+                    if (read_back(&status, &ws.state->status, sizeof(int), gst)) {
+                        grc = -2;
+                        break;
+                    }
+                    if (status != 0) break;
+                }
+            }
+        }
         if (grc != 0) {
             if (graph_exec) cudaGraphExecDestroy(graph_exec);
             if (graph) cudaGraphDestroy(graph);
