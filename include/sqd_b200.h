@@ -542,6 +542,15 @@ int sqd_recover(const uint64_t* d_left, const uint64_t* d_right, int64_t n, int 
                 uint64_t* d_left_out, uint64_t* d_right_out, int32_t* d_status, void* d_workspace,
                 int64_t workspace_bytes, void* stream);
 
+/* Duplicate merge of the repaired rows (configuration_recovery.py:112-126): the distinct (left, right) rows in
+ * first-seen order and, per distinct row, the probabilities of its occurrences added in input order starting
+ * from 0.0 (the reference's row-by-row `freqs[idx] += p`; bit-identical sums).  Outputs hold *h_n_unique
+ * entries.  Hash table over the rows, first occurrences ranked by a scan, members of a group sorted by row. */
+int64_t sqd_merge_rows_workspace_bytes(int64_t n);
+int sqd_merge_rows(const uint64_t* d_left, const uint64_t* d_right, int64_t n, const double* d_prob,
+                   uint64_t* d_out_left, uint64_t* d_out_right, double* d_out_sum, int32_t* h_n_unique,
+                   void* d_workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -257,6 +257,8 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_csr_davidson": (
         _i, [_i64, _vp, _vp, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _pi, _vp, _vp, _i64, _vp]
     ),
+    "sqd_merge_rows_workspace_bytes": (_i64, [_i64]),
+    "sqd_merge_rows": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "sqd_recover_workspace_bytes": (_i64, [_i64, _i]),
     "sqd_recover": (
         _i,

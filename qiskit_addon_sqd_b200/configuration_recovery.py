@@ -14,6 +14,7 @@ instead: same distribution, every row independent.
 
 from __future__ import annotations
 
+import ctypes as C
 import warnings
 from collections.abc import Sequence
 
@@ -128,25 +129,24 @@ def recover_configurations(
         _set_pcg64_words(rng, state_dev.cpu().numpy().view(np.uint64))
     if status_h[0] != 0:
         raise ValueError("Fewer non-zero entries in p than size")
-    lo = left_out.cpu().numpy().view(np.uint64)
-    ro = right_out.cpu().numpy().view(np.uint64)
-
-    # merge duplicates: first-seen order, probabilities summed in input order (:112-126)
-    if norb <= 32:
-        keys = (lo << np.uint64(norb)) | ro
-        _, first, inverse = np.unique(keys, return_index=True, return_inverse=True)
-    else:
-        keys2 = np.stack([lo, ro], axis=1)
-        _, first, inverse = np.unique(keys2, axis=0, return_index=True, return_inverse=True)
-        inverse = inverse.reshape(-1)
-    order = np.argsort(first, kind="stable")          # unique groups in first-seen order
-    rank = np.empty_like(order)
-    rank[order] = np.arange(len(order))
-    # np.bincount accumulates the weights of a bin in input order, one after the other: the same
-    # floating-point sums as the reference's row-by-row ``freqs[idx] += p`` (and as np.add.at, 10x slower)
-    sums = np.bincount(rank[inverse], weights=np.asarray(probabilities, dtype=np.float64),
-                       minlength=len(first)).astype(np.float64)
-    sel = first[order]
-    bs_mat_out = _unpack_halves(lo[sel], ro[sel], norb)
+    # merge duplicates on the device: distinct rows in first-seen order, probabilities of equal rows added in
+    # input order (:112-126); only the distinct rows and their sums come back
+    prob_dev = torch.from_numpy(np.ascontiguousarray(probabilities, dtype=np.float64).reshape(-1)).to(dev)
+    if prob_dev.numel() != n:
+        raise ValueError("probabilities must hold one entry per bitstring")
+    mws_bytes = lib.sqd_merge_rows_workspace_bytes(n)
+    mws = torch.empty(mws_bytes, dtype=torch.uint8, device=dev)
+    uniq_l = torch.empty(n, dtype=torch.int64, device=dev)
+    uniq_r = torch.empty(n, dtype=torch.int64, device=dev)
+    sums_dev = torch.empty(n, dtype=torch.float64, device=dev)
+    n_unique = C.c_int32(0)
+    _lib.check(lib.sqd_merge_rows(_lib.ptr(left_out), _lib.ptr(right_out), n, _lib.ptr(prob_dev), _lib.ptr(uniq_l),
+                                  _lib.ptr(uniq_r), _lib.ptr(sums_dev), C.byref(n_unique), _lib.ptr(mws), mws_bytes,
+                                  st), "sqd_merge_rows")
+    nu = int(n_unique.value)
+    lo = uniq_l[:nu].cpu().numpy().view(np.uint64)
+    ro = uniq_r[:nu].cpu().numpy().view(np.uint64)
+    sums = sums_dev[:nu].cpu().numpy()
+    bs_mat_out = _unpack_halves(lo, ro, norb)
     freqs_out = np.abs(sums) / np.sum(np.abs(sums))
     return bs_mat_out, freqs_out

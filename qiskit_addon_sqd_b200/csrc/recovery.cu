@@ -672,6 +672,116 @@ __global__ void recover_apply_kernel(const RecoverCtl* __restrict__ ctl, const u
     if (rec & 1) right_out[rec >> 1] = word; else left_out[rec >> 1] = word;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// duplicate merge (configuration_recovery.py:112-126): distinct repaired rows in first-seen order, the
+// probabilities of equal rows added IN INPUT ORDER (the reference's row-by-row `freqs[idx] += p`)
+// ---------------------------------------------------------------------------------------------
+constexpr int32_t kMergeEmpty = 0x7fffffff;
+
+__global__ void recover_fill_i32_kernel(int32_t* __restrict__ a, int64_t n, int32_t v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v;
+}
+
+__device__ __forceinline__ uint64_t merge_hash(uint64_t lo, uint64_t ro) {
+    uint64_t h = lo * 0x9E3779B97F4A7C15ull ^ (ro + 0x7F4A7C15ull) * 0xC2B2AE3D27D4EB4Full;
+    h ^= h >> 32;
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 29;
+    return h;
+}
+
+// open addressing over the rows themselves: a slot holds the index of a representative row; equal rows meet
+// in the same slot, which remembers their smallest index (first occurrence) and their number
+__global__ void merge_insert_kernel(const uint64_t* __restrict__ lo, const uint64_t* __restrict__ ro, int n,
+                                    int32_t* slot_rep, int32_t* slot_min, int32_t* slot_cnt,
+                                    int32_t* __restrict__ row_slot, uint32_t mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t l = lo[i], r = ro[i];
+    uint32_t s = (uint32_t)merge_hash(l, r) & mask;
+    for (;;) {
+        int32_t cur = *((volatile int32_t*)(slot_rep + s));
+        if (cur == kMergeEmpty) {
+            const int32_t old = atomicCAS(slot_rep + s, kMergeEmpty, (int32_t)i);
+            cur = old == kMergeEmpty ? i : old;
+        }
+        if (lo[cur] == l && ro[cur] == r) {
+            row_slot[i] = (int32_t)s;
+            atomicMin(slot_min + s, (int32_t)i);
+            atomicAdd(slot_cnt + s, 1);
+            return;
+        }
+        s = (s + 1) & mask;
+    }
+}
+
+__global__ void merge_flag_kernel(int n, const int32_t* __restrict__ row_slot, const int32_t* __restrict__ slot_min,
+                                  int32_t* __restrict__ is_first) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) is_first[i] = slot_min[row_slot[i]] == i ? 1 : 0;
+}
+
+// first occurrences, in input order = output order: rank r = number of first occurrences before row i
+__global__ void merge_groups_kernel(int n, const uint64_t* __restrict__ lo, const uint64_t* __restrict__ ro,
+                                    const int32_t* __restrict__ row_slot, const int32_t* __restrict__ is_first,
+                                    const int32_t* __restrict__ rank, const int32_t* __restrict__ slot_cnt,
+                                    int32_t* __restrict__ slot_rank, int32_t* __restrict__ gcnt,
+                                    uint64_t* __restrict__ out_lo, uint64_t* __restrict__ out_ro) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !is_first[i]) return;
+    const int r = rank[i], s = row_slot[i];
+    slot_rank[s] = r;
+    gcnt[r] = slot_cnt[s];
+    out_lo[r] = lo[i];
+    out_ro[r] = ro[i];
+}
+
+__global__ void merge_scatter_kernel(int n, const int32_t* __restrict__ row_slot, const int32_t* __restrict__ slot_rank,
+                                     const int32_t* __restrict__ goff, int32_t* gcur, int32_t* __restrict__ members) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int r = slot_rank[row_slot[i]];
+    members[goff[r] + atomicAdd(gcur + r, 1)] = i;   // arrival order: sorted by the summing kernel
+}
+
+// one warp per group: members sorted ascending (rank by counting), then ONE lane adds the probabilities in
+// that order, starting from 0.0 -- np.bincount's / the reference loop's floating-point sums
+__global__ void merge_sum_kernel(int n_groups, const int32_t* __restrict__ goff, const int32_t* __restrict__ gcnt,
+                                 const int32_t* __restrict__ members, int32_t* __restrict__ sorted,
+                                 const double* __restrict__ prob, double* __restrict__ sums) {
+    __shared__ double s_p[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nwarp = gridDim.x * (blockDim.x >> 5);
+    for (int g = blockIdx.x * (blockDim.x >> 5) + warp; g < n_groups; g += nwarp) {
+        const int off = goff[g], L = gcnt[g];
+        double acc = 0.0;
+        if (L <= 32) {
+            const int mine = lane < L ? members[off + lane] : 0x7fffffff;
+            int rk = 0;
+            for (int l = 0; l < L; ++l) rk += __shfl_sync(0xffffffffu, mine, l) < mine;
+            if (lane < L) s_p[warp][rk] = prob[mine];
+            __syncwarp();
+            if (lane == 0)
+                for (int k = 0; k < L; ++k) acc = __dadd_rn(acc, s_p[warp][k]);
+            __syncwarp();
+        } else {
+            for (int k = lane; k < L; k += 32) {
+                const int x = members[off + k];
+                int rk = 0;
+                for (int l = 0; l < L; ++l) rk += members[off + l] < x;
+                sorted[off + rk] = x;
+            }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0)
+                for (int k = 0; k < L; ++k) acc = __dadd_rn(acc, prob[sorted[off + k]]);
+        }
+        if (lane == 0) sums[g] = acc;
+    }
+}
+
 }  // namespace sqd
 
 using namespace sqd;
@@ -779,6 +889,63 @@ int sqd_recover(const uint64_t* d_left, const uint64_t* d_right, int64_t n, int 
     recover_select_parallel_kernel<<<(unsigned)((n + 7) / 8), 256, 0, st>>>(
         d_left, d_right, n, norb, hdr, cand, pc, cdf, seed, d_left_out, d_right_out, d_status);
     return check_launch("recover_select_parallel_kernel");
+}
+
+int64_t sqd_merge_rows_workspace_bytes(int64_t n) {
+    if (n < 0 || n >= 2147483647LL / 4) return -1;
+    int64_t cap = 1024;
+    while (cap < 2 * n) cap <<= 1;
+    // slot_rep, slot_min, slot_cnt, slot_rank | row_slot, is_first, rank(+1), gcnt(+1), goff(+1), gcur, members, sorted
+    return 4 * cap * 4 + (int64_t)(8 * (n + 1)) * 4 + 1024;
+}
+
+int sqd_merge_rows(const uint64_t* d_left, const uint64_t* d_right, int64_t n64, const double* d_prob,
+                   uint64_t* d_out_left, uint64_t* d_out_right, double* d_out_sum, int32_t* h_n_unique,
+                   void* d_workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SQD_REQUIRE(n64 >= 0 && workspace_bytes >= sqd_merge_rows_workspace_bytes(n64) &&
+                    sqd_merge_rows_workspace_bytes(n64) >= 0,
+                "sqd_merge_rows: bad size or workspace too small");
+    *h_n_unique = 0;
+    if (n64 == 0) return 0;
+    const int n = (int)n64;
+    int64_t cap = 1024;
+    while (cap < 2 * n64) cap <<= 1;
+    int32_t* p = (int32_t*)d_workspace;
+    int32_t* slot_rep = p;   p += cap;
+    int32_t* slot_min = p;   p += cap;
+    int32_t* slot_cnt = p;   p += cap;
+    int32_t* slot_rank = p;  p += cap;
+    int32_t* row_slot = p;   p += n + 1;
+    int32_t* is_first = p;   p += n + 1;
+    int32_t* rank = p;       p += n + 1;
+    int32_t* gcnt = p;       p += n + 1;
+    int32_t* goff = p;       p += n + 1;
+    int32_t* gcur = p;       p += n + 1;
+    int32_t* members = p;    p += n + 1;
+    int32_t* sorted = p;
+    // slot_rep and slot_min (adjacent) start at kMergeEmpty = INT_MAX
+    recover_fill_i32_kernel<<<(unsigned)((2 * cap + 255) / 256), 256, 0, st>>>(slot_rep, 2 * cap, kMergeEmpty);
+    SQD_CUDA_OK(cudaMemsetAsync(slot_cnt, 0, (size_t)cap * 4, st));
+    SQD_CUDA_OK(cudaMemsetAsync(gcur, 0, (size_t)(n + 1) * 4, st));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    merge_insert_kernel<<<nb, 256, 0, st>>>(d_left, d_right, n, slot_rep, slot_min, slot_cnt, row_slot,
+                                            (uint32_t)(cap - 1));
+    merge_flag_kernel<<<nb, 256, 0, st>>>(n, row_slot, slot_min, is_first);
+    if (check_launch("merge insert/flag kernels", 3)) return -2;
+    int n_unique = 0;
+    if (sqd_exclusive_scan(is_first, rank, n, &n_unique, stream)) return -2;
+    SQD_REQUIRE(n_unique > 0 && n_unique <= n, "sqd_merge_rows: inconsistent group count %d", n_unique);
+    merge_groups_kernel<<<nb, 256, 0, st>>>(n, d_left, d_right, row_slot, is_first, rank, slot_cnt, slot_rank, gcnt,
+                                            d_out_left, d_out_right);
+    if (check_launch("merge_groups_kernel")) return -2;
+    if (sqd_exclusive_scan(gcnt, goff, n_unique, nullptr, stream)) return -2;
+    merge_scatter_kernel<<<nb, 256, 0, st>>>(n, row_slot, slot_rank, goff, gcur, members);
+    const int blocks = (int)min((int64_t)kNumSMs * 8, ((int64_t)n_unique + 7) / 8);
+    merge_sum_kernel<<<blocks, 256, 0, st>>>(n_unique, goff, gcnt, members, sorted, d_prob, d_out_sum);
+    if (check_launch("merge scatter/sum kernels", 2)) return -2;
+    *h_n_unique = n_unique;
+    return 0;
 }
 
 }  // extern "C"
