@@ -332,7 +332,8 @@ constexpr int kMaxDraws = 96;    // draws a tabulated hypothesis may consume (mo
 constexpr int kUBuf = kHyp + kMaxDraws;
 constexpr uint8_t kTabOverflow = 255;   // hypothesis not tabulated: the walk samples the half-row itself
 constexpr uint8_t kTabFail = 254;       // numpy raises at this half-row
-constexpr int kWalkStages = 4;          // chunks of 32 table rows in flight (cp.async ring)
+constexpr int kChunksPerWin = kWinRecs / 32;
+constexpr int16_t kCompSpecial = 0x7FFF;   // chunk not composable for this hypothesis: the walk steps through it
 
 __device__ __forceinline__ u128 pcg_mult() {
     return ((u128)0x2360ED051FC65DA4ull << 64) | (u128)0x4385DF649FCCF645ull;
@@ -427,6 +428,10 @@ struct RecoverCtl {
     int32_t done;                  // 1: all half-rows walked (or numpy's error met)
     int32_t failed;
     int32_t pad;
+    // the window the walk has just finished, for the replay kernel that records the per-row offsets
+    int64_t w_r0, w_off0;
+    uint32_t w_rho;
+    int32_t w_rows;
 };
 
 __device__ __forceinline__ int drift_of(uint32_t rho, int j) { return (int)(((uint64_t)rho * (uint64_t)j) >> 16); }
@@ -518,19 +523,55 @@ recover_table_kernel(const RecoverCtl* __restrict__ ctl, int64_t recs, int norb,
     trow[e] = out;
 }
 
-// The sequential part: one warp, ONE shared-memory lookup per half-row on the critical path
-// (e += table[j][e] - drift increment).  The table rows stream through a ring of kWalkStages chunks of 32 rows
-// filled by cp.async, so the L2 latency of a chunk is hidden behind the walk of the chunks before it.  Records
-// the absolute stream offset of every half-row it passes, ends the window when the hypothesis index leaves
-// [0, kHyp) and re-bases.
+// Composition of the 32 transitions of a chunk, for all hypotheses at once: comp[chunk][e] = the index the
+// walk holds after the chunk's last half-row when it enters the chunk with e (may lie outside [0, kHyp): the
+// window then ends at the chunk boundary), or kCompSpecial when the path meets numpy's error, an untabulated
+// hypothesis or leaves the band inside the chunk.  One CTA per chunk, table slice in shared memory.
+__global__ void __launch_bounds__(kHyp)
+recover_compose_kernel(const RecoverCtl* __restrict__ ctl, int64_t recs, const uint8_t* __restrict__ table,
+                       int16_t* __restrict__ comp) {
+    if (ctl->done) return;
+    __shared__ __align__(16) uint8_t s_tab[32 * kHyp];
+    __shared__ int s_dc[32];
+    const int chunk = blockIdx.x, e0 = threadIdx.x;
+    const int64_t r0 = ctl->cursor;
+    const uint32_t rho = ctl->rho;
+    const int nwin = (int)((recs - r0) < kWinRecs ? (recs - r0) : kWinRecs);
+    const int rows = nwin - chunk * 32 < 32 ? nwin - chunk * 32 : 32;
+    if (rows <= 0) return;
+    const uint4* src = reinterpret_cast<const uint4*>(table + (int64_t)chunk * 32 * kHyp);
+    for (int i = e0; i < rows * (kHyp / 16); i += kHyp) reinterpret_cast<uint4*>(s_tab)[i] = src[i];
+    if (e0 < 32) s_dc[e0] = drift_of(rho, chunk * 32 + e0 + 1) - drift_of(rho, chunk * 32 + e0);
+    __syncthreads();
+    int e = e0;
+    bool special = false;
+    for (int jj = 0; jj < rows; ++jj) {
+        const int t = s_tab[jj * kHyp + e];
+        if (t >= kTabFail) {
+            special = true;
+            break;
+        }
+        e += t - s_dc[jj];
+        if ((unsigned)e >= (unsigned)kHyp && jj + 1 < rows) {
+            special = true;
+            break;
+        }
+    }
+    comp[chunk * kHyp + e0] = special ? kCompSpecial : (int16_t)e;
+}
+
+// The sequential part: one warp, ONE shared-memory lookup per CHUNK of 32 half-rows (the composed transitions);
+// chunks marked special for the current hypothesis are stepped through row by row.  Ends the window when the
+// hypothesis index leaves [0, kHyp) and re-bases.  e_start[chunk] = index at the chunk's first row, for the
+// replay kernel (-1: the walk recorded the offsets of that chunk itself, -2: not walked).
 __global__ void __launch_bounds__(32)
 recover_walk_kernel(RecoverCtl* ctl, int64_t recs, int norb, const HalfHeader* __restrict__ hdr,
                     const double* __restrict__ pc, const double* __restrict__ cdf,
                     const int32_t* __restrict__ kprefix, const uint8_t* __restrict__ table,
+                    const int16_t* __restrict__ comp, int16_t* __restrict__ e_start,
                     uint64_t* __restrict__ rng_state, int64_t* __restrict__ off_abs, int32_t* __restrict__ status) {
     if (ctl->done) return;
-    __shared__ __align__(16) uint8_t s_tab[kWalkStages][32 * kHyp];
-    __shared__ int s_dc[kWalkStages][32];
+    __shared__ __align__(16) int16_t s_comp[kChunksPerWin * kHyp];
     __shared__ double s_cdf[64];
     const int lane = threadIdx.x & 31;
     const int64_t r0 = ctl->cursor;
@@ -540,37 +581,33 @@ recover_walk_kernel(RecoverCtl* ctl, int64_t recs, int norb, const HalfHeader* _
     const int64_t off0 = ctl->offset;
     const int nwin = (int)((recs - r0) < kWinRecs ? (recs - r0) : kWinRecs);
     const int nchunks = (nwin + 31) / 32;
-    auto stage = [&](int chunk) {   // 32 table rows = 8 KB, 16 asynchronous 16-byte copies per lane
-        if (chunk < nchunks) {
-            const int buf = chunk % kWalkStages;
-            const int rows = nwin - chunk * 32 < 32 ? nwin - chunk * 32 : 32;
-            const uint8_t* src = table + (int64_t)chunk * 32 * kHyp;
-            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_tab[buf]);
-            for (int i = lane; i < rows * (kHyp / 16); i += 32)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * i), "l"(src + 16 * i));
-            const int jg = chunk * 32 + lane;
-            s_dc[buf][lane] = drift_of(rho, jg + 1) - drift_of(rho, jg);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");   // (an empty group keeps the count uniform)
-    };
+    for (int i = lane; i < nchunks * (kHyp / 8); i += 32)
+        reinterpret_cast<uint4*>(s_comp)[i] = reinterpret_cast<const uint4*>(comp)[i];
+    for (int c = lane; c < kChunksPerWin; c += 32) e_start[c] = -2;
+    __syncwarp();
     int e = kHyp / 2;        // hypothesis index of the current half-row
     int j = 0;               // half-rows walked
     bool failed = false, out_of_band = false;
-    for (int c = 0; c < kWalkStages - 1; ++c) stage(c);
     for (int chunk = 0; chunk < nchunks && !out_of_band && !failed; ++chunk) {
-        const int buf = chunk % kWalkStages;
-        stage(chunk + kWalkStages - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(kWalkStages - 1) : "memory");   // chunk `chunk` has landed
-        __syncwarp();
         const int rows = nwin - chunk * 32 < 32 ? nwin - chunk * 32 : 32;
-        int e_mine = 0;      // lane jj remembers the index the walk held at row jj of the chunk
-        int done_rows = 0;
+        const int v = s_comp[chunk * kHyp + e];
+        if (v != kCompSpecial) {
+            if (lane == 0) e_start[chunk] = (int16_t)e;
+            e = v;
+            j += rows;
+            if ((unsigned)e >= (unsigned)kHyp) out_of_band = true;
+            continue;
+        }
+        // special chunk: row by row, table entries straight from global memory
+        if (lane == 0) e_start[chunk] = -1;
+        int e_mine = 0, done_rows = 0;
         for (int jj = 0; jj < rows; ++jj) {
             if (lane == jj) e_mine = e;
             done_rows = jj + 1;
-            int extra = s_tab[buf][jj * kHyp + e];
+            const int jg = chunk * 32 + jj;
+            const int64_t rec = r0 + jg;
+            int extra = table[(int64_t)jg * kHyp + e];
             if (extra >= kTabFail) {
-                const int64_t rec = r0 + chunk * 32 + jj;
                 if (extra == kTabFail) {   // numpy raises here: the generator has consumed everything before it
                     failed = true;
                     if (lane == 0) {
@@ -580,7 +617,6 @@ recover_walk_kernel(RecoverCtl* ctl, int64_t recs, int norb, const HalfHeader* _
                     break;
                 }
                 // not tabulated (many retries): sample this half-row here, as the round-1 kernel did
-                const int jg = chunk * 32 + jj;
                 const HalfHeader h = hdr[rec];
                 const int k = h.n_diff > 0 ? h.n_diff : -h.n_diff;
                 const int64_t off_rel = (int64_t)(kprefix[rec] - kprefix[r0]) + drift_of(rho, jg) + e - kHyp / 2;
@@ -602,14 +638,13 @@ recover_walk_kernel(RecoverCtl* ctl, int64_t recs, int norb, const HalfHeader* _
                 }
                 extra = used - k;
             }
-            e += extra - s_dc[buf][jj];
+            e += extra - (drift_of(rho, jg + 1) - drift_of(rho, jg));
             ++j;
             if ((unsigned)e >= (unsigned)kHyp) {
                 out_of_band = true;
                 break;
             }
         }
-        // stream offsets of the rows of this chunk, in parallel
         if (lane < done_rows) {
             const int jg = chunk * 32 + lane;
             const int64_t rec = r0 + jg;
@@ -617,7 +652,12 @@ recover_walk_kernel(RecoverCtl* ctl, int64_t recs, int norb, const HalfHeader* _
         }
         __syncwarp();
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (lane == 0) {
+        ctl->w_r0 = r0;
+        ctl->w_off0 = off0;
+        ctl->w_rho = rho;
+        ctl->w_rows = j;
+    }
     // j half-rows walked (a failing one not counted); e is the hypothesis index AT half-row r0 + j in every
     // exit path, i.e. draws consumed beyond the collision-free count = drift_j + e - kHyp/2
     const int64_t next = r0 + j;
@@ -640,6 +680,36 @@ recover_walk_kernel(RecoverCtl* ctl, int64_t recs, int norb, const HalfHeader* _
             rng_state[0] = (uint64_t)(st >> 64);   // the caller's generator continues from here
             rng_state[1] = (uint64_t)st;
         }
+    }
+}
+
+// Stream offsets of the half-rows of the chunks the walk crossed in one lookup: one warp per chunk repeats the
+// chunk's 32 transitions from the recorded entry index (64 chunks in parallel, table slice in shared memory).
+__global__ void __launch_bounds__(32)
+recover_replay_kernel(const RecoverCtl* __restrict__ ctl, const int32_t* __restrict__ kprefix,
+                      const uint8_t* __restrict__ table, const int16_t* __restrict__ e_start,
+                      int64_t* __restrict__ off_abs) {
+    __shared__ __align__(16) uint8_t s_tab[32 * kHyp];
+    const int chunk = blockIdx.x, lane = threadIdx.x & 31;
+    const int es = e_start[chunk];
+    const int rows_walked = ctl->w_rows;
+    if (es < 0 || chunk * 32 >= rows_walked) return;
+    const int64_t r0 = ctl->w_r0, off0 = ctl->w_off0;
+    const uint32_t rho = ctl->w_rho;
+    const int rows = rows_walked - chunk * 32 < 32 ? rows_walked - chunk * 32 : 32;
+    const uint4* src = reinterpret_cast<const uint4*>(table + (int64_t)chunk * 32 * kHyp);
+    for (int i = lane; i < rows * (kHyp / 16); i += 32) reinterpret_cast<uint4*>(s_tab)[i] = src[i];
+    __syncwarp();
+    int e = es, e_mine = 0;
+    for (int jj = 0; jj < rows; ++jj) {
+        if (lane == jj) e_mine = e;
+        const int jg = chunk * 32 + jj;
+        e += (int)s_tab[jj * kHyp + e] - (drift_of(rho, jg + 1) - drift_of(rho, jg));
+    }
+    if (lane < rows) {
+        const int jg = chunk * 32 + lane;
+        const int64_t rec = r0 + jg;
+        off_abs[rec] = off0 + (int64_t)(kprefix[rec] - kprefix[r0]) + drift_of(rho, jg) + e_mine - kHyp / 2;
     }
 }
 
@@ -801,6 +871,7 @@ int64_t sqd_recover_workspace_bytes(int64_t n, int norb) {
     b += 2 * (((recs + 1) * 4 + 255) / 256) * 256;
     b += ((recs * 8 + 255) / 256) * 256;
     b += (int64_t)kWinRecs * kHyp + 2 * (int64_t)kUBuf * 16 + 512;
+    b += (int64_t)kChunksPerWin * kHyp * 2 + 256;   // composed transitions + chunk entry indices
     return b + 256;
 }
 
@@ -857,6 +928,8 @@ int sqd_recover(const uint64_t* d_left, const uint64_t* d_right, int64_t n, int 
         p += (int64_t)kUBuf * 16;
         RecoverCtl* ctl = (RecoverCtl*)p;
         uint64_t* init_state = (uint64_t*)(p + 256);
+        int16_t* comp = (int16_t*)(p + 512);
+        int16_t* e_start = comp + (int64_t)kChunksPerWin * kHyp;
         recover_counts_kernel<<<(unsigned)((recs + 255) / 256), 256, 0, st>>>(hdr, recs, kq, kcount);
         if (check_launch("recover_counts_kernel")) return -2;
         if (sqd_exclusive_scan(kcount, kprefix, (int)recs, nullptr, stream)) return -2;
@@ -871,10 +944,12 @@ int sqd_recover(const uint64_t* d_left, const uint64_t* d_right, int64_t n, int 
             for (int64_t w = 0; w < batch; ++w) {
                 recover_table_kernel<<<kWinRecs, kHyp, 0, st>>>(ctl, recs, norb, hdr, pc, cdf, kprefix, d_rng_state,
                                                                skipM, skipP, table);
-                recover_walk_kernel<<<1, 32, 0, st>>>(ctl, recs, norb, hdr, pc, cdf, kprefix, table, d_rng_state,
-                                                      off_abs, d_status);
+                recover_compose_kernel<<<kChunksPerWin, kHyp, 0, st>>>(ctl, recs, table, comp);
+                recover_walk_kernel<<<1, 32, 0, st>>>(ctl, recs, norb, hdr, pc, cdf, kprefix, table, comp, e_start,
+                                                      d_rng_state, off_abs, d_status);
+                recover_replay_kernel<<<kChunksPerWin, 32, 0, st>>>(ctl, kprefix, table, e_start, off_abs);
             }
-            if (check_launch("recover table/walk kernels", (int)(2 * batch))) return -2;
+            if (check_launch("recover table/compose/walk/replay kernels", (int)(4 * batch))) return -2;
             launched += batch;
             RecoverCtl h_ctl;
             if (read_back(&h_ctl, ctl, sizeof(RecoverCtl), st)) return -2;
