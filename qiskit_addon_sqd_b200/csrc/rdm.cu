@@ -157,10 +157,15 @@ pair_dots_kernel(const sqd_spin_table T, const int* __restrict__ erow, int nnz, 
 }
 
 constexpr int kD2Threads = 256;
-constexpr int kD2Cap = 2048;
+constexpr int kD2Cap = 2048;   // entries per segment = capacity of the match list: a segment never overflows it
 
 // One CTA per row [P,Q,:,:] of the same-spin dm2.  Writes the WHOLE row (zeros included), so it runs
 // before the singles / diagonal kernels, which then overwrite their own (disjoint) cells.
+// The table is scanned in segments of kD2Cap entries: threads append their matches to a shared list without
+// any barrier (arrival order), then the list is put in entry order by rank counting and every cell's owner
+// thread adds its contributions in that order -- every cell sees its contributions in ascending table order,
+// whatever the arrival order was (bit-reproducible).  Four barriers per segment; the first version compacted
+// with a ballot scan and three barriers per 256 entries, which was most of its 130 us.
 __global__ void __launch_bounds__(kD2Threads)
 rdm2_doubles_kernel(const uint32_t* __restrict__ dinfo, const double* __restrict__ dots, int nnz, int norb,
                     double* __restrict__ dm2) {
@@ -169,69 +174,52 @@ rdm2_doubles_kernel(const uint32_t* __restrict__ dinfo, const double* __restrict
     double* acc = reinterpret_cast<double*>(smem_raw);   // [n2]
     double* lval = acc + n2;                              // [kD2Cap]
     int* lcell = reinterpret_cast<int*>(lval + kD2Cap);   // [kD2Cap]
-    __shared__ int wcnt[kD2Threads / 32];
+    int* lent = lcell + kD2Cap;                           // [kD2Cap] table entry of the match
+    int* order = lent + kD2Cap;                           // [kD2Cap] list position of the r-th match in entry order
     __shared__ int list_n;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int P = blockIdx.x / norb, Q = blockIdx.x % norb;
     for (int c = tid; c < n2; c += kD2Threads) acc[c] = 0.0;
     if (tid == 0) list_n = 0;
     __syncthreads();
-    auto flush = [&]() {
-        const int ln = list_n;
-        for (int k = 0; k < ln; ++k) {
-            const int c = lcell[k];
-            if ((c & (kD2Threads - 1)) == tid) acc[c] += lval[k];  // cell owner: fixed thread, list order
-        }
-        __syncthreads();
-        if (tid == 0) list_n = 0;
-        __syncthreads();
-    };
     if (P != Q) {
-        for (int e0 = 0; e0 < nnz; e0 += kD2Threads) {
-            const int e = e0 + tid;
-            bool match = false;
-            int cell = 0;
-            double val = 0.0;
-            if (e < nnz) {
+        for (int seg = 0; seg < nnz; seg += kD2Cap) {
+            const int seg_end = seg + kD2Cap < nnz ? seg + kD2Cap : nnz;
+            for (int e = seg + tid; e < seg_end; e += kD2Threads) {
                 const uint32_t info = __ldg(dinfo + e);
-                if (info != kNotDouble) {
-                    const int a1 = info & 63, a2 = (info >> 6) & 63, i1 = (info >> 12) & 63,
-                              i2 = (info >> 18) & 63;
-                    const int pa = P == a1 ? 0 : (P == a2 ? 1 : -1);
-                    const int qi = Q == i1 ? 0 : (Q == i2 ? 1 : -1);
-                    if (pa >= 0 && qi >= 0) {
-                        // [a1,i1,a2,i2] carries the table phase; swapping the creators or the
-                        // annihilators flips the sign
-                        const int R = pa ? a1 : a2, S = qi ? i1 : i2;
-                        const int neg = (int)(info >> 31) ^ pa ^ qi;
-                        const double d = __ldg(dots + e);
-                        match = true;
-                        cell = R * norb + S;
-                        val = neg ? -d : d;
-                    }
-                }
-            }
-            const uint32_t bal = __ballot_sync(0xffffffffu, match);
-            if (lane == 0) wcnt[warp] = __popc(bal);
-            __syncthreads();
-            int woff = 0, total = 0;
-#pragma unroll
-            for (int w = 0; w < kD2Threads / 32; ++w) {
-                if (w < warp) woff += wcnt[w];
-                total += wcnt[w];
-            }
-            if (list_n + total > kD2Cap) flush();  // uniform decision; flush ends with a barrier
-            const int base = list_n;
-            if (match) {
-                const int o = base + woff + __popc(bal & ((1u << lane) - 1u));
-                lcell[o] = cell;
-                lval[o] = val;
+                if (info == kNotDouble) continue;
+                const int a1 = info & 63, a2 = (info >> 6) & 63, i1 = (info >> 12) & 63, i2 = (info >> 18) & 63;
+                const int pa = P == a1 ? 0 : (P == a2 ? 1 : -1);
+                const int qi = Q == i1 ? 0 : (Q == i2 ? 1 : -1);
+                if (pa < 0 || qi < 0) continue;
+                // [a1,i1,a2,i2] carries the table phase; swapping the creators or the annihilators flips
+                // the sign
+                const int R = pa ? a1 : a2, S = qi ? i1 : i2;
+                const int neg = (int)(info >> 31) ^ pa ^ qi;
+                const double d = __ldg(dots + e);
+                const int o = atomicAdd(&list_n, 1);
+                lent[o] = e;
+                lcell[o] = R * norb + S;
+                lval[o] = neg ? -d : d;
             }
             __syncthreads();
-            if (tid == 0) list_n = base + total;
+            const int ln = list_n;
+            for (int k = tid; k < ln; k += kD2Threads) {
+                const int ek = lent[k];
+                int r = 0;
+                for (int l = 0; l < ln; ++l) r += lent[l] < ek;
+                order[r] = k;
+            }
+            __syncthreads();
+            for (int r = 0; r < ln; ++r) {
+                const int k = order[r];
+                const int c = lcell[k];
+                if ((c & (kD2Threads - 1)) == tid) acc[c] += lval[k];  // cell owner: fixed thread, entry order
+            }
+            __syncthreads();
+            if (tid == 0) list_n = 0;
             __syncthreads();
         }
-        flush();
     }
     double* row = dm2 + (size_t)blockIdx.x * n2;
     for (int c = tid; c < n2; c += kD2Threads) row[c] = acc[c];
@@ -530,7 +518,7 @@ static int rdm2_same_spin(const sqd_spin_table& T, int64_t nnz, const double* x,
         const int blocks = (int)((nnz + 7) / 8 < kNumSMs * 8 ? (nnz + 7) / 8 : kNumSMs * 8);
         pair_dots_kernel<<<blocks, 256, 0, st>>>(T, erow, (int)nnz, x, ncols, ldx, dots, dinfo);
     }
-    const size_t smem = (size_t)n2 * sizeof(double) + kD2Cap * (sizeof(double) + sizeof(int));
+    const size_t smem = (size_t)n2 * sizeof(double) + kD2Cap * (sizeof(double) + 3 * sizeof(int));
     static bool cfg[64] = {false};
     if (big_smem(rdm2_doubles_kernel, smem, cfg)) return -2;
     rdm2_doubles_kernel<<<n2, kD2Threads, smem, st>>>(dinfo, dots, (int)nnz, norb, dm2);
