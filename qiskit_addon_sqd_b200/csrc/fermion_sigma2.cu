@@ -1079,7 +1079,9 @@ static int v2_num_split(int na, int nb, int ldc) {
     static const int knob_split = v2_env("SQD_V2_SPLIT", 0);
     const int tiles = ((na + 1 + kTM - 1) / kTM) * ((ldc + kTN - 1) / kTN);
     const int ntk = (na + kKT - 1) / kKT + (nb + kKT - 1) / kKT;
-    int ns = knob_split > 0 ? knob_split : (2 * kNumSMs) / (tiles > 0 ? tiles : 1);
+    // one CTA per SM: more splits shorten a lone build by a microsecond but cost partial-tile traffic (K2 writes,
+    // K3 reads ns x n_det x 8 bytes) and SM time when several solves share the GPU (bench step 11.7 -> 11.1 ms)
+    int ns = knob_split > 0 ? knob_split : kNumSMs / (tiles > 0 ? tiles : 1);
     if (ns > ntk / 2) ns = ntk / 2;
     if (ns > 32) ns = 32;
     return ns < 1 ? 1 : ns;
