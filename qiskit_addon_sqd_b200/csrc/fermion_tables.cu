@@ -219,12 +219,8 @@ __global__ void excitation_values_kernel(const uint64_t* __restrict__ strs, int 
                                          double* __restrict__ val, double* __restrict__ diag) {
     const bool have_ints = (h != nullptr) && (g != nullptr);  // structure-only tables when NULL
     const int nnz = row_ptr[n];
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz + n; e += gridDim.x * blockDim.x) {
-        if (e >= nnz) {
-            const int i = e - nnz;
-            diag[i] = have_ints ? diagonal_element(strs[i], norb, h, g) : 0.0;
-            continue;
-        }
+    (void)diag;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nnz; e += gridDim.x * blockDim.x) {
         if (!have_ints) {
             val[e] = 0.0;
             continue;
@@ -244,6 +240,46 @@ __global__ void excitation_values_kernel(const uint64_t* __restrict__ strs, int 
             val[e] = double_element(s, t, norb, g);
         }
     }
+}
+
+// Same-spin diagonal elements, one WARP per string: the n_elec^2 integral loads of a string are spread over the
+// lanes, the additions are made in the order of diagonal_element() (every lane repeats them on shuffled terms),
+// so the values are the sequential ones bit for bit.  (One thread per string -- 2 n_elec^2 dependent loads --
+// was the long pole of the table set-up: 60 us at 15 electrons.)
+__global__ void excitation_diag_kernel(const uint64_t* __restrict__ strs, int n, int norb,
+                                       const double* __restrict__ h, const double* __restrict__ g,
+                                       double* __restrict__ diag) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i >= n) return;
+    if (h == nullptr || g == nullptr) {
+        if (lane == 0) diag[i] = 0.0;
+        return;
+    }
+    const uint64_t s = strs[i];
+    const int ne = popc64(s);
+    // lane l holds the l-th and the (l+32)-th occupied orbital (ascending)
+    int o_lo = 0, o_hi = 0;
+    {
+        uint64_t occ = s;
+        for (int k = 0; occ; ++k) {
+            const int p = lowbit64(occ);
+            occ &= occ - 1;
+            if (k == lane) o_lo = p;
+            if (k == lane + 32) o_hi = p;
+        }
+    }
+    const int64_t n1 = norb, n2 = n1 * n1, n3 = n2 * n1;
+    double e = 0.0;
+    for (int ii = 0; ii < ne; ++ii) {
+        const int p = __shfl_sync(0xffffffffu, ii < 32 ? o_lo : o_hi, ii & 31);
+        double t_lo = 0.0, t_hi = 0.0;
+        if (lane < ne) t_lo = 0.5 * (g[p * n3 + p * n2 + o_lo * n1 + o_lo] - g[p * n3 + o_lo * n2 + o_lo * n1 + p]);
+        if (lane + 32 < ne) t_hi = 0.5 * (g[p * n3 + p * n2 + o_hi * n1 + o_hi] - g[p * n3 + o_hi * n2 + o_hi * n1 + p]);
+        e += h[p * n1 + p];
+        for (int k = 0; k < ne; ++k) e += __shfl_sync(0xffffffffu, k < 32 ? t_lo : t_hi, k & 31);
+    }
+    if (lane == 0) diag[i] = e;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -378,7 +414,8 @@ int sqd_excitation_fill(const uint64_t* d_strs, int n, int norb, const double* d
     const int blocks = (int)min((int64_t)kNumSMs * 8, (guess + 255) / 256);
     excitation_values_kernel<<<blocks, 256, 0, st>>>(d_strs, n, norb, d_h, d_g, d_row_ptr, d_n_single, d_col, d_meta,
                                                     d_val, d_diag);
-    return check_launch("excitation fill/values kernels", 2);
+    excitation_diag_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, st>>>(d_strs, n, norb, d_h, d_g, d_diag);
+    return check_launch("excitation fill/values/diag kernels", 3);
 }
 
 int sqd_make_gab(const double* d_g, int norb, double shift, int mode, double* d_gab, int ldg,

@@ -499,7 +499,8 @@ static int big_smem(K kern, size_t smem, bool* cfg) {
         int dev = 0;
         SQD_CUDA_OK(cudaGetDevice(&dev));
         if (dev < 0 || dev >= 64 || !cfg[dev]) {
-            SQD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+            // (a kernel's static shared memory counts against the same 227 KB: leave it 2 KB)
+            SQD_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(225 * 1024)));
             if (dev >= 0 && dev < 64) cfg[dev] = true;
         }
     }
@@ -575,7 +576,7 @@ extern "C" int sqd_rdm2s(const sqd_operator* op, const double* d_c, int64_t nnz_
     // opposite spin
     const size_t smem_rows = (size_t)ldc * sizeof(double);
     const size_t smem_ab = (size_t)(2 * ldc + n2) * sizeof(double);
-    SQD_REQUIRE(smem_ab <= 227 * 1024, "sqd_rdm2s: nb=%d, norb=%d do not fit the shared-memory row staging",
+    SQD_REQUIRE(smem_ab <= 225 * 1024, "sqd_rdm2s: nb=%d, norb=%d do not fit the shared-memory row staging",
                 nb, norb);
     static bool cfg_rows[64] = {false}, cfg_ab[64] = {false};
     if (big_smem(rdm2_ab_rows_kernel, smem_rows, cfg_rows)) return -2;
