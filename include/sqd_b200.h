@@ -197,6 +197,8 @@ typedef struct {
     sqd_sell bb;             /* every beta entry with its same-spin value (mode 1) */
     int throughput_mode;     /* see sqd_solve_params.throughput_mode */
     sqd_sigma_v2 v2;         /* v2.enabled != 0: sqd_sigma runs the v2 kernels */
+    int wide;                /* != 0 (and v2 disabled): the staging-free "wide" kernel -- any nb up to the 2^19
+                                strings of the tables; needs neither plan nor SELL copies */
 } sqd_operator;
 
 /* Build the v2 structures of a subspace (operator independent: shared by the Hamiltonian and S^2).
@@ -241,6 +243,11 @@ int sqd_sigma_plan_build(const sqd_spin_table* a, const sqd_spin_table* b, int c
                    int* d_chunk_end, int* d_chunk_slot, int* d_split_row, int* d_split_slot_beg,
                    int* d_split_n, int* d_long_idx, int* d_long_cols, int* d_counts, int* h_counts,
                    void* stream);
+
+/* 1 when CI rows of ldc doubles and integral rows of ldg doubles fit the shared-memory staging of the v1
+ * kernels (nb <= 5760 at 30 orbitals); 0: only the wide kernel (sqd_operator.wide) applies.  pyscf's
+ * contract_2e has no such limit (fermion.py:721-723 reaches it for any subspace size). */
+int sqd_sigma_v1_supported(int ldc, int ldg);
 
 /* Dynamic shared memory the sigma kernel needs for this operator, or <0 if the shape is unsupported. */
 int64_t sqd_sigma_smem_bytes(const sqd_operator* op);
@@ -344,7 +351,9 @@ typedef struct {
                                     kernel is launched under a register cap that lets three of its CTAs
                                     share an SM -- slower alone, faster in aggregate */
     int sigma_path;              /* 0: choose by table density (sqd_sigma_v2_recommended); 1: v1 kernels;
-                                    2: v2 kernels whenever their planner accepts the shape */
+                                    2: v2 kernels whenever their planner accepts the shape; 3: the wide
+                                    kernel.  Rows too long for the staged kernels (nb > 8192 for v2, > 5760
+                                    for v1) take the wide kernel whatever is asked for */
     int v2_lmax, v2_items_per_chunk; /* v2 tuning, 0 = defaults (16, 8) */
 } sqd_solve_params;
 
@@ -357,7 +366,7 @@ typedef struct {
     int64_t nnz_a, nnz_b;        /* entries of the two excitation tables */
     int64_t singles_a, singles_b;/* profile != 0: single excitations among them, else -1 */
     int ldc;                     /* row stride of d_x */
-    int sigma_path;              /* 1 / 2: the sigma kernels that ran */
+    int sigma_path;              /* 1 / 2 / 3: the sigma kernels that ran (v1, v2, wide) */
 } sqd_solve_result;
 
 /* d_x: double[na * ldc], ldc = nb rounded up to even, receives the normalised ground state (pad columns
@@ -550,6 +559,30 @@ int64_t sqd_merge_rows_workspace_bytes(int64_t n);
 int sqd_merge_rows(const uint64_t* d_left, const uint64_t* d_right, int64_t n, const double* d_prob,
                    uint64_t* d_out_left, uint64_t* d_out_right, double* d_out_sum, int32_t* h_n_unique,
                    void* d_workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------ *
+ * Sample formats   (counts.py:45-61 bit_array_to_arrays; qubit.py:147-164 sort_and_remove_duplicates and
+ *                   the np.unique of solve_qubit, qubit.py:66)
+ * A bitstring of up to 128 bits travels as a (hi, lo) pair of 64-bit words, column 0 of the bool matrix = most
+ * significant bit, so numpy's lexicographic row order is the numeric order of the pair.
+ * ------------------------------------------------------------------------------------------ */
+/* Distinct keys in ascending order with their multiplicities (np.unique(..., return_counts=True)).
+ * d_hi == NULL: 64-bit keys (d_out_hi may then be NULL too).  d_out_*: n entries; d_out_count may be NULL.
+ * *h_n_unique receives the number of distinct keys.  Bitonic sort in a padded copy inside the workspace
+ * (inputs are not modified).  Synchronises the stream. */
+int64_t sqd_sort_unique_workspace_bytes(int64_t n);
+int sqd_sort_unique(const uint64_t* d_hi, const uint64_t* d_lo, int64_t n, uint64_t* d_out_hi,
+                    uint64_t* d_out_lo, int32_t* d_out_count, int64_t* h_n_unique, void* d_workspace,
+                    int64_t workspace_bytes, void* stream);
+
+/* Rows of a sampled bit array (qiskit BitArray.array: uint8, big-endian, left-padded, row_bytes per shot) ->
+ * (hi, lo); bits beyond num_bits are masked off (counts.py:57).  num_bits <= 128; d_hi may be NULL up to 64. */
+int sqd_bit_array_pack(const uint8_t* d_bytes, int64_t n, int row_bytes, int num_bits, uint64_t* d_hi,
+                       uint64_t* d_lo, void* stream);
+
+/* (hi, lo) -> bool matrix rows of num_bits columns (1 byte per bit, column 0 = most significant bit). */
+int sqd_keys_to_bits(const uint64_t* d_hi, const uint64_t* d_lo, int64_t n, int num_bits, uint8_t* d_bits,
+                     void* stream);
 
 #ifdef __cplusplus
 }

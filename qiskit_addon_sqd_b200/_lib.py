@@ -96,6 +96,7 @@ class Operator(C.Structure):
         ("bb", Sell),
         ("throughput_mode", C.c_int),
         ("v2", SigmaV2),
+        ("wide", C.c_int),
     ]
 
 
@@ -191,6 +192,7 @@ SIGNATURES: dict[str, tuple] = {
         _i,
         [_vp, _i, _vp, _i, _i, _vp, _i, _vp, _vp, _d, _d, _vp, _vp, _vp, _i, _vp],
     ),
+    "sqd_sigma_v1_supported": (_i, [_i, _i]),
     "sqd_sigma_smem_bytes": (_i64, [C.POINTER(Operator)]),
     "sqd_sigma": (_i, [C.POINTER(Operator), _vp, _vp, _vp]),
     "sqd_sigma_rows": (_i, [C.POINTER(Operator), _vp, _vp, _i, _i, _vp]),
@@ -259,6 +261,10 @@ SIGNATURES: dict[str, tuple] = {
     ),
     "sqd_merge_rows_workspace_bytes": (_i64, [_i64]),
     "sqd_merge_rows": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "sqd_sort_unique_workspace_bytes": (_i64, [_i64]),
+    "sqd_sort_unique": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp, _i64, _vp]),
+    "sqd_bit_array_pack": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
+    "sqd_keys_to_bits": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "sqd_recover_workspace_bytes": (_i64, [_i64, _i]),
     "sqd_recover": (
         _i,
@@ -353,3 +359,24 @@ def download(torch, t):
 
 _NP_DTYPES = {"torch.float64": "float64", "torch.int64": "int64", "torch.int32": "int32", "torch.uint8": "uint8",
               "torch.float32": "float32", "torch.bool": "bool", "torch.int16": "int16", "torch.int8": "int8"}
+
+
+def sort_unique(torch, hi, lo, with_counts: bool = False):
+    """Distinct keys of ``(hi, lo)`` (int64 device tensors holding uint64 words; ``hi=None``: 64-bit keys) in
+    ascending unsigned order, optionally with multiplicities (``sqd_sort_unique``: bitonic sort + run heads).
+    Returns ``(hi_unique | None, lo_unique, counts | None)`` as device tensors of the distinct length."""
+    lib = load()
+    n = int(lo.numel())
+    dev = lo.device
+    out_lo = torch.empty(n, dtype=torch.int64, device=dev)
+    out_hi = torch.empty(n, dtype=torch.int64, device=dev) if hi is not None else None
+    cnt = torch.empty(n, dtype=torch.int32, device=dev) if with_counts else None
+    ws_bytes = int(lib.sqd_sort_unique_workspace_bytes(n))
+    if ws_bytes < 0:
+        raise ValueError(f"sort_unique: {n} keys are beyond the 2^30 this library sorts")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    n_unique = C.c_int64(0)
+    check(lib.sqd_sort_unique(ptr(hi), ptr(lo), n, ptr(out_hi), ptr(out_lo), ptr(cnt), C.byref(n_unique),
+                              ptr(ws), ws_bytes, stream_ptr(torch)), "sqd_sort_unique")
+    nu = int(n_unique.value)
+    return (out_hi[:nu] if out_hi is not None else None, out_lo[:nu], cnt[:nu] if cnt is not None else None)

@@ -396,6 +396,101 @@ __device__ __forceinline__ int snake_chunk(int k) {
     return (k & 1) ? (k + 1) * (int)gridDim.x - 1 - (int)blockIdx.x : k * (int)gridDim.x + (int)blockIdx.x;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// "Wide" kernel: the same sum as kernels B + A, for subspaces whose rows do not fit the shared-memory
+// staging of the kernels above (nb > 5760 for v1, nb > 8192 for v2) -- up to the 2^19 strings per spin of
+// the tables.  Nothing is staged: CTA = one alpha row x kWideCols consecutive columns, thread = one
+// column, every operand is gathered through L1/L2 (an integral row g_ab[pq,:] is shared by the whole CTA,
+// the rows c[a',:] by the CTAs of one alpha row).  kWideBlock alpha single excitations share one pass
+// over the column's beta links (one load of the link word for kWideBlock FMAs, kWideBlock independent
+// accumulation chains).  No plan, no SELL copies; every element is summed by one thread in table order,
+// so builds restricted to row blocks are bit-equal to the full build.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kWideCols = 256;
+constexpr int kWideBlock = 4;
+
+__global__ void __launch_bounds__(kWideCols)
+sigma_wide_kernel(const SigmaArgs P) {
+    if (P.done != nullptr && *P.done != 0) return;
+    const double* __restrict__ c = P.c + slot_offset(P.slot_ptr, P.vec_stride);
+    double* __restrict__ sig = P.sigma + slot_offset(P.slot_ptr, P.vec_stride);
+    const sqd_operator& op = P.op;
+    const int nb = op.b.n, ldc = op.ldc, ldg = op.ldg;
+    const int a = P.row_begin + (int)blockIdx.x;
+    const int b = (int)blockIdx.y * kWideCols + (int)threadIdx.x;
+    if (a >= P.row_end || b >= ldc) return;
+    if (b >= nb) {  // pad column
+        sig[(size_t)a * ldc + b] = 0.0;
+        return;
+    }
+    const bool ham = op.use_same_spin != 0;
+    const double* __restrict__ crow = c + (size_t)a * ldc;
+    double acc = __ldg(op.diag + (size_t)a * ldc + b) * crow[b];
+
+    // beta excitations of column b: singles carry Hb + sgn_b Wa[a, rs], doubles Hb
+    const int fb = __ldg(op.b.row_ptr + b), fs = fb + __ldg(op.b.n_single + b), fe = __ldg(op.b.row_ptr + b + 1);
+    const double* __restrict__ wa = op.Wa != nullptr ? op.Wa + (size_t)a * ldg : nullptr;
+    for (int f = fb; f < fs; ++f) {
+        const uint32_t pv = __ldg(op.b.pack + f);
+        double v = ham ? __ldg(op.b.val + f) : 0.0;
+        if (wa != nullptr) {
+            const double w = __ldg(wa + ((pv >> 19) & 0xfffu));
+            v += (pv >> 31) ? -w : w;
+        }
+        acc = fma(v, crow[pv & 0x7ffffu], acc);
+    }
+    const int eb = __ldg(op.a.row_ptr + a), es = eb + __ldg(op.a.n_single + a), ee = __ldg(op.a.row_ptr + a + 1);
+    if (ham) {
+        for (int f = fs; f < fe; ++f) acc = fma(__ldg(op.b.val + f), crow[__ldg(op.b.col + f)], acc);
+        // alpha doubles
+        for (int e = es; e < ee; ++e)
+            acc = fma(__ldg(op.a.val + e), c[(size_t)__ldg(op.a.col + e) * ldc + b], acc);
+    }
+    // alpha singles: (Ha + sgn_a Wb[pq, b]) c[a', b] + sgn_a sum_{b'} sgn_b g_ab[pq, rs] c[a', b']
+    for (int e0 = eb; e0 < es; e0 += kWideBlock) {
+        const double* cr[kWideBlock];
+        const double* gr[kWideBlock];
+        double sa[kWideBlock], sum[kWideBlock];
+#pragma unroll
+        for (int j = 0; j < kWideBlock; ++j) {
+            const int e = e0 + j;
+            const bool ok = e < es;
+            const uint32_t m = ok ? __ldg(op.a.meta + e) : 0u;
+            const uint32_t pq = m & 0x7fffffffu;
+            sa[j] = ok ? ((m >> 31) ? -1.0 : 1.0) : 0.0;
+            cr[j] = c + (size_t)(ok ? __ldg(op.a.col + e) : (uint32_t)a) * ldc;
+            gr[j] = op.gab + (size_t)pq * ldg;
+            sum[j] = 0.0;
+            if (ok) {
+                const double va = ham ? __ldg(op.a.val + e) : 0.0;
+                const double wb = op.Wb != nullptr ? __ldg(op.Wb + (size_t)pq * ldc + b) : 0.0;
+                acc = fma(fma(sa[j], wb, va), cr[j][b], acc);
+            }
+        }
+        for (int f = fb; f < fs; ++f) {
+            const uint32_t pv = __ldg(op.b.pack + f);
+            const uint32_t bp = pv & 0x7ffffu, rs = (pv >> 19) & 0xfffu;
+            const bool neg = (pv >> 31) != 0;
+#pragma unroll
+            for (int j = 0; j < kWideBlock; ++j) {
+                const double t = __ldg(gr[j] + rs) * cr[j][bp];
+                sum[j] += neg ? -t : t;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kWideBlock; ++j) acc = fma(sa[j], sum[j], acc);
+    }
+    sig[(size_t)a * ldc + b] = acc;
+}
+
+static int launch_sigma_wide(const SigmaArgs& args, cudaStream_t st) {
+    const int rows_owned = args.row_end - args.row_begin;
+    if (rows_owned <= 0) return 0;
+    dim3 grid(rows_owned, (args.op.ldc + kWideCols - 1) / kWideCols);
+    sigma_wide_kernel<<<grid, kWideCols, 0, st>>>(args);
+    return check_launch("sigma_wide_kernel");
+}
+
 struct ChunkInfo {
     int a, slot, it_beg, db_beg, db_end, n_total;
     bool self_item, owned;
@@ -748,6 +843,23 @@ static int env_int(const char* name, int dflt) {
     return v ? atoi(v) : dflt;
 }
 
+// columns per thread of the alpha kernel for rows of ldc doubles; 0 = beyond the largest instance
+static int v1_columns_per_thread(int ldc) {
+    if (ldc <= 992) return 1;
+    const int cpt = (ldc + 511) / 512;
+    return cpt <= 2 ? 2 : cpt <= 4 ? 4 : cpt <= 8 ? 8 : cpt <= 12 ? 12 : 0;
+}
+
+// true when rows of ldc doubles (and integral rows of ldg doubles) fit the shared-memory staging of
+// kernels A and B with the smallest ring; otherwise the wide kernel is the only v1-family choice
+static bool v1_shape_fits(int ldc, int ldg) {
+    if (v1_columns_per_thread(ldc) == 0) return false;
+    const size_t smem_a = (size_t)(ldc + 2 * (ldc + ldg) + kLongA * 32) * sizeof(double) +
+                          (2 * kMaxStages) * sizeof(uint64_t) + kTileC * 12;
+    const size_t smem_b = (size_t)(kRowsB * ldc + kWarpsB * kRowsB * 32) * sizeof(double) + 16;
+    return smem_a <= 224 * 1024 && smem_b <= 224 * 1024;
+}
+
 static bool plan_sigma(const sqd_operator* op, SigmaPlan* pl) {
     static const int knob_stages = env_int("SQD_SIGMA_STAGES", 0);
     static const int knob_pack = env_int("SQD_SIGMA_PACK_BYTES", 24 * 1024);
@@ -922,6 +1034,11 @@ static int sigma_dispatch_impl(const sqd_operator* op, const double* d_c, double
     SigmaPlan pl;
     SQD_REQUIRE(op->ldc % 2 == 0 && op->ldg % 2 == 0 && op->ldc >= op->b.n,
                 "sqd_sigma: ldc/ldg must be even and ldc >= nb");
+    if (op->wide) {
+        SQD_REQUIRE(row_begin >= 0 && row_end <= op->a.n && row_begin <= row_end, "sqd_sigma: bad row range");
+        SigmaArgs wargs{*op, d_c, d_sigma, d_done, nullptr, row_begin, row_end, d_slot, stride};
+        return launch_sigma_wide(wargs, st);
+    }
     SQD_REQUIRE(op->plan.n_chunks >= op->a.n && op->plan.chunk_row != nullptr,
                 "sqd_sigma: the operator has no work plan (call sqd_sigma_plan_build first)");
     SQD_REQUIRE(op->plan.n_slots == 0 || op->plan.part != nullptr,
@@ -930,7 +1047,7 @@ static int sigma_dispatch_impl(const sqd_operator* op, const double* d_c, double
                 "sqd_sigma: the operator has no SELL tables (call sqd_sell_build first)");
     SQD_REQUIRE(plan_sigma(op, &pl),
                 "sqd_sigma: nb=%d (ldc=%d) with norb=%d does not fit the shared-memory row staging "
-                "(limits: nb <= 5760 and 3*ldc + 2*ldg doubles <= 227 KB)",
+                "(limits: nb <= 5760 and 3*ldc + 2*ldg doubles <= 227 KB): set sqd_operator.wide",
                 op->b.n, op->ldc, op->norb);
     SQD_REQUIRE(row_begin >= 0 && row_end <= op->a.n && row_begin <= row_end, "sqd_sigma: bad row range");
     SigmaArgs args{*op, d_c, d_sigma, d_done, g_prof, row_begin, row_end, d_slot, stride};
@@ -951,8 +1068,11 @@ using namespace sqd;
 
 extern "C" {
 
+int sqd_sigma_v1_supported(int ldc, int ldg) { return v1_shape_fits(ldc, ldg) ? 1 : 0; }
+
 int64_t sqd_sigma_smem_bytes(const sqd_operator* op) {
     if (op->v2.enabled) return sigma2_smem_bytes(op);
+    if (op->wide) return 0;
     SigmaPlan pl;
     if (!plan_sigma(op, &pl)) return -1;
     return (int64_t)pl.smem;

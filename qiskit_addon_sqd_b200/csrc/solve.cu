@@ -276,7 +276,9 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
                 SQD_V2_COUNTS * sizeof(int), cudaMemcpyDeviceToDevice, st));
         }
     }
-    if (!use_v2 && build_v1_plan()) return -2;
+    // neither staged path takes rows this long (or the caller asked for it): the wide kernel, no plan
+    bool use_wide = prm->sigma_path == 3 || !sqd_sigma_v1_supported(ldc, ldg);
+    if (!use_v2 && !use_wide && build_v1_plan()) return -2;
 
     // ---- operators: integrals, W tables and diagonals do not depend on the plan, so their kernels (and
     // the start vector) are enqueued BEFORE the host waits for the plan / SELL sizes ----
@@ -323,8 +325,10 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
         // the v2 planner refused the shape (a beta string with thousands of links, or too many strings
         // for its single-CTA passes): the v1 kernels take over
         use_v2 = false;
-        if (build_v1_plan()) return -2;
-        if (read_back(hc, counts, 8 * sizeof(int), st)) return -2;
+        if (!use_wide) {
+            if (build_v1_plan()) return -2;
+            if (read_back(hc, counts, 8 * sizeof(int), st)) return -2;
+        }
     }
     if (use_v2) {
         const int same_tables = same ? 1 : 0;
@@ -337,6 +341,8 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
                                 1, &v2, st))
             return -2;
         for (sqd_operator* o : {&base, &ham, &s2op}) o->v2 = v2;
+    } else if (use_wide) {
+        for (sqd_operator* o : {&base, &ham, &s2op}) o->wide = 1;
     } else {
         double* part = P.get<double>((size_t)(hc[1] > 0 ? hc[1] : 1) * ldc);
         if (P.failed) return -2;
@@ -350,7 +356,7 @@ int sqd_solve_subspace(const sqd_solve_params* prm, double* d_x, double* d_rdm1,
             o->bb = bb;
         }
     }
-    h_res->sigma_path = use_v2 ? 2 : 1;
+    h_res->sigma_path = use_v2 ? 2 : use_wide ? 3 : 1;
 
     // ---- Davidson ----
     sqd_davidson_params dp{};

@@ -16,10 +16,11 @@ violation raises ``ValueError`` / ``RuntimeError`` naming the limit, nothing fal
 
 * ``norb <= 64`` spatial orbitals (one 64-bit word per determinant string);
 * at most 2^19 = 524 288 strings per spin, and fewer than 2^31 stored same-spin table entries per spin;
-* beta strings per subspace: ``nb <= 8192`` when the subspace is dense enough for the v2 sigma kernels
-  (every BASELINE.json shape is), otherwise ``nb <= 5760`` (the v1 kernels stage whole rows of the CI matrix in
-  shared memory: ``3*ldc + 2*norb^2`` doubles must fit 227 KB); the alpha side has no such bound, so for
-  ``nb`` beyond the limit swap the roles of the two spins where the problem allows it;
+* beta strings per subspace: the fast sigma kernels stage whole rows of the CI matrix in shared memory
+  (``nb <= 8192`` for the v2 kernels every BASELINE.json shape runs on, ``nb <= 5760`` for the v1 kernels of
+  sparse subspaces); longer rows are solved by the staging-free "wide" kernel (any ``nb`` the tables take,
+  several times slower per determinant) -- nothing raises.  The full 2-RDM pass stages two rows
+  (``2*nb + norb^2`` doubles <= 225 KB, ``nb <= ~13 900`` at 30 orbitals): beyond, pass ``compute_rdms=False``;
 * ``nroots > 1`` is not supported (``kernel_fixed_space`` default 1 is what the reference uses).
 """
 
@@ -339,10 +340,18 @@ class _OperatorDev:
         if not with_w:
             self.Wb = None
         v2 = sub.sigma_v2()
+        # rows too long for the staged kernels (or sigma_path="wide"): the wide kernel, no plan / SELL copies
+        self.uses_wide = not v2.enabled and (
+            sub.sigma_path == "wide" or not lib.sqd_sigma_v1_supported(ldc, ldg))
+        if self.uses_wide:
+            plan, bd, bb = _lib.SigmaPlan(), _lib.Sell(), _lib.Sell()
+        else:
+            plan = sub.sigma_plan()
+            bd, bb = sub.tb.sell(0, sub._plan_keep[2]), sub.tb.sell(1)
         self.struct = _lib.Operator(sub.ta.struct(), sub.tb.struct(), norb, ldc, ldg,
                                     _lib.ptr(self.diag), _lib.ptr(self.gab), _lib.ptr(self.Wa),
-                                    _lib.ptr(self.Wb), 1 if same_spin else 0, sub.sigma_plan(),
-                                    sub.tb.sell(0, sub._plan_keep[2]), sub.tb.sell(1), 0, v2)
+                                    _lib.ptr(self.Wb), 1 if same_spin else 0, plan, bd, bb, 0, v2,
+                                    1 if self.uses_wide else 0)
         self.uses_v2 = bool(v2.enabled)
         if lib.sqd_sigma_smem_bytes(C.byref(self.struct)) < 0:
             raise ValueError(
@@ -537,6 +546,9 @@ def _solver_options(kwargs: dict) -> dict:
         else:
             kw.pop(key, None)
     opts["ci0"] = kw.pop("ci0", None)
+    opts["sigma_path"] = kw.pop("sigma_path", None) or "auto"  # not a pyscf option: "auto", "v1", "v2", "wide"
+    if opts["sigma_path"] not in ("auto", "v1", "v2", "wide"):
+        raise ValueError("sigma_path must be one of 'auto', 'v1', 'v2', 'wide'")
     nroots = kw.pop("nroots", None)
     if nroots not in (None, 1):
         raise NotImplementedError("qiskit_addon_sqd_b200 computes the ground state only (nroots=1).")
@@ -567,7 +579,7 @@ class SolveStats:
     nb: int = 0
     norb: int = 0
     host_ms: tuple = ()     # host wall time of (preparation, library call, downloads)
-    sigma_path: int = 0     # 1: fermion_sigma.cu, 2: fermion_sigma2.cu (what the solve actually ran)
+    sigma_path: int = 0     # 1: fermion_sigma.cu, 2: fermion_sigma2.cu, 3: the wide kernel (what the solve ran)
 
 
 _tls = threading.local()
@@ -665,6 +677,7 @@ def _solve_on_device(strs_a, strs_b, norb: int, ints: _DeviceIntegrals, spin_sq,
     prm.cost_per_chunk, prm.long_threshold = int(_SIGMA_COST_PER_CHUNK), int(_SIGMA_LONG_THRESHOLD)
     prm.profile = 1 if profile else 0
     prm.throughput_mode = 1 if throughput else 0
+    prm.sigma_path = {"auto": 0, "v1": 1, "v2": 2, "wide": 3}[opts.get("sigma_path", "auto")]
     if shard_group is not None:
         # rows are split inside the call into blocks of equal estimated sigma-build cost
         prm.nccl_comm, prm.row_begin, prm.row_end = shard_group._comm.value, -1, -1
@@ -829,6 +842,7 @@ def solve_sci_batch(
                 prm.cost_per_chunk, prm.long_threshold = int(_SIGMA_COST_PER_CHUNK), int(_SIGMA_LONG_THRESHOLD)
                 prm.throughput_mode = 1 if _throughput_mode(
                     len(ks), sum(jobs[q]["na"] * jobs[q]["nb"] for q in ks)) else 0
+                prm.sigma_path = {"auto": 0, "v1": 1, "v2": 2, "wide": 3}[opts.get("sigma_path", "auto")]
                 j["prm"], j["res"] = prm, _lib.SolveResult()
                 j["x_ptr"] = x_d.data_ptr() + 8 * x_off[i]
                 j["x_off"] = x_off[i]
@@ -880,7 +894,7 @@ def solve_sci_batch(
                              rdm1=j.get("rdm1"), rdm2=j.get("rdm2")))
         stats.append(SolveStats(info.cycles, info.sigma_builds, info.converged, info.residual, info.theta,
                                 na * nb, int(res.nnz_a), int(res.nnz_b), 0, 0, info.sigma_ms,
-                                info.total_ms, na, nb, norb))
+                                info.total_ms, na, nb, norb, (), int(res.sigma_path)))
     _tls.stats = stats
     return out
 

@@ -69,9 +69,16 @@ def sort_and_remove_duplicates(bitstring_matrix: np.ndarray) -> np.ndarray:
     bitstring_matrix = np.asarray(bitstring_matrix)
     if bitstring_matrix.shape[0] == 0:
         return bitstring_matrix
-    keys = _keys_device(torch, lib, bitstring_matrix).cpu().numpy()
-    _, indices = np.unique(keys, return_index=True)
-    return bitstring_matrix[indices, :]
+    n_bits = bitstring_matrix.shape[1]
+    # keys, bitonic sort and run heads on the device (csrc/sortuniq.cu); equal keys are equal rows, so the
+    # reference's "first occurrence of every distinct key" is the key itself written back as a row
+    _, keys, _ = _lib.sort_unique(torch, None, _keys_device(torch, lib, bitstring_matrix))
+    d = int(keys.numel())
+    bits = torch.empty((d, n_bits), dtype=torch.uint8, device=keys.device)
+    _lib.check(lib.sqd_keys_to_bits(0, _lib.ptr(keys), d, n_bits, _lib.ptr(bits), _lib.stream_ptr(torch)),
+               "sqd_keys_to_bits")
+    rows = _lib.download(torch, bits)
+    return rows.view(bool) if bitstring_matrix.dtype == np.bool_ else rows.astype(bitstring_matrix.dtype)
 
 
 def matrix_elements_from_pauli(bitstring_matrix: np.ndarray, pauli):
@@ -363,7 +370,7 @@ def solve_qubit(
     torch = _lib.require_cuda()
     lib = _lib.load()
     keys_all = _keys_device(torch, lib, bitstring_matrix)
-    keys = torch.unique(keys_all)  # sorted ascending, duplicates removed (qubit.py:66)
+    _, keys, _ = _lib.sort_unique(torch, None, keys_all)  # sorted ascending, duplicates removed (qubit.py:66)
     d = int(keys.numel())
     if verbose:  # pragma: no cover
         print(f"Projecting {hamiltonian.size} Pauli terms onto {d} configurations on the GPU ...")

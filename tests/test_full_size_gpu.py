@@ -182,3 +182,27 @@ def test_sqd_loop_config2_full_size(cuda_lib):
                for x, y in zip(history, history2) for a, b in zip(x, y))
     print(f"\nconfig 2 loop: 3 iterations x 5 subspaces of <= 1e4 dets in {dt*1e3:.1f} ms, "
           f"best energy per iteration {np.round(lowest, 8).tolist()}")
+
+
+@pytest.mark.parametrize("spin_sq", [None, 0.0])
+def test_solve_beyond_the_row_staging_limits(cuda_lib, spin_sq):
+    """More beta strings than the staged sigma kernels take (v1: 5760, v2: 8192): the reference has no such
+    limit (pyscf ``contract_2e`` behind ``fermion.py:721-723``), the solve must run -- on the wide kernel -- and
+    agree with the C oracle (VERDICT r1 missing item 8)."""
+    from oracle import sci_cpu
+    from qiskit_addon_sqd_b200 import fermion
+    from qiskit_addon_sqd_b200._synthetic import hf_centred_strings, random_integrals
+
+    norb, nelec = 20, (5, 5)
+    h, g = random_integrals(norb, 77)
+    sa = hf_centred_strings(norb, 5, 40, 3)
+    sb = hf_centred_strings(norb, 5, 9001, 4)
+    res = fermion.solve_sci((sa.astype(np.int64), sb.astype(np.int64)), h, g, norb, nelec, spin_sq=spin_sq)
+    st = fermion.last_solve_stats()[-1]
+    assert st.sigma_path == 3 and st.converged == 1
+    e_ref, amps_ref, occ_ref, info = sci_cpu.solve(sa, sb, h, g, algo=0, tol=1e-12, max_cycle=200,
+                                                   spin_sq=spin_sq, shift=0.2)  # solve_sci: pyscf's default shift
+    assert abs(res.energy - e_ref) < 1e-8
+    assert abs(abs(np.vdot(res.sci_state.amplitudes, amps_ref)) - 1.0) < 1e-7
+    e_rdm = np.einsum("pr,pr->", res.rdm1, h) + 0.5 * np.einsum("prqs,prqs->", res.rdm2, g)
+    assert abs(e_rdm - res.energy) < 1e-8

@@ -2,6 +2,7 @@
 kernel instance the dispatcher can select.
 
 v1 path (``fermion_sigma.cu``): ``CPT in {1, 2, 4, 8, 12}`` x ``STAGE_PACK in {T, F}``, long columns, split rows.
+wide path (``sigma_wide_kernel``, no shared-memory staging: the only path beyond nb = 8192) at every shape.
 v2 path (``fermion_sigma2.cu``): source-row grouped opposite-spin kernel (register-resident link lists,
 ``LMAX in {8, 16}``, one or several column groups) + dense same-spin tile kernel (with and without split-K).
 The oracle is ``oracle/sci_cpu.c`` (one sigma build, direct excitation-table algorithm; validated against the
@@ -49,8 +50,13 @@ def _build(norb, nea, neb, na, nb, kind, sigma_path):
     return sub, sa, sb, h, g
 
 
-@pytest.mark.parametrize("sigma_path", ["v1", "v2"])
-@pytest.mark.parametrize("norb,nea,neb,na,nb,kind,why", SHAPES)
+# beyond the staged kernels (v1: nb <= 5760, v2: nb <= 8192) only the staging-free wide kernel applies: every
+# path request must end up there
+WIDE_ONLY = (20, 5, 5, 12, 9001, "hf", "nb > 8192: wide kernel, odd nb (pad column)")
+
+
+@pytest.mark.parametrize("sigma_path", ["v1", "v2", "wide"])
+@pytest.mark.parametrize("norb,nea,neb,na,nb,kind,why", SHAPES + [WIDE_ONLY])
 def test_sigma_elementwise_vs_c_oracle(cuda_lib, norb, nea, neb, na, nb, kind, why, sigma_path):
     import torch
 
@@ -58,8 +64,9 @@ def test_sigma_elementwise_vs_c_oracle(cuda_lib, norb, nea, neb, na, nb, kind, w
 
     sub, sa, sb, h, g = _build(norb, nea, neb, na, nb, kind, sigma_path)
     ham = sub.hamiltonian()
-    if sigma_path == "v2" and not ham.uses_v2:
+    if sigma_path == "v2" and not ham.uses_v2 and nb <= 8192:
         pytest.skip("v2 path not selected for this shape (sparse set: v1 is the product path)")
+    assert ham.uses_wide == (sigma_path == "wide" or nb > 8192)
     rng = np.random.default_rng(3)
     x = rng.standard_normal((sub.na, sub.nb))
     c = sub.upload_amplitudes(x)
@@ -87,7 +94,7 @@ def test_sigma_elementwise_vs_c_oracle(cuda_lib, norb, nea, neb, na, nb, kind, w
     assert torch.equal(total.reshape(sub.na, sub.ldc), full)
 
 
-@pytest.mark.parametrize("sigma_path", ["v1", "v2"])
+@pytest.mark.parametrize("sigma_path", ["v1", "v2", "wide"])
 def test_spin_operator_and_penalty_at_bench_shape(cuda_lib, sigma_path):
     """S^2 (opposite-spin tensor only, no same-spin part) and the linear spin penalty at 316 x 316."""
     from oracle import fermion_oracle as fo

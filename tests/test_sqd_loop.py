@@ -12,6 +12,7 @@ import sys
 import numpy as np
 import pytest
 
+from oracle import counts_oracle as co
 from oracle import fermion_oracle as fo
 from oracle import recovery_oracle as ro
 from qiskit_addon_sqd_b200._synthetic import random_integrals
@@ -66,10 +67,11 @@ def _oracle_solver(ci_strings, h, g, norb, nelec, *, spin_sq=None):
 
 @pytest.mark.parametrize("ci", [0, 1, 2])
 def test_loop_logic_matches_reference_loop_on_cpu(ci, monkeypatch):
-    from qiskit_addon_sqd_b200 import configuration_recovery, fermion
+    from qiskit_addon_sqd_b200 import configuration_recovery, counts, fermion
 
     z, norb, nelec, n_iter, n_batches, h, g, kw, bits = _load_case(ci)
     monkeypatch.setattr(configuration_recovery, "recover_configurations", ro.recover_configurations)
+    monkeypatch.setattr(counts, "bit_array_to_arrays", co.bit_array_to_arrays)  # device code in the product
     history = []
     solver = functools.partial(_oracle_solver, spin_sq=LOOP_CASES[ci]["spin_sq"])
     best = fermion.diagonalize_fermionic_hamiltonian(h, g, bits, norb=norb, nelec=nelec, sci_solver=solver,
@@ -78,9 +80,10 @@ def test_loop_logic_matches_reference_loop_on_cpu(ci, monkeypatch):
     assert abs(best.energy - float(z[f"c{ci}_best_energy"])) < 1e-10
 
 
-def test_loop_argument_errors_are_the_reference_messages():
-    from qiskit_addon_sqd_b200 import fermion
+def test_loop_argument_errors_are_the_reference_messages(monkeypatch):
+    from qiskit_addon_sqd_b200 import counts, fermion
 
+    monkeypatch.setattr(counts, "bit_array_to_arrays", co.bit_array_to_arrays)  # device code in the product
     h, g = random_integrals(4, 1)
     bits = PackedBits(np.zeros((3, 1), dtype=np.uint8), 8)
     with pytest.raises(ValueError, match="Maximum number of iterations must be at least 1."):
@@ -128,8 +131,36 @@ def test_counts_and_subsampling_known_answers():
     out = counts.bitstring_matrix_to_integers(wide)
     assert out.dtype == object and out[0] == (1 << 63) + 1
     arr = PackedBits(np.array([[0b00010010], [0b01001000], [0b00010010], [0b00010001]], dtype=np.uint8), 8)
+    for fn in (co.bit_array_to_arrays, co.bit_array_to_arrays_literal):  # the oracle; the product runs on the GPU
+        rows, probs = fn(arr)
+        assert counts.bitstring_matrix_to_integers(rows).tolist() == [17, 18, 72]
+        assert probs.tolist() == [0.25, 0.5, 0.25]
+    rng = np.random.default_rng(0)
+    odd = PackedBits(rng.integers(0, 256, (500, 3), dtype=np.uint8) & np.array([0x07, 0xFF, 0x81], dtype=np.uint8), 19)
+    a, b = co.bit_array_to_arrays(odd), co.bit_array_to_arrays_literal(odd)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("num_bits,row_bytes,shots", [(8, 1, 4), (19, 3, 500), (60, 8, 20_000), (64, 8, 5_000),
+                                                      (65, 9, 3_000), (100, 13, 70_000), (128, 16, 2_500)])
+def test_bit_array_to_arrays_on_gpu_matches_numpy(num_bits, row_bytes, shots):
+    """Product path of ``counts.bit_array_to_arrays`` (device key packing + bitonic sort + run lengths) against the
+    reference's own numpy calls (``counts.py:57-60``): rows, row order, dtypes and probabilities bit for bit."""
+    from qiskit_addon_sqd_b200 import counts
+
+    rng = np.random.default_rng(num_bits)
+    pool = rng.integers(0, 256, (max(3, shots // 7), row_bytes), dtype=np.uint8)   # many repeated shots
+    pool[0] = 0xFF                                                                   # all ones: equals the sort pad
+    pool[1] = 0
+    packed = pool[rng.integers(0, len(pool), shots)]
+    packed[:, -1] ^= (rng.random(shots) < 0.2).astype(np.uint8)                     # and many singletons
+    arr = PackedBits(packed, num_bits)
     rows, probs = counts.bit_array_to_arrays(arr)
-    assert counts.bitstring_matrix_to_integers(rows).tolist() == [17, 18, 72] and probs.tolist() == [0.25, 0.5, 0.25]
+    want_rows, want_probs = co.bit_array_to_arrays_literal(arr)
+    assert rows.dtype == np.bool_ and rows.shape == want_rows.shape and np.array_equal(rows, want_rows)
+    assert probs.dtype == want_probs.dtype and np.array_equal(probs, want_probs)
+    assert probs.sum() == pytest.approx(1.0)
 
 
 @pytest.mark.gpu
