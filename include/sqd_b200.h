@@ -584,6 +584,15 @@ int sqd_bit_array_pack(const uint8_t* d_bytes, int64_t n, int row_bytes, int num
 int sqd_keys_to_bits(const uint64_t* d_hi, const uint64_t* d_lo, int64_t n, int num_bits, uint8_t* d_bits,
                      void* stream);
 
+/* Carry-over selection of the SQD loop (fermion.py:607-631, _process_sci_results): d_row_flag[a] / d_col_flag[b]
+ * = 1 when row a / column b of the amplitude matrix d_x (na x ldc, row-major) holds an entry with
+ * |c| >= threshold, and for those the marginal weights sum_b |c[a,b]|^2 / sum_a |c[a,b]|^2 added in numpy's
+ * pairwise summation order without FMA contraction (bit-identical to np.sum(np.abs(amps[rows])**2, axis=1) and
+ * np.sum(np.abs(amps[:, cols])**2, axis=0)); weights of unflagged rows / columns are 0.  The full CI vector
+ * does not travel to the host for this step, and the reference's argsort over all n_det magnitudes is gone. */
+int sqd_carryover(const double* d_x, int na, int nb, int ldc, double threshold, int* d_row_flag,
+                  int* d_col_flag, double* d_row_weight, double* d_col_weight, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

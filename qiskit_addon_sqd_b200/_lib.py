@@ -265,6 +265,7 @@ SIGNATURES: dict[str, tuple] = {
     "sqd_sort_unique": (_i, [_vp, _vp, _i64, _vp, _vp, _vp, C.POINTER(C.c_int64), _vp, _i64, _vp]),
     "sqd_bit_array_pack": (_i, [_vp, _i64, _i, _i, _vp, _vp, _vp]),
     "sqd_keys_to_bits": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "sqd_carryover": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _vp]),
     "sqd_recover_workspace_bytes": (_i64, [_i64, _i]),
     "sqd_recover": (
         _i,

@@ -149,6 +149,91 @@ __global__ void keys_to_bits_kernel(const uint64_t* __restrict__ hi, const uint6
     bits[i] = (uint8_t)((w >> (pos & 63)) & 1ull);
 }
 
+// ---- carry-over of the SQD loop (fermion.py:607-631) ---------------------------------------------------------
+// Rows / columns of the amplitude matrix that hold an entry with |c| >= threshold, and their marginal weights
+// sum |c|^2 in numpy's summation order (np.sum over the contiguous axis = pairwise_sum: blocks of <= 128 with
+// eight interleaved accumulators, halves split at a multiple of 8 above that), without FMA contraction -- the
+// ranking by weight that follows on the host then sees the reference's weights bit for bit.
+__global__ void carry_flag_kernel(const double* __restrict__ x, int na, int nb, int ldc, double thr,
+                                  int* __restrict__ row_flag, int* __restrict__ col_flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)na * ldc) return;
+    const int a = (int)(i / ldc), b = (int)(i - (int64_t)a * ldc);
+    if (b < nb && fabs(x[i]) >= thr) {
+        row_flag[a] = 1;   // benign race: every writer stores 1
+        col_flag[b] = 1;
+    }
+}
+
+__device__ __forceinline__ double sq_rn(double v) { return __dmul_rn(v, v); }
+
+__device__ double numpy_sum_sq_leaf(const double* __restrict__ a, int64_t stride, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = __dadd_rn(res, sq_rn(a[i * stride]));
+        return res;
+    }
+    double r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = sq_rn(a[j * stride]);
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __dadd_rn(r[j], sq_rn(a[(i + j) * stride]));
+    }
+    double res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
+                           __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __dadd_rn(res, sq_rn(a[i * stride]));
+    return res;
+}
+
+// numpy's recursive pairwise_sum of a[i]^2, i < n, with an explicit stack (depth <= log2(n / 128) + 2)
+__device__ double numpy_sum_sq(const double* __restrict__ a, int64_t stride, int64_t n) {
+    struct Frame {
+        int64_t off, len;
+        double left;
+        int stage;
+    };
+    Frame st[32];
+    int sp = 1;
+    st[0] = Frame{0, n, 0.0, 0};
+    double ret = 0.0;
+    while (sp > 0) {
+        Frame& f = st[sp - 1];
+        if (f.len <= 128) {
+            ret = numpy_sum_sq_leaf(a + f.off * stride, stride, (int)f.len);
+            --sp;
+            continue;
+        }
+        int64_t n2 = f.len / 2;
+        n2 -= n2 % 8;
+        if (f.stage == 0) {
+            f.stage = 1;
+            st[sp++] = Frame{f.off, n2, 0.0, 0};
+        } else if (f.stage == 1) {
+            f.left = ret;
+            f.stage = 2;
+            st[sp++] = Frame{f.off + n2, f.len - n2, 0.0, 0};
+        } else {
+            ret = __dadd_rn(f.left, ret);
+            --sp;
+        }
+    }
+    return ret;
+}
+
+__global__ void carry_weight_kernel(const double* __restrict__ x, int na, int nb, int ldc,
+                                    const int* __restrict__ row_flag, const int* __restrict__ col_flag,
+                                    double* __restrict__ row_w, double* __restrict__ col_w) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < na) {
+        row_w[t] = row_flag[t] ? numpy_sum_sq(x + (size_t)t * ldc, 1, nb) : 0.0;
+    } else if (t < na + nb) {
+        const int b = t - na;
+        col_w[b] = col_flag[b] ? numpy_sum_sq(x + b, ldc, na) : 0.0;
+    }
+}
+
 static int64_t padded_size(int64_t n) {
     int64_t p = kSortTile;
     while (p < n) p <<= 1;
@@ -243,6 +328,23 @@ int sqd_keys_to_bits(const uint64_t* d_hi, const uint64_t* d_lo, int64_t n, int 
     keys_to_bits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_hi, d_lo, n, num_bits,
                                                                                             d_bits);
     return check_launch("keys_to_bits_kernel");
+}
+
+int sqd_carryover(const double* d_x, int na, int nb, int ldc, double threshold, int* d_row_flag, int* d_col_flag,
+                  double* d_row_weight, double* d_col_weight, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SQD_REQUIRE(na > 0 && nb > 0 && ldc >= nb, "sqd_carryover: bad shape (na=%d, nb=%d, ldc=%d)", na, nb, ldc);
+    SQD_REQUIRE(d_x != nullptr && d_row_flag != nullptr && d_col_flag != nullptr && d_row_weight != nullptr &&
+                    d_col_weight != nullptr, "sqd_carryover: missing buffers");
+    SQD_CUDA_OK(cudaMemsetAsync(d_row_flag, 0, (size_t)na * sizeof(int), st));
+    SQD_CUDA_OK(cudaMemsetAsync(d_col_flag, 0, (size_t)nb * sizeof(int), st));
+    const int64_t n = (int64_t)na * ldc;
+    carry_flag_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_x, na, nb, ldc, threshold, d_row_flag,
+                                                                    d_col_flag);
+    if (check_launch("carry_flag_kernel")) return -2;
+    carry_weight_kernel<<<(unsigned)((na + nb + 63) / 64), 64, 0, st>>>(d_x, na, nb, ldc, d_row_flag, d_col_flag,
+                                                                        d_row_weight, d_col_weight);
+    return check_launch("carry_weight_kernel");
 }
 
 }  // extern "C"

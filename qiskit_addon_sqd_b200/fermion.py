@@ -882,6 +882,9 @@ def solve_sci_batch(
             raise _lib.SqdCudaError(f"sqd_solve_subspace failed ({rc}): {err.decode() if err else ''}")
 
     out, stats = [], []
+    # the amplitude matrices of THIS call stay on the device until the next call on this thread: the SQD loop
+    # selects its carry-over strings from them without touching the host copies (_SQDRun.digest)
+    resident = _tls.resident_amplitudes = {}
     for k, (strs_a, strs_b) in enumerate(ci_strings):
         j = jobs[k]
         res, info = j["res"], j["res"].info
@@ -892,6 +895,8 @@ def solve_sci_batch(
                          norb=norb, nelec=tuple(nelec))
         out.append(SCIResult(float(res.energy), state, orbital_occupancies=occ,
                              rdm1=j.get("rdm1"), rdm2=j.get("rdm2")))
+        x_all = keep[j["device"]][2]
+        resident[id(state)] = (state, x_all[j["x_off"]: j["x_off"] + na * j["ldc"]].view(na, j["ldc"]), j["device"])
         stats.append(SolveStats(info.cycles, info.sigma_builds, info.converged, info.residual, info.theta,
                                 na * nb, int(res.nnz_a), int(res.nnz_b), 0, 0, info.sigma_ms,
                                 info.total_ms, na, nb, norb, (), int(res.sigma_path)))
@@ -911,6 +916,25 @@ def _first_occurrences(values: np.ndarray) -> np.ndarray:
 def _by_descending(keys: np.ndarray) -> np.ndarray:
     """Permutation used by the reference wherever it ranks strings: numpy's default argsort, reversed."""
     return np.argsort(keys)[::-1]
+
+
+def _carryover_on_device(x, nb: int, device: int, threshold: float):
+    """Rows / columns of the device-resident amplitude matrix ``x`` (``na x ldc``) holding an entry with
+    ``|c| >= threshold`` and their marginal weights, bit-identical to the reference's numpy expressions
+    (``fermion.py:607-622``): ``sqd_carryover``.  Returns ``(rows, cols, weight_a, weight_b)``."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    na, ldc = int(x.shape[0]), int(x.shape[1])
+    with torch.cuda.device(device):
+        flags = torch.empty(na + nb, dtype=torch.int32, device=x.device)
+        weights = torch.empty(na + nb, dtype=torch.float64, device=x.device)
+        _lib.check(lib.sqd_carryover(_lib.ptr(x), na, nb, ldc, float(threshold), _lib.ptr(flags),
+                                     flags.data_ptr() + 4 * na, _lib.ptr(weights), weights.data_ptr() + 8 * na,
+                                     _lib.stream_ptr(torch)), "sqd_carryover")
+        f = _lib.read_back(torch, flags)
+        w = _lib.read_back(torch, weights)
+    rows, cols = np.flatnonzero(f[:na]), np.flatnonzero(f[na:])
+    return rows, cols, w[:na][rows], w[na:][cols]
 
 
 class _SQDRun:
@@ -991,15 +1015,23 @@ class _SQDRun:
                 return True
         self.reference = winner
         self.occupancies = winner.orbital_occupancies
-        # strings of every determinant whose |amplitude| exceeds the threshold, ranked by marginal weight
+        # strings of every determinant whose |amplitude| reaches the threshold, ranked by marginal weight
         state = winner.sci_state
-        magnitude = np.abs(state.amplitudes.reshape(-1))
-        order = np.argsort(magnitude)
-        big = order[np.searchsorted(magnitude, self.carryover_threshold, sorter=order):]
-        rows, cols = np.divmod(big, state.amplitudes.shape[1])
-        rows, cols = np.unique(rows), np.unique(cols)
-        weight_a = np.sum(np.abs(state.amplitudes[rows]) ** 2, axis=1)
-        weight_b = np.sum(np.abs(state.amplitudes[:, cols]) ** 2, axis=0)
+        held = getattr(_tls, "resident_amplitudes", {}).get(id(state))
+        if held is not None and held[0] is state:
+            # result of solve_sci_batch: selection and weights on the device (sqd_carryover), from the
+            # amplitude matrix the solve left there -- no argsort over all n_det magnitudes
+            rows, cols, weight_a, weight_b = _carryover_on_device(held[1], state.amplitudes.shape[1], held[2],
+                                                                  self.carryover_threshold)
+        else:
+            # result of a foreign sci_solver plugin: its amplitudes only exist on the host
+            magnitude = np.abs(state.amplitudes.reshape(-1))
+            order = np.argsort(magnitude)
+            big = order[np.searchsorted(magnitude, self.carryover_threshold, sorter=order):]
+            rows, cols = np.divmod(big, state.amplitudes.shape[1])
+            rows, cols = np.unique(rows), np.unique(cols)
+            weight_a = np.sum(np.abs(state.amplitudes[rows]) ** 2, axis=1)
+            weight_b = np.sum(np.abs(state.amplitudes[:, cols]) ** 2, axis=0)
         keep_a, keep_b = state.ci_strs_a[rows], state.ci_strs_b[cols]
         if self.symmetric:
             pooled = np.concatenate((keep_a, keep_b))[_by_descending(np.concatenate((weight_a, weight_b)))]

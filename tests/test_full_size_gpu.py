@@ -202,7 +202,13 @@ def test_solve_beyond_the_row_staging_limits(cuda_lib, spin_sq):
     assert st.sigma_path == 3 and st.converged == 1
     e_ref, amps_ref, occ_ref, info = sci_cpu.solve(sa, sb, h, g, algo=0, tol=1e-12, max_cycle=200,
                                                    spin_sq=spin_sq, shift=0.2)  # solve_sci: pyscf's default shift
-    assert abs(res.energy - e_ref) < 1e-8
+    # Without the penalty the energy is an eigenvalue (second order in the eigenvector error): north_star
+    # tolerance.  With it the REPORTED energy is <x|H|x> in an eigenvector of H + shift (S^2 - ss), first order
+    # in the eigenvector error: the oracle's own answer moves by 3.5e-8 Ha between tol = 1e-12 and 1e-15 here,
+    # so the two solvers are compared at 2e-7 and the energy is pinned through the oracle's sigma instead.
+    assert abs(res.energy - e_ref) < (1e-8 if spin_sq is None else 2e-7)
     assert abs(abs(np.vdot(res.sci_state.amplitudes, amps_ref)) - 1.0) < 1e-7
+    x = res.sci_state.amplitudes
+    assert abs(np.vdot(x, sci_cpu.sigma(sa, sb, h, g, x)) / np.vdot(x, x) - res.energy) < 1e-10
     e_rdm = np.einsum("pr,pr->", res.rdm1, h) + 0.5 * np.einsum("prqs,prqs->", res.rdm2, g)
     assert abs(e_rdm - res.energy) < 1e-8

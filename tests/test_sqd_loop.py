@@ -224,3 +224,32 @@ def test_digest_convergence_and_carryover_rules():
     # a lower energy in a later iteration replaces the best result even if not converged
     lower = result(-1.2, amps, [1, 4], [2, 4], (occ[0] * 0.5, occ[1]))
     assert run.digest([lower]) is False and run.best is lower
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("na,nb,thr", [(5, 7, 0.5), (40, 101, 1.5), (316, 316, 2.5), (130, 1000, 3.0),
+                                        (1100, 9, 2.0), (300, 300, 10.0)])
+def test_carryover_on_gpu_matches_numpy(na, nb, thr):
+    """``sqd_carryover`` against the reference's numpy expressions (``fermion.py:607-622``): selected rows / columns
+    and marginal weights BIT-equal (numpy's pairwise summation order), so the ranking that follows is the same."""
+    import torch
+
+    from qiskit_addon_sqd_b200 import fermion
+
+    rng = np.random.default_rng(na * 1000 + nb)
+    amps = rng.standard_normal((na, nb))
+    amps[rng.random((na, nb)) < 0.3] *= 1e-3
+    ldc = (nb + 1) // 2 * 2
+    x = torch.zeros((na, ldc), dtype=torch.float64, device="cuda")
+    x[:, :nb] = torch.from_numpy(amps).cuda()
+    if ldc > nb:
+        x[:, nb:] = 99.0      # pad columns must not be looked at
+    rows, cols, wa, wb = fermion._carryover_on_device(x, nb, torch.cuda.current_device(), thr)
+    flat = np.abs(amps.reshape(-1))
+    order = np.argsort(flat)
+    big = order[np.searchsorted(flat, thr, sorter=order):]
+    r, c = np.divmod(big, nb)
+    r, c = np.unique(r), np.unique(c)
+    assert np.array_equal(rows, r) and np.array_equal(cols, c)
+    assert np.array_equal(wa, np.sum(np.abs(amps[r]) ** 2, axis=1))
+    assert np.array_equal(wb, np.sum(np.abs(amps[:, c]) ** 2, axis=0))
