@@ -399,58 +399,68 @@ __device__ __forceinline__ int snake_chunk(int k) {
 // ---------------------------------------------------------------------------------------------------
 // "Wide" kernel: the same sum as kernels B + A, for subspaces whose rows do not fit the shared-memory
 // staging of the kernels above (nb > 5760 for v1, nb > 8192 for v2) -- up to the 2^19 strings per spin of
-// the tables.  Nothing is staged: CTA = one alpha row x kWideCols consecutive columns, thread = one
-// column, every operand is gathered through L1/L2 (an integral row g_ab[pq,:] is shared by the whole CTA,
-// the rows c[a',:] by the CTAs of one alpha row).  kWideBlock alpha single excitations share one pass
-// over the column's beta links (one load of the link word for kWideBlock FMAs, kWideBlock independent
-// accumulation chains).  No plan, no SELL copies; every element is summed by one thread in table order,
-// so builds restricted to row blocks are bit-equal to the full build.
+// the tables.  No row of c is staged: CTA = one alpha row x kWideCols consecutive columns, thread = one
+// column, the c[a', b'] operands are gathered through L1/L2 (the rows c[a',:] are shared by the CTAs of one
+// alpha row).  kWideBlock alpha single excitations share one pass over the column's beta links (one load
+// of the link word for kWideBlock FMAs, kWideBlock independent accumulation chains); their integral rows
+// g_ab[pq,:] are copied to shared memory first (kWideBlock * ldg doubles: a random 64-bit gather costs a few
+// bank cycles there against one L1 tag lookup per distinct 128-byte line -- ncu of the first version, with
+// both gathers in L1: 74 % L1 throughput, 0.74 IPC).  No plan, no SELL copies; every element is summed by one
+// thread in table order, so builds restricted to row blocks are bit-equal to the full build.
 // ---------------------------------------------------------------------------------------------------
 constexpr int kWideCols = 256;
-constexpr int kWideBlock = 4;
 
+template <int kWideBlock>
 __global__ void __launch_bounds__(kWideCols)
 sigma_wide_kernel(const SigmaArgs P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     if (P.done != nullptr && *P.done != 0) return;
     const double* __restrict__ c = P.c + slot_offset(P.slot_ptr, P.vec_stride);
     double* __restrict__ sig = P.sigma + slot_offset(P.slot_ptr, P.vec_stride);
     const sqd_operator& op = P.op;
     const int nb = op.b.n, ldc = op.ldc, ldg = op.ldg;
-    const int a = P.row_begin + (int)blockIdx.x;
-    const int b = (int)blockIdx.y * kWideCols + (int)threadIdx.x;
-    if (a >= P.row_end || b >= ldc) return;
-    if (b >= nb) {  // pad column
-        sig[(size_t)a * ldc + b] = 0.0;
-        return;
-    }
+    // column tile = fastest index: the CTAs in flight at any time cover a few alpha rows completely, so the rows
+    // c[a',:] they gather from stay in L2 (row-major CTA order spread 1000 resident CTAs over 1000 alpha rows:
+    // 53 GB of DRAM reads per build at 8.1e7 determinants, ncu)
+    const int n_tiles = (ldc + kWideCols - 1) / kWideCols;
+    const int a = P.row_begin + (int)(blockIdx.x / (unsigned)n_tiles);
+    const int b = (int)(blockIdx.x % (unsigned)n_tiles) * kWideCols + (int)threadIdx.x;
+    if (a >= P.row_end) return;                 // whole CTA
+    double* g_s = reinterpret_cast<double*>(smem_raw);   // [kWideBlock][ldg] integral rows of the current block
+    const bool live = b < nb;                   // pad / out-of-range columns only help with the staging
     const bool ham = op.use_same_spin != 0;
     const double* __restrict__ crow = c + (size_t)a * ldc;
-    double acc = __ldg(op.diag + (size_t)a * ldc + b) * crow[b];
-
-    // beta excitations of column b: singles carry Hb + sgn_b Wa[a, rs], doubles Hb
-    const int fb = __ldg(op.b.row_ptr + b), fs = fb + __ldg(op.b.n_single + b), fe = __ldg(op.b.row_ptr + b + 1);
-    const double* __restrict__ wa = op.Wa != nullptr ? op.Wa + (size_t)a * ldg : nullptr;
-    for (int f = fb; f < fs; ++f) {
-        const uint32_t pv = __ldg(op.b.pack + f);
-        double v = ham ? __ldg(op.b.val + f) : 0.0;
-        if (wa != nullptr) {
-            const double w = __ldg(wa + ((pv >> 19) & 0xfffu));
-            v += (pv >> 31) ? -w : w;
-        }
-        acc = fma(v, crow[pv & 0x7ffffu], acc);
-    }
+    double acc = 0.0;
+    int fb = 0, fs = 0;
     const int eb = __ldg(op.a.row_ptr + a), es = eb + __ldg(op.a.n_single + a), ee = __ldg(op.a.row_ptr + a + 1);
-    if (ham) {
-        for (int f = fs; f < fe; ++f) acc = fma(__ldg(op.b.val + f), crow[__ldg(op.b.col + f)], acc);
-        // alpha doubles
-        for (int e = es; e < ee; ++e)
-            acc = fma(__ldg(op.a.val + e), c[(size_t)__ldg(op.a.col + e) * ldc + b], acc);
+    if (live) {
+        acc = __ldg(op.diag + (size_t)a * ldc + b) * crow[b];
+        // beta excitations of column b: singles carry Hb + sgn_b Wa[a, rs], doubles Hb
+        fb = __ldg(op.b.row_ptr + b);
+        fs = fb + __ldg(op.b.n_single + b);
+        const int fe = __ldg(op.b.row_ptr + b + 1);
+        const double* __restrict__ wa = op.Wa != nullptr ? op.Wa + (size_t)a * ldg : nullptr;
+        for (int f = fb; f < fs; ++f) {
+            const uint32_t pv = __ldg(op.b.pack + f);
+            double v = ham ? __ldg(op.b.val + f) : 0.0;
+            if (wa != nullptr) {
+                const double w = __ldg(wa + ((pv >> 19) & 0xfffu));
+                v += (pv >> 31) ? -w : w;
+            }
+            acc = fma(v, crow[pv & 0x7ffffu], acc);
+        }
+        if (ham) {
+            for (int f = fs; f < fe; ++f) acc = fma(__ldg(op.b.val + f), crow[__ldg(op.b.col + f)], acc);
+            // alpha doubles
+            for (int e = es; e < ee; ++e)
+                acc = fma(__ldg(op.a.val + e), c[(size_t)__ldg(op.a.col + e) * ldc + b], acc);
+        }
     }
     // alpha singles: (Ha + sgn_a Wb[pq, b]) c[a', b] + sgn_a sum_{b'} sgn_b g_ab[pq, rs] c[a', b']
     for (int e0 = eb; e0 < es; e0 += kWideBlock) {
         const double* cr[kWideBlock];
-        const double* gr[kWideBlock];
         double sa[kWideBlock], sum[kWideBlock];
+        __syncthreads();   // the previous block's rows are no longer read
 #pragma unroll
         for (int j = 0; j < kWideBlock; ++j) {
             const int e = e0 + j;
@@ -459,37 +469,32 @@ sigma_wide_kernel(const SigmaArgs P) {
             const uint32_t pq = m & 0x7fffffffu;
             sa[j] = ok ? ((m >> 31) ? -1.0 : 1.0) : 0.0;
             cr[j] = c + (size_t)(ok ? __ldg(op.a.col + e) : (uint32_t)a) * ldc;
-            gr[j] = op.gab + (size_t)pq * ldg;
             sum[j] = 0.0;
-            if (ok) {
+            const double* __restrict__ grow = op.gab + (size_t)pq * ldg;
+            for (int t = threadIdx.x; t < ldg; t += kWideCols) g_s[j * ldg + t] = __ldg(grow + t);
+            if (ok && live) {
                 const double va = ham ? __ldg(op.a.val + e) : 0.0;
                 const double wb = op.Wb != nullptr ? __ldg(op.Wb + (size_t)pq * ldc + b) : 0.0;
                 acc = fma(fma(sa[j], wb, va), cr[j][b], acc);
             }
         }
-        for (int f = fb; f < fs; ++f) {
+        __syncthreads();
+        for (int f = fb; f < fs; ++f) {   // empty for columns that are not live
             const uint32_t pv = __ldg(op.b.pack + f);
             const uint32_t bp = pv & 0x7ffffu, rs = (pv >> 19) & 0xfffu;
             const bool neg = (pv >> 31) != 0;
 #pragma unroll
             for (int j = 0; j < kWideBlock; ++j) {
-                const double t = __ldg(gr[j] + rs) * cr[j][bp];
+                const double t = g_s[j * ldg + rs] * cr[j][bp];
                 sum[j] += neg ? -t : t;
             }
         }
 #pragma unroll
         for (int j = 0; j < kWideBlock; ++j) acc = fma(sa[j], sum[j], acc);
     }
-    sig[(size_t)a * ldc + b] = acc;
+    if (b < ldc) sig[(size_t)a * ldc + b] = live ? acc : 0.0;   // pad column: zero
 }
 
-static int launch_sigma_wide(const SigmaArgs& args, cudaStream_t st) {
-    const int rows_owned = args.row_end - args.row_begin;
-    if (rows_owned <= 0) return 0;
-    dim3 grid(rows_owned, (args.op.ldc + kWideCols - 1) / kWideCols);
-    sigma_wide_kernel<<<grid, kWideCols, 0, st>>>(args);
-    return check_launch("sigma_wide_kernel");
-}
 
 struct ChunkInfo {
     int a, slot, it_beg, db_beg, db_end, n_total;
@@ -992,6 +997,29 @@ static int launch_sigma(const SigmaArgs& args, const SigmaPlan& pl, cudaStream_t
         return check_launch("sigma_combine_kernel");
     }
     return 0;
+}
+
+static int launch_sigma_wide(const SigmaArgs& args, cudaStream_t st) {
+    const int rows_owned = args.row_end - args.row_begin;
+    if (rows_owned <= 0) return 0;
+    // alpha single excitations per pass over a column's beta links: SQD_WIDE_BLOCK = 2 (default), 4 or 8
+    // (1e8 determinants, (30e,30o): 228 / 249 / 410 ms per build -- more rows of c in flight thrash L1)
+    static const int knob_block = env_int("SQD_WIDE_BLOCK", 2);
+    const int wb = (knob_block == 4 || knob_block == 8) ? knob_block : 2;
+    static bool cfg_w[3][64] = {};
+    const size_t smem = (size_t)wb * args.op.ldg * sizeof(double);
+    const unsigned grid = (unsigned)rows_owned * (unsigned)((args.op.ldc + kWideCols - 1) / kWideCols);
+    if (wb == 2) {
+        if (opt_in_smem(sigma_wide_kernel<2>, smem, cfg_w[0])) return -2;
+        sigma_wide_kernel<2><<<grid, kWideCols, smem, st>>>(args);
+    } else if (wb == 8) {
+        if (opt_in_smem(sigma_wide_kernel<8>, smem, cfg_w[2])) return -2;
+        sigma_wide_kernel<8><<<grid, kWideCols, smem, st>>>(args);
+    } else {
+        if (opt_in_smem(sigma_wide_kernel<4>, smem, cfg_w[1])) return -2;
+        sigma_wide_kernel<4><<<grid, kWideCols, smem, st>>>(args);
+    }
+    return check_launch("sigma_wide_kernel");
 }
 
 static thread_local long long* g_prof = nullptr;

@@ -10,7 +10,7 @@ from qiskit_addon_sqd_b200 import _lib, qubit
 
 rows, op = bx._c3_inputs()
 lib = _lib.load()
-keys = torch.unique(qubit._keys_device(torch, lib, rows))
+_, keys, _ = _lib.sort_unique(torch, None, qubit._keys_device(torch, lib, rows))
 for _ in range(2):
     csr = qubit._project_device(torch, lib, keys, op)
 torch.cuda.synchronize()
