@@ -46,7 +46,7 @@ from . import _lib
 # size (measured on the bench workloads: 234 cycles in total for 8 solves at max_space 12, 238 at 6, 241 at
 # 5) while every basis vector costs a pass over HBM/L2 in three kernels of every cycle: 6 is ~8 % faster per
 # step than 12 and halves the workspace.  ``max_space=`` passes through literally.
-_PYSCF_DEFAULTS = dict(max_cycle=100, max_space=6, lindep=1e-14, level_shift=1e-4)
+_PYSCF_DEFAULTS = dict(max_cycle=100, max_space=int(os.environ.get("SQD_MAX_SPACE", "6")), lindep=1e-14, level_shift=1e-4)
 # pyscf's conv_tol is 1e-9 with |r| < sqrt(tol).  That leaves O(1e-9/gap) in the energy; to meet the
 # 1e-8 Ha parity bar against any converged solver the default here is tighter.  Passing ``tol=`` gives
 # pyscf's rule (|dE| < tol and |r| < sqrt(tol)) literally.
