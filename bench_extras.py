@@ -264,6 +264,82 @@ def recovery_extras(torch, dev, cpu: bool = True) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
+# sample formats and loop glue: bit_array_to_arrays, carry-over selection, the whole SQD loop
+# ------------------------------------------------------------------------------------------------
+def formats_extras(torch, fermion, dev, cpu: bool = True) -> dict:
+    from qiskit_addon_sqd_b200 import counts
+    from qiskit_addon_sqd_b200._synthetic import noisy_samples
+
+    out = {}
+    norb, nelec, shots = 30, (15, 15), 1_000_000
+    ba = noisy_samples(norb, nelec, shots, 3162, 0.03, 110)
+    ms, (rows, probs) = _wall_ms(torch, lambda: counts.bit_array_to_arrays(ba), 3)
+    rec = {"workload": f"bit_array_to_arrays: {shots} shots of {2 * norb} bits (packed bytes in, bool matrix of the "
+                       "distinct rows + probabilities out, host arrays)", "e2e_ms": ms, "unique_rows": int(rows.shape[0]),
+           "shots_per_s": shots / (ms * 1e-3)}
+    if cpu:
+        # the reference's own three numpy calls (counts.py:57-60) on a bounded sample of the same shots
+        ns = 100_000
+        sub = ba.array[:ns]
+        t0 = time.perf_counter()
+        bool_array = np.unpackbits(sub, axis=-1)[..., -2 * norb:].astype(bool)
+        np.unique(bool_array, axis=0, return_counts=True)
+        dt = time.perf_counter() - t0
+        rec["cpu_baseline"] = {"kind": "reference", "cores": 1, "sample": f"first {ns} shots, the numpy calls of "
+                               "counts.py:57-60 verbatim", "seconds": dt, "shots_per_s": ns / dt}
+    out["bit_array_to_arrays"] = rec
+
+    # carry-over selection at 1e5 and 1e6 amplitudes: device (resident amplitudes) vs the reference's numpy lines
+    for na in (316, 1000):
+        rng = np.random.default_rng(na)
+        amps = rng.standard_normal((na, na)) * np.exp(-6.0 * rng.random((na, na)))
+        amps /= np.linalg.norm(amps)
+        x = torch.from_numpy(amps).to(dev)
+        thr = 1e-4
+        ms, sel = _wall_ms(torch, lambda: fermion._carryover_on_device(x, na, dev.index or 0, thr), 5)
+        rec = {"n_det": na * na, "e2e_ms": ms, "rows_selected": int(len(sel[0])), "cols_selected": int(len(sel[1]))}
+        if cpu:
+            t0 = time.perf_counter()
+            flat = np.abs(amps.reshape(-1))
+            order = np.argsort(flat)
+            big = order[np.searchsorted(flat, thr, sorter=order):]
+            r, c = np.divmod(big, na)
+            r, c = np.unique(r), np.unique(c)
+            wa = np.sum(np.abs(amps[r]) ** 2, axis=1)
+            wb = np.sum(np.abs(amps[:, c]) ** 2, axis=0)
+            rec["cpu_reference_ms"] = 1e3 * (time.perf_counter() - t0)
+            rec["bit_equal"] = bool(np.array_equal(sel[0], r) and np.array_equal(sel[1], c)
+                                    and np.array_equal(sel[2], wa) and np.array_equal(sel[3], wb))
+        out[f"carryover_{na * na}"] = rec
+    out["carryover_note"] = ("sqd_carryover on amplitudes resident on the device + read-back of na+nb flags/weights, "
+                             "against the reference's lines fermion.py:607-622 (argsort over all amplitudes) on the host")
+    return out
+
+
+def sqd_loop_extras(torch, fermion) -> dict:
+    """BASELINE configs[1]: the whole SQD loop, (10e,16o), 5 batches x <= 1e4 determinants, 3 recovery iterations."""
+    import functools
+
+    from qiskit_addon_sqd_b200._synthetic import noisy_samples, random_integrals
+
+    norb, nelec = 16, (5, 5)
+    h, g = random_integrals(norb, 102)
+    record = noisy_samples(norb, nelec, shots=10_000, n_strings=400, noise=0.04, seed=202)
+    solver = functools.partial(fermion.solve_sci_batch, spin_sq=0.0, compute_rdms=False)
+
+    def run():
+        return fermion.diagonalize_fermionic_hamiltonian(
+            h, g, record, samples_per_batch=300, norb=norb, nelec=nelec, num_batches=5, max_iterations=3,
+            max_dim=100, sci_solver=solver, symmetrize_spin=True, seed=5)
+
+    ms, best = _wall_ms(torch, run, 3)
+    return {"workload": "configs[1]: diagonalize_fermionic_hamiltonian, (10e,16o), 10 000 shots, 3 iterations x 5 "
+                        "subspaces of <= 100 x 100 strings, spin_sq = 0, host arrays in and out",
+            "loop_ms": ms, "ms_per_iteration": ms / 3, "best_energy": float(best.energy),
+            "n_det_best": int(best.sci_state.amplitudes.size)}
+
+
+# ------------------------------------------------------------------------------------------------
 # N > 1: sharded single solve and strong scaling of the literal configs[3]
 # ------------------------------------------------------------------------------------------------
 def sharded_extras(bench, torch, dist, fermion, rank: int, world: int, dev, workload: str = "c5") -> dict:
