@@ -32,10 +32,11 @@ with open(os.path.join(out, "r2_other_kernels_ncu.md"), "w") as md:
     md.write("# ncu `--set full` summaries: kernels outside the fermion sigma build (round 2)\n\n"
              "Captured by `tools/gpu_profile_r2b.sh` (`--clock-control none`, cold cache per launch, every launch "
              "replayed ~40 times: durations here are NOT bench values).  Workloads: `qubit` = BASELINE configs[2] "
-             "(40 qubits, 1e4 Pauli terms, 74 637 unique rows: projection + `solve_qubit`), `recover` = 1e5 "
+             "(40 qubits, 1e4 Pauli terms, 3e5 sampled rows, 74 637 unique: the first 14 launches are the key sort of "
+             "`sqd_sort_unique`; `pauli2` = the projection kernels of the same workload, count and fill pass), `recover` = 1e5 "
              "bitstrings of (30e,30o), exact numpy stream, `wide` = the staging-free sigma kernel at one "
              "9000 x 9000 = 8.1e7-determinant subspace.  Full metric tables: `profiles/r2_<name>_ncu_raw.csv`.\n")
-    for name in ("qubit", "recover", "wide"):
+    for name in ("qubit", "pauli2", "recover", "wide"):
         rep = os.path.join(go, f"r2prof_{name}.ncu-rep")
         if not os.path.exists(rep):
             continue
