@@ -19,6 +19,13 @@ def bitstring_matrix_to_integers(bitstring_matrix: np.ndarray) -> np.ndarray:
     (reference ``counts.py:186-201``)."""
     bits = np.asarray(bitstring_matrix)
     n_rows, n_bits = bits.shape
+    if 0 < n_bits < 64:
+        # packbits fills the LAST byte with zero bits: the row is left-aligned in a big-endian 64-bit word,
+        # one shift brings it down (no padded copy of the matrix: the loop calls this twice per batch)
+        packed = np.packbits(bits.astype(bool, copy=False), axis=1)
+        wide = np.zeros((n_rows, 8), dtype=np.uint8)
+        wide[:, : packed.shape[1]] = packed
+        return (wide.view(">u8").reshape(n_rows) >> np.uint64(64 - n_bits)).astype(int)
     pad = (-n_bits) % 8
     packed = np.packbits(np.pad(bits.astype(bool), ((0, 0), (pad, 0))), axis=1)  # left-padded bytes
     if n_bits < 64:

@@ -753,6 +753,7 @@ def solve_sci_batch(
     norb, _ = one_body_tensor.shape  # as the reference: norb comes from the tensor (fermion.py:711)
     devices = kwargs.pop("devices", None)
     want_rdm = bool(kwargs.pop("compute_rdms", True))
+    ints_cache = kwargs.pop("_resident_integrals", None)   # private: set by diagonalize_fermionic_hamiltonian
     shift = float(kwargs.pop("shift", _FIX_SPIN_DEFAULT_SHIFT))
     opts = _solver_options(kwargs)
     if devices is None:
@@ -796,7 +797,12 @@ def solve_sci_batch(
             continue
         with torch.cuda.device(d):
             dev = torch.device("cuda", d)
-            ints = _DeviceIntegrals(torch, one_body_tensor, two_body_tensor, dev)
+            # inside the SQD loop the integrals are uploaded once per device and stay resident between iterations
+            ints = ints_cache.get(d) if ints_cache is not None else None
+            if ints is None:
+                ints = _DeviceIntegrals(torch, one_body_tensor, two_body_tensor, dev)
+                if ints_cache is not None:
+                    ints_cache[d] = ints
             # strings of every subspace of this device in one array -> one host-to-device copy
             parts, off = [], 0
             for k in ks:
@@ -1098,6 +1104,12 @@ def diagonalize_fermionic_hamiltonian(
         include = (include_configurations, include_configurations)
     include = (np.unique(include[0]), np.unique(include[1]))
     solver = solve_sci_batch if sci_solver is None else sci_solver
+    if getattr(solver, "func", solver) is solve_sci_batch:
+        # our own solver (plain or functools.partial of it): the Hamiltonian does not change inside this call,
+        # so its device copy is made once (per device) instead of once per iteration
+        import functools
+
+        solver = functools.partial(solver, _resident_integrals={})
     raw_bitstrings, raw_probs = bit_array_to_arrays(bit_array)
     run = _SQDRun(raw_bitstrings, raw_probs, norb, (n_alpha, n_beta), samples_per_batch, num_batches,
                   symmetrize_spin, include, dims, energy_tol, occupancies_tol, carryover_threshold,
