@@ -347,6 +347,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 extra["recovery"] = bx.recovery_extras(torch, dev, cpu)
                 extra["formats"] = bx.formats_extras(torch, fermion, dev, cpu)
                 extra["sqd_loop_c2"] = bx.sqd_loop_extras(torch, fermion)
+                extra["s8"] = bx.s8_extras(torch, fermion, dev, peak_gbs)
     sig_ms = np.mean([s.sigma_ms / max(s.cycles, 1) for s in stats_prof])
     sig_bytes = np.mean([sigma_algorithmic_bytes(s) for s in stats_prof])
     v2 = all(s.sigma_path == 2 for s in stats_prof)

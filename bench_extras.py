@@ -340,6 +340,49 @@ def sqd_loop_extras(torch, fermion) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------
+# scale-up point of SURVEY 8(d): one subspace of 1e8 determinants (vectors >> L2, rows beyond the sigma staging)
+# ------------------------------------------------------------------------------------------------
+def s8_extras(torch, fermion, dev, peak_gbs: float, n: int = 10_000, cycles: int = 4) -> dict:
+    from qiskit_addon_sqd_b200._synthetic import hf_centred_strings, random_integrals
+
+    free, _total = torch.cuda.mem_get_info()
+    need = 22.0 * 8.0 * n * n   # vectors of the Davidson workspace + diagonal + sigma + tables, with headroom
+    if free < need:
+        return {"skipped": f"needs {need / 1e9:.0f} GB of free device memory, {free / 1e9:.0f} GB available"}
+    norb, ne = 30, 15
+    h, g = random_integrals(norb, 108)
+    sa = hf_centred_strings(norb, ne, n, 21)
+    sb = hf_centred_strings(norb, ne, n, 22)
+    ints = fermion._DeviceIntegrals(torch, h, g, dev)
+    opts = fermion._solver_options({"max_cycle": cycles})
+    t0 = time.perf_counter()
+    r = fermion._solve_on_device(sa, sb, norb, ints, None, 0.2, opts, want_spin=False, want_rdm=False,
+                                 download=False, profile=True)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    st = r["stats"]
+    fma = (st.singles_a / st.na) * (st.singles_b / st.nb) * st.n_det + st.nnz_a * st.nb + st.nnz_b * st.na
+    sigma_ms = st.sigma_ms / max(st.sigma_builds, 1)
+    rest_ms = (st.davidson_ms - st.sigma_ms) / max(st.cycles, 1)
+    # basis sizes m = 1 .. cycles (no restart within `cycles` <= max_space): gram m+1, residual 2m+3, ortho1/2 m+2 each
+    ms_ = range(1, st.cycles + 1)
+    vec_bytes = 8.0 * st.n_det * sum((m + 1) + (2 * m + 3) + 2 * (m + 2) for m in ms_) / max(st.cycles, 1)
+    del r
+    return {
+        "workload": f"s8: ONE (30e,30o) subspace of {n} x {n} = {st.n_det} determinants, {st.cycles} Davidson cycles "
+                    "(not converged: a timing of the kernels at the scale where vectors no longer fit in L2)",
+        "sigma_path": {1: "v1", 2: "v2", 3: "wide"}.get(st.sigma_path, "?"),
+        "nnz_a": st.nnz_a, "nnz_b": st.nnz_b, "singles_a": st.singles_a, "singles_b": st.singles_b,
+        "sigma_ms_per_build": sigma_ms, "gathered_fma_per_build": fma,
+        "sigma_gfma_per_s": fma / (sigma_ms * 1e-3) / 1e9,
+        "vector_kernels_ms_per_cycle": rest_ms, "vector_bytes_per_cycle_model": vec_bytes,
+        "vector_kernels_gbs": vec_bytes / (rest_ms * 1e-3) / 1e9,
+        "vector_kernels_frac_of_hbm_peak": vec_bytes / (rest_ms * 1e-3) / 1e9 / peak_gbs,
+        "wall_s_incl_tables": wall,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
 # N > 1: sharded single solve and strong scaling of the literal configs[3]
 # ------------------------------------------------------------------------------------------------
 def sharded_extras(bench, torch, dist, fermion, rank: int, world: int, dev, workload: str = "c5") -> dict:

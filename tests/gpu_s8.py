@@ -33,8 +33,8 @@ links = st.singles_a * st.nb + st.singles_b * st.na
 fma = (st.singles_a / st.na) * (st.singles_b / st.nb) * n_det + st.nnz_a * st.nb + st.nnz_b * st.na
 sigma_ms = st.sigma_ms / max(st.sigma_builds, 1)
 rest_ms = (st.davidson_ms - st.sigma_ms) / max(st.cycles, 1)
-m_avg = min(cycles, opts["max_space"]) / 2 + 1
-vec_bytes = 8.0 * n_det * ((m_avg + 1) + (2 * m_avg + 3) + 2 * (m_avg + 2))
+# basis sizes m = 1 .. cycles: gram m+1 vectors, residual 2m+3, ortho1 / ortho2 m+2 each
+vec_bytes = 8.0 * n_det * sum((m + 1) + (2 * m + 3) + 2 * (m + 2) for m in range(1, st.cycles + 1)) / max(st.cycles, 1)
 print(json.dumps({
     "workload": f"s8: (30e,30o) {n}x{n} = {n_det} determinants, one subspace",
     "sigma_path": {1: "v1", 2: "v2", 3: "wide"}[st.sigma_path],
