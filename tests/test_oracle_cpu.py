@@ -49,6 +49,30 @@ def test_product_path_refuses_to_run_without_cuda():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         configuration_recovery.recover_configurations(
             np.zeros((1, 4), dtype=bool), np.ones(1), (np.ones(2), np.ones(2)), 1, 1, rand_seed=0)
+    # the sample-format functions that moved to the device this round refuse as well
+    from qiskit_addon_sqd_b200 import counts
+    from qiskit_addon_sqd_b200._synthetic import PackedBitArray
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        counts.bit_array_to_arrays(PackedBitArray(np.array([[3], [1]], dtype=np.uint8), 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        qubit.sort_and_remove_duplicates(np.zeros((2, 3), dtype=bool))
+
+
+def test_solver_option_mapping():
+    """pyscf ``kernel_fixed_space`` keywords (reference ``fermion.py:651, 722, 817``) and our ``sigma_path`` extra."""
+    from qiskit_addon_sqd_b200 import fermion
+
+    o = fermion._solver_options({"tol": 1e-9, "max_cycle": 7, "max_space": 5, "lindep": 1e-12, "verbose": 4})
+    assert o["tol"] == 1e-9 and o["tol_residual"] == pytest.approx(np.sqrt(1e-9))
+    assert (o["max_cycle"], o["max_space"], o["lindep"], o["sigma_path"]) == (7, 5, 1e-12, "auto")
+    assert fermion._solver_options({"sigma_path": "wide"})["sigma_path"] == "wide"
+    with pytest.raises(ValueError, match="sigma_path"):
+        fermion._solver_options({"sigma_path": "fast"})
+    with pytest.raises(NotImplementedError, match="nroots=1"):
+        fermion._solver_options({"nroots": 2})
+    with pytest.warns(UserWarning, match="unsupported solver options"):
+        fermion._solver_options({"frobnicate": 1})
 
 
 def test_product_package_does_not_import_the_oracle():
